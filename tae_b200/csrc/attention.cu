@@ -1,0 +1,608 @@
+// attention.cu — short-sequence attention, whole sequence resident in shared memory.
+//
+// Replaces F.scaled_dot_product_attention(q, k, v) (tae.py:78; non-causal, no mask, scale 1/sqrt(hd)) together
+// with the qkv un-bind permute (tae.py:74-75) and the head merge (tae.py:80): the kernels index the packed
+// [B*N, 3*H*hd] qkv buffer directly and write the merged [B*N, H*hd] layout, so neither permute is materialised.
+//
+// Two code paths:
+//   * tensor-core path (hd == 64, N in {64, 256}: the patch32 / patch16 grids): one CTA per (image, head),
+//     one warp per 16 query rows, bf16 mma.sync.m16n8k16 with fp32 accumulation, exp2-domain online softmax with
+//     quad shuffles.  Backward recomputes P from the saved log-sum-exp and runs two register-resident phases
+//     (dK/dV with one warp per 16 keys, then dQ with one warp per 16 queries) — no atomics, deterministic.
+//   * generic path (any N <= 128, hd <= 128; the 4- and 16-token grids of patch128 / patch64 with hd = 80):
+//     one warp per (image, head), fp32 FMA in shared memory — these problems are a few KB each and are
+//     launch/latency-bound, tensor cores do not pay.
+#include "common.cuh"
+
+namespace tae {
+namespace attn {
+
+// =============================================================================================
+// Tensor-core path
+// =============================================================================================
+constexpr int HD = 64;
+constexpr int LDS = 72;  // padded smem row (144 B): ldmatrix of 8 rows hits 32 distinct banks
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// smem byte addresses of ldmatrix row pointers (see fragment layouts of mma.m16n8k16)
+// A operand: 16 rows (r0..) x 16 k (k0..) of a row-major [row][k] tile
+__device__ __forceinline__ uint32_t addr_a(uint32_t base, int r0, int k0, int lane) {
+  const int row = r0 + (lane & 7) + ((lane >> 3) & 1) * 8;
+  const int col = k0 + (lane >> 4) * 8;
+  return base + (uint32_t)(row * LDS + col) * 2u;
+}
+// B operand from smem stored [n][k] (k contiguous): two n-tiles (n0.., n0+8..) x 16 k; regs {b0,b1 | b0,b1}
+__device__ __forceinline__ uint32_t addr_b(uint32_t base, int n0, int k0, int lane) {
+  const int row = n0 + (lane & 7) + (lane >> 4) * 8;
+  const int col = k0 + ((lane >> 3) & 1) * 8;
+  return base + (uint32_t)(row * LDS + col) * 2u;
+}
+// B operand from smem stored [k][n] (n contiguous), loaded with .trans: 16 k (k0..) x two n-tiles (n0.., n0+8..)
+__device__ __forceinline__ uint32_t addr_bt(uint32_t base, int k0, int n0, int lane) {
+  const int row = k0 + (lane & 7) + ((lane >> 3) & 1) * 8;
+  const int col = n0 + (lane >> 4) * 8;
+  return base + (uint32_t)(row * LDS + col) * 2u;
+}
+
+// cooperative load of `count` matrices [N][HD] (row stride = ld_g elements in global) into padded smem
+template <int N, int NTHREADS>
+__device__ __forceinline__ void load_rows(bf16* s, const bf16* g, size_t ld_g, int tid) {
+  for (int c = tid; c < N * 8; c += NTHREADS) {
+    const int row = c >> 3, ch = c & 7;
+    const uint4 v = ld_nc_v4(g + (size_t)row * ld_g + ch * 8);
+    *reinterpret_cast<uint4*>(s + row * LDS + ch * 8) = v;
+  }
+}
+
+template <int N>
+__global__ void __launch_bounds__(N * 2, 1)
+attn_fwd_mma(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* __restrict__ lse, int H, float scale_log2) {
+  constexpr int NT = N * 2;  // threads: one warp per 16 queries
+  extern __shared__ uint4 smem_u4[];
+  bf16* sQ = reinterpret_cast<bf16*>(smem_u4);
+  bf16* sK = sQ + N * LDS;
+  bf16* sV = sK + N * LDS;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.x / H, h = blockIdx.x % H;
+  const int D = H * HD;
+  const size_t ldq = (size_t)3 * D;
+  const bf16* gq = qkv + (size_t)b * N * ldq + (size_t)h * HD;
+  load_rows<N, NT>(sQ, gq, ldq, tid);
+  load_rows<N, NT>(sK, gq + D, ldq, tid);
+  load_rows<N, NT>(sV, gq + 2 * D, ldq, tid);
+  __syncthreads();
+
+  const uint32_t bQ = smem_u32(sQ), bK = smem_u32(sK), bV = smem_u32(sV);
+  const int q0 = warp * 16;
+  uint32_t qf[4][4];
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) ldsm_x4(qf[ks], addr_a(bQ, q0, ks * 16, lane));
+
+  float o[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+
+#pragma unroll 1
+  for (int kc = 0; kc < N / 64; ++kc) {
+    float s[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {
+        uint32_t kb[4];
+        ldsm_x4(kb, addr_b(bK, kc * 64 + np * 16, ks * 16, lane));
+        mma16816(s[2 * np], qf[ks], kb[0], kb[1]);
+        mma16816(s[2 * np + 1], qf[ks], kb[2], kb[3]);
+      }
+    }
+    // online softmax in the exp2 domain (scores pre-multiplied by scale*log2(e))
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      s[i][0] *= scale_log2;
+      s[i][1] *= scale_log2;
+      s[i][2] *= scale_log2;
+      s[i][3] *= scale_log2;
+      mx0 = fmaxf(mx0, fmaxf(s[i][0], s[i][1]));
+      mx1 = fmaxf(mx1, fmaxf(s[i][2], s[i][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+    const float c0 = exp2f(m0 - mn0), c1 = exp2f(m1 - mn1);
+    m0 = mn0;
+    m1 = mn1;
+    float rs0 = 0.f, rs1 = 0.f;
+    uint32_t pf[4][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float p0 = exp2f(s[i][0] - mn0), p1 = exp2f(s[i][1] - mn0);
+      const float p2 = exp2f(s[i][2] - mn1), p3 = exp2f(s[i][3] - mn1);
+      rs0 += p0 + p1;
+      rs1 += p2 + p3;
+      // C fragments of n-tiles (2kk, 2kk+1) are the A fragment of k-step kk
+      pf[i >> 1][(i & 1) * 2 + 0] = pack_bf16x2(p0, p1);
+      pf[i >> 1][(i & 1) * 2 + 1] = pack_bf16x2(p2, p3);
+    }
+    l0 = l0 * c0 + rs0;
+    l1 = l1 * c1 + rs1;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      o[i][0] *= c0;
+      o[i][1] *= c0;
+      o[i][2] *= c1;
+      o[i][3] *= c1;
+    }
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+      for (int dp = 0; dp < 4; ++dp) {
+        uint32_t vb[4];
+        ldsm_x4_t(vb, addr_bt(bV, kc * 64 + kk * 16, dp * 16, lane));
+        mma16816(o[2 * dp], pf[kk], vb[0], vb[1]);
+        mma16816(o[2 * dp + 1], pf[kk], vb[2], vb[3]);
+      }
+    }
+  }
+  // finish: row sums across the quad, normalise, log-sum-exp (natural log)
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float inv0 = 1.f / l0, inv1 = 1.f / l1;
+  const int g = lane >> 2, t = lane & 3;
+  if (t == 0) {
+    float* lrow = lse + ((size_t)b * H + h) * N;
+    lrow[q0 + g] = (m0 + log2f(l0)) * 0.69314718055994530942f;
+    lrow[q0 + g + 8] = (m1 + log2f(l1)) * 0.69314718055994530942f;
+  }
+  // stage this warp's 16x64 output tile through its own (now dead) Q rows, then 128-bit coalesced stores
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    *reinterpret_cast<uint32_t*>(sQ + (q0 + g) * LDS + i * 8 + 2 * t) = pack_bf16x2(o[i][0] * inv0, o[i][1] * inv0);
+    *reinterpret_cast<uint32_t*>(sQ + (q0 + g + 8) * LDS + i * 8 + 2 * t) = pack_bf16x2(o[i][2] * inv1, o[i][3] * inv1);
+  }
+  __syncwarp();
+  bf16* go = out + (size_t)b * N * D + (size_t)h * HD;
+#pragma unroll
+  for (int c = lane; c < 16 * 8; c += 32) {
+    const int row = q0 + (c >> 3), ch = c & 7;
+    *reinterpret_cast<uint4*>(go + (size_t)row * D + ch * 8) = *reinterpret_cast<const uint4*>(sQ + row * LDS + ch * 8);
+  }
+}
+
+template <int N>
+__global__ void __launch_bounds__(N * 2, 1)
+attn_bwd_mma(const bf16* __restrict__ qkv, const bf16* __restrict__ out, const bf16* __restrict__ dout,
+             const float* __restrict__ lse, bf16* __restrict__ dqkv, int H, float scale, float scale_log2) {
+  constexpr int NT = N * 2;
+  extern __shared__ uint4 smem_u4[];
+  bf16* sQ = reinterpret_cast<bf16*>(smem_u4);
+  bf16* sK = sQ + N * LDS;
+  bf16* sV = sK + N * LDS;
+  bf16* sdO = sV + N * LDS;
+  float* sLse = reinterpret_cast<float*>(sdO + N * LDS);  // lse * log2(e)
+  float* sDelta = sLse + N;                               // rowsum(dO * O)
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.x / H, h = blockIdx.x % H;
+  const int D = H * HD;
+  const size_t ldq = (size_t)3 * D;
+  const bf16* gq = qkv + (size_t)b * N * ldq + (size_t)h * HD;
+  const bf16* go = out + (size_t)b * N * D + (size_t)h * HD;
+  const bf16* gdo = dout + (size_t)b * N * D + (size_t)h * HD;
+  load_rows<N, NT>(sQ, gq, ldq, tid);
+  load_rows<N, NT>(sK, gq + D, ldq, tid);
+  load_rows<N, NT>(sV, gq + 2 * D, ldq, tid);
+  // dO rows + delta = rowsum(dO * O): 8 consecutive lanes own the 8 16-byte chunks of one row
+  for (int c = tid; c < N * 8; c += NT) {
+    const int row = c >> 3, ch = c & 7;
+    const uint4 dv = ld_nc_v4(gdo + (size_t)row * D + ch * 8);
+    const uint4 ov = ld_nc_v4(go + (size_t)row * D + ch * 8);
+    *reinterpret_cast<uint4*>(sdO + row * LDS + ch * 8) = dv;
+    const uint32_t dw[4] = {dv.x, dv.y, dv.z, dv.w}, ow[4] = {ov.x, ov.y, ov.z, ov.w};
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 d2 = unpack_bf16x2(dw[j]), o2 = unpack_bf16x2(ow[j]);
+      acc += d2.x * o2.x + d2.y * o2.y;
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    if (ch == 0) sDelta[row] = acc;
+  }
+  for (int r = tid; r < N; r += NT) sLse[r] = lse[((size_t)b * H + h) * N + r] * 1.44269504088896340736f;
+  __syncthreads();
+
+  const uint32_t bQ = smem_u32(sQ), bK = smem_u32(sK), bV = smem_u32(sV), bdO = smem_u32(sdO);
+  const int g = lane >> 2, t = lane & 3;
+  bf16* gdq = dqkv + (size_t)b * N * ldq + (size_t)h * HD;
+
+  // ---------------- phase 1: this warp owns keys j0..j0+15 -> dK, dV ----------------
+  {
+    const int j0 = warp * 16;
+    uint32_t kf[4][4];
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) ldsm_x4(kf[ks], addr_a(bK, j0, ks * 16, lane));
+    float dk[8][4], dv[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = 0.f;
+      dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f;
+    }
+#pragma unroll 1
+    for (int i0 = 0; i0 < N; i0 += 16) {
+      // S^T[key, query] = K_j Q_i^T ; dP^T[key, query] = V_j dO_i^T
+      float st[2][4], dpt[2][4];
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        st[nt][0] = st[nt][1] = st[nt][2] = st[nt][3] = 0.f;
+        dpt[nt][0] = dpt[nt][1] = dpt[nt][2] = dpt[nt][3] = 0.f;
+      }
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        uint32_t qb[4], vf[4], ob[4];
+        ldsm_x4(qb, addr_b(bQ, i0, ks * 16, lane));
+        mma16816(st[0], kf[ks], qb[0], qb[1]);
+        mma16816(st[1], kf[ks], qb[2], qb[3]);
+        ldsm_x4(vf, addr_a(bV, j0, ks * 16, lane));
+        ldsm_x4(ob, addr_b(bdO, i0, ks * 16, lane));
+        mma16816(dpt[0], vf, ob[0], ob[1]);
+        mma16816(dpt[1], vf, ob[2], ob[3]);
+      }
+      // P^T = exp2(S^T*scale*log2e - lse2[query]); dS^T = P^T * (dP^T - delta[query])   (queries index columns)
+      uint32_t pa[4], dsa[4];
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        const int qc = i0 + nt * 8 + 2 * t;
+        const float l0 = sLse[qc], l1 = sLse[qc + 1];
+        const float d0 = sDelta[qc], d1 = sDelta[qc + 1];
+        const float p0 = exp2f(st[nt][0] * scale_log2 - l0), p1 = exp2f(st[nt][1] * scale_log2 - l1);
+        const float p2 = exp2f(st[nt][2] * scale_log2 - l0), p3 = exp2f(st[nt][3] * scale_log2 - l1);
+        pa[nt * 2 + 0] = pack_bf16x2(p0, p1);
+        pa[nt * 2 + 1] = pack_bf16x2(p2, p3);
+        dsa[nt * 2 + 0] = pack_bf16x2(p0 * (dpt[nt][0] - d0), p1 * (dpt[nt][1] - d1));
+        dsa[nt * 2 + 1] = pack_bf16x2(p2 * (dpt[nt][2] - d0), p3 * (dpt[nt][3] - d1));
+      }
+      // dV += P^T dO_i ; dK += dS^T Q_i     (k = 16 queries; B operands [query][hd] loaded transposed)
+#pragma unroll
+      for (int dp = 0; dp < 4; ++dp) {
+        uint32_t ob[4], qb[4];
+        ldsm_x4_t(ob, addr_bt(bdO, i0, dp * 16, lane));
+        mma16816(dv[2 * dp], pa, ob[0], ob[1]);
+        mma16816(dv[2 * dp + 1], pa, ob[2], ob[3]);
+        ldsm_x4_t(qb, addr_bt(bQ, i0, dp * 16, lane));
+        mma16816(dk[2 * dp], dsa, qb[0], qb[1]);
+        mma16816(dk[2 * dp + 1], dsa, qb[2], qb[3]);
+      }
+    }
+    bf16* gdk = gdq + D;
+    bf16* gdv = gdq + 2 * D;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int col = i * 8 + 2 * t;
+      *reinterpret_cast<uint32_t*>(gdk + (size_t)(j0 + g) * ldq + col) = pack_bf16x2(dk[i][0] * scale, dk[i][1] * scale);
+      *reinterpret_cast<uint32_t*>(gdk + (size_t)(j0 + g + 8) * ldq + col) = pack_bf16x2(dk[i][2] * scale, dk[i][3] * scale);
+      *reinterpret_cast<uint32_t*>(gdv + (size_t)(j0 + g) * ldq + col) = pack_bf16x2(dv[i][0], dv[i][1]);
+      *reinterpret_cast<uint32_t*>(gdv + (size_t)(j0 + g + 8) * ldq + col) = pack_bf16x2(dv[i][2], dv[i][3]);
+    }
+  }
+
+  // ---------------- phase 2: this warp owns queries i0..i0+15 -> dQ ----------------
+  {
+    const int i0 = warp * 16;
+    uint32_t qf[4][4], of[4][4];
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      ldsm_x4(qf[ks], addr_a(bQ, i0, ks * 16, lane));
+      ldsm_x4(of[ks], addr_a(bdO, i0, ks * 16, lane));
+    }
+    const float l0 = sLse[i0 + g], l1 = sLse[i0 + g + 8];
+    const float d0 = sDelta[i0 + g], d1 = sDelta[i0 + g + 8];
+    float dq[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
+#pragma unroll 1
+    for (int j0 = 0; j0 < N; j0 += 16) {
+      float s[2][4], dp_[2][4];
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+        dp_[nt][0] = dp_[nt][1] = dp_[nt][2] = dp_[nt][3] = 0.f;
+      }
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        uint32_t kb[4], vb[4];
+        ldsm_x4(kb, addr_b(bK, j0, ks * 16, lane));
+        mma16816(s[0], qf[ks], kb[0], kb[1]);
+        mma16816(s[1], qf[ks], kb[2], kb[3]);
+        ldsm_x4(vb, addr_b(bV, j0, ks * 16, lane));
+        mma16816(dp_[0], of[ks], vb[0], vb[1]);
+        mma16816(dp_[1], of[ks], vb[2], vb[3]);
+      }
+      uint32_t dsa[4];
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        const float p0 = exp2f(s[nt][0] * scale_log2 - l0), p1 = exp2f(s[nt][1] * scale_log2 - l0);
+        const float p2 = exp2f(s[nt][2] * scale_log2 - l1), p3 = exp2f(s[nt][3] * scale_log2 - l1);
+        dsa[nt * 2 + 0] = pack_bf16x2(p0 * (dp_[nt][0] - d0), p1 * (dp_[nt][1] - d0));
+        dsa[nt * 2 + 1] = pack_bf16x2(p2 * (dp_[nt][2] - d1), p3 * (dp_[nt][3] - d1));
+      }
+#pragma unroll
+      for (int dp = 0; dp < 4; ++dp) {
+        uint32_t kb[4];
+        ldsm_x4_t(kb, addr_bt(bK, j0, dp * 16, lane));
+        mma16816(dq[2 * dp], dsa, kb[0], kb[1]);
+        mma16816(dq[2 * dp + 1], dsa, kb[2], kb[3]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int col = i * 8 + 2 * t;
+      *reinterpret_cast<uint32_t*>(gdq + (size_t)(i0 + g) * ldq + col) = pack_bf16x2(dq[i][0] * scale, dq[i][1] * scale);
+      *reinterpret_cast<uint32_t*>(gdq + (size_t)(i0 + g + 8) * ldq + col) = pack_bf16x2(dq[i][2] * scale, dq[i][3] * scale);
+    }
+  }
+}
+
+// =============================================================================================
+// Generic path: one warp per (image, head), fp32 math in shared memory
+// =============================================================================================
+__device__ __forceinline__ void load_head_f32(float* s, const bf16* g, size_t ld_g, int N, int hd, int ldp, int lane) {
+  const int cpr = hd >> 3;  // 16-byte chunks per row
+  for (int c = lane; c < N * cpr; c += 32) {
+    const int row = c / cpr, ch = c - row * cpr;
+    const uint4 v = ld_nc_v4(g + (size_t)row * ld_g + ch * 8);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    float* dst = s + row * ldp + ch * 8;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = unpack_bf16x2(w[j]);
+      dst[2 * j] = f.x;
+      dst[2 * j + 1] = f.y;
+    }
+  }
+}
+
+// per-warp smem floats: fwd 3*N*ldp + N*(N+1); bwd 4*N*ldp + 2*N*(N+1) + N
+__global__ void attn_fwd_simt(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* __restrict__ lse, int BH,
+                              int N, int H, int hd, float scale, int per_warp_floats) {
+  extern __shared__ float smem_f[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wg = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (wg >= BH) return;  // no CTA-wide barriers below
+  const int b = wg / H, h = wg % H;
+  const int D = H * hd, ldp = hd + 1, ldn = N + 1;
+  const size_t ldq = (size_t)3 * D;
+  float* sq = smem_f + (size_t)warp * per_warp_floats;
+  float* sk = sq + N * ldp;
+  float* sv = sk + N * ldp;
+  float* sp = sv + N * ldp;
+  const bf16* gq = qkv + (size_t)b * N * ldq + (size_t)h * hd;
+  load_head_f32(sq, gq, ldq, N, hd, ldp, lane);
+  load_head_f32(sk, gq + D, ldq, N, hd, ldp, lane);
+  load_head_f32(sv, gq + 2 * D, ldq, N, hd, ldp, lane);
+  __syncwarp();
+  for (int e = lane; e < N * N; e += 32) {
+    const int i = e / N, j = e - i * N;
+    const float* a = sq + i * ldp;
+    const float* c = sk + j * ldp;
+    float acc = 0.f;
+    for (int d = 0; d < hd; ++d) acc = fmaf(a[d], c[d], acc);
+    sp[i * ldn + j] = acc * scale;
+  }
+  __syncwarp();
+  for (int i = lane; i < N; i += 32) {
+    float* row = sp + i * ldn;
+    float m = -INFINITY;
+    for (int j = 0; j < N; ++j) m = fmaxf(m, row[j]);
+    float l = 0.f;
+    for (int j = 0; j < N; ++j) {
+      const float p = __expf(row[j] - m);
+      row[j] = p;
+      l += p;
+    }
+    const float inv = 1.f / l;
+    for (int j = 0; j < N; ++j) row[j] *= inv;
+    lse[((size_t)b * H + h) * N + i] = m + __logf(l);
+  }
+  __syncwarp();
+  bf16* go = out + (size_t)b * N * D + (size_t)h * hd;
+  for (int e = lane; e < N * hd; e += 32) {
+    const int i = e / hd, d = e - i * hd;
+    const float* p = sp + i * ldn;
+    float acc = 0.f;
+    for (int j = 0; j < N; ++j) acc = fmaf(p[j], sv[j * ldp + d], acc);
+    go[(size_t)i * D + d] = __float2bfloat16_rn(acc);
+  }
+}
+
+__global__ void attn_bwd_simt(const bf16* __restrict__ qkv, const bf16* __restrict__ dout, const float* __restrict__ lse,
+                              bf16* __restrict__ dqkv, int BH, int N, int H, int hd, float scale, int per_warp_floats) {
+  extern __shared__ float smem_f[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wg = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (wg >= BH) return;
+  const int b = wg / H, h = wg % H;
+  const int D = H * hd, ldp = hd + 1, ldn = N + 1;
+  const size_t ldq = (size_t)3 * D;
+  float* sq = smem_f + (size_t)warp * per_warp_floats;
+  float* sk = sq + N * ldp;
+  float* sv = sk + N * ldp;
+  float* sdo = sv + N * ldp;
+  float* sp = sdo + N * ldp;   // P
+  float* sds = sp + N * ldn;   // dP, then dS
+  float* sdelta = sds + N * ldn;
+  const bf16* gq = qkv + (size_t)b * N * ldq + (size_t)h * hd;
+  load_head_f32(sq, gq, ldq, N, hd, ldp, lane);
+  load_head_f32(sk, gq + D, ldq, N, hd, ldp, lane);
+  load_head_f32(sv, gq + 2 * D, ldq, N, hd, ldp, lane);
+  load_head_f32(sdo, dout + (size_t)b * N * D + (size_t)h * hd, (size_t)D, N, hd, ldp, lane);
+  __syncwarp();
+  const float* lrow = lse + ((size_t)b * H + h) * N;
+  for (int e = lane; e < N * N; e += 32) {
+    const int i = e / N, j = e - i * N;
+    const float* qa = sq + i * ldp;
+    const float* ka = sk + j * ldp;
+    const float* da = sdo + i * ldp;
+    const float* va = sv + j * ldp;
+    float s = 0.f, dp = 0.f;
+    for (int d = 0; d < hd; ++d) {
+      s = fmaf(qa[d], ka[d], s);
+      dp = fmaf(da[d], va[d], dp);
+    }
+    sp[i * ldn + j] = __expf(s * scale - lrow[i]);
+    sds[i * ldn + j] = dp;
+  }
+  __syncwarp();
+  for (int i = lane; i < N; i += 32) {
+    float acc = 0.f;
+    for (int j = 0; j < N; ++j) acc = fmaf(sp[i * ldn + j], sds[i * ldn + j], acc);
+    sdelta[i] = acc;
+  }
+  __syncwarp();
+  for (int e = lane; e < N * N; e += 32) {
+    const int i = e / N, j = e - i * N;
+    sds[i * ldn + j] = sp[i * ldn + j] * (sds[i * ldn + j] - sdelta[i]) * scale;
+  }
+  __syncwarp();
+  bf16* gdq = dqkv + (size_t)b * N * ldq + (size_t)h * hd;
+  for (int e = lane; e < N * hd; e += 32) {
+    const int r = e / hd, d = e - r * hd;
+    float aq = 0.f, ak = 0.f, av = 0.f;
+    for (int j = 0; j < N; ++j) {
+      aq = fmaf(sds[r * ldn + j], sk[j * ldp + d], aq);   // dQ[r] = sum_j dS[r,j] K[j]
+      ak = fmaf(sds[j * ldn + r], sq[j * ldp + d], ak);   // dK[r] = sum_i dS[i,r] Q[i]
+      av = fmaf(sp[j * ldn + r], sdo[j * ldp + d], av);   // dV[r] = sum_i P[i,r] dO[i]
+    }
+    gdq[(size_t)r * ldq + d] = __float2bfloat16_rn(aq);
+    gdq[(size_t)r * ldq + D + d] = __float2bfloat16_rn(ak);
+    gdq[(size_t)r * ldq + 2 * D + d] = __float2bfloat16_rn(av);
+  }
+}
+
+constexpr int SIMT_MAX_SMEM = 200 * 1024;
+
+static int simt_config(int N, int hd, bool bwd, int* wpc, int* per_warp_floats) {
+  const int ldp = hd + 1, ldn = N + 1;
+  const int pw = bwd ? (4 * N * ldp + 2 * N * ldn + N) : (3 * N * ldp + N * ldn);
+  const int bytes = pw * 4;
+  if (bytes > SIMT_MAX_SMEM) return -1;
+  int w = SIMT_MAX_SMEM / bytes;
+  if (w > 4) w = 4;
+  // keep several CTAs per SM when the problem is tiny
+  while (w > 1 && w * bytes > 96 * 1024) --w;
+  *wpc = w;
+  *per_warp_floats = pw;
+  return 0;
+}
+
+template <typename K>
+static int set_smem(K kernel, int bytes) {
+  if (bytes > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(smem=%d) failed: %s", bytes, cudaGetErrorString(e));
+      return TAE_ERR_CUDA;
+    }
+  }
+  return TAE_OK;
+}
+
+}  // namespace attn
+}  // namespace tae
+
+extern "C" int tae_attention_fwd(const tae_bf16* qkv_, tae_bf16* out_, float* lse, int32_t B, int32_t N, int32_t H,
+                                 int32_t hd, void* stream_) {
+  using namespace tae;
+  using namespace tae::attn;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const bf16* qkv = reinterpret_cast<const bf16*>(qkv_);
+  bf16* out = reinterpret_cast<bf16*>(out_);
+  TAE_CHECK_SHAPE(B > 0 && N > 0 && H > 0 && hd > 0, "tae_attention_fwd: non-positive dims");
+  TAE_CHECK_SHAPE(hd % 8 == 0 && hd <= 128, "tae_attention_fwd: hd=%d unsupported (need hd %% 8 == 0, hd <= 128)", hd);
+  const float scale = 1.0f / sqrtf((float)hd);
+  if (hd == HD && (N == 64 || N == 256)) {
+    const float sl2 = scale * 1.44269504088896340736f;
+    const int smem = 3 * N * LDS * 2;
+    if (N == 256) {
+      int rc = set_smem(attn_fwd_mma<256>, smem);
+      if (rc) return rc;
+      attn_fwd_mma<256><<<B * H, 512, smem, stream>>>(qkv, out, lse, H, sl2);
+    } else {
+      int rc = set_smem(attn_fwd_mma<64>, smem);
+      if (rc) return rc;
+      attn_fwd_mma<64><<<B * H, 128, smem, stream>>>(qkv, out, lse, H, sl2);
+    }
+    TAE_CHECK_LAUNCH();
+    return TAE_OK;
+  }
+  int wpc, pw;
+  TAE_CHECK_SHAPE(simt_config(N, hd, false, &wpc, &pw) == 0, "tae_attention_fwd: N=%d hd=%d does not fit shared memory", N, hd);
+  const int smem = wpc * pw * 4;
+  int rc = set_smem(attn_fwd_simt, smem);
+  if (rc) return rc;
+  const int BH = B * H;
+  attn_fwd_simt<<<(BH + wpc - 1) / wpc, wpc * 32, smem, stream>>>(qkv, out, lse, BH, N, H, hd, scale, pw);
+  TAE_CHECK_LAUNCH();
+  return TAE_OK;
+}
+
+extern "C" int tae_attention_bwd(const tae_bf16* qkv_, const tae_bf16* out_, const tae_bf16* dout_, const float* lse,
+                                 tae_bf16* dqkv_, int32_t B, int32_t N, int32_t H, int32_t hd, void* stream_) {
+  using namespace tae;
+  using namespace tae::attn;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const bf16* qkv = reinterpret_cast<const bf16*>(qkv_);
+  const bf16* out = reinterpret_cast<const bf16*>(out_);
+  const bf16* dout = reinterpret_cast<const bf16*>(dout_);
+  bf16* dqkv = reinterpret_cast<bf16*>(dqkv_);
+  TAE_CHECK_SHAPE(B > 0 && N > 0 && H > 0 && hd > 0, "tae_attention_bwd: non-positive dims");
+  TAE_CHECK_SHAPE(hd % 8 == 0 && hd <= 128, "tae_attention_bwd: hd=%d unsupported", hd);
+  const float scale = 1.0f / sqrtf((float)hd);
+  if (hd == HD && (N == 64 || N == 256)) {
+    const float sl2 = scale * 1.44269504088896340736f;
+    const int smem = 4 * N * LDS * 2 + 2 * N * 4;
+    if (N == 256) {
+      int rc = set_smem(attn_bwd_mma<256>, smem);
+      if (rc) return rc;
+      attn_bwd_mma<256><<<B * H, 512, smem, stream>>>(qkv, out, dout, lse, dqkv, H, scale, sl2);
+    } else {
+      int rc = set_smem(attn_bwd_mma<64>, smem);
+      if (rc) return rc;
+      attn_bwd_mma<64><<<B * H, 128, smem, stream>>>(qkv, out, dout, lse, dqkv, H, scale, sl2);
+    }
+    TAE_CHECK_LAUNCH();
+    return TAE_OK;
+  }
+  int wpc, pw;
+  TAE_CHECK_SHAPE(simt_config(N, hd, true, &wpc, &pw) == 0, "tae_attention_bwd: N=%d hd=%d does not fit shared memory", N, hd);
+  const int smem = wpc * pw * 4;
+  int rc = set_smem(attn_bwd_simt, smem);
+  if (rc) return rc;
+  const int BH = B * H;
+  attn_bwd_simt<<<(BH + wpc - 1) / wpc, wpc * 32, smem, stream>>>(qkv, dout, lse, dqkv, BH, N, H, hd, scale, pw);
+  TAE_CHECK_LAUNCH();
+  return TAE_OK;
+}

@@ -1,0 +1,116 @@
+// common.cuh — shared host/device helpers for libtae_b200 (sm_100a only).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <atomic>
+
+#include "../../include/tae_b200.h"
+
+namespace tae {
+
+// ---- host-side error plumbing -------------------------------------------------------------
+void set_error(const char* fmt, ...);
+extern std::atomic<uint64_t> g_launch_count;
+inline void count_launch(int n = 1) { g_launch_count.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+#define TAE_CHECK_SHAPE(cond, ...)          \
+  do {                                      \
+    if (!(cond)) {                          \
+      ::tae::set_error(__VA_ARGS__);        \
+      return TAE_ERR_SHAPE;                 \
+    }                                       \
+  } while (0)
+
+#define TAE_CHECK_CUDA(expr)                                                              \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess) {                                                              \
+      ::tae::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__,  \
+                       __LINE__);                                                         \
+      return TAE_ERR_CUDA;                                                                \
+    }                                                                                     \
+  } while (0)
+
+#define TAE_CHECK_LAUNCH()                                                                \
+  do {                                                                                    \
+    cudaError_t _e = cudaGetLastError();                                                  \
+    if (_e != cudaSuccess) {                                                              \
+      ::tae::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e),        \
+                       __FILE__, __LINE__);                                               \
+      return TAE_ERR_CUDA;                                                                \
+    }                                                                                     \
+    ::tae::count_launch();                                                                \
+  } while (0)
+
+int num_sms();  // cached per process (current device)
+
+// ---- device helpers -----------------------------------------------------------------------
+#ifdef __CUDACC__
+
+typedef __nv_bfloat16 bf16;
+typedef __nv_bfloat162 bf162;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// round-to-nearest-even fp32 -> bf16 -> fp32 (the autocast rounding point of the reference)
+__device__ __forceinline__ float round_bf16(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  bf162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
+  bf162 t = *reinterpret_cast<bf162*>(&u);
+  return __bfloat1622float2(t);
+}
+
+// exact (erf) GELU and its derivative, as nn.GELU() with approximate='none' (tae.py:96,102)
+__device__ __forceinline__ float gelu_erf(float x) {
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+  const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+
+// 128-bit streaming loads/stores (read-once data: do not allocate in L1)
+__device__ __forceinline__ uint4 ld_nc_v4(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint2 ld_nc_v2(const void* p) {
+  uint2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float4 ld_nc_f4(const void* p) {
+  uint4 r = ld_nc_v4(p);
+  return make_float4(__uint_as_float(r.x), __uint_as_float(r.y), __uint_as_float(r.z),
+                     __uint_as_float(r.w));
+}
+
+#endif  // __CUDACC__
+
+}  // namespace tae

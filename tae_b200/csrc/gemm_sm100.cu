@@ -1,0 +1,607 @@
+// gemm_sm100.cu — persistent, warp-specialised bf16 GEMM on the 5th-gen tensor cores (tcgen05) of sm_100a.
+//
+//   D[M,N] = sum_k A(m,k) * B(n,k)     fp32 accumulation in tensor memory (TMEM)
+//
+// Replaces every nn.Linear call site of the reference's hot path and its autograd dgrad/wgrad
+// (tae.py:50,74,81,101,104,237,242,253) — see include/tae_b200.h for the operand conventions.
+//
+// Structure (one CTA per SM, 384 threads, static round-robin tile scheduler):
+//   warp 0      TMA producer: cp.async.bulk.tensor 2-D boxes (128B swizzle) into a 4-stage smem ring
+//   warp 1      MMA issuer: one thread issues tcgen05.mma.cta_group::1.kind::f16 (128x256x16 per instruction)
+//   warp 2      TMEM allocator (512 columns = two 128x256 fp32 accumulators, double-buffered)
+//   warps 4-11  epilogue: tcgen05.ld 32 lanes x 32 columns per warp step -> fused epilogue -> global
+// Pipelines: smem full/empty mbarriers (TMA <-> MMA) and TMEM full/empty mbarriers (MMA <-> epilogue), so
+// the epilogue of tile i overlaps the main loop of tile i+1.
+//
+// Operand majors: both operands may be K-major (k contiguous; forward) or MN-major (m/n contiguous; the
+// transposed operands of dgrad/wgrad) — handled by the TMA box shape + UMMA smem-descriptor strides, so no
+// transposed copy of any activation or weight is ever materialised.
+#include <mutex>
+
+#include "common.cuh"
+
+namespace tae {
+namespace gemm {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_N = 256;
+constexpr int BLOCK_K = 64;  // 64 bf16 = 128 bytes = one swizzle-128B span
+constexpr int UMMA_K = 16;
+constexpr int STAGES = 4;
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
+constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;  // 32 KB
+constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+constexpr int MN_BOX_BYTES = 64 * BLOCK_K * 2;        // one MN-major box: 64 (mn) x 64 (k) bf16 = 8 KB
+constexpr int NUM_ACC = 2;                            // TMEM accumulator double buffer
+constexpr int TMEM_COLS = NUM_ACC * BLOCK_N;          // 512
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = 128 + NUM_EPI_WARPS * 32;  // 384
+constexpr int SMEM_BARRIER_BYTES = 256;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + SMEM_BARRIER_BYTES + 1024;  // +1024: manual alignment slack
+
+struct Params {
+  int M, N, K;
+  int a_mn, b_mn;
+  int m_tiles, n_tiles, kb_total, kb_per_split, splits;
+  void* out;
+  int ldo;
+  void* out2;
+  const float* bias;
+  const float* resid;
+  int ldr;
+  int resid_rows;
+  const bf16* aux;
+  int ldaux;
+  int beta;
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must fault (trap) instead of hanging the device.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 26)) __trap();
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int c0,
+                                            int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot_in_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_in_smem)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], bf16 x bf16 -> fp32, issued by ONE thread for the CTA
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// mbarrier arrives when all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory matrix descriptor (sm_100 format, version 1), 128-byte swizzle.
+//   bits [0,14)  start address >> 4        bits [16,30) leading-dim byte offset >> 4
+//   bits [32,46) stride-dim byte offset >> 4   bits [46,48) version = 1   bits [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// K-major tile [rows x 64] (128 B per row, 8-row swizzle atoms of 1024 B): SBO = 1024 between 8-row groups;
+// one UMMA_K=16 slice = 32 B inside the swizzle span.
+__device__ __forceinline__ uint64_t desc_k_major(uint32_t tile_base, int k16) {
+  return make_smem_desc(tile_base + (uint32_t)k16 * 32u, 0u, 1024u);
+}
+// MN-major tile stored as consecutive boxes of [64 k-rows x 64 mn] (128 B per k-row): atoms are 8 k-rows
+// (SBO = 1024 between k-groups), LBO = 8192 between 64-wide mn chunks; one UMMA_K=16 slice = 2 k-groups = 2048 B.
+__device__ __forceinline__ uint64_t desc_mn_major(uint32_t tile_base, int k16) {
+  return make_smem_desc(tile_base + (uint32_t)k16 * 2048u, (uint32_t)MN_BOX_BYTES, 1024u);
+}
+// Instruction descriptor for kind::f16: c=F32 (bit 4), a=b=BF16 (bits 7,10), majors (bits 15,16),
+// N>>3 at bit 17, M>>4 at bit 24.
+__device__ __forceinline__ uint32_t make_idesc(int a_mn, int b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+         ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Epilogues: one thread owns one output row and 32 consecutive columns (fp32 accumulators in v).
+// ---------------------------------------------------------------------------------------------
+template <int EPI>
+__device__ __forceinline__ void epilogue_store(const Params& p, int row, int col0, int split, float (&v)[32]) {
+  if (row >= p.M) return;
+  const int ncol = min(32, p.N - col0);  // multiple of 8
+  if (EPI != TAE_EPI_F32_ACC && EPI != TAE_EPI_BF16_DGELU) {
+    if (p.bias != nullptr) {
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        if (g * 4 < ncol) {
+          const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + g * 4));
+          // autocast hands the GEMM a bf16 copy of the fp32 bias: same rounding here
+          v[g * 4 + 0] += round_bf16(b.x);
+          v[g * 4 + 1] += round_bf16(b.y);
+          v[g * 4 + 2] += round_bf16(b.z);
+          v[g * 4 + 3] += round_bf16(b.w);
+        }
+      }
+    }
+  }
+  if (EPI == TAE_EPI_BF16 || EPI == TAE_EPI_BF16_GELU || EPI == TAE_EPI_BF16_DGELU) {
+    bf16* out = reinterpret_cast<bf16*>(p.out) + (size_t)row * p.ldo + col0;
+    bf16* out2 = (EPI == TAE_EPI_BF16_GELU) ? reinterpret_cast<bf16*>(p.out2) + (size_t)row * p.ldo + col0 : nullptr;
+    const bf16* aux = (EPI == TAE_EPI_BF16_DGELU) ? p.aux + (size_t)row * p.ldaux + col0 : nullptr;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      if (g * 8 < ncol) {
+        float* x = &v[g * 8];
+        if (EPI == TAE_EPI_BF16_DGELU) {
+          const uint4 hraw = ld_nc_v4(aux + g * 8);
+          const uint32_t hw[4] = {hraw.x, hraw.y, hraw.z, hraw.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 h = unpack_bf16x2(hw[j]);
+            x[2 * j] = round_bf16(x[2 * j]) * gelu_erf_grad(h.x);
+            x[2 * j + 1] = round_bf16(x[2 * j + 1]) * gelu_erf_grad(h.y);
+          }
+        }
+        uint4 o;
+        o.x = pack_bf16x2(x[0], x[1]);
+        o.y = pack_bf16x2(x[2], x[3]);
+        o.z = pack_bf16x2(x[4], x[5]);
+        o.w = pack_bf16x2(x[6], x[7]);
+        *reinterpret_cast<uint4*>(out + g * 8) = o;
+        if (EPI == TAE_EPI_BF16_GELU) {
+          const uint32_t hw[4] = {o.x, o.y, o.z, o.w};
+          uint32_t aw[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 h = unpack_bf16x2(hw[j]);
+            aw[j] = pack_bf16x2(gelu_erf(h.x), gelu_erf(h.y));
+          }
+          *reinterpret_cast<uint4*>(out2 + g * 8) = make_uint4(aw[0], aw[1], aw[2], aw[3]);
+        }
+      }
+    }
+  } else if (EPI == TAE_EPI_F32_RESID) {
+    float* out = reinterpret_cast<float*>(p.out) + (size_t)row * p.ldo + col0;
+    const float* res = p.resid + (size_t)(row % p.resid_rows) * p.ldr + col0;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      if (g * 4 < ncol) {
+        const float4 r = *reinterpret_cast<const float4*>(res + g * 4);
+        float4 o;
+        o.x = r.x + round_bf16(v[g * 4 + 0]);
+        o.y = r.y + round_bf16(v[g * 4 + 1]);
+        o.z = r.z + round_bf16(v[g * 4 + 2]);
+        o.w = r.w + round_bf16(v[g * 4 + 3]);
+        *reinterpret_cast<float4*>(out + g * 4) = o;
+      }
+    }
+  } else {  // TAE_EPI_F32_ACC
+    float* out = reinterpret_cast<float*>(p.out) + (size_t)row * p.ldo + col0;
+    if (p.splits > 1) {
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        if (g * 4 < ncol) {
+          atomicAdd(reinterpret_cast<float4*>(out + g * 4),
+                    make_float4(v[g * 4 + 0], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]));
+        }
+      }
+    } else {
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        if (g * 4 < ncol) {
+          float4 o = make_float4(v[g * 4 + 0], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+          if (p.beta) {
+            const float4 r = *reinterpret_cast<const float4*>(out + g * 4);
+            o.x += r.x;
+            o.y += r.y;
+            o.z += r.z;
+            o.w += r.w;
+          }
+          *reinterpret_cast<float4*>(out + g * 4) = o;
+        }
+      }
+    }
+  }
+  (void)split;
+}
+
+// ---------------------------------------------------------------------------------------------
+// The kernel
+// ---------------------------------------------------------------------------------------------
+struct WorkItem {
+  int mt, nt, kb0, kb1, split;
+};
+__device__ __forceinline__ WorkItem decode_work(const Params& p, int w) {
+  WorkItem it;
+  it.nt = w % p.n_tiles;
+  const int t = w / p.n_tiles;
+  it.mt = t % p.m_tiles;
+  it.split = t / p.m_tiles;
+  it.kb0 = it.split * p.kb_per_split;
+  it.kb1 = min(p.kb_total, it.kb0 + p.kb_per_split);
+  return it;
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                  const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  // 128B-swizzled TMA/UMMA tiles need 1024-byte alignment
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full_bar = bars;                       // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;             // [STAGES]
+  uint64_t* tmem_full_bar = bars + 2 * STAGES;     // [NUM_ACC]
+  uint64_t* tmem_empty_bar = bars + 2 * STAGES + NUM_ACC;  // [NUM_ACC]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2 * NUM_ACC);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_work = p.m_tiles * p.n_tiles * p.splits;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < NUM_ACC; ++a) {
+      mbar_init(&tmem_full_bar[a], 1);
+      mbar_init(&tmem_empty_bar[a], NUM_EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        const WorkItem it = decode_work(p, w);
+        const int m0 = it.mt * BLOCK_M, n0 = it.nt * BLOCK_N;
+        for (int kb = it.kb0; kb < it.kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          uint8_t* sa = smem + stage * STAGE_BYTES;
+          uint8_t* sb = sa + A_STAGE_BYTES;
+          mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+          const int k0 = kb * BLOCK_K;
+          if (!p.a_mn) {
+            tma_load_2d(sa, &tmap_a, &full_bar[stage], k0, m0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BLOCK_M / 64; ++j)
+              tma_load_2d(sa + j * MN_BOX_BYTES, &tmap_a, &full_bar[stage], m0 + j * 64, k0);
+          }
+          if (!p.b_mn) {
+            tma_load_2d(sb, &tmap_b, &full_bar[stage], k0, n0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BLOCK_N / 64; ++j)
+              tma_load_2d(sb + j * MN_BOX_BYTES, &tmap_b, &full_bar[stage], n0 + j * 64, k0);
+          }
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (single thread) =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(p.a_mn, p.b_mn);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        const WorkItem it = decode_work(p, w);
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+        for (int kb = it.kb0; kb < it.kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t a_base = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t b_base = a_base + A_STAGE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t adesc = p.a_mn ? desc_mn_major(a_base, k) : desc_k_major(a_base, k);
+            const uint64_t bdesc = p.b_mn ? desc_mn_major(b_base, k) : desc_k_major(b_base, k);
+            umma_f16(d_tmem, adesc, bdesc, idesc, (kb > it.kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
+        if (++acc == NUM_ACC) {
+          acc = 0;
+          acc_phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue warps =====================
+    const int ew = warp - 4;
+    const int q = ew & 3;       // TMEM lane quarter this warp may access (== warp % 4)
+    const int half = ew >> 2;   // which 128-column half of the accumulator
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      const WorkItem it = decode_work(p, w);
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tcgen05_fence_after();
+      const int row = it.mt * BLOCK_M + q * 32 + lane;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        const int col0 = it.nt * BLOCK_N + half * 128 + c * 32;
+        if (col0 >= p.N) break;  // warp-uniform
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + half * 128 + c * 32);
+        uint32_t raw[32];
+        tmem_ld_32x32b_x32(taddr, raw);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+        epilogue_store<EPI>(p, row, col0, it.split, v);
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+      if (++acc == NUM_ACC) {
+        acc = 0;
+        acc_phase ^= 1u;
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, []() {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres);
+    if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) fn = reinterpret_cast<EncodeTiledFn>(sym);
+  });
+  return fn;
+}
+
+// 2-D bf16 tensor map over a row-major matrix [outer, inner] (inner contiguous), box [box_outer, 64], 128B swizzle
+static int make_tmap(CUtensorMap* tm, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld_elems,
+                     uint32_t box_outer) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return TAE_ERR_CUDA;
+  }
+  cuuint64_t gdim[2] = {inner, outer};
+  cuuint64_t gstride[1] = {ld_elems * 2};
+  cuuint32_t box[2] = {64, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (inner=%llu outer=%llu ld=%llu box_outer=%u ptr=%p)",
+              (int)r, (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld_elems, box_outer,
+              ptr);
+    return TAE_ERR_CUDA;
+  }
+  return TAE_OK;
+}
+
+template <int EPI>
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, int grid, cudaStream_t stream) {
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, []() {
+    attr_err = cudaFuncSetAttribute(gemm_bf16_tcgen05<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  });
+  if (attr_err != cudaSuccess) {
+    set_error("cudaFuncSetAttribute(smem=%d) failed: %s", SMEM_BYTES, cudaGetErrorString(attr_err));
+    return TAE_ERR_CUDA;
+  }
+  gemm_bf16_tcgen05<EPI><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, p);
+  TAE_CHECK_LAUNCH();
+  return TAE_OK;
+}
+
+}  // namespace gemm
+}  // namespace tae
+
+extern "C" int tae_gemm(const tae_gemm_args* a, void* stream_) {
+  using namespace tae;
+  using namespace tae::gemm;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  TAE_CHECK_SHAPE(a != nullptr, "tae_gemm: args is NULL");
+  TAE_CHECK_SHAPE(a->M > 0 && a->N > 0 && a->K > 0, "tae_gemm: M,N,K must be positive (got %d,%d,%d)", a->M, a->N, a->K);
+  TAE_CHECK_SHAPE(a->N % 8 == 0 && a->K % 8 == 0, "tae_gemm: N and K must be multiples of 8 (got N=%d K=%d)", a->N, a->K);
+  TAE_CHECK_SHAPE(a->lda % 8 == 0 && a->ldb % 8 == 0, "tae_gemm: lda/ldb must be multiples of 8");
+  TAE_CHECK_SHAPE(!a->a_mn_major || a->M % 8 == 0, "tae_gemm: MN-major A requires M %% 8 == 0");
+  TAE_CHECK_SHAPE((reinterpret_cast<uintptr_t>(a->A) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->B) & 15) == 0 &&
+                      (reinterpret_cast<uintptr_t>(a->out) & 15) == 0,
+                  "tae_gemm: A, B and out must be 16-byte aligned");
+  TAE_CHECK_SHAPE(a->out != nullptr && a->A != nullptr && a->B != nullptr, "tae_gemm: NULL operand");
+  TAE_CHECK_SHAPE(a->epilogue >= TAE_EPI_BF16 && a->epilogue <= TAE_EPI_BF16_DGELU, "tae_gemm: bad epilogue %d", a->epilogue);
+  const bool out_f32 = (a->epilogue == TAE_EPI_F32_RESID || a->epilogue == TAE_EPI_F32_ACC);
+  TAE_CHECK_SHAPE(a->ldo % (out_f32 ? 4 : 8) == 0 && a->ldo >= a->N, "tae_gemm: bad ldo %d", a->ldo);
+  if (a->epilogue == TAE_EPI_BF16_GELU)
+    TAE_CHECK_SHAPE(a->out2 != nullptr && (reinterpret_cast<uintptr_t>(a->out2) & 15) == 0, "tae_gemm: GELU epilogue needs out2");
+  if (a->epilogue == TAE_EPI_F32_RESID)
+    TAE_CHECK_SHAPE(a->resid != nullptr && a->resid_rows > 0 && a->ldr % 4 == 0 && (reinterpret_cast<uintptr_t>(a->resid) & 15) == 0,
+                    "tae_gemm: RESID epilogue needs resid/resid_rows/ldr");
+  if (a->epilogue == TAE_EPI_BF16_DGELU)
+    TAE_CHECK_SHAPE(a->aux != nullptr && a->ldaux % 8 == 0 && (reinterpret_cast<uintptr_t>(a->aux) & 15) == 0,
+                    "tae_gemm: DGELU epilogue needs aux/ldaux");
+  if (a->bias) TAE_CHECK_SHAPE((reinterpret_cast<uintptr_t>(a->bias) & 15) == 0, "tae_gemm: bias must be 16-byte aligned");
+
+  Params p{};
+  p.M = a->M;
+  p.N = a->N;
+  p.K = a->K;
+  p.a_mn = a->a_mn_major ? 1 : 0;
+  p.b_mn = a->b_mn_major ? 1 : 0;
+  p.m_tiles = (a->M + BLOCK_M - 1) / BLOCK_M;
+  p.n_tiles = (a->N + BLOCK_N - 1) / BLOCK_N;
+  p.kb_total = (a->K + BLOCK_K - 1) / BLOCK_K;
+  const int sms = num_sms();
+  if (sms <= 0) return TAE_ERR_CUDA;
+  int splits = a->splits;
+  if (a->epilogue != TAE_EPI_F32_ACC) {
+    TAE_CHECK_SHAPE(splits <= 1, "tae_gemm: split-K only with TAE_EPI_F32_ACC");
+    splits = 1;
+  } else if (splits <= 0) {
+    // auto: fill the machine when the tile count alone cannot (weight-gradient GEMMs: few tiles, huge K)
+    const int tiles = p.m_tiles * p.n_tiles;
+    splits = 1;
+    if (tiles < sms && p.kb_total >= 32) {
+      splits = (2 * sms + tiles - 1) / tiles;  // ~2 waves worth of work items
+      if (splits > p.kb_total / 8) splits = p.kb_total / 8;
+      if (splits < 1) splits = 1;
+    }
+  }
+  if (splits > p.kb_total) splits = p.kb_total;
+  p.kb_per_split = (p.kb_total + splits - 1) / splits;
+  splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;  // no empty splits
+  p.splits = splits;
+  p.out = a->out;
+  p.ldo = a->ldo;
+  p.out2 = a->out2;
+  p.bias = a->bias;
+  p.resid = a->resid;
+  p.ldr = a->ldr;
+  p.resid_rows = a->resid_rows > 0 ? a->resid_rows : 1;
+  p.aux = reinterpret_cast<const bf16*>(a->aux);
+  p.ldaux = a->ldaux;
+  p.beta = a->beta;
+
+  if (a->epilogue == TAE_EPI_F32_ACC && p.splits > 1 && !a->beta) {
+    // split-K partial sums are accumulated with red.global.add: start from zero
+    TAE_CHECK_CUDA(cudaMemset2DAsync(a->out, (size_t)a->ldo * 4, 0, (size_t)a->N * 4, (size_t)a->M, stream));
+  }
+
+  CUtensorMap ta, tb;
+  int rc;
+  if (!p.a_mn)
+    rc = make_tmap(&ta, a->A, (uint64_t)a->K, (uint64_t)a->M, (uint64_t)a->lda, BLOCK_M);
+  else
+    rc = make_tmap(&ta, a->A, (uint64_t)a->M, (uint64_t)a->K, (uint64_t)a->lda, BLOCK_K);
+  if (rc) return rc;
+  if (!p.b_mn)
+    rc = make_tmap(&tb, a->B, (uint64_t)a->K, (uint64_t)a->N, (uint64_t)a->ldb, BLOCK_N);
+  else
+    rc = make_tmap(&tb, a->B, (uint64_t)a->N, (uint64_t)a->K, (uint64_t)a->ldb, BLOCK_K);
+  if (rc) return rc;
+
+  const int total = p.m_tiles * p.n_tiles * p.splits;
+  const int grid = total < sms ? total : sms;
+  switch (a->epilogue) {
+    case TAE_EPI_BF16: return launch<TAE_EPI_BF16>(ta, tb, p, grid, stream);
+    case TAE_EPI_BF16_GELU: return launch<TAE_EPI_BF16_GELU>(ta, tb, p, grid, stream);
+    case TAE_EPI_F32_RESID: return launch<TAE_EPI_F32_RESID>(ta, tb, p, grid, stream);
+    case TAE_EPI_F32_ACC: return launch<TAE_EPI_F32_ACC>(ta, tb, p, grid, stream);
+    case TAE_EPI_BF16_DGELU: return launch<TAE_EPI_BF16_DGELU>(ta, tb, p, grid, stream);
+  }
+  return TAE_ERR_SHAPE;
+}

@@ -1,0 +1,68 @@
+// lib.cu — library-level entry points of libtae_b200.so: version, error string, device capability cache.
+#include <stdarg.h>
+#include <string.h>
+
+#include <mutex>
+
+#include "common.cuh"
+
+namespace tae {
+
+static thread_local char tl_error[512] = "";
+std::atomic<uint64_t> g_launch_count{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(tl_error, sizeof(tl_error), fmt, ap);
+  va_end(ap);
+}
+
+// The only global state: an immutable per-process capability cache (filled once).
+static int g_sms = 0;
+static int g_cc = 0;
+static std::once_flag g_dev_once;
+
+static void query_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    g_sms = -1;
+    return;
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
+    g_sms = -1;
+    return;
+  }
+  g_sms = prop.multiProcessorCount;
+  g_cc = prop.major * 10 + prop.minor;
+}
+
+int num_sms() {
+  std::call_once(g_dev_once, query_device);
+  if (g_sms <= 0) set_error("no CUDA device available");
+  return g_sms;
+}
+
+}  // namespace tae
+
+extern "C" int tae_version(void) { return 1; }
+
+extern "C" const char* tae_last_error_string(void) { return tae::tl_error; }
+
+extern "C" int tae_num_sms(void) {
+  const int n = tae::num_sms();
+  return n > 0 ? n : TAE_ERR_CUDA;
+}
+
+extern "C" int tae_device_check(void) {
+  if (tae::num_sms() <= 0) return TAE_ERR_CUDA;
+  if (tae::g_cc != 100) {
+    tae::set_error("libtae_b200 is built for sm_100a only; current device has compute capability %d.%d",
+                   tae::g_cc / 10, tae::g_cc % 10);
+    return TAE_ERR_UNSUPPORTED;
+  }
+  return TAE_OK;
+}
+
+extern "C" uint64_t tae_launch_count(void) { return tae::g_launch_count.load(std::memory_order_relaxed); }

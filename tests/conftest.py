@@ -1,0 +1,45 @@
+import json
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a B200 (sm_100a) GPU; run with `-m gpu` on the GPU box")
+
+
+@pytest.fixture(scope="session")
+def golden_meta():
+    with open(os.path.join(GOLDEN_DIR, "golden_meta.json")) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="session")
+def golden_tensors():
+    import torch
+
+    cache = {}
+
+    def load(name):
+        if name not in cache:
+            cache[name] = torch.load(os.path.join(GOLDEN_DIR, f"{name}.pt"), map_location="cpu")
+        return cache[name]
+
+    return load
+
+
+TINY_CASES = ["tiny_p8_n64_hd64", "tiny_p8_n16_hd32", "tiny_p16_n4_hd80"]
+
+
+def oracle_cfg(kw):
+    from oracle import tae_oracle as O
+
+    return O.TAEConfig(kw["img_size"], kw["patch_size"], kw["embed_dim"], kw["vocab_size"], kw["depth"], kw["num_heads"],
+                       kw["decoder_embed_dim"], kw["decoder_depth"], kw["decoder_num_heads"], kw["mlp_ratio"])

@@ -1,0 +1,309 @@
+"""Per-kernel parity tests: every C-ABI entry point against the oracle's restatement of the same op (GPU only).
+
+Tolerances: bf16 outputs are compared within a few bf16 ulps of the result magnitude (2e-2 relative is the
+north-star gate for bf16); fp32 outputs of fp32 inputs within 1e-4 relative; integer index maps bit-exact.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import tae_oracle as O  # noqa: E402  (checker only)
+
+
+def _ops():
+    from tae_b200 import ops
+
+    return ops
+
+
+def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def max_err_scaled(a, b) -> float:
+    a, b = a.double(), b.double()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def randn(*shape, dtype=torch.bfloat16, seed=0, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(dtype).cuda()
+
+
+# ------------------------------------------------------------------------------------------------
+# GEMM
+# ------------------------------------------------------------------------------------------------
+GEMM_SHAPES = [
+    (128, 256, 64), (256, 512, 128), (512, 768, 256), (384, 1024, 1024), (1000, 264, 72), (4, 16, 128), (128, 16, 1024),
+    (1024, 1024, 16), (130, 3072, 1024), (2048, 4096, 1024),
+]
+
+
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True), (True, False)])
+def test_gemm_majors(M, N, K, a_mn, b_mn):
+    ops = _ops()
+    from tae_b200._lib import EPI_BF16
+
+    if a_mn and M % 8:
+        pytest.skip("MN-major A needs M % 8 == 0")
+    A = randn(M, K, seed=1)
+    B = randn(N, K, seed=2)
+    ref = A.float() @ B.float().t()
+    Ain = A.t().contiguous() if a_mn else A
+    Bin = B.t().contiguous() if b_mn else B
+    out = ops.gemm(Ain, Bin, a_mn=a_mn, b_mn=b_mn, epilogue=EPI_BF16)
+    torch.cuda.synchronize()
+    assert out.shape == (M, N) and out.dtype == torch.bfloat16
+    assert max_err_scaled(out.float(), ref) < 1e-2, (rel_err(out.float(), ref))
+    assert rel_err(out.float(), ref) < 5e-3
+
+
+def test_gemm_epilogue_bias_gelu():
+    ops = _ops()
+    from tae_b200._lib import EPI_BF16, EPI_BF16_GELU
+
+    M, N, K = 640, 512, 256
+    A, B = randn(M, K, seed=3), randn(N, K, seed=4, scale=0.1)
+    bias = randn(N, dtype=torch.float32, seed=5)
+    acc = A.float() @ B.float().t() + bias.to(torch.bfloat16).float()
+    out = ops.gemm(A, B, epilogue=EPI_BF16, bias=bias)
+    assert rel_err(out.float(), acc) < 5e-3
+    h, a = ops.gemm(A, B, epilogue=EPI_BF16_GELU, bias=bias)
+    href = acc.to(torch.bfloat16)
+    assert rel_err(h.float(), href.float()) < 5e-3
+    aref = O.gelu(h)  # GELU of the kernel's own bf16 h: isolates the activation
+    assert max_err_scaled(a.float(), aref.float()) < 1e-2
+    assert rel_err(a.float(), aref.float()) < 4e-3
+
+
+def test_gemm_epilogue_residual_and_posembed():
+    ops = _ops()
+    from tae_b200._lib import EPI_F32_RESID
+
+    M, N, K = 512, 256, 128
+    A, B = randn(M, K, seed=6), randn(N, K, seed=7, scale=0.2)
+    bias = randn(N, dtype=torch.float32, seed=8)
+    resid = randn(M, N, dtype=torch.float32, seed=9)
+    y = (A.float() @ B.float().t() + bias.to(torch.bfloat16).float()).to(torch.bfloat16).float()
+    out = ops.gemm(A, B, epilogue=EPI_F32_RESID, bias=bias, resid=resid)
+    assert out.dtype == torch.float32
+    assert max_err_scaled(out - resid, y) < 1e-2
+    # broadcast residual (pos-embed): rows repeat every 64 tokens
+    pos = randn(64, N, dtype=torch.float32, seed=10)
+    out2 = ops.gemm(A, B, epilogue=EPI_F32_RESID, bias=bias, resid=pos, resid_rows=64)
+    ref2 = y + pos.repeat(M // 64, 1)
+    assert max_err_scaled(out2, ref2) < 1e-2
+
+
+@pytest.mark.parametrize("splits", [1, 3, 0])
+@pytest.mark.parametrize("beta", [0, 1])
+def test_gemm_wgrad_accumulate(splits, beta):
+    ops = _ops()
+    from tae_b200._lib import EPI_F32_ACC
+
+    T, Nout, Kin = 4096, 384, 256  # dW[Nout,Kin] = dY[T,Nout]^T X[T,Kin]
+    dY, X = randn(T, Nout, seed=11, scale=0.1), randn(T, Kin, seed=12)
+    ref = dY.float().t() @ X.float()
+    out = randn(Nout, Kin, dtype=torch.float32, seed=13)
+    prev = out.clone()
+    ops.gemm(dY, X, a_mn=True, b_mn=True, epilogue=EPI_F32_ACC, out=out, beta=beta, splits=splits)
+    want = ref + (prev if beta else 0)
+    assert rel_err(out, want) < 1e-3
+
+
+def test_gemm_dgelu_epilogue():
+    ops = _ops()
+    from tae_b200._lib import EPI_BF16_DGELU
+
+    M, N, K = 384, 512, 128  # da[M,N] = dy[M,K] W[K,N];  dh = da * gelu'(h)
+    dy, W = randn(M, K, seed=14), randn(K, N, seed=15, scale=0.1)
+    h = randn(M, N, seed=16)
+    out = ops.gemm(dy, W, b_mn=True, epilogue=EPI_BF16_DGELU, aux=h)
+    da = (dy.float() @ W.float()).to(torch.bfloat16).float()
+    hf = h.float()
+    gp = 0.5 * (1 + torch.erf(hf / math.sqrt(2))) + hf * torch.exp(-0.5 * hf * hf) / math.sqrt(2 * math.pi)
+    ref = da * gp
+    assert max_err_scaled(out.float(), ref) < 1e-2
+    assert rel_err(out.float(), ref) < 5e-3
+
+
+def test_gemm_rejects_bad_shapes():
+    ops = _ops()
+    from tae_b200._lib import TaeError
+
+    with pytest.raises(TaeError):
+        ops.gemm(randn(8, 12), randn(16, 12))  # K % 8 != 0
+    with pytest.raises(TaeError):
+        ops.gemm(torch.zeros(8, 16, dtype=torch.bfloat16), torch.zeros(16, 16, dtype=torch.bfloat16))  # CPU tensors
+
+
+# ------------------------------------------------------------------------------------------------
+# LayerNorm
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("rows,D", [(512, 1024), (1030, 2048), (77, 2560), (256, 128), (64, 640)])
+def test_layernorm_fwd_bwd(rows, D):
+    ops = _ops()
+    x = randn(rows, D, dtype=torch.float32, seed=20) * 2 + 0.5
+    w = randn(D, dtype=torch.float32, seed=21) * 0.2 + 1
+    b = randn(D, dtype=torch.float32, seed=22) * 0.1
+    y, mean, rstd = ops.layernorm_fwd(x, w, b, 1e-6)
+    xr = x.detach().clone().requires_grad_(True)
+    wr, br = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    yr = O.layer_norm(xr, wr, br, 1e-6)
+    assert max_err_scaled(y.float(), yr.detach()) < 8e-3
+    assert rel_err(mean, x.mean(-1)) < 1e-5
+    assert rel_err(rstd, 1 / torch.sqrt(x.var(-1, unbiased=False) + 1e-6)) < 1e-5
+    dy = randn(rows, D, seed=23)
+    dres = randn(rows, D, dtype=torch.float32, seed=24)
+    yr.backward(dy.float())
+    dx, dx_b, dg, db, cs = ops.layernorm_bwd(dy, x, mean, rstd, w, dres)
+    assert rel_err(dx - dres, xr.grad) < 1e-4
+    assert rel_err(dg, wr.grad) < 1e-4
+    assert rel_err(db, br.grad) < 1e-4
+    assert torch.equal(dx_b, dx.to(torch.bfloat16))
+    assert rel_err(cs, dx_b.float().sum(0)) < 1e-4
+    # accumulate mask: dgamma += , dbeta overwritten
+    dg2, db2 = torch.ones_like(dg), torch.ones_like(db)
+    ops.layernorm_bwd(dy, x, mean, rstd, w, None, dgamma=dg2, dbeta=db2, acc_mask=1)
+    assert rel_err(dg2, wr.grad + 1) < 1e-4 and rel_err(db2, br.grad) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------------
+# Attention
+# ------------------------------------------------------------------------------------------------
+def _attn_ref(qkv, B, N, H, hd, dout=None):
+    D = H * hd
+    q5 = qkv.float().reshape(B, N, 3, H, hd).permute(2, 0, 3, 1, 4).detach().clone().requires_grad_(True)
+    q, k, v = q5[0], q5[1], q5[2]
+    s = q @ k.transpose(-2, -1) * hd ** -0.5
+    p = torch.softmax(s, -1)
+    o = (p @ v).transpose(1, 2).reshape(B * N, D)
+    lse = torch.logsumexp(s, -1)
+    if dout is None:
+        return o, lse, None
+    o.backward(dout.float())
+    dqkv = q5.grad.permute(1, 3, 0, 2, 4).reshape(B * N, 3 * D)
+    return o.detach(), lse.detach(), dqkv
+
+
+@pytest.mark.parametrize("B,N,H,hd", [(3, 256, 4, 64), (5, 64, 8, 64), (6, 16, 8, 80), (7, 4, 8, 80), (2, 16, 4, 32),
+                                      (2, 64, 2, 32)])
+def test_attention_fwd_bwd(B, N, H, hd):
+    ops = _ops()
+    D = H * hd
+    qkv = randn(B * N, 3 * D, seed=30)
+    dout = randn(B * N, D, seed=31)
+    out, lse = ops.attention_fwd(qkv, B, N, H, hd)
+    oref, lref, dref = _attn_ref(qkv, B, N, H, hd, dout)
+    assert max_err_scaled(out.float(), oref) < 1.5e-2
+    assert rel_err(out.float(), oref) < 8e-3
+    assert float((lse - lref).abs().max()) < 2e-3
+    dqkv = ops.attention_bwd(qkv, out, dout, lse, B, N, H, hd)
+    assert rel_err(dqkv.float(), dref) < 1.5e-2
+    assert max_err_scaled(dqkv.float(), dref) < 2e-2
+    for part in range(3):  # q, k, v gradients separately
+        sl = slice(part * D, (part + 1) * D)
+        assert rel_err(dqkv[:, sl].float(), dref[:, sl]) < 2e-2, f"part {part}"
+
+
+# ------------------------------------------------------------------------------------------------
+# Integer index maps: bit-exact
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("S,p", [(256, 16), (256, 32), (256, 64), (256, 128), (64, 8), (32, 16)])
+def test_patch_index_maps_bit_exact(S, p):
+    ops = _ops()
+    B = 2
+    rng = np.random.default_rng(S + p)
+    imgs_np = rng.standard_normal((B, 3, S, S), dtype=np.float32)
+    imgs = torch.from_numpy(imgs_np).cuda()
+    pat = ops.patchify(imgs, p)
+    assert np.array_equal(pat.cpu().numpy(), O.patchify_np(imgs_np, p))
+    back = ops.unpatchify(pat, p)
+    assert torch.equal(back, imgs)
+    h = imgs.to(torch.bfloat16)
+    pat16 = ops.patchify(h, p)
+    assert torch.equal(pat16, O.patchify(h, p))
+    assert torch.equal(ops.unpatchify(pat16, p), h)
+    if p % 8 == 0:
+        cols = ops.im2col(imgs, p)
+        want = torch.from_numpy(O.im2col_np(imgs_np, p)).to(torch.bfloat16)
+        assert torch.equal(cols.cpu(), want)
+
+
+def test_patchify_integer_payload_roundtrip():
+    """Indices carried as int32 payloads: the permutation itself, independent of float formatting."""
+    ops = _ops()
+    S, p, B = 256, 16, 1
+    idx = torch.arange(B * 3 * S * S, dtype=torch.int32).reshape(B, 3, S, S).cuda()
+    pat = ops.patchify(idx, p)
+    want = O.patchify_np(idx.cpu().numpy(), p)
+    assert np.array_equal(pat.cpu().numpy(), want)
+    assert torch.equal(ops.unpatchify(pat, p), idx)
+
+
+# ------------------------------------------------------------------------------------------------
+# Loss, reductions, optimizer
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,S,p", [(2, 256, 16), (3, 64, 8), (2, 256, 128)])
+def test_mse_loss_and_grad(B, S, p):
+    ops = _ops()
+    g = S // p
+    imgs = randn(B, 3, S, S, dtype=torch.float32, seed=40)
+    pred = randn(B, g * g, 3 * p * p, seed=41)
+    loss, _ = ops.mse_loss(pred, imgs, p)
+    pr = pred.float().clone().requires_grad_(True)
+    lref = O.forward_loss(imgs, pr, p)
+    assert abs(float(loss) - float(lref)) < 1e-5 * abs(float(lref))
+    lref.backward()
+    scale = torch.tensor([3.0], device="cuda")
+    _, dpred = ops.mse_loss(pred, imgs, p, want_grad=True, grad_scale=scale)
+    assert rel_err(dpred.float(), 3.0 * pr.grad) < 4e-3
+
+
+def test_colsum_and_batch_sum():
+    ops = _ops()
+    x = randn(3000, 1544, seed=50)
+    out = ops.colsum(x)
+    assert rel_err(out, x.float().sum(0)) < 1e-5
+    acc = torch.ones(1544, device="cuda")
+    ops.colsum(x, out=acc, accumulate=True)
+    assert rel_err(acc, x.float().sum(0) + 1) < 1e-5
+    y = randn(5 * 64, 256, dtype=torch.float32, seed=51)
+    bs = ops.batch_sum(y, 5, 64)
+    assert rel_err(bs, y.reshape(5, 64, 256).sum(0)) < 1e-6
+
+
+@pytest.mark.parametrize("n", [4096 * 3 + 5, 1 << 20])
+def test_adamw_matches_oracle_and_torch(n):
+    ops = _ops()
+    p = randn(n, dtype=torch.float32, seed=60)
+    g = randn(n, dtype=torch.float32, seed=61) * 0.01
+    m = torch.zeros_like(p)
+    v = torch.zeros_like(p)
+    pb = torch.empty(n, dtype=torch.bfloat16, device="cuda")
+    pt = p.clone().requires_grad_(True)
+    opt = torch.optim.AdamW([pt], lr=1e-3, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.05)
+    po, mo, vo = p.clone(), m.clone(), v.clone()
+    sq = torch.zeros(1, device="cuda")
+    for step in (1, 2, 3):
+        pt.grad = g.clone()
+        opt.step()
+        po, mo, vo = O.adamw_step(po, g, mo, vo, step, 1e-3, 0.9, 0.95, 1e-8, 0.05)
+        sq.zero_()
+        ops.adamw_step(p, g, m, v, pb, lr=1e-3, beta1=0.9, beta2=0.95, eps=1e-8, weight_decay=0.05, step=step,
+                       grad_sq_sum=sq)
+    assert rel_err(p, pt.detach()) < 1e-6
+    assert rel_err(p, po) < 1e-6
+    assert torch.equal(pb, p.to(torch.bfloat16))
+    assert abs(float(sq) - float((g * g).sum())) < 1e-4 * float((g * g).sum())
+    # found_inf skips the update
+    flag = torch.ones(1, dtype=torch.int32, device="cuda")
+    before = p.clone()
+    ops.adamw_step(p, g, m, v, pb, lr=1e-3, beta1=0.9, beta2=0.95, eps=1e-8, weight_decay=0.05, step=4, found_inf=flag)
+    assert torch.equal(p, before)
