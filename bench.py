@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""Benchmark of the TAE hot path on B200: training images/sec at px256 / patch16 (BASELINE.json `metric`).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--model tae_patch16_vocab256_px256] [--batch 256]
+    python bench.py --impl reference ...      # the reference algorithm on the host CPU cores (oracle port)
+
+N > 1 is launched by torchrun (one rank per GPU, NCCL); rank 0 prints ONE JSON line.
+
+Workload (BASELINE.json configs[1]): tae_patch16_vocab256_px256, bf16 compute, batch 256 per GPU, one full
+training step = forward + loss + backward (+ bucketed gradient all-reduce) + fused AdamW + zero_grad, on synthetic
+256x256x3 inputs and reference-style random-init weights.  `value` times K steps with the inputs resident in HBM;
+`e2e` times the same steps fed from pinned host memory through the public API (H2D copy of every batch and a D2H
+read of every step's loss inside the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--model", default="tae_patch16_vocab256_px256")
+    ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
+    ap.add_argument("--mode", default="train", choices=["train", "encode"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--cpu-batch", type=int, default=2)
+    return ap.parse_args()
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+def train_flops_per_image(cfg) -> float:
+    """F_train = 3 F_fwd - 2*196608*D."""
+    N, D, L, V = cfg.num_patches, cfg.embed_dim, cfg.depth, cfg.vocab_size
+    pix = 3 * cfg.img_size * cfg.img_size
+    f_fwd = 2 * pix * D + 2 * L * (24 * N * D * D + 4 * N * N * D) + 4 * N * D * V + 2 * pix * D
+    return 3.0 * f_fwd - 2.0 * pix * D
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled every 200 ms during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [x.strip() for x in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx = float(parts[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------------
+# CPU arm: the reference algorithm (oracle port) on the host cores
+# ----------------------------------------------------------------------------------------------------
+def cpu_reference_step_time(model_name: str, batch: int, steps: int, warmup: int):
+    """Times the reference's training step (train.py:122-150 restated: forward+loss, backward, AdamW, zero_grad) with
+    the oracle port on all host threads.  Returns (images_per_sec, cores, seconds_per_step)."""
+    import torch
+
+    from oracle import tae_oracle as O
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = O.zoo_config(model_name)
+    sd = O.init_state_dict(cfg, seed=0)
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    no_decay, decay = O.add_weight_decay_names([(k, tuple(v.shape)) for k, v in sd.items()], 0.05)
+    opt = torch.optim.AdamW([{"params": [params[k] for k in no_decay], "weight_decay": 0.0},
+                             {"params": [params[k] for k in decay], "weight_decay": 0.05}], lr=1e-4, betas=(0.9, 0.95))
+    x = torch.randn(batch, 3, cfg.img_size, cfg.img_size, generator=torch.Generator().manual_seed(1234))
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        loss, _, _ = O.forward(params, x, cfg, "fp32")
+        loss.backward()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    sec = sum(times) / len(times)
+    return batch / sec, cores, sec
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    # bounded: each step is `cpu_batch` images of the same workload; cap the number of CPU steps to stay in minutes
+    steps_run, warm_run = min(steps, 3), min(warmup, 1)
+    ips, cores, sec = cpu_reference_step_time(args.model, args.cpu_batch, steps_run, warm_run)
+    line = {
+        "impl": "reference", "metric": "train images/sec at px256 patch16", "value": ips, "unit": "images/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.model} training step (fwd+loss+bwd+AdamW), px256", "batch_per_step": args.cpu_batch,
+                   "note": f"bounded sample: {steps_run} timed CPU steps of {args.cpu_batch} images (requested "
+                           f"steps={steps}); reference algorithm = oracle port of tae.py on host cores"},
+        "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
+                         "sample": f"{steps_run} steps x {args.cpu_batch} images, fp32, torch CPU, {cores} threads"},
+        "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------
+# B200 arm
+# ----------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    from oracle import tae_oracle as O  # config table + FLOP model only; never on the timed path
+    from tae_b200 import _lib, engine, misc, ops
+    from tae_b200.ddp import DistributedDataParallel
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.require_device()
+    cfg = O.zoo_config(args.model)
+    B = args.batch
+
+    torch.manual_seed(0)
+    model = engine.build_model(args.model, dev)
+    model.train()
+    optimizer = engine.build_optimizer(model, max_lr=1e-4, weight_decay=0.05)
+    scaler = misc.NativeScalerWithGradNormCount(compute_norm=False)
+    net = DistributedDataParallel(model, optimizer=optimizer) if world > 1 else model
+
+    gen = torch.Generator(device="cpu").manual_seed(1234 + rank)
+    n_host = 2
+    host = [torch.randn(B, 3, cfg.img_size, cfg.img_size, generator=gen).pin_memory() for _ in range(n_host)]
+    resident = [h.to(dev) for h in host]
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def step_resident(i):
+        return engine.train_step(net, optimizer, scaler, resident[i % n_host], i)
+
+    for i in range(args.warmup):
+        step_resident(i)
+    sync_all()
+
+    # ---- timed region 1: inputs resident in HBM ----
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = ops.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        loss = step_resident(i)
+    e1.record()
+    sync_all()
+    launches = ops.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t)
+    final_loss = float(loss)
+
+    # ---- timed region 2: end to end through the public API, host buffers ----
+    feeder = engine.HostBatchFeeder(host, dev)
+    loss_host = torch.zeros(args.steps, dtype=torch.float32).pin_memory()
+    sync_all()
+    e0.record()
+    for i in range(args.steps):
+        x = feeder.next()
+        loss = engine.train_step(net, optimizer, scaler, x, i)
+        feeder.release()
+        loss_host[i:i + 1].copy_(loss.reshape(1), non_blocking=True)  # D2H read of the step's result
+    e1.record()
+    sync_all()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_e2e = float(t)
+    assert all(map(lambda v: v == v, loss_host.tolist())), "non-finite loss in e2e region"
+
+    # ---- roofline of the dominant kernel (the tcgen05 GEMM), instrumented pass after the timed regions ----
+    roof, detail = None, None
+    if not args.no_roofline and rank == 0:
+        roof, detail = gemm_roofline(torch, ops, lambda i: step_resident(i), measured_peaks())
+    if world > 1:
+        dist.barrier()
+
+    ips = world * B * args.steps / (ms_total / 1e3)
+    ips_e2e = world * B * args.steps / (ms_e2e / 1e3)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = measured_peaks()
+    fpi = train_flops_per_image(cfg)
+    line = {
+        "metric": "train images/sec at px256 patch16", "value": ips, "unit": "images/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"{args.model} bf16 training step (fwd+loss+bwd+allreduce+AdamW), px256",
+                   "batch_per_gpu": B, "global_batch": B * world, "tokens_per_image": cfg.num_patches,
+                   "parallelism": f"dp{world}", "l2": "per-step working set (201 MB batch, ~70 GB activations) >> 126 MB L2",
+                   "final_loss": final_loss},
+        "model_tflops_per_gpu": fpi * ips / world / 1e12,
+        "frac_of_bf16_peak_sustained": fpi * ips / world / 1e12 / peaks["bf16_tflops_sustained"],
+        "clocks": clocks,
+        "e2e": {"value": ips_e2e, "unit": "images/s", "h2d_bytes_per_step": feeder.bytes_per_batch,
+                "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches),
+    }
+    if roof is not None:
+        line["roofline"] = roof
+        line["roofline_detail"] = detail
+    if not args.no_cpu_baseline and world == 1:
+        cips, cores, csec = cpu_reference_step_time(args.model, args.cpu_batch, 2, 1)
+        line["cpu_baseline"] = {"value": cips, "unit": "images/s", "cores": cores, "kind": "port",
+                                "sample": f"2 timed steps x {args.cpu_batch} images of the same training step, fp32, oracle port, "
+                                          f"{cores} threads ({csec:.1f} s/step)"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def gemm_roofline(torch, ops, step_fn, peaks):
+    """Per-launch CUDA-event timing of every tae_gemm launch during 2 instrumented training steps."""
+    records = []
+    orig = ops.gemm
+
+    def timed_gemm(A, B, **kw):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        out = orig(A, B, **kw)
+        e.record()
+        K = A.shape[0] if kw.get("a_mn") else A.shape[1]
+        M = A.shape[1] if kw.get("a_mn") else A.shape[0]
+        N = B.shape[1] if kw.get("b_mn") else B.shape[0]
+        records.append((kw.get("epilogue", 0), 2.0 * M * N * K, s, e))
+        return out
+
+    import tae_b200.tae as model_mod
+
+    ops.gemm = timed_gemm
+    model_mod.ops.gemm = timed_gemm
+    try:
+        for i in range(2):
+            step_fn(i)
+        torch.cuda.synchronize()
+    finally:
+        ops.gemm = orig
+        model_mod.ops.gemm = orig
+    names = {0: "bf16", 1: "bf16_gelu", 2: "f32_resid", 3: "f32_acc(wgrad)", 4: "bf16_dgelu"}
+    per = {}
+    tot_fl = tot_ms = 0.0
+    for epi, fl, s, e in records:
+        ms = s.elapsed_time(e)
+        d = per.setdefault(names[epi], [0.0, 0.0, 0])
+        d[0] += fl
+        d[1] += ms
+        d[2] += 1
+        tot_fl += fl
+        tot_ms += ms
+    achieved = tot_fl / (tot_ms * 1e-3) / 1e12
+    peak = peaks["bf16_tflops_sustained"]
+    roof = {"bound": "tensor", "kernel": "gemm_bf16_tcgen05 (all epilogue instantiations)", "achieved": achieved,
+            "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+            "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a long step)",
+            "launches": len(records), "avg_launch_ms": tot_ms / max(1, len(records)),
+            "algorithmic_flops_per_launch": tot_fl / max(1, len(records))}
+    detail = {k: {"tflops": v[0] / (v[1] * 1e-3) / 1e12, "ms_per_step": v[1] / 2, "launches_per_step": v[2] // 2}
+              for k, v in per.items()}
+    return roof, detail
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

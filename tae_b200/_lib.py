@@ -84,7 +84,8 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not LIB_PATH.exists() and build_if_missing:
+    if build_if_missing:
+        # no-op when the in-tree library matches the sources' fingerprint; rebuilds (nvcc) when csrc/ changed
         from . import build as _build
 
         _build.build()

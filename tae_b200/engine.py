@@ -1,0 +1,112 @@
+"""The reference's step loops restated around the B200 path (no data loading: callers hand in tensors).
+
+  train_step        train.py:122-150   lr schedule -> forward -> backward (+ bucketed all-reduce) -> AdamW -> zero_grad
+  evaluate_batch    train.py:203-223 / evaluate.py:84-102   forward under no_grad, loss only
+  encode_batch      encode.py:80-88    forward_encoder under no_grad
+  HostBatchFeeder   train.py:134 / encode.py:82   pinned-host -> device copies, double-buffered on a copy stream
+                    (the synchronous 201 MB H2D per step is the adjacent host overhead)
+  shard_for_rank    batch sharding for multi-GPU encode / evaluate (no communication; rank r takes slice r)
+"""
+from __future__ import annotations
+
+import math
+import sys
+
+import torch
+
+from . import misc
+from . import tae as tae_models
+from .optim import FusedAdamW
+
+
+def build_model(name: str, device="cuda"):
+    """tae.__dict__[args.model]() (train.py:94) + .to(device)."""
+    model = tae_models.__dict__[name]()
+    return model.to(device)
+
+
+def build_optimizer(model, max_lr=1e-4, weight_decay=0.05, track_grad_norm=False):
+    """train.py:108-109: two param groups from add_weight_decay, AdamW betas (0.9, 0.95)."""
+    groups = misc.add_weight_decay(model, weight_decay, bias_wd=False)
+    return FusedAdamW(groups, lr=max_lr, betas=(0.9, 0.95), track_grad_norm=track_grad_norm)
+
+
+def train_step(model, optimizer, loss_scaler, samples, it: int, *, max_lr=1e-4, min_lr=1e-5, switch_it=450_000,
+               accum_iter=1, check_finite=False):
+    """One iteration of the hot loop (train.py:122-150).  Returns the (device) loss tensor of this micro-step.
+
+    The reference reads `loss.item()` and calls `torch.cuda.synchronize()` every step (train.py:139,150); here both are
+    opt-in (`check_finite`) so the host can run ahead of the device."""
+    if it % accum_iter == 0:
+        misc.adjust_learning_rate(optimizer, max_lr, min_lr, it, switch_it)
+    loss, _ = model(samples)
+    if check_finite:
+        v = loss.item()
+        if not math.isfinite(v):
+            print("Loss is {}, stopping training".format(v))
+            sys.exit(1)
+    step_loss = loss / accum_iter if accum_iter != 1 else loss
+    update = (it + 1) % accum_iter == 0
+    loss_scaler(step_loss, optimizer, parameters=None, update_grad=update)
+    if update:
+        optimizer.zero_grad()
+    return loss.detach()
+
+
+@torch.no_grad()
+def evaluate_batch(model, samples):
+    loss, _ = model(samples)
+    return loss
+
+
+@torch.no_grad()
+def encode_batch(model, samples):
+    return model.forward_encoder(samples)
+
+
+def shard_for_rank(n_items: int, rank: int, world: int):
+    """Contiguous, order-preserving shard [lo, hi) of n_items for `rank` of `world` (encode / evaluate sharding)."""
+    per = (n_items + world - 1) // world
+    lo = min(n_items, rank * per)
+    return lo, min(n_items, lo + per)
+
+
+class HostBatchFeeder:
+    """Streams host batches to the device on a dedicated copy stream, two batches in flight.
+
+    `host_batches`: list of pinned fp32 host tensors that is cycled.  `next()` returns a device tensor whose copy
+    has been ordered before the current stream; the buffer is recycled two calls later."""
+
+    def __init__(self, host_batches, device="cuda", depth: int = 2):
+        self.host = host_batches
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.depth = depth
+        self.bufs = [torch.empty_like(host_batches[0], device=self.device) for _ in range(depth)]
+        self.ready = [torch.cuda.Event() for _ in range(depth)]
+        self.freed = [torch.cuda.Event() for _ in range(depth)]
+        self.i = 0
+        self.bytes_per_batch = host_batches[0].numel() * host_batches[0].element_size()
+        for k in range(depth):
+            self.freed[k].record(torch.cuda.current_stream(self.device))
+        self._issue(0)
+
+    def _issue(self, idx):
+        slot = idx % self.depth
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(self.freed[slot])
+            self.bufs[slot].copy_(self.host[idx % len(self.host)], non_blocking=True)
+            self.ready[slot].record(self.stream)
+
+    def next(self):
+        slot = self.i % self.depth
+        cur = torch.cuda.current_stream(self.device)
+        self._issue(self.i + 1)  # prefetch the following batch while this one is consumed
+        cur.wait_event(self.ready[slot])
+        return self.bufs[slot]
+
+    def release(self):
+        """Call after the step that consumed the batch has been enqueued."""
+        slot = self.i % self.depth
+        self.freed[slot].record(torch.cuda.current_stream(self.device))
+        self.i += 1

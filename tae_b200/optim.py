@@ -1,0 +1,176 @@
+"""Fused AdamW over flat parameter arenas (replaces `torch.optim.AdamW(param_groups, fused=True)`, train.py:109).
+
+Each parameter group is flattened into five contiguous arenas — fp32 master parameters, fp32 gradients, exp_avg,
+exp_avg_sq and a bf16 shadow copy of the parameters — laid out in REVERSE parameter order (the order gradients
+become ready in backward), so that
+  * one `tae_adamw_step` launch per group updates everything at HBM speed and refreshes the bf16 weights the
+    GEMMs read (no separate cast pass, no 373 small launches);
+  * the hand-written backward passes write weight gradients straight into the arena (`p._tae_grad`), with
+    beta=0 on the first write after `zero_grad()` — no gradient memset and no autograd accumulate pass;
+  * data-parallel buckets are contiguous slices of the gradient arena (tae_b200/ddp.py).
+The object protocol matches what the reference's drivers use (train.py:108-116,146-148,165-168; util/misc.py:
+400-412): `param_groups[i]["lr"]` is writable and read every step, `zero_grad()`, `state_dict()` /
+`load_state_dict()` in torch.optim.AdamW's format (`step`, `exp_avg`, `exp_avg_sq` per parameter).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from . import ops
+
+_ALIGN = 64  # elements; keeps every parameter 256-byte aligned in the fp32 arenas (128 B in the bf16 one)
+
+
+class _Arena:
+    def __init__(self, params, device):
+        self.params = list(params)
+        order = list(reversed(self.params))  # gradient-ready order
+        self.offsets = {}
+        off = 0
+        for p in order:
+            self.offsets[id(p)] = off
+            off += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
+        self.numel = off
+        self.order = order
+        f32, dev = torch.float32, device
+        self.p = torch.zeros(off, dtype=f32, device=dev)
+        self.g = torch.zeros(off, dtype=f32, device=dev)
+        self.m = torch.zeros(off, dtype=f32, device=dev)
+        self.v = torch.zeros(off, dtype=f32, device=dev)
+        self.pb = torch.zeros(off, dtype=torch.bfloat16, device=dev)
+
+    def view(self, arena, p):
+        o = self.offsets[id(p)]
+        return arena[o:o + p.numel()].view(p.shape)
+
+
+class FusedAdamW(torch.optim.Optimizer):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, grad_scale=1.0,
+                 track_grad_norm=False, fused=True):
+        if lr < 0 or eps < 0 or not (0 <= betas[0] < 1) or not (0 <= betas[1] < 1) or weight_decay < 0:
+            raise ValueError("invalid AdamW hyper-parameters")
+        defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+        super().__init__(params, defaults)
+        self.grad_scale = float(grad_scale)
+        self.track_grad_norm = track_grad_norm
+        self._arenas = []
+        self._steps = []
+        self._grad_sq = None
+        self._build()
+
+    # ------------------------------------------------------------------------------------------
+    def _build(self):
+        for group in self.param_groups:
+            ps = [p for p in group["params"] if p.requires_grad]
+            if not ps:
+                self._arenas.append(None)
+                self._steps.append(0)
+                continue
+            dev = ps[0].device
+            if dev.type != "cuda":
+                raise RuntimeError("FusedAdamW needs CUDA parameters (move the model to the GPU first); no CPU fallback")
+            for p in ps:
+                if p.dtype != torch.float32 or p.device != dev:
+                    raise RuntimeError("FusedAdamW: parameters must be fp32 and on one device")
+            ar = _Arena(ps, dev)
+            with torch.no_grad():
+                for p in ps:
+                    ar.view(ar.p, p).copy_(p)
+                    old_grad = p.grad
+                    p.data = ar.view(ar.p, p)
+                    g = ar.view(ar.g, p)
+                    if old_grad is not None:
+                        g.copy_(old_grad)
+                    p.grad = g
+                    p._tae_grad = g
+                    p._tae_dirty = 1 if old_grad is not None else 0
+                    p._tae_bf16 = ar.view(ar.pb, p)
+                    p._tae_bf16_version = p._version
+                    p._tae_bf16_ptr = p.data_ptr()
+                ops.cast_bf16(ar.p, ar.pb)
+            self._arenas.append(ar)
+            self._steps.append(0)
+        dev = next((a.p.device for a in self._arenas if a is not None), None)
+        if dev is not None:
+            self._grad_sq = torch.zeros(1, dtype=torch.float32, device=dev)
+
+    @property
+    def arenas(self):
+        return [a for a in self._arenas if a is not None]
+
+    # ------------------------------------------------------------------------------------------
+    def zero_grad(self, set_to_none: bool = True):
+        """Gradients live in the arena permanently; 'zeroing' just arms beta=0 for the next backward's first write."""
+        for ar in self.arenas:
+            for p in ar.params:
+                p._tae_dirty = 0
+                if p.grad is None or p.grad.data_ptr() != p._tae_grad.data_ptr():
+                    p.grad = p._tae_grad
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        if self._grad_sq is not None and self.track_grad_norm:
+            self._grad_sq.zero_()
+        for gi, (group, ar) in enumerate(zip(self.param_groups, self._arenas)):
+            if ar is None:
+                continue
+            for p in ar.params:
+                if p._tae_dirty == 0:
+                    # parameter received no gradient since zero_grad(): its arena slice is stale -> treat as zero
+                    g = p.grad
+                    if g is not None and g.data_ptr() != p._tae_grad.data_ptr():
+                        p._tae_grad.copy_(g)  # a foreign backward produced a separate .grad tensor
+                    else:
+                        p._tae_grad.zero_()
+                elif p.grad is not None and p.grad.data_ptr() != p._tae_grad.data_ptr():
+                    p._tae_grad.add_(p.grad)
+            self._steps[gi] += 1
+            b1, b2 = group["betas"]
+            ops.adamw_step(ar.p, ar.g, ar.m, ar.v, ar.pb, lr=group["lr"], beta1=b1, beta2=b2, eps=group["eps"],
+                           weight_decay=group["weight_decay"], step=self._steps[gi], grad_scale=self.grad_scale,
+                           grad_sq_sum=self._grad_sq if self.track_grad_norm else None)
+        return loss
+
+    def grad_norm(self) -> torch.Tensor:
+        """L2 norm of all (scaled) gradients seen by the last step() (needs track_grad_norm=True); device tensor."""
+        return self._grad_sq.sqrt().squeeze(0)
+
+    # ------------------------------------------------------------------------------------------
+    # torch.optim.AdamW-compatible checkpoint format
+    def state_dict(self):
+        state, groups, idx = {}, [], 0
+        for gi, (group, ar) in enumerate(zip(self.param_groups, self._arenas)):
+            ids = []
+            for p in group["params"]:
+                ids.append(idx)
+                if ar is not None and id(p) in ar.offsets and self._steps[gi] > 0:
+                    state[idx] = {"step": torch.tensor(float(self._steps[gi])),
+                                  "exp_avg": ar.view(ar.m, p).clone(), "exp_avg_sq": ar.view(ar.v, p).clone()}
+                idx += 1
+            g = {k: v for k, v in group.items() if k != "params"}
+            g["params"] = ids
+            groups.append(g)
+        return {"state": state, "param_groups": groups}
+
+    @torch.no_grad()
+    def load_state_dict(self, sd):
+        idx = 0
+        for gi, (group, ar, saved) in enumerate(zip(self.param_groups, self._arenas, sd["param_groups"])):
+            for k, v in saved.items():
+                if k != "params":
+                    group[k] = v
+            step = 0
+            for p in group["params"]:
+                st = sd["state"].get(idx, sd["state"].get(str(idx)))
+                if st is not None and ar is not None and id(p) in ar.offsets:
+                    ar.view(ar.m, p).copy_(st["exp_avg"])
+                    ar.view(ar.v, p).copy_(st["exp_avg_sq"])
+                    step = max(step, int(float(st["step"])))
+                idx += 1
+            self._steps[gi] = step
