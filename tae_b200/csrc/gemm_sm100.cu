@@ -9,7 +9,8 @@
 //   warp 0      TMA producer: cp.async.bulk.tensor 2-D boxes (128B swizzle) into a 4-stage smem ring
 //   warp 1      MMA issuer: one thread issues tcgen05.mma.cta_group::1.kind::f16 (128x256x16 per instruction)
 //   warp 2      TMEM allocator (512 columns = two 128x256 fp32 accumulators, double-buffered)
-//   warps 4-11  epilogue: tcgen05.ld 32 lanes x 32 columns per warp step -> fused epilogue -> global
+//   warps 4-11  epilogue: tcgen05.ld (one accumulator row per thread) -> swizzled smem transpose -> fused epilogue
+//               with 128-byte coalesced global loads/stores
 // Pipelines: smem full/empty mbarriers (TMA <-> MMA) and TMEM full/empty mbarriers (MMA <-> epilogue), so
 // the epilogue of tile i overlaps the main loop of tile i+1.
 //
@@ -37,7 +38,8 @@ constexpr int TMEM_COLS = NUM_ACC * BLOCK_N;          // 512
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_THREADS = 128 + NUM_EPI_WARPS * 32;  // 384
 constexpr int SMEM_BARRIER_BYTES = 256;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + SMEM_BARRIER_BYTES + 1024;  // +1024: manual alignment slack
+constexpr int SMEM_STAGING_BYTES = NUM_EPI_WARPS * 32 * 128;  // 4 KB transpose tile per epilogue warp
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + SMEM_BARRIER_BYTES + SMEM_STAGING_BYTES + 1024;  // +1024: alignment slack
 
 struct Params {
   int M, N, K;
@@ -177,106 +179,121 @@ __device__ __forceinline__ uint32_t make_idesc(int a_mn, int b_mn) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Epilogues: one thread owns one output row and 32 consecutive columns (fp32 accumulators in v).
+// Epilogue.  tcgen05.ld hands each thread one accumulator ROW (32 consecutive columns per load); writing global
+// memory in that layout would touch 32 different 128-byte lines per instruction.  Each epilogue warp therefore
+// transposes through a private 4 KB shared-memory tile (32 rows x 128 B, 16-byte chunks XOR-swizzled by row so both
+// the row-wise writes and the line-wise reads are bank-conflict free) and then runs the fused epilogue in a
+// COALESCED layout: 8 consecutive lanes own the 8 16-byte chunks of one 128-byte row segment, 4 rows per instruction.
+// One step covers 32 accumulator columns; bias, bf16 rounding, GELU, residual all happen in the coalesced layout.
 // ---------------------------------------------------------------------------------------------
+constexpr int STG_BYTES_PER_WARP = 32 * 128;
+
+__device__ __forceinline__ uint32_t stg_off(int row, int chunk) {
+  return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4));
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+  uint4 r;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr) : "memory");
+  return r;
+}
+
+constexpr int EPI_COLS = 32;  // accumulator columns per staging step (32 fp32 = one 128-byte row segment)
+
+// Row phase: this thread's accumulator row (32 fp32 columns) -> swizzled staging tile.  Pure transpose.
+__device__ __forceinline__ void epi_stage_rows(uint32_t stg, uint32_t taddr, int lane) {
+  uint32_t raw[32];
+  tmem_ld_32x32b_x32(taddr, raw);
+  tmem_ld_wait();
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+    st_shared_v4(stg + stg_off(lane, c), raw[4 * c], raw[4 * c + 1], raw[4 * c + 2], raw[4 * c + 3]);
+}
+
+// Coalesced phase: lane -> (row = it*4 + lane/8, 4 fp32 columns = chunk lane%8).  Every shared and global load of
+// the step is issued before the first use (8 rows in flight per lane); the bias of the lane's 4 fixed columns is
+// loaded and rounded once per step; the math of the 8 rows is independent, so the scheduler has 32 chains to overlap.
 template <int EPI>
-__device__ __forceinline__ void epilogue_store(const Params& p, int row, int col0, int split, float (&v)[32]) {
-  if (row >= p.M) return;
-  const int ncol = min(32, p.N - col0);  // multiple of 8
-  if (EPI != TAE_EPI_F32_ACC && EPI != TAE_EPI_BF16_DGELU) {
-    if (p.bias != nullptr) {
+__device__ __forceinline__ void epi_write_coalesced(const Params& p, uint32_t stg, int row_base, int col0, int lane) {
+  const int c = lane & 7, rsub = lane >> 3;
+  const int col = col0 + c * 4;
+  const bool col_ok = col < p.N;
+  uint4 val[8];
 #pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        if (g * 4 < ncol) {
-          const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + g * 4));
-          // autocast hands the GEMM a bf16 copy of the fp32 bias: same rounding here
-          v[g * 4 + 0] += round_bf16(b.x);
-          v[g * 4 + 1] += round_bf16(b.y);
-          v[g * 4 + 2] += round_bf16(b.z);
-          v[g * 4 + 3] += round_bf16(b.w);
-        }
+  for (int it = 0; it < 8; ++it) val[it] = ld_shared_v4(stg + stg_off(it * 4 + rsub, c));
+  if (!col_ok) return;
+  constexpr bool kSide16 = (EPI == TAE_EPI_F32_RESID || EPI == TAE_EPI_F32_ACC);
+  uint4 side[8];
+  if (kSide16) {
+    const bool want = (EPI == TAE_EPI_F32_RESID) || (p.beta && p.splits <= 1);
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int grow = row_base + it * 4 + rsub;
+      side[it] = make_uint4(0u, 0u, 0u, 0u);
+      if (want && grow < p.M) {
+        if (EPI == TAE_EPI_F32_RESID)
+          side[it] = *reinterpret_cast<const uint4*>(p.resid + (size_t)(grow % p.resid_rows) * p.ldr + col);
+        else
+          side[it] = *reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.out) + (size_t)grow * p.ldo + col);
+      }
+    }
+  } else if (EPI == TAE_EPI_BF16_DGELU) {
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int grow = row_base + it * 4 + rsub;
+      side[it] = make_uint4(0u, 0u, 0u, 0u);
+      if (grow < p.M) {
+        const uint2 h = ld_nc_v2(p.aux + (size_t)grow * p.ldaux + col);
+        side[it].x = h.x;
+        side[it].y = h.y;
       }
     }
   }
-  if (EPI == TAE_EPI_BF16 || EPI == TAE_EPI_BF16_GELU || EPI == TAE_EPI_BF16_DGELU) {
-    bf16* out = reinterpret_cast<bf16*>(p.out) + (size_t)row * p.ldo + col0;
-    bf16* out2 = (EPI == TAE_EPI_BF16_GELU) ? reinterpret_cast<bf16*>(p.out2) + (size_t)row * p.ldo + col0 : nullptr;
-    const bf16* aux = (EPI == TAE_EPI_BF16_DGELU) ? p.aux + (size_t)row * p.ldaux + col0 : nullptr;
+  float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (EPI != TAE_EPI_F32_ACC && EPI != TAE_EPI_BF16_DGELU && p.bias != nullptr) {
+    // autocast hands the GEMM a bf16 copy of the fp32 bias: same rounding here
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+    bias4 = make_float4(round_bf16(b.x), round_bf16(b.y), round_bf16(b.z), round_bf16(b.w));
+  }
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      if (g * 8 < ncol) {
-        float* x = &v[g * 8];
-        if (EPI == TAE_EPI_BF16_DGELU) {
-          const uint4 hraw = ld_nc_v4(aux + g * 8);
-          const uint32_t hw[4] = {hraw.x, hraw.y, hraw.z, hraw.w};
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float2 h = unpack_bf16x2(hw[j]);
-            x[2 * j] = round_bf16(x[2 * j]) * gelu_erf_grad(h.x);
-            x[2 * j + 1] = round_bf16(x[2 * j + 1]) * gelu_erf_grad(h.y);
-          }
-        }
-        uint4 o;
-        o.x = pack_bf16x2(x[0], x[1]);
-        o.y = pack_bf16x2(x[2], x[3]);
-        o.z = pack_bf16x2(x[4], x[5]);
-        o.w = pack_bf16x2(x[6], x[7]);
-        *reinterpret_cast<uint4*>(out + g * 8) = o;
-        if (EPI == TAE_EPI_BF16_GELU) {
-          const uint32_t hw[4] = {o.x, o.y, o.z, o.w};
-          uint32_t aw[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float2 h = unpack_bf16x2(hw[j]);
-            aw[j] = pack_bf16x2(gelu_erf(h.x), gelu_erf(h.y));
-          }
-          *reinterpret_cast<uint4*>(out2 + g * 8) = make_uint4(aw[0], aw[1], aw[2], aw[3]);
-        }
+  for (int it = 0; it < 8; ++it) {
+    const int grow = row_base + it * 4 + rsub;
+    if (grow >= p.M) continue;
+    const float a0 = __uint_as_float(val[it].x), a1 = __uint_as_float(val[it].y);
+    const float a2 = __uint_as_float(val[it].z), a3 = __uint_as_float(val[it].w);
+    if (EPI == TAE_EPI_BF16 || EPI == TAE_EPI_BF16_GELU) {
+      const uint32_t h01 = pack_bf16x2(a0 + bias4.x, a1 + bias4.y), h23 = pack_bf16x2(a2 + bias4.z, a3 + bias4.w);
+      *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out) + (size_t)grow * p.ldo + col) = make_uint2(h01, h23);
+      if (EPI == TAE_EPI_BF16_GELU) {
+        const float2 f01 = unpack_bf16x2(h01), f23 = unpack_bf16x2(h23);
+        *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out2) + (size_t)grow * p.ldo + col) =
+            make_uint2(pack_bf16x2(gelu_fast(f01.x), gelu_fast(f01.y)), pack_bf16x2(gelu_fast(f23.x), gelu_fast(f23.y)));
       }
-    }
-  } else if (EPI == TAE_EPI_F32_RESID) {
-    float* out = reinterpret_cast<float*>(p.out) + (size_t)row * p.ldo + col0;
-    const float* res = p.resid + (size_t)(row % p.resid_rows) * p.ldr + col0;
-#pragma unroll
-    for (int g = 0; g < 8; ++g) {
-      if (g * 4 < ncol) {
-        const float4 r = *reinterpret_cast<const float4*>(res + g * 4);
-        float4 o;
-        o.x = r.x + round_bf16(v[g * 4 + 0]);
-        o.y = r.y + round_bf16(v[g * 4 + 1]);
-        o.z = r.z + round_bf16(v[g * 4 + 2]);
-        o.w = r.w + round_bf16(v[g * 4 + 3]);
-        *reinterpret_cast<float4*>(out + g * 4) = o;
-      }
-    }
-  } else {  // TAE_EPI_F32_ACC
-    float* out = reinterpret_cast<float*>(p.out) + (size_t)row * p.ldo + col0;
-    if (p.splits > 1) {
-#pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        if (g * 4 < ncol) {
-          atomicAdd(reinterpret_cast<float4*>(out + g * 4),
-                    make_float4(v[g * 4 + 0], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]));
-        }
-      }
-    } else {
-#pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        if (g * 4 < ncol) {
-          float4 o = make_float4(v[g * 4 + 0], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
-          if (p.beta) {
-            const float4 r = *reinterpret_cast<const float4*>(out + g * 4);
-            o.x += r.x;
-            o.y += r.y;
-            o.z += r.z;
-            o.w += r.w;
-          }
-          *reinterpret_cast<float4*>(out + g * 4) = o;
-        }
+    } else if (EPI == TAE_EPI_BF16_DGELU) {
+      const float2 h01 = unpack_bf16x2(side[it].x), h23 = unpack_bf16x2(side[it].y);
+      // bf16(acc) first: the dgrad GEMM's own output rounding in the reference
+      const uint32_t o01 = pack_bf16x2(round_bf16(a0) * gelu_grad_fast(h01.x), round_bf16(a1) * gelu_grad_fast(h01.y));
+      const uint32_t o23 = pack_bf16x2(round_bf16(a2) * gelu_grad_fast(h23.x), round_bf16(a3) * gelu_grad_fast(h23.y));
+      *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out) + (size_t)grow * p.ldo + col) = make_uint2(o01, o23);
+    } else if (EPI == TAE_EPI_F32_RESID) {
+      float4 o;
+      o.x = __uint_as_float(side[it].x) + round_bf16(a0 + bias4.x);
+      o.y = __uint_as_float(side[it].y) + round_bf16(a1 + bias4.y);
+      o.z = __uint_as_float(side[it].z) + round_bf16(a2 + bias4.z);
+      o.w = __uint_as_float(side[it].w) + round_bf16(a3 + bias4.w);
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (size_t)grow * p.ldo + col) = o;
+    } else {  // TAE_EPI_F32_ACC
+      float* dst = reinterpret_cast<float*>(p.out) + (size_t)grow * p.ldo + col;
+      if (p.splits > 1) {
+        atomicAdd(reinterpret_cast<float4*>(dst), make_float4(a0, a1, a2, a3));
+      } else {
+        *reinterpret_cast<float4*>(dst) = make_float4(a0 + __uint_as_float(side[it].x), a1 + __uint_as_float(side[it].y),
+                                                      a2 + __uint_as_float(side[it].z), a3 + __uint_as_float(side[it].w));
       }
     }
   }
-  (void)split;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -412,25 +429,24 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     const int ew = warp - 4;
     const int q = ew & 3;       // TMEM lane quarter this warp may access (== warp % 4)
     const int half = ew >> 2;   // which 128-column half of the accumulator
+    const uint32_t stg = smem_u32(smem + STAGES * STAGE_BYTES + SMEM_BARRIER_BYTES + ew * STG_BYTES_PER_WARP);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
       const WorkItem it = decode_work(p, w);
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tcgen05_fence_after();
-      const int row = it.mt * BLOCK_M + q * 32 + lane;
+      const int row_base = it.mt * BLOCK_M + q * 32;
+      constexpr int COLS = EPI_COLS;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        const int col0 = it.nt * BLOCK_N + half * 128 + c * 32;
+      for (int c = 0; c < 128 / COLS; ++c) {
+        const int col0 = it.nt * BLOCK_N + half * 128 + c * COLS;
         if (col0 >= p.N) break;  // warp-uniform
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + half * 128 + c * 32);
-        uint32_t raw[32];
-        tmem_ld_32x32b_x32(taddr, raw);
-        tmem_ld_wait();
-        float v[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
-        epilogue_store<EPI>(p, row, col0, it.split, v);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + half * 128 + c * COLS);
+        epi_stage_rows(stg, taddr, lane);
+        __syncwarp();
+        epi_write_coalesced<EPI>(p, stg, row_base, col0, lane);
+        __syncwarp();
       }
       tcgen05_fence_before();
       __syncwarp();

@@ -14,7 +14,8 @@
 namespace tae {
 namespace ln {
 
-constexpr int ROWS = 4;       // rows per CTA iteration
+constexpr int FWD_ROWS = 4;   // rows per CTA iteration (forward)
+constexpr int BWD_ROWS = 2;   // rows per CTA iteration (backward: more live state per row)
 constexpr int MAX_WARPS = 16;  // blockDim <= 512
 
 // CTA-wide sum of NV values per thread (all threads get the result). red: smem [NV][MAX_WARPS].
@@ -36,11 +37,63 @@ __device__ __forceinline__ void block_sum(float (&v)[NV], float* red) {
   }
 }
 
+// CTA-wide (mean, M2) of NR rows in ONE barrier round: every thread enters with the mean / sum of squared deviations
+// of its own `cnt0` elements; equal-count pairwise merges (Chan et al.) through the shuffle tree, then a sequential
+// merge over the warps.  Numerically a two-pass variance, at the synchronisation cost of a single sum.
+template <int NR>
+__device__ __forceinline__ void block_mean_m2(float (&mean)[NR], float (&m2)[NR], float cnt0, float* red) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  float cnt = cnt0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      const float mb = __shfl_xor_sync(0xffffffffu, mean[r], o);
+      const float qb = __shfl_xor_sync(0xffffffffu, m2[r], o);
+      const float d = mb - mean[r];
+      mean[r] = 0.5f * (mean[r] + mb);
+      m2[r] = m2[r] + qb + d * d * (0.5f * cnt);
+    }
+    cnt *= 2.0f;
+  }
+  __syncthreads();
+  if (lane == 0) {
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      red[(2 * r) * MAX_WARPS + warp] = mean[r];
+      red[(2 * r + 1) * MAX_WARPS + warp] = m2[r];
+    }
+  }
+  __syncthreads();
+  // sequential equal-count merge over the warps: after w groups, n = w*cnt, so cnt/(n+cnt) = 1/(w+1)
+  for (int w = 1; w < nwarps; ++w) {
+    const float inv = __frcp_rn((float)(w + 1));
+    const float wgt = cnt * (float)w * inv;
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      const float mu = (w == 1) ? red[(2 * r) * MAX_WARPS] : mean[r];
+      const float q = (w == 1) ? red[(2 * r + 1) * MAX_WARPS] : m2[r];
+      const float mw = red[(2 * r) * MAX_WARPS + w], qw = red[(2 * r + 1) * MAX_WARPS + w];
+      const float d = mw - mu;
+      mean[r] = fmaf(d, inv, mu);
+      m2[r] = q + qw + d * d * wgt;
+    }
+  }
+  if (nwarps == 1) {
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      mean[r] = red[(2 * r) * MAX_WARPS];
+      m2[r] = red[(2 * r + 1) * MAX_WARPS];
+    }
+  }
+}
+
 template <int VPT>
 __global__ void __launch_bounds__(512)
 ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
               bf16* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows, int D,
               float eps) {
+  constexpr int ROWS = FWD_ROWS;
   __shared__ float red[2 * ROWS * MAX_WARPS];
   const int tid = threadIdx.x, nthr = blockDim.x;
   float4 g[VPT], b[VPT];
@@ -53,10 +106,9 @@ ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, cons
   const float invD = 1.0f / (float)D;
   for (int r0 = blockIdx.x * ROWS; r0 < rows; r0 += gridDim.x * ROWS) {
     float4 xv[ROWS][VPT];
-    float s[ROWS];
+    float mu[ROWS], q[ROWS];
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) {
-      s[r] = 0.0f;
       const int row = r0 + r;
 #pragma unroll
       for (int v = 0; v < VPT; ++v) {
@@ -65,22 +117,22 @@ ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, cons
         } else {
           xv[r][v] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        s[r] += (xv[r][v].x + xv[r][v].y) + (xv[r][v].z + xv[r][v].w);
       }
     }
-    block_sum<ROWS>(s, red);
-    float mu[ROWS], q[ROWS];
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) {
-      mu[r] = s[r] * invD;
-      q[r] = 0.0f;
+      float s = 0.f;
+#pragma unroll
+      for (int v = 0; v < VPT; ++v) s += (xv[r][v].x + xv[r][v].y) + (xv[r][v].z + xv[r][v].w);
+      mu[r] = s * (1.0f / (4 * VPT));
+      q[r] = 0.f;
 #pragma unroll
       for (int v = 0; v < VPT; ++v) {
         const float dx = xv[r][v].x - mu[r], dy = xv[r][v].y - mu[r], dz = xv[r][v].z - mu[r], dw = xv[r][v].w - mu[r];
         q[r] += (dx * dx + dy * dy) + (dz * dz + dw * dw);
       }
     }
-    block_sum<ROWS>(q, red);
+    block_mean_m2<ROWS>(mu, q, (float)(4 * VPT), red);
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) {
       const int row = r0 + r;
@@ -105,12 +157,68 @@ ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, cons
   }
 }
 
+// Forward, warp-per-row variant (D = NV*128 <= 4096): the whole row lives in one warp's registers, statistics are
+// two shuffle reductions (mean, then centred sum of squares) and there is no block-level barrier at all; every lane
+// has NV independent 128-bit loads in flight.  gamma/beta are re-read through L1 (they are 2*D*4 bytes, L1-resident).
+template <int NV>
+__global__ void __launch_bounds__(256)
+ln_fwd_warp_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                   bf16* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows,
+                   float eps) {
+  constexpr int D = NV * 128;
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const float invD = 1.0f / (float)D;
+  for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += gridDim.x * wpb) {
+    const float* xr = x + (size_t)row * D;
+    float4 v[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = ld_nc_f4(xr + (i * 32 + lane) * 4);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    const float mu = warp_sum(s) * invD;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float a = v[i].x - mu, b = v[i].y - mu, c = v[i].z - mu, d = v[i].w - mu;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+    const float rs = rsqrtf(warp_sum(q) * invD + eps);
+    if (lane == 0) {
+      mean_out[row] = mu;
+      rstd_out[row] = rs;
+    }
+    bf16* yr = y + (size_t)row * D;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int col = (i * 32 + lane) * 4;
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + col));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(beta + col));
+      uint2 o;
+      o.x = pack_bf16x2((v[i].x - mu) * rs * g.x + b.x, (v[i].y - mu) * rs * g.y + b.y);
+      o.y = pack_bf16x2((v[i].z - mu) * rs * g.z + b.z, (v[i].w - mu) * rs * g.w + b.w);
+      *reinterpret_cast<uint2*>(yr + col) = o;
+    }
+  }
+}
+
+template <int NV>
+static void launch_fwd_warp(const float* x, const float* gamma, const float* beta, bf16* y, float* mean, float* rstd,
+                            int rows, float eps, cudaStream_t stream) {
+  const int sms = num_sms() > 0 ? num_sms() : 148;
+  int grid = (rows + 7) / 8;
+  if (grid > sms * 8) grid = sms * 8;
+  ln_fwd_warp_kernel<NV><<<grid, 256, 0, stream>>>(x, gamma, beta, y, mean, rstd, rows, eps);
+}
+
 // Backward.  partials layout: [gridDim.x][3][D]  (0: dgamma, 1: dbeta, 2: colsum(bf16(dres_out)))
 template <int VPT>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(512, (VPT == 1 ? 2 : 1))
 ln_bwd_kernel(const bf16* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
               const float* __restrict__ rstd, const float* __restrict__ gamma, const float* dres_in,
               float* dres_out, bf16* __restrict__ dres_out_b, float* __restrict__ partials, int rows, int D) {
+  constexpr int ROWS = BWD_ROWS;
   __shared__ float red[2 * ROWS * MAX_WARPS];
   const int tid = threadIdx.x, nthr = blockDim.x;
   float4 g[VPT], acc_dg[VPT], acc_db[VPT], acc_cs[VPT];
@@ -123,14 +231,13 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const float* __restrict__ x, const fl
   }
   const float invD = 1.0f / (float)D;
   for (int r0 = blockIdx.x * ROWS; r0 < rows; r0 += gridDim.x * ROWS) {
-    float4 xh[ROWS][VPT], gy[ROWS][VPT];  // xhat and dy*gamma
+    float4 xh[ROWS][VPT], gy[ROWS][VPT], din[ROWS][VPT];  // xhat, dy*gamma, incoming residual gradient
     float sums[2 * ROWS];
     float rs[ROWS];
+    // issue every global load of this iteration up front (x, dy AND the residual gradient)
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) {
       const int row = r0 + r;
-      sums[2 * r] = 0.f;
-      sums[2 * r + 1] = 0.f;
       float mu = 0.f;
       rs[r] = 0.f;
       if (row < rows) {
@@ -139,37 +246,39 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const float* __restrict__ x, const fl
       }
 #pragma unroll
       for (int v = 0; v < VPT; ++v) {
+        xh[r][v] = make_float4(0.f, 0.f, 0.f, 0.f);
+        gy[r][v] = make_float4(0.f, 0.f, 0.f, 0.f);
+        din[r][v] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (row < rows) {
           const size_t off = (size_t)row * D + (v * nthr + tid) * 4;
           const float4 xv = ld_nc_f4(x + off);
           const uint2 draw = ld_nc_v2(dy + off);
+          if (dres_in != nullptr) din[r][v] = *reinterpret_cast<const float4*>(dres_in + off);
           const float2 d01 = unpack_bf16x2(draw.x), d23 = unpack_bf16x2(draw.y);
-          float4 h;
-          h.x = (xv.x - mu) * rs[r];
-          h.y = (xv.y - mu) * rs[r];
-          h.z = (xv.z - mu) * rs[r];
-          h.w = (xv.w - mu) * rs[r];
-          xh[r][v] = h;
-          acc_dg[v].x += d01.x * h.x;
-          acc_dg[v].y += d01.y * h.y;
-          acc_dg[v].z += d23.x * h.z;
-          acc_dg[v].w += d23.y * h.w;
-          acc_db[v].x += d01.x;
-          acc_db[v].y += d01.y;
-          acc_db[v].z += d23.x;
-          acc_db[v].w += d23.y;
-          float4 t;
-          t.x = d01.x * g[v].x;
-          t.y = d01.y * g[v].y;
-          t.z = d23.x * g[v].z;
-          t.w = d23.y * g[v].w;
-          gy[r][v] = t;
-          sums[2 * r] += (t.x + t.y) + (t.z + t.w);
-          sums[2 * r + 1] += (t.x * h.x + t.y * h.y) + (t.z * h.z + t.w * h.w);
-        } else {
-          xh[r][v] = make_float4(0.f, 0.f, 0.f, 0.f);
-          gy[r][v] = make_float4(0.f, 0.f, 0.f, 0.f);
+          xh[r][v] = make_float4((xv.x - mu) * rs[r], (xv.y - mu) * rs[r], (xv.z - mu) * rs[r], (xv.w - mu) * rs[r]);
+          gy[r][v] = make_float4(d01.x, d01.y, d23.x, d23.y);  // dy for now
         }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      sums[2 * r] = 0.f;
+      sums[2 * r + 1] = 0.f;
+#pragma unroll
+      for (int v = 0; v < VPT; ++v) {
+        const float4 d = gy[r][v], h = xh[r][v];
+        acc_dg[v].x += d.x * h.x;
+        acc_dg[v].y += d.y * h.y;
+        acc_dg[v].z += d.z * h.z;
+        acc_dg[v].w += d.w * h.w;
+        acc_db[v].x += d.x;
+        acc_db[v].y += d.y;
+        acc_db[v].z += d.z;
+        acc_db[v].w += d.w;
+        const float4 t = make_float4(d.x * g[v].x, d.y * g[v].y, d.z * g[v].z, d.w * g[v].w);
+        gy[r][v] = t;
+        sums[2 * r] += (t.x + t.y) + (t.z + t.w);
+        sums[2 * r + 1] += (t.x * h.x + t.y * h.y) + (t.z * h.z + t.w * h.w);
       }
     }
     block_sum<2 * ROWS>(sums, red);
@@ -182,17 +291,10 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const float* __restrict__ x, const fl
       for (int v = 0; v < VPT; ++v) {
         const size_t off = (size_t)row * D + (v * nthr + tid) * 4;
         float4 o;
-        o.x = rs[r] * (gy[r][v].x - c1 - xh[r][v].x * c2);
-        o.y = rs[r] * (gy[r][v].y - c1 - xh[r][v].y * c2);
-        o.z = rs[r] * (gy[r][v].z - c1 - xh[r][v].z * c2);
-        o.w = rs[r] * (gy[r][v].w - c1 - xh[r][v].w * c2);
-        if (dres_in != nullptr) {
-          const float4 din = *reinterpret_cast<const float4*>(dres_in + off);
-          o.x += din.x;
-          o.y += din.y;
-          o.z += din.z;
-          o.w += din.w;
-        }
+        o.x = rs[r] * (gy[r][v].x - c1 - xh[r][v].x * c2) + din[r][v].x;
+        o.y = rs[r] * (gy[r][v].y - c1 - xh[r][v].y * c2) + din[r][v].y;
+        o.z = rs[r] * (gy[r][v].z - c1 - xh[r][v].z * c2) + din[r][v].z;
+        o.w = rs[r] * (gy[r][v].w - c1 - xh[r][v].w * c2) + din[r][v].w;
         *reinterpret_cast<float4*>(dres_out + off) = o;
         const uint32_t p01 = pack_bf16x2(o.x, o.y), p23 = pack_bf16x2(o.z, o.w);
         if (dres_out_b != nullptr) *reinterpret_cast<uint2*>(dres_out_b + off) = make_uint2(p01, p23);
@@ -250,11 +352,13 @@ static bool pick_config(int D, int* vpt, int* threads) {
   return false;
 }
 
-static int grid_for(int rows, int threads) {
+static int grid_for(int rows, int threads, bool bwd) {
   const int sms = num_sms();
-  const int ctas_per_sm = threads <= 256 ? 4 : 2;
+  // forward: fill the SM's 2048 thread slots; backward: 64-register kernels -> 1024 threads per SM
+  const int ctas_per_sm = (bwd ? 1024 : 2048) / threads > 0 ? (bwd ? 1024 : 2048) / threads : 1;
   int grid = sms * ctas_per_sm;
-  const int need = (rows + ROWS - 1) / ROWS;
+  const int rows_per_it = bwd ? BWD_ROWS : FWD_ROWS;
+  const int need = (rows + rows_per_it - 1) / rows_per_it;
   if (grid > need) grid = need;
   if (grid < 1) grid = 1;
   return grid;
@@ -271,8 +375,23 @@ extern "C" int tae_layernorm_fwd(const float* x, const float* gamma, const float
   TAE_CHECK_SHAPE(rows > 0 && D > 0, "tae_layernorm_fwd: rows/D must be positive");
   int vpt, threads;
   TAE_CHECK_SHAPE(pick_config(D, &vpt, &threads), "tae_layernorm_fwd: unsupported D=%d (need D %% 128 == 0, D <= 8192)", D);
-  const int grid = grid_for(rows, threads);
+  const int grid = grid_for(rows, threads, false);
   bf16* yy = reinterpret_cast<bf16*>(y);
+  bool done = true;
+  switch (D / 128) {  // warp-per-row kernel for the widths the model zoo uses
+    case 1: launch_fwd_warp<1>(x, gamma, beta, yy, mean, rstd, rows, eps, stream); break;
+    case 2: launch_fwd_warp<2>(x, gamma, beta, yy, mean, rstd, rows, eps, stream); break;
+    case 5: launch_fwd_warp<5>(x, gamma, beta, yy, mean, rstd, rows, eps, stream); break;
+    case 6: launch_fwd_warp<6>(x, gamma, beta, yy, mean, rstd, rows, eps, stream); break;
+    case 8: launch_fwd_warp<8>(x, gamma, beta, yy, mean, rstd, rows, eps, stream); break;
+    case 16: launch_fwd_warp<16>(x, gamma, beta, yy, mean, rstd, rows, eps, stream); break;
+    case 20: launch_fwd_warp<20>(x, gamma, beta, yy, mean, rstd, rows, eps, stream); break;
+    default: done = false;
+  }
+  if (done) {
+    TAE_CHECK_LAUNCH();
+    return TAE_OK;
+  }
   switch (vpt) {
     case 1: ln_fwd_kernel<1><<<grid, threads, 0, stream>>>(x, gamma, beta, yy, mean, rstd, rows, D, eps); break;
     case 2: ln_fwd_kernel<2><<<grid, threads, 0, stream>>>(x, gamma, beta, yy, mean, rstd, rows, D, eps); break;
@@ -287,7 +406,7 @@ extern "C" int tae_layernorm_bwd_num_partials(int32_t rows, int32_t D) {
   using namespace tae::ln;
   int vpt, threads;
   if (rows <= 0 || !pick_config(D, &vpt, &threads)) return TAE_ERR_SHAPE;
-  return grid_for(rows, threads);
+  return grid_for(rows, threads, true);
 }
 
 extern "C" int tae_layernorm_bwd(const tae_bf16* dy, const float* x, const float* mean, const float* rstd,
@@ -300,7 +419,7 @@ extern "C" int tae_layernorm_bwd(const tae_bf16* dy, const float* x, const float
   TAE_CHECK_SHAPE(dres_out != nullptr && partials != nullptr, "tae_layernorm_bwd: dres_out and partials are required");
   int vpt, threads;
   TAE_CHECK_SHAPE(pick_config(D, &vpt, &threads), "tae_layernorm_bwd: unsupported D=%d", D);
-  const int grid = grid_for(rows, threads);
+  const int grid = grid_for(rows, threads, true);
   const bf16* dyy = reinterpret_cast<const bf16*>(dy);
   bf16* ob = reinterpret_cast<bf16*>(dres_out_bf16);
   switch (vpt) {

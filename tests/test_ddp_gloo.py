@@ -1,0 +1,110 @@
+"""CPU test of the data-parallel bucket logic with the gloo backend, world_size 2 (no GPU needed).
+
+The gradient arena, bucket planning, ready-callbacks, end-of-backward finalisation and the rank-0 parameter broadcast
+of tae_b200.ddp are device-agnostic; here two processes run a fake "backward" that writes per-rank gradients into the
+arena exactly the way the hand-written CUDA backward does (`p._tae_grad`, `p._tae_ready(p)`) and check that every
+rank ends up with the rank-average, bucket by bucket."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+class _WriteGrads(torch.autograd.Function):
+    """Stands in for the CUDA backward: writes gradients straight into the arena and reports readiness."""
+
+    @staticmethod
+    def forward(ctx, x, params, rank):
+        ctx.params, ctx.rank = params, rank
+        return x.sum()
+
+    @staticmethod
+    def backward(ctx, g):
+        for i, p in enumerate(reversed(ctx.params)):  # gradient-ready order = reverse parameter order
+            p._tae_grad.fill_(float(ctx.rank + 1) * (i + 1))
+            p._tae_dirty = 1
+            p._tae_ready(p)
+        return torch.ones(1) * g, None, None
+
+
+def _worker(rank, world, port, q):
+    try:
+        os.environ["MASTER_ADDR"] = "127.0.0.1"
+        os.environ["MASTER_PORT"] = str(port)
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        from tae_b200.ddp import DistributedDataParallel
+        from tae_b200.optim import _Arena
+
+        torch.manual_seed(rank)  # different initial params per rank: the broadcast must equalise them
+        lin = torch.nn.Sequential(torch.nn.Linear(40, 30), torch.nn.Linear(30, 7), torch.nn.LayerNorm(7))
+        params = list(lin.parameters())
+        ar = _Arena(params, torch.device("cpu"))
+        with torch.no_grad():
+            for p in params:
+                ar.view(ar.p, p).copy_(p)
+                p.data = ar.view(ar.p, p)
+                p._tae_grad = ar.view(ar.g, p)
+                p.grad = p._tae_grad
+                p._tae_dirty = 0
+
+        class Opt:
+            arenas = [ar]
+
+        ddp = DistributedDataParallel(lin, optimizer=Opt(), bucket_mb=0.0005)  # ~128-element buckets -> several buckets
+        assert len(ddp._buckets) >= 2
+        # parameters broadcast from rank 0
+        ref = [torch.empty_like(ar.p) for _ in range(world)]
+        dist.all_gather(ref, ar.p)
+        assert torch.equal(ref[0], ref[1])
+
+        x = torch.ones(1, requires_grad=True)
+        for it in range(2):  # two steps: bucket state must reset
+            with torch.enable_grad():
+                ddp._lazy_attach()
+                for b in ddp._buckets:
+                    b.pending, b.work = len(b.params), None
+                ddp._callback_queued = False
+                loss = _WriteGrads.apply(x, params, rank)
+                loss.backward()
+            mean_scale = sum(r + 1 for r in range(world)) / world
+            for i, p in enumerate(reversed(params)):
+                want = mean_scale * (i + 1)
+                assert torch.allclose(p.grad, torch.full_like(p.grad, want)), (rank, i, p.grad.flatten()[:3], want)
+        # no_sync: gradients stay local
+        with ddp.no_sync():
+            for b in ddp._buckets:
+                b.pending, b.work = len(b.params), None
+            _WriteGrads.apply(x, params, rank).backward()
+        assert torch.allclose(params[-1].grad, torch.full_like(params[-1].grad, float(rank + 1)))
+        dist.barrier()
+        dist.destroy_process_group()
+        q.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        import traceback
+
+        q.put((rank, "FAIL: " + traceback.format_exc()))
+
+
+@pytest.mark.timeout(180)
+def test_bucketed_allreduce_gloo_world2():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=150) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=30)
+    assert all(msg == "ok" for _, msg in results), results
