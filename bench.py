@@ -183,7 +183,10 @@ def run_b200(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+
+        # short collective timeout: a rank mismatch must abort in minutes, not hang the box
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=240))
     _lib.require_device()
     cfg = O.zoo_config(args.model)
     B = args.batch
@@ -253,7 +256,8 @@ def run_b200(args):
 
     # ---- roofline of the dominant kernel (the tcgen05 GEMM), instrumented pass after the timed regions ----
     roof, detail = None, None
-    if not args.no_roofline and rank == 0:
+    if not args.no_roofline:
+        # every rank runs the instrumented steps (they contain collectives); only rank 0 reports
         roof, detail = gemm_roofline(torch, ops, lambda i: step_resident(i), measured_peaks())
     if world > 1:
         dist.barrier()

@@ -14,8 +14,26 @@
 //     launch/latency-bound, tensor cores do not pay.
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace tae {
+
+// tcgen05 path for the 256-token grid (attention_sm100.cu)
+int attention_fwd_tcgen05(const bf16* qkv, bf16* out, float* lse, int B, int H, cudaStream_t stream);
+int attention_bwd_tcgen05(const bf16* qkv, const bf16* out, const bf16* dout, const float* lse, bf16* dqkv, int B, int H,
+                          cudaStream_t stream);
+
 namespace attn {
+
+// TAE_ATTN_LEGACY=1 forces the mma.sync kernels for N=256 (A/B testing of the tcgen05 path)
+static bool use_tcgen05() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TAE_ATTN_LEGACY");
+    v = (e != nullptr && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
+}
 
 // =============================================================================================
 // Tensor-core path
@@ -543,6 +561,7 @@ extern "C" int tae_attention_fwd(const tae_bf16* qkv_, tae_bf16* out_, float* ls
   TAE_CHECK_SHAPE(B > 0 && N > 0 && H > 0 && hd > 0, "tae_attention_fwd: non-positive dims");
   TAE_CHECK_SHAPE(hd % 8 == 0 && hd <= 128, "tae_attention_fwd: hd=%d unsupported (need hd %% 8 == 0, hd <= 128)", hd);
   const float scale = 1.0f / sqrtf((float)hd);
+  if (hd == HD && N == 256 && use_tcgen05()) return attention_fwd_tcgen05(qkv, out, lse, B, H, stream);
   if (hd == HD && (N == 64 || N == 256)) {
     const float sl2 = scale * 1.44269504088896340736f;
     const int smem = 3 * N * LDS * 2;
@@ -581,6 +600,7 @@ extern "C" int tae_attention_bwd(const tae_bf16* qkv_, const tae_bf16* out_, con
   TAE_CHECK_SHAPE(B > 0 && N > 0 && H > 0 && hd > 0, "tae_attention_bwd: non-positive dims");
   TAE_CHECK_SHAPE(hd % 8 == 0 && hd <= 128, "tae_attention_bwd: hd=%d unsupported", hd);
   const float scale = 1.0f / sqrtf((float)hd);
+  if (hd == HD && N == 256 && use_tcgen05()) return attention_bwd_tcgen05(qkv, out, dout, lse, dqkv, B, H, stream);
   if (hd == HD && (N == 64 || N == 256)) {
     const float sl2 = scale * 1.44269504088896340736f;
     const int smem = 4 * N * LDS * 2 + 2 * N * 4;

@@ -1,0 +1,461 @@
+// attention_sm100.cu — whole-sequence attention on the tcgen05 tensor cores for the 256-token grid (patch16:
+// N = 256, head_dim = 64), forward and backward.  Same contract as attention.cu (tae.py:74-80): packed qkv
+// [B*N, 3*H*64] in, merged [B*N, H*64] out, log-sum-exp saved for backward.
+//
+// Forward: one CTA per (image, head, 128-query tile), two CTAs per SM (96 KB smem, 256 TMEM columns each).
+//   TMA: Q tile, K, V (128B-swizzled boxes straight out of the packed qkv buffer)
+//   MMA1 (tcgen05, 128x256x64):  S = Q K^T into TMEM
+//   softmax: one thread per query row reads its 256 scores from TMEM (no shuffles: the row is thread-private),
+//            two passes (max, then exp2/sum), writes bf16 P into smem in the UMMA K-major operand layout
+//            (over the dead Q/K tiles)
+//   MMA2 (128x64x256):  O = P V  with V consumed MN-major exactly as it sits in the qkv buffer
+//   epilogue: O / l -> bf16 -> swizzled smem -> TMA store; lse = m*scale + ln(l)
+//
+// Backward: one CTA per (image, head); everything is computed transposed (keys on TMEM lanes) so that every
+// product is a plain UMMA with operands that already exist in shared memory:
+//   S^T = K Q^T, dP^T = V dO^T                               (K-major x K-major)
+//   P^T = exp2(S^T*c - lse2[q]),  dS^T = P^T (dP^T - delta[q]) * scale      (thread-per-key-row, written as bf16 A tiles)
+//   dV += P^T dO,  dK += dS^T Q                              (A K-major, B = dO / Q MN-major in place)
+//   dQ += dS K                                               (A = the SAME dS^T tile read MN-major, B = K MN-major)
+// in 128x128 (key tile x query tile) blocks; TMEM holds S^T, dP^T (128 cols each) and the dV, dK, dQ0, dQ1
+// accumulators (64 cols each) = 512 columns.  No atomics, deterministic.
+#include "sm100.cuh"
+
+namespace tae {
+namespace attn_tc {
+
+using namespace tae::sm100;
+
+constexpr int N = 256;
+constexpr int HD = 64;
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// byte offset of 16-byte chunk `chunk` of row `row` inside a [rows x 128 B] 128B-swizzled tile
+__device__ __forceinline__ uint32_t sw128(int row, int chunk) { return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4)); }
+
+// =============================================================================================
+// Forward
+// =============================================================================================
+constexpr int F_OFF_Q = 0;          // [128 x 64] bf16, 16 KB   (K-major A of MMA1)
+constexpr int F_OFF_K = 16384;      // [256 x 64] bf16, 32 KB   (K-major B of MMA1)
+constexpr int F_OFF_V = 65536;      // [256 x 64] bf16, 32 KB   (MN-major B of MMA2); later the O staging tile
+constexpr int F_OFF_P = 0;          // P [128 x 256] bf16 = 4 k-blocks of 16 KB, overlays Q, K and 16 KB of slack
+constexpr int F_OFF_BAR = 98304;
+constexpr int F_SMEM = F_OFF_BAR + 64 + 1024;
+constexpr int F_THREADS = 160;      // warp 0: TMA + MMA + TMEM alloc; warps 1-4: softmax / epilogue
+
+__global__ void __launch_bounds__(F_THREADS, 2)
+attn_fwd_tc(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
+            const __grid_constant__ CUtensorMap tm_o, float* __restrict__ lse, int H, float scale, float sl2) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + F_OFF_BAR);
+  uint64_t* bar_load = bars;
+  uint64_t* bar_s = bars + 1;
+  uint64_t* bar_p = bars + 2;
+  uint64_t* bar_o = bars + 3;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bh = blockIdx.x >> 1, qt = blockIdx.x & 1;
+  const int b = bh / H, h = bh - b * H;
+  const int D = H * HD;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_q);
+    tma_prefetch_desc(&tm_kv);
+    tma_prefetch_desc(&tm_o);
+    mbar_init(bar_load, 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_p, 128);
+    mbar_init(bar_o, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 256);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t sQ = smem_u32(smem + F_OFF_Q), sK = smem_u32(smem + F_OFF_K), sV = smem_u32(smem + F_OFF_V);
+  const uint32_t sP = smem_u32(smem + F_OFF_P);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(bar_load, 16384 + 32768 + 32768);
+      tma_load_2d(smem + F_OFF_Q, &tm_q, bar_load, h * HD, b * N + qt * 128);
+      tma_load_2d(smem + F_OFF_K, &tm_kv, bar_load, D + h * HD, b * N);
+      tma_load_2d(smem + F_OFF_V, &tm_kv, bar_load, 2 * D + h * HD, b * N);
+      mbar_wait(bar_load, 0);
+      tcgen05_fence_after();
+      const uint32_t idesc1 = make_idesc_bf16(128, 256, 0, 0);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma_f16(tmem, make_smem_desc(sQ + k * 32, 0, 1024), make_smem_desc(sK + k * 32, 0, 1024), idesc1, k > 0);
+      umma_commit(bar_s);
+      mbar_wait(bar_p, 0);
+      tcgen05_fence_after();
+      const uint32_t idesc2 = make_idesc_bf16(128, 64, 0, 1);
+#pragma unroll
+      for (int j = 0; j < 16; ++j)  // 16 keys per instruction
+        umma_f16(tmem, make_smem_desc(sP + (j >> 2) * 16384 + (j & 3) * 32, 0, 1024),
+                 make_smem_desc(sV + j * 2048, 8192, 1024), idesc2, j > 0);
+      umma_commit(bar_o);
+    }
+  } else {
+    const int q = warp & 3;          // TMEM lane quarter of this warp
+    const int r = q * 32 + lane;     // query row inside the tile == TMEM lane
+    const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16);
+    mbar_wait(bar_s, 0);
+    tcgen05_fence_after();
+    float mx = -INFINITY;
+#pragma unroll 1
+    for (int c = 0; c < 8; ++c) {
+      uint32_t raw[32];
+      tmem_ld_32x32b_x32(taddr + c * 32, raw);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(raw[i]));
+    }
+    const float m2 = mx * sl2;
+    float l = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < 8; ++c) {
+      uint32_t raw[32];
+      tmem_ld_32x32b_x32(taddr + c * 32, raw);
+      tmem_ld_wait();
+      uint32_t pk[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float p0 = ex2_approx(fmaf(__uint_as_float(raw[2 * i]), sl2, -m2));
+        const float p1 = ex2_approx(fmaf(__uint_as_float(raw[2 * i + 1]), sl2, -m2));
+        l += p0 + p1;
+        pk[i] = pack_bf16x2(p0, p1);
+      }
+      const uint32_t base = sP + (c >> 1) * 16384;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        st_shared_v4(base + sw128(r, (c & 1) * 4 + i), pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+    }
+    fence_proxy_async_smem();
+    tcgen05_fence_before();
+    mbar_arrive(bar_p);
+    // ---- epilogue ----
+    lse[((size_t)b * H + h) * N + qt * 128 + r] = mx * scale + __logf(l);
+    const float inv = 1.0f / l;
+    mbar_wait(bar_o, 0);
+    tcgen05_fence_after();
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t raw[32];
+      tmem_ld_32x32b_x32(taddr + c * 32, raw);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          o[j] = pack_bf16x2(__uint_as_float(raw[i * 8 + 2 * j]) * inv, __uint_as_float(raw[i * 8 + 2 * j + 1]) * inv);
+        st_shared_v4(sV + sw128(r, c * 4 + i), o[0], o[1], o[2], o[3]);
+      }
+    }
+    fence_proxy_async_smem();
+    named_bar_sync(1, 128);
+    if (warp == 1 && lane == 0) {
+      tma_store_2d(&tm_o, smem + F_OFF_V, h * HD, b * N + qt * 128);
+      tma_store_commit();
+      tma_store_wait_all();
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+// =============================================================================================
+// Backward
+// =============================================================================================
+constexpr int B_OFF_Q = 0;
+constexpr int B_OFF_K = 32768;
+constexpr int B_OFF_V = 65536;
+constexpr int B_OFF_DO = 98304;
+constexpr int B_OFF_PT = 131072;    // P^T  [128 keys x 128 q] bf16: 2 k-blocks of 16 KB
+constexpr int B_OFF_DST = 163840;   // dS^T [128 keys x 128 q] bf16
+constexpr int B_OFF_LSE = 196608;   // lse * log2(e)  [256] fp32
+constexpr int B_OFF_DELTA = 197632; // rowsum(dO * O) [256] fp32
+constexpr int B_OFF_BAR = 198656;
+constexpr int B_SMEM = B_OFF_BAR + 128 + 1024;
+constexpr int B_THREADS = 384;      // warp 0: TMA + MMA + TMEM alloc; warps 4-11: element-wise + epilogues
+constexpr int TC_S = 0, TC_DP = 128, TC_DV = 256, TC_DK = 320, TC_DQ = 384;  // TMEM column map
+
+__global__ void __launch_bounds__(B_THREADS, 1)
+attn_bwd_tc(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
+            const bf16* __restrict__ out, const bf16* __restrict__ dout, const float* __restrict__ lse,
+            bf16* __restrict__ dqkv, int H, float scale, float sl2) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + B_OFF_BAR);
+  uint64_t* bar_load = bars;
+  uint64_t* bar_s = bars + 1;      // S^T / dP^T of a block are in TMEM          (once per block)
+  uint64_t* bar_p = bars + 2;      // P^T / dS^T tiles written, S/dP TMEM drained  (once per block, 256 arrivals)
+  uint64_t* bar_g = bars + 3;      // dV / dK (and, at the end, dQ) accumulators complete (once per key tile)
+  uint64_t* bar_dfree = bars + 4;  // dV / dK of key tile 0 drained from TMEM      (once, 256 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+  float* sLse = reinterpret_cast<float*>(smem + B_OFF_LSE);
+  float* sDelta = reinterpret_cast<float*>(smem + B_OFF_DELTA);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x / H, h = blockIdx.x - b * H;
+  const int D = H * HD;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_qkv);
+    tma_prefetch_desc(&tm_do);
+    mbar_init(bar_load, 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_p, 256);
+    mbar_init(bar_g, 1);
+    mbar_init(bar_dfree, 256);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t sQ = smem_u32(smem + B_OFF_Q), sK = smem_u32(smem + B_OFF_K), sV = smem_u32(smem + B_OFF_V);
+  const uint32_t sdO = smem_u32(smem + B_OFF_DO), sPT = smem_u32(smem + B_OFF_PT), sdST = smem_u32(smem + B_OFF_DST);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(bar_load, 4 * 32768);
+      tma_load_2d(smem + B_OFF_Q, &tm_qkv, bar_load, h * HD, b * N);
+      tma_load_2d(smem + B_OFF_K, &tm_qkv, bar_load, D + h * HD, b * N);
+      tma_load_2d(smem + B_OFF_V, &tm_qkv, bar_load, 2 * D + h * HD, b * N);
+      tma_load_2d(smem + B_OFF_DO, &tm_do, bar_load, h * HD, b * N);
+      mbar_wait(bar_load, 0);
+      tcgen05_fence_after();
+      const uint32_t id_ss = make_idesc_bf16(128, 128, 0, 0);   // S^T, dP^T
+      const uint32_t id_kn = make_idesc_bf16(128, 64, 0, 1);    // dV, dK : A K-major, B MN-major
+      const uint32_t id_nn = make_idesc_bf16(128, 64, 1, 1);    // dQ     : A MN-major (dS^T re-read), B MN-major
+#pragma unroll 1
+      for (int blk = 0; blk < 4; ++blk) {
+        const int kt = blk >> 1, qt = blk & 1;
+        // S^T = K_kt Q_qt^T ; dP^T = V_kt dO_qt^T       (TMEM S/dP drained: bar_p of the previous block was waited)
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_f16(tmem + TC_S, make_smem_desc(sK + kt * 16384 + k * 32, 0, 1024),
+                   make_smem_desc(sQ + qt * 16384 + k * 32, 0, 1024), id_ss, k > 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_f16(tmem + TC_DP, make_smem_desc(sV + kt * 16384 + k * 32, 0, 1024),
+                   make_smem_desc(sdO + qt * 16384 + k * 32, 0, 1024), id_ss, k > 0);
+        umma_commit(bar_s);
+        mbar_wait(bar_p, blk & 1);
+        tcgen05_fence_after();
+        if (blk == 2) {  // dV/dK accumulators of key tile 0 must have been drained before they are overwritten
+          mbar_wait(bar_dfree, 0);
+          tcgen05_fence_after();
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {  // 16 queries (dV, dK) / 16 keys (dQ) per instruction
+          const uint64_t a_pt = make_smem_desc(sPT + (j >> 2) * 16384 + (j & 3) * 32, 0, 1024);
+          const uint64_t a_dst = make_smem_desc(sdST + (j >> 2) * 16384 + (j & 3) * 32, 0, 1024);
+          const uint64_t b_do = make_smem_desc(sdO + qt * 16384 + j * 2048, 8192, 1024);
+          const uint64_t b_q = make_smem_desc(sQ + qt * 16384 + j * 2048, 8192, 1024);
+          umma_f16(tmem + TC_DV, a_pt, b_do, id_kn, (qt > 0 || j > 0));
+          umma_f16(tmem + TC_DK, a_dst, b_q, id_kn, (qt > 0 || j > 0));
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint64_t a_ds = make_smem_desc(sdST + j * 2048, 16384, 1024);  // dS [q x keys], q contiguous
+          const uint64_t b_k = make_smem_desc(sK + kt * 16384 + j * 2048, 8192, 1024);
+          umma_f16(tmem + TC_DQ + qt * 64, a_ds, b_k, id_nn, (kt > 0 || j > 0));
+        }
+        if (qt == 1) umma_commit(bar_g);
+      }
+    }
+  } else if (warp >= 4) {
+    const int te = threadIdx.x - 128;        // 0..255
+    const int q4 = warp & 3;                 // TMEM lane quarter
+    const int half = (warp - 4) >> 2;        // which 64-column half of a 128-column block
+    const int r = q4 * 32 + lane;            // key row inside the key tile == TMEM lane
+    const uint32_t tlane = tmem + ((uint32_t)(q4 * 32) << 16);
+    // ---- prologue: delta = rowsum(dO * O), lse in the exp2 domain ----
+    {
+      const bf16* go = out + (size_t)b * N * D + (size_t)h * HD;
+      const bf16* gdo = dout + (size_t)b * N * D + (size_t)h * HD;
+#pragma unroll
+      for (int pass = 0; pass < 8; ++pass) {
+        const int row = pass * 32 + (te >> 3), ch = te & 7;
+        const uint4 dv = ld_nc_v4(gdo + (size_t)row * D + ch * 8);
+        const uint4 ov = ld_nc_v4(go + (size_t)row * D + ch * 8);
+        const uint32_t dw[4] = {dv.x, dv.y, dv.z, dv.w}, ow[4] = {ov.x, ov.y, ov.z, ov.w};
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 d2 = unpack_bf16x2(dw[j]), o2 = unpack_bf16x2(ow[j]);
+          acc += d2.x * o2.x + d2.y * o2.y;
+        }
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+        if (ch == 0) sDelta[row] = acc;
+      }
+      sLse[te] = lse[((size_t)b * H + h) * N + te] * 1.44269504088896340736f;
+      named_bar_sync(1, 256);
+    }
+    bf16* gd = dqkv + (size_t)b * N * 3 * D + (size_t)h * HD;
+    const size_t ldq = (size_t)3 * D;
+
+#pragma unroll 1
+    for (int blk = 0; blk < 4; ++blk) {
+      const int kt = blk >> 1, qt = blk & 1;
+      mbar_wait(bar_s, blk & 1);
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int sub = 0; sub < 2; ++sub) {
+        const int c0 = half * 64 + sub * 32;  // first query column of this chunk inside the block
+        uint32_t sraw[32], draw[32];
+        tmem_ld_32x32b_x32(tlane + TC_S + c0, sraw);
+        tmem_ld_32x32b_x32(tlane + TC_DP + c0, draw);
+        tmem_ld_wait();
+        const float4* l4 = reinterpret_cast<const float4*>(sLse + qt * 128 + c0);
+        const float4* d4 = reinterpret_cast<const float4*>(sDelta + qt * 128 + c0);
+        uint32_t pk[16], dk[16];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 lv = l4[i], dl = d4[i];
+          const float p0 = ex2_approx(fmaf(__uint_as_float(sraw[4 * i + 0]), sl2, -lv.x));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(sraw[4 * i + 1]), sl2, -lv.y));
+          const float p2 = ex2_approx(fmaf(__uint_as_float(sraw[4 * i + 2]), sl2, -lv.z));
+          const float p3 = ex2_approx(fmaf(__uint_as_float(sraw[4 * i + 3]), sl2, -lv.w));
+          pk[2 * i] = pack_bf16x2(p0, p1);
+          pk[2 * i + 1] = pack_bf16x2(p2, p3);
+          dk[2 * i] = pack_bf16x2(p0 * (__uint_as_float(draw[4 * i + 0]) - dl.x) * scale,
+                                  p1 * (__uint_as_float(draw[4 * i + 1]) - dl.y) * scale);
+          dk[2 * i + 1] = pack_bf16x2(p2 * (__uint_as_float(draw[4 * i + 2]) - dl.z) * scale,
+                                      p3 * (__uint_as_float(draw[4 * i + 3]) - dl.w) * scale);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t off = (uint32_t)half * 16384u + sw128(r, sub * 4 + i);
+          st_shared_v4(sPT + off, pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+          st_shared_v4(sdST + off, dk[4 * i], dk[4 * i + 1], dk[4 * i + 2], dk[4 * i + 3]);
+        }
+      }
+      fence_proxy_async_smem();
+      tcgen05_fence_before();
+      mbar_arrive(bar_p);
+      if (qt == 1) {
+        // dV_kt (half 0) / dK_kt (half 1): TMEM -> bf16 -> global, one 128-byte row per thread
+        mbar_wait(bar_g, kt & 1);
+        tcgen05_fence_after();
+        const uint32_t tcol = half == 0 ? TC_DV : TC_DK;
+        bf16* dst = gd + (size_t)(kt * 128 + r) * ldq + (half == 0 ? 2 * D : D);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t raw[32];
+          tmem_ld_32x32b_x32(tlane + tcol + c * 32, raw);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 o;
+            o.x = pack_bf16x2(__uint_as_float(raw[i * 8 + 0]), __uint_as_float(raw[i * 8 + 1]));
+            o.y = pack_bf16x2(__uint_as_float(raw[i * 8 + 2]), __uint_as_float(raw[i * 8 + 3]));
+            o.z = pack_bf16x2(__uint_as_float(raw[i * 8 + 4]), __uint_as_float(raw[i * 8 + 5]));
+            o.w = pack_bf16x2(__uint_as_float(raw[i * 8 + 6]), __uint_as_float(raw[i * 8 + 7]));
+            *reinterpret_cast<uint4*>(dst + c * 32 + i * 8) = o;
+          }
+        }
+        if (kt == 0) {
+          tcgen05_fence_before();
+          mbar_arrive(bar_dfree);
+        }
+      }
+    }
+    // dQ (bar_g of key tile 1 covers every MMA): half 0 -> queries 0..127, half 1 -> queries 128..255
+    {
+      bf16* dst = gd + (size_t)(half * 128 + r) * ldq;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t raw[32];
+        tmem_ld_32x32b_x32(tlane + TC_DQ + half * 64 + c * 32, raw);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 o;
+          o.x = pack_bf16x2(__uint_as_float(raw[i * 8 + 0]), __uint_as_float(raw[i * 8 + 1]));
+          o.y = pack_bf16x2(__uint_as_float(raw[i * 8 + 2]), __uint_as_float(raw[i * 8 + 3]));
+          o.z = pack_bf16x2(__uint_as_float(raw[i * 8 + 4]), __uint_as_float(raw[i * 8 + 5]));
+          o.w = pack_bf16x2(__uint_as_float(raw[i * 8 + 6]), __uint_as_float(raw[i * 8 + 7]));
+          *reinterpret_cast<uint4*>(dst + c * 32 + i * 8) = o;
+        }
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+template <typename K>
+static int set_smem_once(K kernel, int bytes, cudaError_t* cached, std::once_flag* once) {
+  std::call_once(*once, [&]() { *cached = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); });
+  if (*cached != cudaSuccess) {
+    set_error("cudaFuncSetAttribute(smem=%d) failed: %s", bytes, cudaGetErrorString(*cached));
+    return TAE_ERR_CUDA;
+  }
+  return TAE_OK;
+}
+
+}  // namespace attn_tc
+
+// entry points used by attention.cu's dispatcher (N == 256, hd == 64)
+int attention_fwd_tcgen05(const bf16* qkv, bf16* out, float* lse, int B, int H, cudaStream_t stream) {
+  using namespace attn_tc;
+  static cudaError_t err = cudaSuccess;
+  static std::once_flag once;
+  int rc = set_smem_once(attn_fwd_tc, F_SMEM, &err, &once);
+  if (rc) return rc;
+  const int D = H * HD;
+  CUtensorMap tq, tkv, to;
+  rc = sm100::make_tmap(&tq, qkv, (uint64_t)3 * D, (uint64_t)B * N, (uint64_t)3 * D, 128);
+  if (rc) return rc;
+  rc = sm100::make_tmap(&tkv, qkv, (uint64_t)3 * D, (uint64_t)B * N, (uint64_t)3 * D, 256);
+  if (rc) return rc;
+  rc = sm100::make_tmap(&to, out, (uint64_t)D, (uint64_t)B * N, (uint64_t)D, 128);
+  if (rc) return rc;
+  const float scale = 1.0f / sqrtf((float)HD);
+  attn_fwd_tc<<<B * H * 2, F_THREADS, F_SMEM, stream>>>(tq, tkv, to, lse, H, scale, scale * 1.44269504088896340736f);
+  TAE_CHECK_LAUNCH();
+  return TAE_OK;
+}
+
+int attention_bwd_tcgen05(const bf16* qkv, const bf16* out, const bf16* dout, const float* lse, bf16* dqkv, int B, int H,
+                          cudaStream_t stream) {
+  using namespace attn_tc;
+  static cudaError_t err = cudaSuccess;
+  static std::once_flag once;
+  int rc = set_smem_once(attn_bwd_tc, B_SMEM, &err, &once);
+  if (rc) return rc;
+  const int D = H * HD;
+  CUtensorMap tqkv, tdo;
+  rc = sm100::make_tmap(&tqkv, qkv, (uint64_t)3 * D, (uint64_t)B * N, (uint64_t)3 * D, 256);
+  if (rc) return rc;
+  rc = sm100::make_tmap(&tdo, dout, (uint64_t)D, (uint64_t)B * N, (uint64_t)D, 256);
+  if (rc) return rc;
+  const float scale = 1.0f / sqrtf((float)HD);
+  attn_bwd_tc<<<B * H, B_THREADS, B_SMEM, stream>>>(tqkv, tdo, out, dout, lse, dqkv, H, scale,
+                                                    scale * 1.44269504088896340736f);
+  TAE_CHECK_LAUNCH();
+  return TAE_OK;
+}
+
+}  // namespace tae
