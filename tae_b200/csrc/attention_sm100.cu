@@ -48,8 +48,9 @@ constexpr int F_OFF_K = 16384;      // [256 x 64] bf16, 32 KB   (K-major B of MM
 constexpr int F_OFF_V = 65536;      // [256 x 64] bf16, 32 KB   (MN-major B of MMA2); later the O staging tile
 constexpr int F_OFF_P = 0;          // P [128 x 256] bf16 = 4 k-blocks of 16 KB, overlays Q, K and 16 KB of slack
 constexpr int F_OFF_BAR = 98304;
-constexpr int F_SMEM = F_OFF_BAR + 64 + 1024;
-constexpr int F_THREADS = 160;      // warp 0: TMA + MMA + TMEM alloc; warps 1-4: softmax / epilogue
+constexpr int F_OFF_RED = F_OFF_BAR + 64;   // row max / row sum exchange between the two column halves: 4 x 128 fp32
+constexpr int F_SMEM = F_OFF_RED + 2048 + 1024;
+constexpr int F_THREADS = 288;      // warp 0: TMA + MMA + TMEM alloc; warps 1-8: softmax / epilogue (2 threads per row)
 
 __global__ void __launch_bounds__(F_THREADS, 2)
 attn_fwd_tc(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
@@ -62,6 +63,8 @@ attn_fwd_tc(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CU
   uint64_t* bar_p = bars + 2;
   uint64_t* bar_o = bars + 3;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  float* s_max = reinterpret_cast<float*>(smem + F_OFF_RED);  // [2][128]
+  float* s_sum = s_max + 256;                                  // [2][128]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bh = blockIdx.x >> 1, qt = blockIdx.x & 1;
   const int b = bh / H, h = bh - b * H;
@@ -73,7 +76,7 @@ attn_fwd_tc(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CU
     tma_prefetch_desc(&tm_o);
     mbar_init(bar_load, 1);
     mbar_init(bar_s, 1);
-    mbar_init(bar_p, 128);
+    mbar_init(bar_p, 256);
     mbar_init(bar_o, 1);
     fence_barrier_init();
   }
@@ -108,52 +111,61 @@ attn_fwd_tc(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CU
       umma_commit(bar_o);
     }
   } else {
-    const int q = warp & 3;          // TMEM lane quarter of this warp
-    const int r = q * 32 + lane;     // query row inside the tile == TMEM lane
+    const int q = warp & 3;              // TMEM lane quarter of this warp
+    const int half = (warp - 1) >> 2;    // which 128 score columns of the row this thread owns
+    const int r = q * 32 + lane;         // query row inside the tile == TMEM lane
     const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16);
+    const uint32_t tcol = taddr + half * 128;
     mbar_wait(bar_s, 0);
     tcgen05_fence_after();
+    // pass 1: row max over this thread's 128 columns (TMEM loads software-pipelined one chunk ahead)
+    uint32_t buf[2][32];
     float mx = -INFINITY;
-#pragma unroll 1
-    for (int c = 0; c < 8; ++c) {
-      uint32_t raw[32];
-      tmem_ld_32x32b_x32(taddr + c * 32, raw);
-      tmem_ld_wait();
+    tmem_ld_32x32b_x32(tcol, buf[0]);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(raw[i]));
+    for (int c = 0; c < 4; ++c) {
+      tmem_ld_wait_regs(buf[c & 1]);
+      if (c + 1 < 4) tmem_ld_32x32b_x32(tcol + (c + 1) * 32, buf[(c + 1) & 1]);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(buf[c & 1][i]));
     }
+    s_max[half * 128 + r] = mx;
+    tmem_ld_32x32b_x32(tcol, buf[0]);  // first chunk of pass 2 in flight across the barrier
+    named_bar_sync(2, 256);
+    mx = fmaxf(mx, s_max[(half ^ 1) * 128 + r]);
     const float m2 = mx * sl2;
     float l = 0.f;
-#pragma unroll 1
-    for (int c = 0; c < 8; ++c) {
-      uint32_t raw[32];
-      tmem_ld_32x32b_x32(taddr + c * 32, raw);
-      tmem_ld_wait();
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      tmem_ld_wait_regs(buf[c & 1]);
+      if (c + 1 < 4) tmem_ld_32x32b_x32(tcol + (c + 1) * 32, buf[(c + 1) & 1]);
       uint32_t pk[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        const float p0 = ex2_approx(fmaf(__uint_as_float(raw[2 * i]), sl2, -m2));
-        const float p1 = ex2_approx(fmaf(__uint_as_float(raw[2 * i + 1]), sl2, -m2));
+        const float p0 = ex2_approx(fmaf(__uint_as_float(buf[c & 1][2 * i]), sl2, -m2));
+        const float p1 = ex2_approx(fmaf(__uint_as_float(buf[c & 1][2 * i + 1]), sl2, -m2));
         l += p0 + p1;
         pk[i] = pack_bf16x2(p0, p1);
       }
-      const uint32_t base = sP + (c >> 1) * 16384;
+      const uint32_t base = sP + (half * 2 + (c >> 1)) * 16384;  // k-block of 64 keys
 #pragma unroll
       for (int i = 0; i < 4; ++i)
         st_shared_v4(base + sw128(r, (c & 1) * 4 + i), pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
     }
+    s_sum[half * 128 + r] = l;
     fence_proxy_async_smem();
     tcgen05_fence_before();
     mbar_arrive(bar_p);
-    // ---- epilogue ----
-    lse[((size_t)b * H + h) * N + qt * 128 + r] = mx * scale + __logf(l);
-    const float inv = 1.0f / l;
+    // ---- epilogue: each thread normalises 32 of the row's 64 output columns ----
+    named_bar_sync(2, 256);  // partner's s_sum write is ordered before this read
     mbar_wait(bar_o, 0);
     tcgen05_fence_after();
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
+    l += s_sum[(half ^ 1) * 128 + r];
+    if (half == 0) lse[((size_t)b * H + h) * N + qt * 128 + r] = mx * scale + __logf(l);
+    const float inv = 1.0f / l;
+    {
       uint32_t raw[32];
-      tmem_ld_32x32b_x32(taddr + c * 32, raw);
+      tmem_ld_32x32b_x32(taddr + half * 32, raw);
       tmem_ld_wait();
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -161,11 +173,11 @@ attn_fwd_tc(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CU
 #pragma unroll
         for (int j = 0; j < 4; ++j)
           o[j] = pack_bf16x2(__uint_as_float(raw[i * 8 + 2 * j]) * inv, __uint_as_float(raw[i * 8 + 2 * j + 1]) * inv);
-        st_shared_v4(sV + sw128(r, c * 4 + i), o[0], o[1], o[2], o[3]);
+        st_shared_v4(sV + sw128(r, half * 4 + i), o[0], o[1], o[2], o[3]);
       }
     }
     fence_proxy_async_smem();
-    named_bar_sync(1, 128);
+    named_bar_sync(1, 256);
     if (warp == 1 && lane == 0) {
       tma_store_2d(&tm_o, smem + F_OFF_V, h * HD, b * N + qt * 128);
       tma_store_commit();

@@ -17,6 +17,8 @@
 // Operand majors: both operands may be K-major (k contiguous; forward) or MN-major (m/n contiguous; the
 // transposed operands of dgrad/wgrad) — handled by the TMA box shape + UMMA smem-descriptor strides, so no
 // transposed copy of any activation or weight is ever materialised.
+#include <stdlib.h>
+
 #include "sm100.cuh"
 
 namespace tae {
@@ -361,6 +363,170 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 }
 
 // ---------------------------------------------------------------------------------------------
+// CTA-pair variant: a 2-CTA cluster (two SMs of one TPC) computes a 256x256 tile with tcgen05.mma.cta_group::2.
+// Each CTA stages its own 128 rows of A and only HALF of the B tile (128 of the 256 n-rows) — the tensor cores of
+// both SMs read both halves — so shared-memory traffic per SM drops by a third and the ring deepens to 6 stages.
+// The leader (even) CTA issues every MMA; both CTAs run a TMA producer (its bytes are credited to the leader's
+// `full` barrier) and the epilogue for their own 128 accumulator rows.
+// ---------------------------------------------------------------------------------------------
+constexpr int STAGES2 = 6;
+constexpr int B2_STAGE_BYTES = (BLOCK_N / 2) * BLOCK_K * 2;          // 16 KB: this CTA's half of the B tile
+constexpr int STAGE2_BYTES = A_STAGE_BYTES + B2_STAGE_BYTES;         // 32 KB
+constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + SMEM_BARRIER_BYTES + SMEM_STAGING_BYTES + 1024;
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                      const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES2 * STAGE2_BYTES);
+  uint64_t* full_bar = bars;                                  // [STAGES2]  (the leader's copy is the live one)
+  uint64_t* empty_bar = bars + STAGES2;                       // [STAGES2]  (both CTAs, multicast commit)
+  uint64_t* tmem_full_bar = bars + 2 * STAGES2;               // [NUM_ACC]  (both CTAs, multicast commit)
+  uint64_t* tmem_empty_bar = bars + 2 * STAGES2 + NUM_ACC;    // [NUM_ACC]  (leader's copy, 16 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES2 + 2 * NUM_ACC);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  const int total_work = p.m_tiles * p.n_tiles * p.splits;  // m_tiles counts 256-row tiles here
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES2; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < NUM_ACC; ++a) {
+      mbar_init(&tmem_full_bar[a], 1);
+      mbar_init(&tmem_empty_bar[a], 2 * NUM_EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_2sm(tmem_slot, TMEM_COLS);
+  tcgen05_fence_before();
+  cluster_sync_all();  // barriers of BOTH CTAs are initialised before any remote signal can arrive
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = cluster_id; w < total_work; w += num_clusters) {
+        const WorkItem it = decode_work(p, w);
+        const int m0 = it.mt * (2 * BLOCK_M) + (int)rank * BLOCK_M;
+        const int n0 = it.nt * BLOCK_N + (int)rank * (BLOCK_N / 2);
+        for (int kb = it.kb0; kb < it.kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          uint8_t* sa = smem + stage * STAGE2_BYTES;
+          uint8_t* sb = sa + A_STAGE_BYTES;
+          if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * STAGE2_BYTES);  // bytes of both CTAs
+          const int k0 = kb * BLOCK_K;
+          if (!p.a_mn) {
+            tma_load_2d_2sm(sa, &tmap_a, &full_bar[stage], k0, m0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BLOCK_M / 64; ++j)
+              tma_load_2d_2sm(sa + j * MN_BOX_BYTES, &tmap_a, &full_bar[stage], m0 + j * 64, k0);
+          }
+          if (!p.b_mn) {
+            tma_load_2d_2sm(sb, &tmap_b, &full_bar[stage], k0, n0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BLOCK_N / 128; ++j)
+              tma_load_2d_2sm(sb + j * MN_BOX_BYTES, &tmap_b, &full_bar[stage], n0 + j * 64, k0);
+          }
+          if (++stage == STAGES2) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread of the leader CTA) =====================
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = make_idesc_bf16(2 * BLOCK_M, BLOCK_N, p.a_mn, p.b_mn);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int w = cluster_id; w < total_work; w += num_clusters) {
+        const WorkItem it = decode_work(p, w);
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+        for (int kb = it.kb0; kb < it.kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t a_base = smem_u32(smem + stage * STAGE2_BYTES);
+          const uint32_t b_base = a_base + A_STAGE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t adesc = p.a_mn ? desc_mn_major(a_base, k) : desc_k_major(a_base, k);
+            const uint64_t bdesc = p.b_mn ? desc_mn_major(b_base, k) : desc_k_major(b_base, k);
+            umma_f16_2sm(d_tmem, adesc, bdesc, idesc, (kb > it.kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit_2sm(&empty_bar[stage]);
+          if (++stage == STAGES2) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit_2sm(&tmem_full_bar[acc]);
+        if (++acc == NUM_ACC) {
+          acc = 0;
+          acc_phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue warps (both CTAs, own 128 rows) =====================
+    const int ew = warp - 4;
+    const int q = ew & 3;
+    const int half = ew >> 2;
+    const uint32_t stg = smem_u32(smem + STAGES2 * STAGE2_BYTES + SMEM_BARRIER_BYTES + ew * STG_BYTES_PER_WARP);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int w = cluster_id; w < total_work; w += num_clusters) {
+      const WorkItem it = decode_work(p, w);
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tcgen05_fence_after();
+      const int row_base = it.mt * (2 * BLOCK_M) + (int)rank * BLOCK_M + q * 32;
+#pragma unroll 1
+      for (int c = 0; c < 128 / EPI_COLS; ++c) {
+        const int col0 = it.nt * BLOCK_N + half * 128 + c * EPI_COLS;
+        if (col0 >= p.N) break;  // warp-uniform
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + half * 128 + c * EPI_COLS);
+        epi_stage_rows(stg, taddr, lane);
+        __syncwarp();
+        epi_write_coalesced<EPI>(p, stg, row_base, col0, lane);
+        __syncwarp();
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(&tmem_empty_bar[acc], 0);  // the leader's MMA thread owns the accumulators
+      if (++acc == NUM_ACC) {
+        acc = 0;
+        acc_phase ^= 1u;
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  cluster_sync_all();  // neither CTA may exit (or free TMEM) while its peer can still touch its smem / barriers
+  tcgen05_fence_after();
+  if (warp == 2) tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------------------------
 template <int EPI>
@@ -377,6 +543,32 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p,
   gemm_bf16_tcgen05<EPI><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, p);
   TAE_CHECK_LAUNCH();
   return TAE_OK;
+}
+
+template <int EPI>
+static int launch_2sm(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, int clusters, cudaStream_t stream) {
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, []() {
+    attr_err = cudaFuncSetAttribute(gemm_bf16_tcgen05_2sm<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES);
+  });
+  if (attr_err != cudaSuccess) {
+    set_error("cudaFuncSetAttribute(smem=%d) failed: %s", SMEM2_BYTES, cudaGetErrorString(attr_err));
+    return TAE_ERR_CUDA;
+  }
+  gemm_bf16_tcgen05_2sm<EPI><<<2 * clusters, NUM_THREADS, SMEM2_BYTES, stream>>>(ta, tb, p);
+  TAE_CHECK_LAUNCH();
+  return TAE_OK;
+}
+
+// TAE_GEMM_1SM=1 forces the single-CTA kernel (A/B testing)
+static bool allow_2sm() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TAE_GEMM_1SM");
+    v = (e != nullptr && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
 }
 
 }  // namespace gemm
@@ -414,23 +606,35 @@ extern "C" int tae_gemm(const tae_gemm_args* a, void* stream_) {
   p.K = a->K;
   p.a_mn = a->a_mn_major ? 1 : 0;
   p.b_mn = a->b_mn_major ? 1 : 0;
-  p.m_tiles = (a->M + BLOCK_M - 1) / BLOCK_M;
-  p.n_tiles = (a->N + BLOCK_N - 1) / BLOCK_N;
-  p.kb_total = (a->K + BLOCK_K - 1) / BLOCK_K;
   const int sms = num_sms();
   if (sms <= 0) return TAE_ERR_CUDA;
+  // CTA-pair kernel (256-row tiles on two SMs) whenever there are at least two 128-row tiles of work
+  const bool use2 = allow_2sm() && a->M > BLOCK_M && sms >= 2;
+  const int tile_m = use2 ? 2 * BLOCK_M : BLOCK_M;
+  const int units = use2 ? sms / 2 : sms;  // concurrently resident work items (clusters or CTAs)
+  p.m_tiles = (a->M + tile_m - 1) / tile_m;
+  p.n_tiles = (a->N + BLOCK_N - 1) / BLOCK_N;
+  p.kb_total = (a->K + BLOCK_K - 1) / BLOCK_K;
   int splits = a->splits;
   if (a->epilogue != TAE_EPI_F32_ACC) {
     TAE_CHECK_SHAPE(splits <= 1, "tae_gemm: split-K only with TAE_EPI_F32_ACC");
     splits = 1;
   } else if (splits <= 0) {
-    // auto: fill the machine when the tile count alone cannot (weight-gradient GEMMs: few tiles, huge K)
+    // auto: weight-gradient GEMMs have few output tiles and a huge K.  Pick the split factor whose work-item count
+    // wastes the least of the last wave (items / (waves * SMs)); ties go to the smaller factor.
     const int tiles = p.m_tiles * p.n_tiles;
     splits = 1;
-    if (tiles < sms && p.kb_total >= 32) {
-      splits = (2 * sms + tiles - 1) / tiles;  // ~2 waves worth of work items
-      if (splits > p.kb_total / 8) splits = p.kb_total / 8;
-      if (splits < 1) splits = 1;
+    if (p.kb_total >= 32) {
+      double best = (double)tiles / (double)(((tiles + units - 1) / units) * units);
+      const int max_s = p.kb_total / 16 < 16 ? p.kb_total / 16 : 16;
+      for (int sp = 2; sp <= max_s; ++sp) {
+        const long items = (long)tiles * sp;
+        const double eff = (double)items / (double)(((items + units - 1) / units) * units);
+        if (eff > best + 0.02) {
+          best = eff;
+          splits = sp;
+        }
+      }
     }
   }
   if (splits > p.kb_total) splits = p.kb_total;
@@ -461,12 +665,23 @@ extern "C" int tae_gemm(const tae_gemm_args* a, void* stream_) {
     rc = make_tmap(&ta, a->A, (uint64_t)a->M, (uint64_t)a->K, (uint64_t)a->lda, BLOCK_K);
   if (rc) return rc;
   if (!p.b_mn)
-    rc = make_tmap(&tb, a->B, (uint64_t)a->K, (uint64_t)a->N, (uint64_t)a->ldb, BLOCK_N);
+    rc = make_tmap(&tb, a->B, (uint64_t)a->K, (uint64_t)a->N, (uint64_t)a->ldb, use2 ? BLOCK_N / 2 : BLOCK_N);
   else
     rc = make_tmap(&tb, a->B, (uint64_t)a->N, (uint64_t)a->K, (uint64_t)a->ldb, BLOCK_K);
   if (rc) return rc;
 
   const int total = p.m_tiles * p.n_tiles * p.splits;
+  if (use2) {
+    const int clusters = total < units ? total : units;
+    switch (a->epilogue) {
+      case TAE_EPI_BF16: return launch_2sm<TAE_EPI_BF16>(ta, tb, p, clusters, stream);
+      case TAE_EPI_BF16_GELU: return launch_2sm<TAE_EPI_BF16_GELU>(ta, tb, p, clusters, stream);
+      case TAE_EPI_F32_RESID: return launch_2sm<TAE_EPI_F32_RESID>(ta, tb, p, clusters, stream);
+      case TAE_EPI_F32_ACC: return launch_2sm<TAE_EPI_F32_ACC>(ta, tb, p, clusters, stream);
+      case TAE_EPI_BF16_DGELU: return launch_2sm<TAE_EPI_BF16_DGELU>(ta, tb, p, clusters, stream);
+    }
+    return TAE_ERR_SHAPE;
+  }
   const int grid = total < sms ? total : sms;
   switch (a->epilogue) {
     case TAE_EPI_BF16: return launch<TAE_EPI_BF16>(ta, tb, p, grid, stream);

@@ -316,25 +316,33 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const float* __restrict__ x, const fl
   }
 }
 
-// out_k[col] (+)= sum_p partials[p][k][col]
-__global__ void ln_bwd_finalize_kernel(const float* __restrict__ partials, int num_partials, int D, float* dgamma,
-                                       float* dbeta, float* dcolsum, int accumulate) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // over 3*D
-  if (idx >= 3 * D) return;
-  const int k = idx / D, col = idx - k * D;
+// out_k[col] (+)= sum_p partials[p][k][col].  Block = 32 columns x 8 partial-slices (coalesced 128-byte rows),
+// grid = 3*D/32 blocks, so the few hundred partial rows are summed by 8 threads per column in parallel.
+__global__ void __launch_bounds__(256)
+ln_bwd_finalize_kernel(const float* __restrict__ partials, int num_partials, int D, float* dgamma, float* dbeta,
+                       float* dcolsum, int accumulate) {
+  __shared__ float red[8][33];
+  const int cx = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const int idx = blockIdx.x * 32 + cx;  // over 3*D
+  const int k = idx / D, col = idx - k * D;  // D % 32 == 0: a block never straddles two outputs
   float* out = (k == 0) ? dgamma : (k == 1) ? dbeta : dcolsum;
-  if (out == nullptr) return;
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  int pidx = 0;
-  for (; pidx + 3 < num_partials; pidx += 4) {
-    s0 += partials[((size_t)(pidx + 0) * 3 + k) * D + col];
-    s1 += partials[((size_t)(pidx + 1) * 3 + k) * D + col];
-    s2 += partials[((size_t)(pidx + 2) * 3 + k) * D + col];
-    s3 += partials[((size_t)(pidx + 3) * 3 + k) * D + col];
+  float s0 = 0.f, s1 = 0.f;
+  if (out != nullptr) {
+    int p = sl;
+    for (; p + 8 < num_partials; p += 16) {
+      s0 += partials[((size_t)p * 3 + k) * D + col];
+      s1 += partials[((size_t)(p + 8) * 3 + k) * D + col];
+    }
+    if (p < num_partials) s0 += partials[((size_t)p * 3 + k) * D + col];
   }
-  for (; pidx < num_partials; ++pidx) s0 += partials[((size_t)pidx * 3 + k) * D + col];
-  const float s = (s0 + s1) + (s2 + s3);
-  out[col] = ((accumulate >> k) & 1) ? out[col] + s : s;
+  red[sl][cx] = s0 + s1;
+  __syncthreads();
+  if (sl == 0 && out != nullptr) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += red[i][cx];
+    out[col] = ((accumulate >> k) & 1) ? out[col] + s : s;
+  }
 }
 
 // choose VPT and block size: D = 4 * VPT * threads, threads multiple of 32, <= 512
@@ -439,7 +447,7 @@ extern "C" int tae_layernorm_bwd_finalize(const float* partials, int32_t num_par
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   TAE_CHECK_SHAPE(num_partials > 0 && D > 0 && partials != nullptr, "tae_layernorm_bwd_finalize: bad arguments");
   const int total = 3 * D;
-  ln_bwd_finalize_kernel<<<(total + 255) / 256, 256, 0, stream>>>(partials, num_partials, D, dgamma, dbeta, dcolsum,
+  ln_bwd_finalize_kernel<<<total / 32, 256, 0, stream>>>(partials, num_partials, D, dgamma, dbeta, dcolsum,
                                                                    accumulate);
   TAE_CHECK_LAUNCH();
   return TAE_OK;

@@ -1,0 +1,14 @@
+"""ncu target: tcgen05 attention fwd + bwd at the patch16 shape (B=64 keeps replays short)."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from tae_b200 import ops
+B, N, H, hd = 64, 256, 16, 64
+D = H * hd
+qkv = (torch.randn(B * N, 3 * D, device="cuda") * 0.5).to(torch.bfloat16)
+dout = (torch.randn(B * N, D, device="cuda") * 0.5).to(torch.bfloat16)
+for rep in range(2):
+    out, lse = ops.attention_fwd(qkv, B, N, H, hd)
+    dqkv = ops.attention_bwd(qkv, out, dout, lse, B, N, H, hd)
+torch.cuda.synchronize()
+print("ok")
