@@ -62,7 +62,9 @@ uint64_t tae_launch_count(void);
 enum tae_gemm_epilogue {
   /* out(bf16)[m,n] = acc + bias[n]                      (bias may be NULL) */
   TAE_EPI_BF16 = 0,
-  /* h = bf16(acc + bias[n]); out = h; out2 = bf16(gelu_erf(h))      tae.py:101-102 */
+  /* h = bf16(acc + bias[n]);  out2 = bf16(gelu_erf(h))  (tae.py:101-102);  out = bf16(gelu_erf'(h)) — the only
+   * thing backward needs from the pre-activation, so it is saved instead of h and the fc2 dgrad epilogue
+   * (TAE_EPI_BF16_DGELU) is a plain multiply */
   TAE_EPI_BF16_GELU = 1,
   /* out(f32)[m,n] = resid[(m % resid_rows), n] + float(bf16(acc + bias[n]))
    * residual add tae.py:129-130; pos-embed add tae.py:229,245 (resid_rows = tokens per image) */
@@ -70,8 +72,8 @@ enum tae_gemm_epilogue {
   /* out(f32)[m,n] = (beta ? out[m,n] : 0) + acc; with splits > 1 the partial sums are added with
    * red.global.add (out must then be pre-initialised; beta is implied)      weight gradients */
   TAE_EPI_F32_ACC = 3,
-  /* out(bf16)[m,n] = bf16( float(bf16(acc)) * gelu_erf'(aux[m,n]) )       GELU backward fused into
-   * the fc2 dgrad */
+  /* out(bf16)[m,n] = bf16( float(bf16(acc)) * aux[m,n] ),  aux = gelu_erf'(h) saved by TAE_EPI_BF16_GELU:
+   * GELU backward fused into the fc2 dgrad */
   TAE_EPI_BF16_DGELU = 4
 };
 
@@ -84,12 +86,12 @@ typedef struct tae_gemm_args {
   int32_t epilogue;        /* enum tae_gemm_epilogue */
   void* out;               /* bf16 or fp32 per epilogue, row-major [M, N], leading dim ldo */
   int32_t ldo;
-  void* out2;              /* TAE_EPI_BF16_GELU: second bf16 output, same layout as out */
+  void* out2;              /* TAE_EPI_BF16_GELU: bf16 gelu(h), same layout as out (which receives gelu'(h)) */
   const float* bias;       /* [N] fp32 or NULL */
   const float* resid;      /* TAE_EPI_F32_RESID: fp32 [resid_rows, N], leading dim ldr (may alias out) */
   int32_t ldr;
   int32_t resid_rows;
-  const tae_bf16* aux;     /* TAE_EPI_BF16_DGELU: bf16 [M, N], leading dim ldaux */
+  const tae_bf16* aux;     /* TAE_EPI_BF16_DGELU: bf16 multiplier [M, N], leading dim ldaux */
   int32_t ldaux;
   int32_t beta;            /* TAE_EPI_F32_ACC */
   int32_t splits;          /* split-K factor, >= 1; only TAE_EPI_F32_ACC may use > 1; 0 = auto */

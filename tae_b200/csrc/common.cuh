@@ -92,30 +92,36 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
   return cdf + x * pdf;
 }
 
-// Epilogue-rate GELU: Phi(x) from the Abramowitz-Stegun 7.1.26 erfc form (|abs err| <= 1.5e-7, far below bf16
-// resolution), sharing ONE exp2 and ONE rcp between Phi and phi:  q = poly(t) e^{-x^2/2}, t = 1/(1 + p|x|/sqrt2),
-// Phi(x) = x >= 0 ? 1 - q/2 : q/2.  ~14 instructions per element instead of erff + expf.
-__device__ __forceinline__ void gelu_parts(float x, float& cdf, float& e) {
-  const float ax = fabsf(x);
-  float t;  // one MUFU.RCP, one MUFU.EX2 (approx units: ~1e-7 relative, below the polynomial's own error)
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(ax, 0.3275911f * 0.70710678118654752440f, 1.0f)));
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-0.72134752044448170368f * x * x));  // e^{-x^2/2}
-  float poly = fmaf(t, 0.5f * 1.061405429f, 0.5f * -1.453152027f);  // coefficients pre-halved: q = erfc/2
+// Epilogue-rate exact GELU.  q(x) = erfc(|x|/sqrt2)/2 from the Abramowitz-Stegun 7.1.26 form (|abs err| <= 1.5e-7 on
+// erf, far below bf16 resolution) with ONE rcp and ONE exp2 shared between Phi and phi:
+//   t = 1/(1 + p|x|/sqrt2),  e = e^{-x^2/2},  q = t (a1 + t (a2 + t (a3 + t (a4 + t a5)))) e / 2
+//   gelu(x)  = x Phi(x)          = max(x, 0) - |x| q
+//   gelu'(x) = Phi(x) + x phi(x) = 1/2 + copysign(1/2 - q, x) + x e / sqrt(2 pi)
+__device__ __forceinline__ void gelu_qe(float x, float& q, float& e) {
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(fabsf(x), 0.3275911f * 0.70710678118654752440f, 1.0f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"((x * -0.72134752044448170368f) * x));
+  float poly = fmaf(t, 0.5f * 1.061405429f, 0.5f * -1.453152027f);
   poly = fmaf(t, poly, 0.5f * 1.421413741f);
   poly = fmaf(t, poly, 0.5f * -0.284496736f);
   poly = fmaf(t, poly, 0.5f * 0.254829592f);
-  const float q = poly * t * e;
-  cdf = x >= 0.f ? 1.0f - q : q;
+  q = (poly * t) * e;
 }
 __device__ __forceinline__ float gelu_fast(float x) {
-  float cdf, e;
-  gelu_parts(x, cdf, e);
-  return x * cdf;
+  float q, e;
+  gelu_qe(x, q, e);
+  return fmaf(-fabsf(x), q, fmaxf(x, 0.f));
 }
 __device__ __forceinline__ float gelu_grad_fast(float x) {
-  float cdf, e;
-  gelu_parts(x, cdf, e);
-  return fmaf(x * 0.39894228040143267794f, e, cdf);
+  float q, e;
+  gelu_qe(x, q, e);
+  return fmaf(x * 0.39894228040143267794f, e, 0.5f + copysignf(0.5f - q, x));
+}
+__device__ __forceinline__ void gelu_and_grad_fast(float x, float& g, float& gp) {
+  float q, e;
+  gelu_qe(x, q, e);
+  g = fmaf(-fabsf(x), q, fmaxf(x, 0.f));
+  gp = fmaf(x * 0.39894228040143267794f, e, 0.5f + copysignf(0.5f - q, x));
 }
 
 // 128-bit streaming loads/stores (read-once data: do not allocate in L1)

@@ -113,21 +113,21 @@ __device__ __forceinline__ void epi_stage_rows(uint32_t stg, uint32_t taddr, int
 // Coalesced phase: lane -> (row = it*4 + lane/8, 4 fp32 columns = chunk lane%8).  Every shared and global load of
 // the step is issued before the first use (8 rows in flight per lane); the bias of the lane's 4 fixed columns is
 // loaded and rounded once per step; the math of the 8 rows is independent, so the scheduler has 32 chains to overlap.
-template <int EPI>
+template <int EPI, int IT0 = 0, int NIT = 8>
 __device__ __forceinline__ void epi_write_coalesced(const Params& p, uint32_t stg, int row_base, int col0, int lane) {
   const int c = lane & 7, rsub = lane >> 3;
   const int col = col0 + c * 4;
   const bool col_ok = col < p.N;
   uint4 val[8];
 #pragma unroll
-  for (int it = 0; it < 8; ++it) val[it] = ld_shared_v4(stg + stg_off(it * 4 + rsub, c));
+  for (int it = IT0; it < IT0 + NIT; ++it) val[it] = ld_shared_v4(stg + stg_off(it * 4 + rsub, c));
   if (!col_ok) return;
   constexpr bool kSide16 = (EPI == TAE_EPI_F32_RESID || EPI == TAE_EPI_F32_ACC);
   uint4 side[8];
   if (kSide16) {
     const bool want = (EPI == TAE_EPI_F32_RESID) || (p.beta && p.splits <= 1);
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
+    for (int it = IT0; it < IT0 + NIT; ++it) {
       const int grow = row_base + it * 4 + rsub;
       side[it] = make_uint4(0u, 0u, 0u, 0u);
       if (want && grow < p.M) {
@@ -139,7 +139,7 @@ __device__ __forceinline__ void epi_write_coalesced(const Params& p, uint32_t st
     }
   } else if (EPI == TAE_EPI_BF16_DGELU) {
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
+    for (int it = IT0; it < IT0 + NIT; ++it) {
       const int grow = row_base + it * 4 + rsub;
       side[it] = make_uint4(0u, 0u, 0u, 0u);
       if (grow < p.M) {
@@ -156,24 +156,30 @@ __device__ __forceinline__ void epi_write_coalesced(const Params& p, uint32_t st
     bias4 = make_float4(round_bf16(b.x), round_bf16(b.y), round_bf16(b.z), round_bf16(b.w));
   }
 #pragma unroll
-  for (int it = 0; it < 8; ++it) {
+  for (int it = IT0; it < IT0 + NIT; ++it) {
     const int grow = row_base + it * 4 + rsub;
     if (grow >= p.M) continue;
     const float a0 = __uint_as_float(val[it].x), a1 = __uint_as_float(val[it].y);
     const float a2 = __uint_as_float(val[it].z), a3 = __uint_as_float(val[it].w);
-    if (EPI == TAE_EPI_BF16 || EPI == TAE_EPI_BF16_GELU) {
-      const uint32_t h01 = pack_bf16x2(a0 + bias4.x, a1 + bias4.y), h23 = pack_bf16x2(a2 + bias4.z, a3 + bias4.w);
-      *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out) + (size_t)grow * p.ldo + col) = make_uint2(h01, h23);
-      if (EPI == TAE_EPI_BF16_GELU) {
-        const float2 f01 = unpack_bf16x2(h01), f23 = unpack_bf16x2(h23);
-        *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out2) + (size_t)grow * p.ldo + col) =
-            make_uint2(pack_bf16x2(gelu_fast(f01.x), gelu_fast(f01.y)), pack_bf16x2(gelu_fast(f23.x), gelu_fast(f23.y)));
-      }
+    if (EPI == TAE_EPI_BF16) {
+      *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out) + (size_t)grow * p.ldo + col) =
+          make_uint2(pack_bf16x2(a0 + bias4.x, a1 + bias4.y), pack_bf16x2(a2 + bias4.z, a3 + bias4.w));
+    } else if (EPI == TAE_EPI_BF16_GELU) {
+      // h = bf16(acc + bias) is the reference's fc1 output; GELU and its derivative are evaluated on that rounded value
+      float g[4], gp[4];
+      gelu_and_grad_fast(round_bf16(a0 + bias4.x), g[0], gp[0]);
+      gelu_and_grad_fast(round_bf16(a1 + bias4.y), g[1], gp[1]);
+      gelu_and_grad_fast(round_bf16(a2 + bias4.z), g[2], gp[2]);
+      gelu_and_grad_fast(round_bf16(a3 + bias4.w), g[3], gp[3]);
+      *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out) + (size_t)grow * p.ldo + col) =
+          make_uint2(pack_bf16x2(gp[0], gp[1]), pack_bf16x2(gp[2], gp[3]));
+      *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out2) + (size_t)grow * p.ldo + col) =
+          make_uint2(pack_bf16x2(g[0], g[1]), pack_bf16x2(g[2], g[3]));
     } else if (EPI == TAE_EPI_BF16_DGELU) {
-      const float2 h01 = unpack_bf16x2(side[it].x), h23 = unpack_bf16x2(side[it].y);
-      // bf16(acc) first: the dgrad GEMM's own output rounding in the reference
-      const uint32_t o01 = pack_bf16x2(round_bf16(a0) * gelu_grad_fast(h01.x), round_bf16(a1) * gelu_grad_fast(h01.y));
-      const uint32_t o23 = pack_bf16x2(round_bf16(a2) * gelu_grad_fast(h23.x), round_bf16(a3) * gelu_grad_fast(h23.y));
+      const float2 m01 = unpack_bf16x2(side[it].x), m23 = unpack_bf16x2(side[it].y);
+      // bf16(acc) first: the dgrad GEMM's own output rounding in the reference; aux holds gelu'(h) from the forward
+      const uint32_t o01 = pack_bf16x2(round_bf16(a0) * m01.x, round_bf16(a1) * m01.y);
+      const uint32_t o23 = pack_bf16x2(round_bf16(a2) * m23.x, round_bf16(a3) * m23.y);
       *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out) + (size_t)grow * p.ldo + col) = make_uint2(o01, o23);
     } else if (EPI == TAE_EPI_F32_RESID) {
       float4 o;
@@ -365,17 +371,20 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 // ---------------------------------------------------------------------------------------------
 // CTA-pair variant: a 2-CTA cluster (two SMs of one TPC) computes a 256x256 tile with tcgen05.mma.cta_group::2.
 // Each CTA stages its own 128 rows of A and only HALF of the B tile (128 of the 256 n-rows) — the tensor cores of
-// both SMs read both halves — so shared-memory traffic per SM drops by a third and the ring deepens to 6 stages.
+// both SMs read both halves — so shared-memory traffic per SM drops by a third and the ring has 5 stages of 32 KB.
 // The leader (even) CTA issues every MMA; both CTAs run a TMA producer (its bytes are credited to the leader's
 // `full` barrier) and the epilogue for their own 128 accumulator rows.
 // ---------------------------------------------------------------------------------------------
-constexpr int STAGES2 = 6;
+constexpr int STAGES2 = 5;
+constexpr int NUM_EPI_WARPS2 = 16;                                   // 4 per TMEM lane quarter, 64 columns each
+constexpr int NUM_THREADS2 = 128 + NUM_EPI_WARPS2 * 32;              // 640
+constexpr int SMEM2_STAGING_BYTES = NUM_EPI_WARPS2 * 32 * 128;       // 64 KB
 constexpr int B2_STAGE_BYTES = (BLOCK_N / 2) * BLOCK_K * 2;          // 16 KB: this CTA's half of the B tile
 constexpr int STAGE2_BYTES = A_STAGE_BYTES + B2_STAGE_BYTES;         // 32 KB
-constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + SMEM_BARRIER_BYTES + SMEM_STAGING_BYTES + 1024;
+constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + SMEM_BARRIER_BYTES + SMEM2_STAGING_BYTES + 1024;
 
 template <int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS2, 1)
 gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                       const Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -404,7 +413,7 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     }
     for (int a = 0; a < NUM_ACC; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
-      mbar_init(&tmem_empty_bar[a], 2 * NUM_EPI_WARPS);
+      mbar_init(&tmem_empty_bar[a], 2 * NUM_EPI_WARPS2);
     }
     fence_barrier_init();
   }
@@ -490,8 +499,8 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
   } else if (warp >= 4) {
     // ===================== epilogue warps (both CTAs, own 128 rows) =====================
     const int ew = warp - 4;
-    const int q = ew & 3;
-    const int half = ew >> 2;
+    const int q = ew & 3;       // TMEM lane quarter (== warp % 4)
+    const int cg = ew >> 2;     // which 64-column group of the accumulator
     const uint32_t stg = smem_u32(smem + STAGES2 * STAGE2_BYTES + SMEM_BARRIER_BYTES + ew * STG_BYTES_PER_WARP);
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -501,13 +510,15 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       tcgen05_fence_after();
       const int row_base = it.mt * (2 * BLOCK_M) + (int)rank * BLOCK_M + q * 32;
 #pragma unroll 1
-      for (int c = 0; c < 128 / EPI_COLS; ++c) {
-        const int col0 = it.nt * BLOCK_N + half * 128 + c * EPI_COLS;
+      for (int c = 0; c < 64 / EPI_COLS; ++c) {
+        const int col0 = it.nt * BLOCK_N + cg * 64 + c * EPI_COLS;
         if (col0 >= p.N) break;  // warp-uniform
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + half * 128 + c * EPI_COLS);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + cg * 64 + c * EPI_COLS);
         epi_stage_rows(stg, taddr, lane);
         __syncwarp();
-        epi_write_coalesced<EPI>(p, stg, row_base, col0, lane);
+        // two passes of 16 rows keep the live register set under the 640-thread budget
+        epi_write_coalesced<EPI, 0, 4>(p, stg, row_base, col0, lane);
+        epi_write_coalesced<EPI, 4, 4>(p, stg, row_base, col0, lane);
         __syncwarp();
       }
       tcgen05_fence_before();
@@ -556,7 +567,7 @@ static int launch_2sm(const CUtensorMap& ta, const CUtensorMap& tb, const Params
     set_error("cudaFuncSetAttribute(smem=%d) failed: %s", SMEM2_BYTES, cudaGetErrorString(attr_err));
     return TAE_ERR_CUDA;
   }
-  gemm_bf16_tcgen05_2sm<EPI><<<2 * clusters, NUM_THREADS, SMEM2_BYTES, stream>>>(ta, tb, p);
+  gemm_bf16_tcgen05_2sm<EPI><<<2 * clusters, NUM_THREADS2, SMEM2_BYTES, stream>>>(ta, tb, p);
   TAE_CHECK_LAUNCH();
   return TAE_OK;
 }

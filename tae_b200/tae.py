@@ -184,15 +184,15 @@ class _BlockFn(torch.autograd.Function):
         att, lse = ops.attention_fwd(qkv, B, N, H, hd)
         xm = ops.gemm(att, shadow_bf16(pw), epilogue=EPI_F32_RESID, bias=det(pb), resid=x2)
         ln2, mean2, rstd2 = ops.layernorm_fwd(xm, det(n2w), det(n2b), blk.norm2.eps)
-        h, a = ops.gemm(ln2, shadow_bf16(f1w), epilogue=EPI_BF16_GELU, bias=det(f1b))
+        gp, a = ops.gemm(ln2, shadow_bf16(f1w), epilogue=EPI_BF16_GELU, bias=det(f1b))  # gelu'(h), gelu(h)
         xo = ops.gemm(a, shadow_bf16(f2w), epilogue=EPI_F32_RESID, bias=det(f2b), resid=xm)
         ctx.blk, ctx.dims = blk, (B, N, D, H, hd)
-        ctx.save_for_backward(x2, mean1, rstd1, ln1, qkv, att, lse, xm, mean2, rstd2, ln2, h, a)
+        ctx.save_for_backward(x2, mean1, rstd1, ln1, qkv, att, lse, xm, mean2, rstd2, ln2, gp, a)
         return xo.view(B, N, D)
 
     @staticmethod
     def backward(ctx, dxo):
-        x2, mean1, rstd1, ln1, qkv, att, lse, xm, mean2, rstd2, ln2, h, a = ctx.saved_tensors
+        x2, mean1, rstd1, ln1, qkv, att, lse, xm, mean2, rstd2, ln2, gp, a = ctx.saved_tensors
         blk = ctx.blk
         B, N, D, H, hd = ctx.dims
         need = ctx.needs_input_grad
@@ -203,7 +203,7 @@ class _BlockFn(torch.autograd.Function):
         # ---- MLP branch: y = fc2(gelu(fc1(norm2(xm)))) ----
         g_f2b = _bgrad(mlp.fc2.bias, precomputed=csum) if (mlp.fc2.bias is not None and need[12]) else None
         g_f2w = _wgrad(mlp.fc2.weight, dy_b, a) if need[11] else None
-        dh = ops.gemm(dy_b, shadow_bf16(mlp.fc2.weight), b_mn=True, epilogue=EPI_BF16_DGELU, aux=h)
+        dh = ops.gemm(dy_b, shadow_bf16(mlp.fc2.weight), b_mn=True, epilogue=EPI_BF16_DGELU, aux=gp)
         g_f1b = _bgrad(mlp.fc1.bias, dy_b=dh) if (mlp.fc1.bias is not None and need[10]) else None
         g_f1w = _wgrad(mlp.fc1.weight, dh, ln2) if need[9] else None
         dln2 = ops.gemm(dh, shadow_bf16(mlp.fc1.weight), b_mn=True, epilogue=EPI_BF16)
