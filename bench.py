@@ -38,6 +38,8 @@ def parse():
     ap.add_argument("--mode", default="train", choices=["train", "encode"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--no-encode", action="store_true", help="skip the secondary encode.py-path measurement")
+    ap.add_argument("--encode-model", default="tae_patch64_vocab4096_px256")
     ap.add_argument("--cpu-batch", type=int, default=2)
     return ap.parse_args()
 
@@ -262,6 +264,12 @@ def run_b200(args):
     if world > 1:
         dist.barrier()
 
+    enc = None
+    if not args.no_encode:
+        optimizer.zero_grad()
+        torch.cuda.empty_cache()
+        enc = encode_throughput(torch, dist, engine, args.encode_model, B, dev, world)
+
     ips = world * B * args.steps / (ms_total / 1e3)
     ips_e2e = world * B * args.steps / (ms_e2e / 1e3)
     if rank != 0:
@@ -288,6 +296,8 @@ def run_b200(args):
     if roof is not None:
         line["roofline"] = roof
         line["roofline_detail"] = detail
+    if enc is not None:
+        line["encode"] = enc
     if not args.no_cpu_baseline and world == 1:
         cips, cores, csec = cpu_reference_step_time(args.model, args.cpu_batch, 2, 1)
         line["cpu_baseline"] = {"value": cips, "unit": "images/s", "cores": cores, "kind": "port",
@@ -296,6 +306,52 @@ def run_b200(args):
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def encode_throughput(torch, dist, engine, model_name, B, dev, world, iters=10, warmup=3):
+    """BASELINE.json configs[4]: the encode.py path (forward_encoder under no_grad, encode.py:80-88), batch-sharded over
+    the ranks with no communication.  Returns (images/s resident, images/s end-to-end with H2D + latent D2H)."""
+    from tae_b200 import tae as T
+
+    torch.manual_seed(0)
+    with torch.device(dev):
+        model = T.__dict__[model_name]()
+    model.eval()
+    host = [torch.randn(B, 3, 256, 256).pin_memory() for _ in range(2)]
+    res = [h.to(dev) for h in host]
+    for i in range(warmup):
+        z = engine.encode_batch(model, res[i % 2])
+    lat_host = torch.empty(z.shape, dtype=z.dtype).pin_memory()
+
+    def timed(fn):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(iters):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return world * B * iters / (float(t) / 1e3)
+
+    ips = timed(lambda i: engine.encode_batch(model, res[i % 2]))
+    feeder = engine.HostBatchFeeder(host, dev)
+
+    def e2e_step(i):
+        x = feeder.next()
+        z = engine.encode_batch(model, x)
+        feeder.release()
+        lat_host.copy_(z, non_blocking=True)  # encode.py:87 `latents.cpu()`
+
+    ips_e2e = timed(e2e_step)
+    del model
+    torch.cuda.empty_cache()
+    return {"metric": "encode images/sec", "model": model_name, "batch_per_gpu": B, "value": ips, "e2e": ips_e2e,
+            "unit": "images/s", "h2d_bytes_per_step": host[0].numel() * 4, "d2h_bytes_per_step": lat_host.numel() * 2}
 
 
 def gemm_roofline(torch, ops, step_fn, peaks):

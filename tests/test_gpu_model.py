@@ -137,3 +137,112 @@ def test_grad_accumulation_and_upstream_scale(golden_meta, golden_tensors):
         (loss / 2).backward()
     for n, p in model.named_parameters():
         assert rel(p.grad, ref[n]) < 5e-3, n
+
+
+# ----------------------------------------------------------------------------------------------------
+# The real model zoo at reduced batch: every code path of BASELINE.json's configs (N = 256/64/16/4 tokens,
+# head_dim 64/80, latent widths 256..16384, split-K weight gradients, tcgen05 and generic attention) against the
+# oracle on the same device, same weights, same inputs.
+# ----------------------------------------------------------------------------------------------------
+FULL_CASES = [("tae_patch16_vocab256_px256", 4), ("tae_patch32_vocab1024_px256", 4), ("tae_patch64_vocab4096_px256", 3),
+              ("tae_patch128_vocab16384_px256", 2), ("tae_patch16_vocab16_px256", 2)]
+
+
+@pytest.mark.parametrize("name,batch", FULL_CASES)
+def test_full_size_models_match_oracle(name, batch):
+    from tae_b200 import tae as T
+
+    torch.manual_seed(0)
+    with torch.device("cuda"):
+        model = T.__dict__[name]()
+    model.train()
+    cfg = O.zoo_config(name)
+    x = torch.randn(batch, 3, 256, 256, generator=torch.Generator().manual_seed(1234)).cuda()
+    loss, pred, latent = model(x, return_latent=True)
+    loss.backward()
+    torch.cuda.synchronize()
+    assert pred.shape == (batch, cfg.num_patches, 3 * cfg.patch_size ** 2) and latent.shape == (batch, cfg.num_patches, cfg.vocab_size)
+
+    # oracle forward (no autograd graph needed for the activations)
+    sd = {k: v.detach() for k, v in model.state_dict().items()}
+    with torch.no_grad():
+        lo, po, zo = O.forward(sd, x, cfg, "bf16")
+    assert abs(float(loss) - float(lo)) < 5e-3 * float(lo), (float(loss), float(lo))
+    assert rel(pred.float(), po.float()) < BF16_TOL
+    assert rel(latent.float(), zo.float()) < BF16_TOL
+    del po, zo
+
+    # gradients: oracle autograd on the same weights, compared per tensor, then freed block by block
+    leaves = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items()}
+    lo2, _, _ = O.forward(leaves, x, cfg, "bf16")
+    lo2.backward()
+    worst, nbad = ("", 0.0), 0
+    for n, p in model.named_parameters():
+        g, go = p.grad, leaves[n].grad
+        assert g is not None and go is not None, n
+        e = rel(g, go.float())
+        if e > worst[1]:
+            worst = (n, e)
+        nbad += e > 3e-2
+    assert nbad == 0, (worst, nbad)
+    gn = float(torch.norm(torch.stack([p.grad.norm() for p in model.parameters()])))
+    gno = float(torch.norm(torch.stack([v.grad.float().norm() for v in leaves.values()])))
+    assert abs(gn - gno) < BF16_TOL * gno
+
+
+def test_encode_sharding_matches_unsharded():
+    """encode.py path, batch-sharded (engine.shard_for_rank): concatenated shard outputs == the unsharded batch."""
+    from tae_b200 import engine
+    from tae_b200 import tae as T
+
+    torch.manual_seed(0)
+    with torch.device("cuda"):
+        model = T.tae_patch64_vocab4096_px256()
+    model.eval()
+    x = torch.randn(8, 3, 256, 256, generator=torch.Generator().manual_seed(7)).cuda()
+    full = engine.encode_batch(model, x)
+    parts = []
+    for r in range(4):
+        lo, hi = engine.shard_for_rank(8, r, 4)
+        parts.append(engine.encode_batch(model, x[lo:hi].contiguous()))
+    assert torch.equal(torch.cat(parts, 0), full)
+    assert full.shape == (8, 16, 4096) and full.dtype == torch.bfloat16
+
+
+def test_fused_adamw_training_matches_torch_adamw():
+    """FusedAdamW (direct-gradient arenas, bf16 shadows) vs torch.optim.AdamW on the same model, 3 steps."""
+    from tae_b200 import engine, misc
+    from tae_b200 import tae as T
+
+    kw = dict(img_size=64, patch_size=8, in_chans=3, embed_dim=128, vocab_size=16, depth=2, num_heads=2,
+              decoder_embed_dim=128, decoder_depth=2, decoder_num_heads=2, mlp_ratio=4.)
+    x = torch.randn(4, 3, 64, 64, generator=torch.Generator().manual_seed(3)).cuda()
+    torch.manual_seed(0)
+    m1 = T.TAE(norm_layer=partial(torch.nn.LayerNorm, eps=1e-6), **kw).cuda()
+    torch.manual_seed(0)
+    m2 = T.TAE(norm_layer=partial(torch.nn.LayerNorm, eps=1e-6), **kw).cuda()
+    o1 = engine.build_optimizer(m1, max_lr=1e-3, weight_decay=0.05, track_grad_norm=True)
+    o2 = torch.optim.AdamW(misc.add_weight_decay(m2, 0.05), lr=1e-3, betas=(0.9, 0.95))
+    scaler = misc.NativeScalerWithGradNormCount()
+    for it in range(3):
+        l1, _ = m1(x)
+        norm = scaler(l1, o1, parameters=m1.parameters())
+        o1.zero_grad()
+        l2, _ = m2(x)
+        l2.backward()
+        ref_norm = misc.get_grad_norm_(m2.parameters())
+        o2.step()
+        o2.zero_grad(set_to_none=True)
+        assert abs(float(l1) - float(l2)) < 2e-3 * float(l2), it
+        assert abs(float(norm) - float(ref_norm)) < 1e-2 * float(ref_norm), it
+    for (n, p1), (_, p2) in zip(m1.named_parameters(), m2.named_parameters()):
+        if n.endswith("attn.qkv.bias"):
+            # the key bias has an exactly-zero true gradient (softmax shift invariance): Adam normalises pure
+            # rounding noise to +-lr there, so only the q and v thirds are comparable
+            D = p1.numel() // 3
+            p1, p2 = torch.cat([p1[:D], p1[2 * D:]]), torch.cat([p2[:D], p2[2 * D:]])
+        assert rel(p1, p2) < 5e-3, n
+    sd = o1.state_dict()
+    ref = o2.state_dict()
+    assert len(sd["state"]) == len(ref["state"]) and [g["params"] for g in sd["param_groups"]] == [g["params"] for g in ref["param_groups"]]
+    assert set(sd["state"][0].keys()) == {"step", "exp_avg", "exp_avg_sq"}
