@@ -371,22 +371,32 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 // ---------------------------------------------------------------------------------------------
 // CTA-pair variant: a 2-CTA cluster (two SMs of one TPC) computes a 256x256 tile with tcgen05.mma.cta_group::2.
 // Each CTA stages its own 128 rows of A and only HALF of the B tile (128 of the 256 n-rows) — the tensor cores of
-// both SMs read both halves — so shared-memory traffic per SM drops by a third and the ring has 5 stages of 32 KB.
+// both SMs read both halves — so shared-memory traffic per SM drops by a third and a stage is 32 KB.
 // The leader (even) CTA issues every MMA; both CTAs run a TMA producer (its bytes are credited to the leader's
 // `full` barrier) and the epilogue for their own 128 accumulator rows.
 // ---------------------------------------------------------------------------------------------
-constexpr int STAGES2 = 5;
-constexpr int NUM_EPI_WARPS2 = 16;                                   // 4 per TMEM lane quarter, 64 columns each
-constexpr int NUM_THREADS2 = 128 + NUM_EPI_WARPS2 * 32;              // 640
-constexpr int SMEM2_STAGING_BYTES = NUM_EPI_WARPS2 * 32 * 128;       // 64 KB
 constexpr int B2_STAGE_BYTES = (BLOCK_N / 2) * BLOCK_K * 2;          // 16 KB: this CTA's half of the B tile
 constexpr int STAGE2_BYTES = A_STAGE_BYTES + B2_STAGE_BYTES;         // 32 KB
-constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + SMEM_BARRIER_BYTES + SMEM2_STAGING_BYTES + 1024;
 
-template <int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS2, 1)
+// Two shapes of the kernel: EW = 8 epilogue warps (128 columns each, 32 KB of transpose staging, 6 pipeline stages) for
+// main-loop-bound GEMMs, EW = 16 (64 columns each, 64 KB staging, 5 stages) when the epilogue carries the work
+// (GELU, short-K residual GEMMs).
+template <int EW>
+struct Cfg2 {
+  static constexpr int kStages = EW == 8 ? 6 : 5;
+  static constexpr int kThreads = 128 + EW * 32;
+  static constexpr int kStagingBytes = EW * 32 * 128;
+  static constexpr int kSmemBytes = kStages * STAGE2_BYTES + SMEM_BARRIER_BYTES + kStagingBytes + 1024;
+  static constexpr int kColsPerWarp = 256 / (EW / 4);
+};
+
+template <int EPI, int EW>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg2<EW>::kThreads, 1)
 gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                       const Params p) {
+  constexpr int STAGES2 = Cfg2<EW>::kStages;
+  constexpr int NUM_EPI_WARPS2 = EW;
+  constexpr int COLS_PER_WARP = Cfg2<EW>::kColsPerWarp;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES2 * STAGE2_BYTES);
@@ -500,7 +510,7 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     // ===================== epilogue warps (both CTAs, own 128 rows) =====================
     const int ew = warp - 4;
     const int q = ew & 3;       // TMEM lane quarter (== warp % 4)
-    const int cg = ew >> 2;     // which 64-column group of the accumulator
+    const int cg = ew >> 2;     // which column group of the accumulator
     const uint32_t stg = smem_u32(smem + STAGES2 * STAGE2_BYTES + SMEM_BARRIER_BYTES + ew * STG_BYTES_PER_WARP);
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -510,15 +520,19 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       tcgen05_fence_after();
       const int row_base = it.mt * (2 * BLOCK_M) + (int)rank * BLOCK_M + q * 32;
 #pragma unroll 1
-      for (int c = 0; c < 64 / EPI_COLS; ++c) {
-        const int col0 = it.nt * BLOCK_N + cg * 64 + c * EPI_COLS;
+      for (int c = 0; c < COLS_PER_WARP / EPI_COLS; ++c) {
+        const int col0 = it.nt * BLOCK_N + cg * COLS_PER_WARP + c * EPI_COLS;
         if (col0 >= p.N) break;  // warp-uniform
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + cg * 64 + c * EPI_COLS);
+        const uint32_t taddr =
+            tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + cg * COLS_PER_WARP + c * EPI_COLS);
         epi_stage_rows(stg, taddr, lane);
         __syncwarp();
-        // two passes of 16 rows keep the live register set under the 640-thread budget
-        epi_write_coalesced<EPI, 0, 4>(p, stg, row_base, col0, lane);
-        epi_write_coalesced<EPI, 4, 4>(p, stg, row_base, col0, lane);
+        if (EW == 8) {
+          epi_write_coalesced<EPI, 0, 8>(p, stg, row_base, col0, lane);
+        } else {  // two passes of 16 rows keep the live register set under the 640-thread budget
+          epi_write_coalesced<EPI, 0, 4>(p, stg, row_base, col0, lane);
+          epi_write_coalesced<EPI, 4, 4>(p, stg, row_base, col0, lane);
+        }
         __syncwarp();
       }
       tcgen05_fence_before();
@@ -556,20 +570,29 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p,
   return TAE_OK;
 }
 
-template <int EPI>
-static int launch_2sm(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, int clusters, cudaStream_t stream) {
+template <int EPI, int EW>
+static int launch_2sm_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, int clusters, cudaStream_t stream) {
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, []() {
-    attr_err = cudaFuncSetAttribute(gemm_bf16_tcgen05_2sm<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES);
+    attr_err = cudaFuncSetAttribute(gemm_bf16_tcgen05_2sm<EPI, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    Cfg2<EW>::kSmemBytes);
   });
   if (attr_err != cudaSuccess) {
-    set_error("cudaFuncSetAttribute(smem=%d) failed: %s", SMEM2_BYTES, cudaGetErrorString(attr_err));
+    set_error("cudaFuncSetAttribute(smem=%d) failed: %s", Cfg2<EW>::kSmemBytes, cudaGetErrorString(attr_err));
     return TAE_ERR_CUDA;
   }
-  gemm_bf16_tcgen05_2sm<EPI><<<2 * clusters, NUM_THREADS2, SMEM2_BYTES, stream>>>(ta, tb, p);
+  gemm_bf16_tcgen05_2sm<EPI, EW><<<2 * clusters, Cfg2<EW>::kThreads, Cfg2<EW>::kSmemBytes, stream>>>(ta, tb, p);
   TAE_CHECK_LAUNCH();
   return TAE_OK;
+}
+
+template <int EPI>
+static int launch_2sm(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, int clusters, cudaStream_t stream) {
+  // epilogue-heavy: GELU always; residual / GELU' epilogues when the main loop per tile is short (K <= 2048)
+  const bool heavy = (EPI == TAE_EPI_BF16_GELU) || ((EPI == TAE_EPI_F32_RESID || EPI == TAE_EPI_BF16_DGELU) && p.K <= 2048);
+  if (heavy) return launch_2sm_cfg<EPI, 16>(ta, tb, p, clusters, stream);
+  return launch_2sm_cfg<EPI, 8>(ta, tb, p, clusters, stream);
 }
 
 // TAE_GEMM_1SM=1 forces the single-CTA kernel (A/B testing)
