@@ -95,6 +95,9 @@ typedef struct tae_gemm_args {
   int32_t ldaux;
   int32_t beta;            /* TAE_EPI_F32_ACC */
   int32_t splits;          /* split-K factor, >= 1; only TAE_EPI_F32_ACC may use > 1; 0 = auto */
+  float* colsum_partials;  /* TAE_EPI_BF16_DGELU, optional: fp32 [ceil(M/32), N]; row r receives the column sums of output
+                            * rows 32r..32r+31 (of the bf16-rounded values).  tae_colsum_f32 reduces it to the bias
+                            * gradient without re-reading the [M, N] output */
 } tae_gemm_args;
 
 int tae_gemm(const tae_gemm_args* args, void* stream);
@@ -166,6 +169,8 @@ int tae_mse_loss(const tae_bf16* pred, const float* imgs, float* loss_accum, tae
 size_t tae_colsum_workspace_floats(int32_t M, int32_t N);
 int tae_colsum_bf16(const tae_bf16* x, int32_t M, int32_t N, int32_t ldx, float* out, int32_t accumulate,
                     float* workspace, void* stream);
+/* out[n] (+)= sum_r x[r, n],  x fp32 [R, N] (e.g. the colsum_partials of tae_gemm). */
+int tae_colsum_f32(const float* x, int32_t R, int32_t N, float* out, int32_t accumulate, void* stream);
 /* out[r, :] (+)= sum_b x[b*R + r, :],  x fp32 [B*R, D].  pos_embed / decoder_pos_embed gradients. */
 int tae_batch_sum_f32(const float* x, int32_t B, int32_t R, int32_t D, float* out, int32_t accumulate,
                       void* stream);

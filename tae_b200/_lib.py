@@ -45,6 +45,7 @@ class GemmArgs(C.Structure):
         ("ldaux", C.c_int32),
         ("beta", C.c_int32),
         ("splits", C.c_int32),
+        ("colsum_partials", C.c_void_p),
     ]
 
 
@@ -70,6 +71,7 @@ PROTOTYPES = {
     "tae_mse_loss": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     "tae_colsum_workspace_floats": (C.c_size_t, [_i32, _i32]),
     "tae_colsum_bf16": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _i32, _vp, _vp]),
+    "tae_colsum_f32": (C.c_int, [_vp, _i32, _i32, _vp, _i32, _vp]),
     "tae_batch_sum_f32": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _i32, _vp]),
     "tae_adamw_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _sz, _f32, _f32, _f32, _f32, _f32, _i32, _f32, _vp, _vp, _vp]),
     "tae_cast_f32_to_bf16": (C.c_int, [_vp, _vp, _sz, _vp]),

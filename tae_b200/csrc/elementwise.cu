@@ -198,6 +198,32 @@ static void colsum_config(int M, int N, int* chunks, int* rows_per_chunk) {
   *chunks = (M + rpc - 1) / rpc;
 }
 
+// out[n] (+)= sum_r x[r, n] for a (small) fp32 [R, N] matrix: block = 32 columns x 16 row-slices, 4 loads in flight
+__global__ void __launch_bounds__(512) colsum_f32_kernel(const float* __restrict__ x, int R, int N, float* out, int accumulate) {
+  __shared__ float red[16][33];
+  const int cx = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + cx;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (col < N) {
+    int r = sl;
+    for (; r + 48 < R; r += 64) {
+      s0 += x[(size_t)r * N + col];
+      s1 += x[(size_t)(r + 16) * N + col];
+      s2 += x[(size_t)(r + 32) * N + col];
+      s3 += x[(size_t)(r + 48) * N + col];
+    }
+    for (; r < R; r += 16) s0 += x[(size_t)r * N + col];
+  }
+  red[sl][cx] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (sl == 0 && col < N) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += red[i][cx];
+    out[col] = accumulate ? out[col] + s : s;
+  }
+}
+
 // out[r, :] (+)= sum_b x[b*R + r, :]
 __global__ void batch_sum_kernel(const float* __restrict__ x, int B, int R, int D, float* out, int accumulate) {
   const int d4 = D / 4;
@@ -327,6 +353,16 @@ extern "C" int tae_colsum_bf16(const tae_bf16* x, int32_t M, int32_t N, int32_t 
   colsum_stage1<<<grid, 256, 0, stream>>>(reinterpret_cast<const bf16*>(x), M, N, ldx, workspace, rpc);
   TAE_CHECK_LAUNCH();
   colsum_stage2<<<(N + 255) / 256, 256, 0, stream>>>(workspace, chunks, N, out, accumulate);
+  TAE_CHECK_LAUNCH();
+  return TAE_OK;
+}
+
+extern "C" int tae_colsum_f32(const float* x, int32_t R, int32_t N, float* out, int32_t accumulate, void* stream_) {
+  using namespace tae;
+  using namespace tae::ew;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  TAE_CHECK_SHAPE(R > 0 && N > 0 && x != nullptr && out != nullptr, "tae_colsum_f32: bad arguments");
+  colsum_f32_kernel<<<(N + 31) / 32, 512, 0, stream>>>(x, R, N, out, accumulate);
   TAE_CHECK_LAUNCH();
   return TAE_OK;
 }

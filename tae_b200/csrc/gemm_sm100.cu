@@ -57,6 +57,7 @@ struct Params {
   const bf16* aux;
   int ldaux;
   int beta;
+  float* colsum_part;  // optional [ceil(M/32), N] fp32: per-32-row column sums of the bf16 output (bias gradients)
 };
 
 // K-major tile [rows x 64] (128 B per row, 8-row swizzle atoms of 1024 B): SBO = 1024 between 8-row groups;
@@ -114,7 +115,8 @@ __device__ __forceinline__ void epi_stage_rows(uint32_t stg, uint32_t taddr, int
 // the step is issued before the first use (8 rows in flight per lane); the bias of the lane's 4 fixed columns is
 // loaded and rounded once per step; the math of the 8 rows is independent, so the scheduler has 32 chains to overlap.
 template <int EPI, int IT0 = 0, int NIT = 8>
-__device__ __forceinline__ void epi_write_coalesced(const Params& p, uint32_t stg, int row_base, int col0, int lane) {
+__device__ __forceinline__ void epi_write_coalesced(const Params& p, uint32_t stg, int row_base, int col0, int lane,
+                                                    float4& csum) {
   const int c = lane & 7, rsub = lane >> 3;
   const int col = col0 + c * 4;
   const bool col_ok = col < p.N;
@@ -181,6 +183,12 @@ __device__ __forceinline__ void epi_write_coalesced(const Params& p, uint32_t st
       const uint32_t o01 = pack_bf16x2(round_bf16(a0) * m01.x, round_bf16(a1) * m01.y);
       const uint32_t o23 = pack_bf16x2(round_bf16(a2) * m23.x, round_bf16(a3) * m23.y);
       *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out) + (size_t)grow * p.ldo + col) = make_uint2(o01, o23);
+      // column sums of the ROUNDED output (the bias gradient the reference derives from its bf16 dh)
+      const float2 r01 = unpack_bf16x2(o01), r23 = unpack_bf16x2(o23);
+      csum.x += r01.x;
+      csum.y += r01.y;
+      csum.z += r23.x;
+      csum.w += r23.y;
     } else if (EPI == TAE_EPI_F32_RESID) {
       float4 o;
       o.x = __uint_as_float(side[it].x) + round_bf16(a0 + bias4.x);
@@ -198,6 +206,22 @@ __device__ __forceinline__ void epi_write_coalesced(const Params& p, uint32_t st
       }
     }
   }
+}
+
+// Column-sum by-product: lanes {c, c+8, c+16, c+24} hold the partial sums of the same 4 columns over the 32 rows of
+// the step; fold them with two shuffles and let lanes 0-7 write one 128-byte row of the partial-sum matrix.
+__device__ __forceinline__ void epi_flush_colsum(const Params& p, float4 csum, int row_base, int col0, int lane) {
+  csum.x += __shfl_xor_sync(0xffffffffu, csum.x, 8);
+  csum.y += __shfl_xor_sync(0xffffffffu, csum.y, 8);
+  csum.z += __shfl_xor_sync(0xffffffffu, csum.z, 8);
+  csum.w += __shfl_xor_sync(0xffffffffu, csum.w, 8);
+  csum.x += __shfl_xor_sync(0xffffffffu, csum.x, 16);
+  csum.y += __shfl_xor_sync(0xffffffffu, csum.y, 16);
+  csum.z += __shfl_xor_sync(0xffffffffu, csum.z, 16);
+  csum.w += __shfl_xor_sync(0xffffffffu, csum.w, 16);
+  const int col = col0 + (lane & 7) * 4;
+  if (lane < 8 && col < p.N && row_base < p.M)
+    *reinterpret_cast<float4*>(p.colsum_part + (size_t)(row_base >> 5) * p.N + col) = csum;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -349,7 +373,9 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + half * 128 + c * COLS);
         epi_stage_rows(stg, taddr, lane);
         __syncwarp();
-        epi_write_coalesced<EPI>(p, stg, row_base, col0, lane);
+        float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
+        epi_write_coalesced<EPI>(p, stg, row_base, col0, lane, csum);
+        if (EPI == TAE_EPI_BF16_DGELU && p.colsum_part != nullptr) epi_flush_colsum(p, csum, row_base, col0, lane);
         __syncwarp();
       }
       tcgen05_fence_before();
@@ -527,12 +553,14 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
             tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + cg * COLS_PER_WARP + c * EPI_COLS);
         epi_stage_rows(stg, taddr, lane);
         __syncwarp();
+        float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
         if (EW == 8) {
-          epi_write_coalesced<EPI, 0, 8>(p, stg, row_base, col0, lane);
+          epi_write_coalesced<EPI, 0, 8>(p, stg, row_base, col0, lane, csum);
         } else {  // two passes of 16 rows keep the live register set under the 640-thread budget
-          epi_write_coalesced<EPI, 0, 4>(p, stg, row_base, col0, lane);
-          epi_write_coalesced<EPI, 4, 4>(p, stg, row_base, col0, lane);
+          epi_write_coalesced<EPI, 0, 4>(p, stg, row_base, col0, lane, csum);
+          epi_write_coalesced<EPI, 4, 4>(p, stg, row_base, col0, lane, csum);
         }
+        if (EPI == TAE_EPI_BF16_DGELU && p.colsum_part != nullptr) epi_flush_colsum(p, csum, row_base, col0, lane);
         __syncwarp();
       }
       tcgen05_fence_before();
@@ -632,6 +660,9 @@ extern "C" int tae_gemm(const tae_gemm_args* a, void* stream_) {
   if (a->epilogue == TAE_EPI_BF16_DGELU)
     TAE_CHECK_SHAPE(a->aux != nullptr && a->ldaux % 8 == 0 && (reinterpret_cast<uintptr_t>(a->aux) & 15) == 0,
                     "tae_gemm: DGELU epilogue needs aux/ldaux");
+  if (a->colsum_partials)
+    TAE_CHECK_SHAPE(a->epilogue == TAE_EPI_BF16_DGELU && (reinterpret_cast<uintptr_t>(a->colsum_partials) & 15) == 0,
+                    "tae_gemm: colsum_partials is only produced by the TAE_EPI_BF16_DGELU epilogue (16-byte aligned)");
   if (a->bias) TAE_CHECK_SHAPE((reinterpret_cast<uintptr_t>(a->bias) & 15) == 0, "tae_gemm: bias must be 16-byte aligned");
 
   Params p{};
@@ -685,6 +716,7 @@ extern "C" int tae_gemm(const tae_gemm_args* a, void* stream_) {
   p.aux = reinterpret_cast<const bf16*>(a->aux);
   p.ldaux = a->ldaux;
   p.beta = a->beta;
+  p.colsum_part = a->colsum_partials;
 
   if (a->epilogue == TAE_EPI_F32_ACC && p.splits > 1 && !a->beta) {
     // split-K partial sums are accumulated with red.global.add: start from zero

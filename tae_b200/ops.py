@@ -42,7 +42,7 @@ def _req(t: torch.Tensor, dtype, name: str) -> None:
 def gemm(A: torch.Tensor, B: torch.Tensor, *, a_mn: bool = False, b_mn: bool = False, epilogue: int = EPI_BF16,
          out: torch.Tensor | None = None, out2: torch.Tensor | None = None, bias: torch.Tensor | None = None,
          resid: torch.Tensor | None = None, resid_rows: int = 0, aux: torch.Tensor | None = None, beta: int = 0,
-         splits: int = 0):
+         splits: int = 0, colsum_partials: torch.Tensor | None = None):
     """D[M,N] = sum_k A(m,k) B(n,k) on the tcgen05 tensor cores; see include/tae_b200.h for the conventions.
 
     A: [M,K] (or [K,M] if a_mn); B: [N,K] (or [K,N] if b_mn); 2-D bf16, inner stride 1.
@@ -93,6 +93,10 @@ def gemm(A: torch.Tensor, B: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
         a.aux, a.ldaux = aux.data_ptr(), aux.stride(0)
     a.beta = int(beta)
     a.splits = int(splits)
+    if colsum_partials is not None:
+        _req(colsum_partials, f32, "gemm colsum_partials")
+        assert colsum_partials.is_contiguous() and colsum_partials.shape == ((M + 31) // 32, N)
+        a.colsum_partials = colsum_partials.data_ptr()
     check(_L().tae_gemm(C.byref(a), _stream()), "tae_gemm")
     if epilogue == EPI_BF16_GELU:
         return out, out2
@@ -246,6 +250,18 @@ def colsum(x: torch.Tensor, out: torch.Tensor | None = None, accumulate: bool = 
         accumulate = False
     check(L.tae_colsum_bf16(x.data_ptr(), M, N, x.stride(0), out.data_ptr(), int(accumulate), ws.data_ptr(), _stream()),
           "tae_colsum_bf16")
+    return out
+
+
+def colsum_f32(x: torch.Tensor, out: torch.Tensor | None = None, accumulate: bool = False) -> torch.Tensor:
+    """sum over rows of a small fp32 [R,N] matrix (the per-32-row partial sums a GEMM epilogue emitted) -> fp32 [N]."""
+    _req(x, f32, "colsum_f32 x")
+    assert x.dim() == 2 and x.is_contiguous()
+    R, N = x.shape
+    if out is None:
+        out = torch.empty((N,), dtype=f32, device=x.device)
+        accumulate = False
+    check(_L().tae_colsum_f32(x.data_ptr(), R, N, out.data_ptr(), int(accumulate), _stream()), "tae_colsum_f32")
     return out
 
 

@@ -203,8 +203,14 @@ class _BlockFn(torch.autograd.Function):
         # ---- MLP branch: y = fc2(gelu(fc1(norm2(xm)))) ----
         g_f2b = _bgrad(mlp.fc2.bias, precomputed=csum) if (mlp.fc2.bias is not None and need[12]) else None
         g_f2w = _wgrad(mlp.fc2.weight, dy_b, a) if need[11] else None
-        dh = ops.gemm(dy_b, shadow_bf16(mlp.fc2.weight), b_mn=True, epilogue=EPI_BF16_DGELU, aux=gp)
-        g_f1b = _bgrad(mlp.fc1.bias, dy_b=dh) if (mlp.fc1.bias is not None and need[10]) else None
+        want_b1 = mlp.fc1.bias is not None and need[10]
+        # the dgrad epilogue also emits per-32-row column sums of dh: the fc1 bias gradient without re-reading dh
+        part = torch.empty(((B * N + 31) // 32, gp.shape[1]), dtype=torch.float32, device=gp.device) if want_b1 else None
+        dh = ops.gemm(dy_b, shadow_bf16(mlp.fc2.weight), b_mn=True, epilogue=EPI_BF16_DGELU, aux=gp, colsum_partials=part)
+        g_f1b = None
+        if want_b1:
+            t, acc = _sink(mlp.fc1.bias)
+            g_f1b = _done(mlp.fc1.bias, ops.colsum_f32(part, out=t, accumulate=bool(acc)))
         g_f1w = _wgrad(mlp.fc1.weight, dh, ln2) if need[9] else None
         dln2 = ops.gemm(dh, shadow_bf16(mlp.fc1.weight), b_mn=True, epilogue=EPI_BF16)
         del dh

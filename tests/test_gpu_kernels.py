@@ -124,11 +124,21 @@ def test_gemm_dgelu_epilogue():
     M, N, K = 384, 512, 128  # da[M,N] = dy[M,K] W[K,N];  dh = bf16(da) * gp,  gp = gelu'(h) saved by the forward
     dy, W = randn(M, K, seed=14), randn(K, N, seed=15, scale=0.1)
     gp = randn(M, N, seed=16, scale=0.5)
-    out = ops.gemm(dy, W, b_mn=True, epilogue=EPI_BF16_DGELU, aux=gp)
+    part = torch.empty((M + 31) // 32, N, device="cuda")
+    out = ops.gemm(dy, W, b_mn=True, epilogue=EPI_BF16_DGELU, aux=gp, colsum_partials=part)
     da = (dy.float() @ W.float()).to(torch.bfloat16).float()
     ref = da * gp.float()
     assert max_err_scaled(out.float(), ref) < 1e-2
     assert rel_err(out.float(), ref) < 5e-3
+    # the epilogue's column-sum by-product == sums of the bf16 output it wrote (32-row groups), and its reduction
+    want = out.float().reshape(M // 32, 32, N).sum(1)
+    assert rel_err(part, want) < 1e-5
+    assert rel_err(ops.colsum_f32(part), out.float().sum(0)) < 1e-5
+    # ragged M: rows beyond M contribute nothing
+    M2 = 200
+    part2 = torch.full(((M2 + 31) // 32, N), 7.0, device="cuda")
+    out2 = ops.gemm(dy[:M2].contiguous(), W, b_mn=True, epilogue=EPI_BF16_DGELU, aux=gp[:M2].contiguous(), colsum_partials=part2)
+    assert rel_err(ops.colsum_f32(part2), out2.float().sum(0)) < 1e-5
 
 
 def test_gemm_rejects_bad_shapes():
