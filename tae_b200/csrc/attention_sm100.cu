@@ -19,9 +19,12 @@
 //   dQ += dS K                                               (A = the SAME dS^T tile read MN-major, B = K MN-major)
 // in 128x128 (key tile x query tile) blocks; TMEM holds S^T, dP^T (128 cols each) and the dV, dK, dQ0, dQ1
 // accumulators (64 cols each) = 512 columns.  No atomics, deterministic.
+#include <stdlib.h>
+
 #include "sm100.cuh"
 
 namespace tae {
+extern long long* g_attn_trace;
 namespace attn_tc {
 
 using namespace tae::sm100;
@@ -97,17 +100,17 @@ attn_fwd_tc(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CU
       mbar_wait(bar_load, 0);
       tcgen05_fence_after();
       const uint32_t idesc1 = make_idesc_bf16(128, 256, 0, 0);
+      const uint32_t q_lo = desc_lo(sQ), k_lo = desc_lo(sK);
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        umma_f16(tmem, make_smem_desc(sQ + k * 32, 0, 1024), make_smem_desc(sK + k * 32, 0, 1024), idesc1, k > 0);
+      for (int k = 0; k < 4; ++k) umma_f16_lo(tmem, q_lo + k * 2, k_lo + k * 2, idesc1, k > 0);
       umma_commit(bar_s);
       mbar_wait(bar_p, 0);
       tcgen05_fence_after();
       const uint32_t idesc2 = make_idesc_bf16(128, 64, 0, 1);
+      const uint32_t p_lo = desc_lo(sP), v_lo = desc_lo(sV, 8192);
 #pragma unroll
       for (int j = 0; j < 16; ++j)  // 16 keys per instruction
-        umma_f16(tmem, make_smem_desc(sP + (j >> 2) * 16384 + (j & 3) * 32, 0, 1024),
-                 make_smem_desc(sV + j * 2048, 8192, 1024), idesc2, j > 0);
+        umma_f16_lo(tmem, p_lo + (j >> 2) * (16384 >> 4) + (j & 3) * 2, v_lo + j * (2048 >> 4), idesc2, j > 0);
       umma_commit(bar_o);
     }
   } else {
@@ -417,6 +420,266 @@ attn_bwd_tc(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ 
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
+// =============================================================================================
+// Backward, software-pipelined variant (default).  Same math as attn_bwd_tc, but in [128 keys x 64 queries] blocks with
+// DOUBLE-BUFFERED S^T/dP^T accumulators (TMEM) and P^T/dS^T operand tiles (smem), so that while the element-wise warps
+// work on block b the tensor cores run the gradient MMAs of block b-1 and the score MMAs of block b+1.
+// dQ for a 64-query block is an M=64 UMMA (A = the dS^T tile read MN-major); its accumulator occupies 16 lanes of each
+// TMEM lane quarter, and two query blocks are interleaved in the same 64 columns (lane offsets 0 and 16).
+//   TMEM columns: S^T[2] 0/64, dP^T[2] 128/192, dV 256, dK 320, dQ 384..511 (4 query blocks)
+// =============================================================================================
+constexpr int P_OFF_Q = 0, P_OFF_K = 32768, P_OFF_V = 65536, P_OFF_DO = 98304;
+constexpr int P_OFF_PT = 131072;     // 2 x [128 x 64] bf16 (16 KB each)
+constexpr int P_OFF_DST = 163840;    // 2 x [128 x 64] bf16
+constexpr int P_OFF_LSE = 196608, P_OFF_DELTA = 197632, P_OFF_BAR = 198656;
+constexpr int P_SMEM = P_OFF_BAR + 128 + 1024;
+constexpr int PC_S = 0, PC_DP = 128, PC_DV = 256, PC_DK = 320, PC_DQ = 384;
+
+__device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
+  float4 r;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr));
+  return r;
+}
+
+__global__ void __launch_bounds__(B_THREADS, 1)
+attn_bwd_tc_pipe(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
+                 const bf16* __restrict__ out, const bf16* __restrict__ dout, const float* __restrict__ lse,
+                 bf16* __restrict__ dqkv, int H, float scale, float sl2, long long* trace) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P_OFF_BAR);
+  // debug timeline (tools/attn_trace.py): CTA `gridDim.x/2` stamps clock64() at pipeline milestones
+  const bool tr = trace != nullptr && blockIdx.x == gridDim.x / 2;
+#define TRACE_C(i) do { if (tr) trace[(i)] = clock64(); } while (0)
+#define TRACE_E(i) do { if (tr && threadIdx.x == 128) trace[32 + (i)] = clock64(); } while (0)
+  if (tr && threadIdx.x == 0) trace[63] = clock64();
+  uint64_t* bar_load = bars;
+  uint64_t* bar_s = bars + 1;       // [2] S^T/dP^T buffer filled by the tensor cores
+  uint64_t* bar_p = bars + 3;       // [2] P^T/dS^T tile written (and S/dP buffer drained): 256 arrivals
+  uint64_t* bar_pfree = bars + 5;   // [2] gradient MMAs that read the P^T/dS^T tile have retired
+  uint64_t* bar_g = bars + 7;       // dV/dK (and at the end dQ) accumulators complete
+  uint64_t* bar_dfree = bars + 8;   // dV/dK of key tile 0 drained: 256 arrivals
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  float* sLse = reinterpret_cast<float*>(smem + P_OFF_LSE);
+  float* sDelta = reinterpret_cast<float*>(smem + P_OFF_DELTA);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x / H, h = blockIdx.x - b * H;
+  const int D = H * HD;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_qkv);
+    tma_prefetch_desc(&tm_do);
+    mbar_init(bar_load, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar_s[i], 1);
+      mbar_init(&bar_p[i], 256);
+      mbar_init(&bar_pfree[i], 1);
+    }
+    mbar_init(bar_g, 1);
+    mbar_init(bar_dfree, 256);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t sQ = smem_u32(smem + P_OFF_Q), sK = smem_u32(smem + P_OFF_K), sV = smem_u32(smem + P_OFF_V);
+  const uint32_t sdO = smem_u32(smem + P_OFF_DO), sPT = smem_u32(smem + P_OFF_PT), sdST = smem_u32(smem + P_OFF_DST);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(bar_load, 4 * 32768);
+      tma_load_2d(smem + P_OFF_Q, &tm_qkv, bar_load, h * HD, b * N);
+      tma_load_2d(smem + P_OFF_K, &tm_qkv, bar_load, D + h * HD, b * N);
+      tma_load_2d(smem + P_OFF_V, &tm_qkv, bar_load, 2 * D + h * HD, b * N);
+      tma_load_2d(smem + P_OFF_DO, &tm_do, bar_load, h * HD, b * N);
+      mbar_wait(bar_load, 0);
+      tcgen05_fence_after();
+      TRACE_C(0);
+      const uint32_t id_s = make_idesc_bf16(128, 64, 0, 0);    // S^T, dP^T: [128 keys x 64 q]
+      const uint32_t id_kn = make_idesc_bf16(128, 64, 0, 1);   // dV, dK
+      const uint32_t id_q = make_idesc_bf16(64, 64, 1, 1);     // dQ: M = 64 queries
+      // descriptor `lo` words (start address >> 4 [| LBO]); byte offsets below are added as (bytes >> 4)
+      const uint32_t q_lo = desc_lo(sQ), k_lo = desc_lo(sK), v_lo = desc_lo(sV), do_lo = desc_lo(sdO);
+      const uint32_t pt_lo = desc_lo(sPT), dst_lo = desc_lo(sdST);
+      const uint32_t qmn_lo = desc_lo(sQ, 8192), kmn_lo = desc_lo(sK, 8192), domn_lo = desc_lo(sdO, 8192);
+      const uint32_t dstmn_lo = desc_lo(sdST, 8192);
+      auto issue_scores = [&](int blk) {
+        const int kt = blk >> 2, j = blk & 3, buf = blk & 1;
+        const uint32_t ka = k_lo + kt * (16384 >> 4), va = v_lo + kt * (16384 >> 4);
+        const uint32_t qb = q_lo + j * (8192 >> 4), ob = do_lo + j * (8192 >> 4);
+        const uint32_t ds = tmem + PC_S + buf * 64, dp = tmem + PC_DP + buf * 64;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16_lo(ds, ka + k * 2, qb + k * 2, id_s, k > 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16_lo(dp, va + k * 2, ob + k * 2, id_s, k > 0);
+        umma_commit(&bar_s[buf]);
+      };
+      issue_scores(0);
+      issue_scores(1);
+#pragma unroll 1
+      for (int blk = 0; blk < 8; ++blk) {
+        const int kt = blk >> 2, j = blk & 3, buf = blk & 1;
+        mbar_wait(&bar_p[buf], (blk >> 1) & 1);
+        tcgen05_fence_after();
+        TRACE_C(1 + 2 * blk);
+        if (blk == 4) {  // dV/dK of key tile 0 must be drained before they are overwritten
+          mbar_wait(bar_dfree, 0);
+          tcgen05_fence_after();
+        }
+        const uint32_t a_pt = pt_lo + buf * (16384 >> 4), a_dst = dst_lo + buf * (16384 >> 4);
+        const uint32_t b_do = domn_lo + j * (8192 >> 4), b_q = qmn_lo + j * (8192 >> 4);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {  // 16 queries per instruction
+          umma_f16_lo(tmem + PC_DV, a_pt + k * 2, b_do + k * (2048 >> 4), id_kn, (j > 0 || k > 0));
+          umma_f16_lo(tmem + PC_DK, a_dst + k * 2, b_q + k * (2048 >> 4), id_kn, (j > 0 || k > 0));
+        }
+        const uint32_t dq_addr = tmem + PC_DQ + (j >> 1) * 64 + ((uint32_t)((j & 1) * 16) << 16);
+        const uint32_t a_ds = dstmn_lo + buf * (16384 >> 4), b_k = kmn_lo + kt * (16384 >> 4);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)  // 16 keys per instruction; A = dS^T tile read MN-major (64 queries contiguous)
+          umma_f16_lo(dq_addr, a_ds + k * (2048 >> 4), b_k + k * (2048 >> 4), id_q, (kt > 0 || k > 0));
+        umma_commit(&bar_pfree[buf]);
+        if (j == 3) umma_commit(bar_g);
+        if (blk + 2 < 8) issue_scores(blk + 2);
+        TRACE_C(2 + 2 * blk);
+      }
+    }
+  } else if (warp >= 4) {
+    const int te = threadIdx.x - 128;
+    const int q4 = warp & 3;
+    const int half = (warp - 4) >> 2;   // which 32 query columns of the 64-wide block
+    const int r = q4 * 32 + lane;       // key row inside the key tile == TMEM lane
+    const uint32_t tlane = tmem + ((uint32_t)(q4 * 32) << 16);
+    {
+      const bf16* go = out + (size_t)b * N * D + (size_t)h * HD;
+      const bf16* gdo = dout + (size_t)b * N * D + (size_t)h * HD;
+#pragma unroll
+      for (int pass = 0; pass < 8; ++pass) {
+        const int row = pass * 32 + (te >> 3), ch = te & 7;
+        const uint4 dv = ld_nc_v4(gdo + (size_t)row * D + ch * 8);
+        const uint4 ov = ld_nc_v4(go + (size_t)row * D + ch * 8);
+        const uint32_t dw[4] = {dv.x, dv.y, dv.z, dv.w}, ow[4] = {ov.x, ov.y, ov.z, ov.w};
+        float acc = 0.f;
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const float2 d2 = unpack_bf16x2(dw[jj]), o2 = unpack_bf16x2(ow[jj]);
+          acc += d2.x * o2.x + d2.y * o2.y;
+        }
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+        if (ch == 0) sDelta[row] = acc;
+      }
+      sLse[te] = lse[((size_t)b * H + h) * N + te] * 1.44269504088896340736f;
+      named_bar_sync(1, 256);
+    }
+    TRACE_E(0);
+    bf16* gd = dqkv + (size_t)b * N * 3 * D + (size_t)h * HD;
+    const size_t ldq = (size_t)3 * D;
+    const uint32_t sLseA = smem_u32(sLse), sDeltaA = smem_u32(sDelta);
+
+#pragma unroll 1
+    for (int blk = 0; blk < 8; ++blk) {
+      const int kt = blk >> 2, j = blk & 3, buf = blk & 1;
+      mbar_wait(&bar_s[buf], (blk >> 1) & 1);
+      tcgen05_fence_after();
+      TRACE_E(1 + 3 * blk);
+      uint32_t sraw[32], draw[32];
+      tmem_ld_32x32b_x32(tlane + PC_S + buf * 64 + half * 32, sraw);
+      tmem_ld_32x32b_x32(tlane + PC_DP + buf * 64 + half * 32, draw);
+      tmem_ld_wait();
+      const int qcol = j * 64 + half * 32;
+      uint32_t pk[16], dk[16];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 lv = ld_shared_f4(sLseA + (qcol + 4 * i) * 4), dl = ld_shared_f4(sDeltaA + (qcol + 4 * i) * 4);
+        const float p0 = ex2_approx(fmaf(__uint_as_float(sraw[4 * i + 0]), sl2, -lv.x));
+        const float p1 = ex2_approx(fmaf(__uint_as_float(sraw[4 * i + 1]), sl2, -lv.y));
+        const float p2 = ex2_approx(fmaf(__uint_as_float(sraw[4 * i + 2]), sl2, -lv.z));
+        const float p3 = ex2_approx(fmaf(__uint_as_float(sraw[4 * i + 3]), sl2, -lv.w));
+        pk[2 * i] = pack_bf16x2(p0, p1);
+        pk[2 * i + 1] = pack_bf16x2(p2, p3);
+        dk[2 * i] = pack_bf16x2(p0 * (__uint_as_float(draw[4 * i + 0]) - dl.x) * scale,
+                                p1 * (__uint_as_float(draw[4 * i + 1]) - dl.y) * scale);
+        dk[2 * i + 1] = pack_bf16x2(p2 * (__uint_as_float(draw[4 * i + 2]) - dl.z) * scale,
+                                    p3 * (__uint_as_float(draw[4 * i + 3]) - dl.w) * scale);
+      }
+      TRACE_E(2 + 3 * blk);
+      if (blk >= 2) mbar_wait(&bar_pfree[buf], ((blk >> 1) - 1) & 1);  // MMAs of block blk-2 are done with this tile
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t off = (uint32_t)buf * 16384u + sw128(r, half * 4 + i);
+        st_shared_v4(sPT + off, pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+        st_shared_v4(sdST + off, dk[4 * i], dk[4 * i + 1], dk[4 * i + 2], dk[4 * i + 3]);
+      }
+      fence_proxy_async_smem();
+      tcgen05_fence_before();
+      mbar_arrive(&bar_p[buf]);
+      TRACE_E(3 + 3 * blk);
+      if (j == 3) {
+        mbar_wait(bar_g, kt & 1);
+        tcgen05_fence_after();
+        const uint32_t tcol = half == 0 ? PC_DV : PC_DK;
+        bf16* dst = gd + (size_t)(kt * 128 + r) * ldq + (half == 0 ? 2 * D : D);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t raw[32];
+          tmem_ld_32x32b_x32(tlane + tcol + c * 32, raw);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 o;
+            o.x = pack_bf16x2(__uint_as_float(raw[i * 8 + 0]), __uint_as_float(raw[i * 8 + 1]));
+            o.y = pack_bf16x2(__uint_as_float(raw[i * 8 + 2]), __uint_as_float(raw[i * 8 + 3]));
+            o.z = pack_bf16x2(__uint_as_float(raw[i * 8 + 4]), __uint_as_float(raw[i * 8 + 5]));
+            o.w = pack_bf16x2(__uint_as_float(raw[i * 8 + 6]), __uint_as_float(raw[i * 8 + 7]));
+            *reinterpret_cast<uint4*>(dst + c * 32 + i * 8) = o;
+          }
+        }
+        if (kt == 0) {
+          tcgen05_fence_before();
+          mbar_arrive(bar_dfree);
+        }
+      }
+    }
+    // dQ: M=64 accumulators.  Query block jq lives in columns PC_DQ + (jq>>1)*64 on lanes 16*(jq&1) + {0..15} of every
+    // lane quarter; thread (quarter q4, lane l) therefore owns query  (2*half + (l>>4))*64 + 16*q4 + (l&15).
+    {
+      const int qrow = (2 * half + (lane >> 4)) * 64 + 16 * q4 + (lane & 15);
+      bf16* dst = gd + (size_t)qrow * ldq;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t raw[32];
+        tmem_ld_32x32b_x32(tlane + PC_DQ + half * 64 + c * 32, raw);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 o;
+          o.x = pack_bf16x2(__uint_as_float(raw[i * 8 + 0]), __uint_as_float(raw[i * 8 + 1]));
+          o.y = pack_bf16x2(__uint_as_float(raw[i * 8 + 2]), __uint_as_float(raw[i * 8 + 3]));
+          o.z = pack_bf16x2(__uint_as_float(raw[i * 8 + 4]), __uint_as_float(raw[i * 8 + 5]));
+          o.w = pack_bf16x2(__uint_as_float(raw[i * 8 + 6]), __uint_as_float(raw[i * 8 + 7]));
+          *reinterpret_cast<uint4*>(dst + c * 32 + i * 8) = o;
+        }
+      }
+    }
+    TRACE_E(28);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+  if (tr && threadIdx.x == 0) trace[62] = clock64();
+#undef TRACE_C
+#undef TRACE_E
+}
+
+}  // namespace attn_tc
+long long* g_attn_trace = nullptr;  // debug: device buffer of 64 int64 set through tae_debug_set_attn_trace
+namespace attn_tc {
+
 template <typename K>
 static int set_smem_once(K kernel, int bytes, cudaError_t* cached, std::once_flag* once) {
   std::call_once(*once, [&]() { *cached = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); });
@@ -464,10 +727,28 @@ int attention_bwd_tcgen05(const bf16* qkv, const bf16* out, const bf16* dout, co
   rc = sm100::make_tmap(&tdo, dout, (uint64_t)D, (uint64_t)B * N, (uint64_t)D, 256);
   if (rc) return rc;
   const float scale = 1.0f / sqrtf((float)HD);
-  attn_bwd_tc<<<B * H, B_THREADS, B_SMEM, stream>>>(tqkv, tdo, out, dout, lse, dqkv, H, scale,
-                                                    scale * 1.44269504088896340736f);
+  // TAE_ATTN_BWD_V1=1 selects the unpipelined kernel (A/B testing)
+  static int v1 = -1;
+  if (v1 < 0) {
+    const char* e = getenv("TAE_ATTN_BWD_V1");
+    v1 = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  if (v1) {
+    attn_bwd_tc<<<B * H, B_THREADS, B_SMEM, stream>>>(tqkv, tdo, out, dout, lse, dqkv, H, scale,
+                                                      scale * 1.44269504088896340736f);
+  } else {
+    static cudaError_t err2 = cudaSuccess;
+    static std::once_flag once2;
+    rc = set_smem_once(attn_bwd_tc_pipe, P_SMEM, &err2, &once2);
+    if (rc) return rc;
+    attn_bwd_tc_pipe<<<B * H, B_THREADS, P_SMEM, stream>>>(tqkv, tdo, out, dout, lse, dqkv, H, scale,
+                                                           scale * 1.44269504088896340736f, g_attn_trace);
+  }
   TAE_CHECK_LAUNCH();
   return TAE_OK;
 }
 
 }  // namespace tae
+
+// debug hook (not part of the public ABI): device buffer of 64 int64 receiving a clock64() timeline of one CTA
+extern "C" void tae_debug_set_attn_trace(void* buf) { tae::g_attn_trace = reinterpret_cast<long long*>(buf); }

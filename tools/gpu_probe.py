@@ -41,6 +41,7 @@ def timeit(fn, iters=10, warmup=3):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--attn-only", action="store_true")
     args = ap.parse_args()
     hbm, tf, how = peaks()
     dev = "cuda"
@@ -55,7 +56,7 @@ def main():
     D = 1024
     x = rnd(M, D)
     shapes = [("qkv  fwd", D, 3 * D), ("proj fwd", D, D), ("fc1  fwd", D, 4 * D), ("fc2  fwd", 4 * D, D)]
-    for name, K, N in shapes:
+    for name, K, N in ([] if args.attn_only else shapes):
         A, W = rnd(M, K), rnd(N, K)
         bias = torch.randn(N, device=dev)
         fl = 2.0 * M * N * K
@@ -97,6 +98,8 @@ def main():
     med, _ = timeit(lambda: ops.attention_bwd(qkv, out, dout, lse, B, 256, 16, 64))
     print(f"attention bwd: {med:.3f} ms  {2.5 * fl / med / 1e9:.0f} TFLOP/s (algorithmic 2.5x fwd)")
 
+    if args.attn_only:
+        return
     # ---- LayerNorm ----
     xf = torch.randn(M, D, device=dev)
     w, b = torch.ones(D, device=dev), torch.zeros(D, device=dev)
