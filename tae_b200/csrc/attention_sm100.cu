@@ -92,7 +92,7 @@ attn_fwd_tc(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CU
   const uint32_t sP = smem_u32(smem + F_OFF_P);
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_expect_tx(bar_load, 16384 + 32768 + 32768);
       tma_load_2d(smem + F_OFF_Q, &tm_q, bar_load, h * HD, b * N + qt * 128);
       tma_load_2d(smem + F_OFF_K, &tm_kv, bar_load, D + h * HD, b * N);
@@ -247,7 +247,7 @@ attn_bwd_tc(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ 
   const uint32_t sdO = smem_u32(smem + B_OFF_DO), sPT = smem_u32(smem + B_OFF_PT), sdST = smem_u32(smem + B_OFF_DST);
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_expect_tx(bar_load, 4 * 32768);
       tma_load_2d(smem + B_OFF_Q, &tm_qkv, bar_load, h * HD, b * N);
       tma_load_2d(smem + B_OFF_K, &tm_qkv, bar_load, D + h * HD, b * N);
@@ -488,7 +488,7 @@ attn_bwd_tc_pipe(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
   const uint32_t sdO = smem_u32(smem + P_OFF_DO), sPT = smem_u32(smem + P_OFF_PT), sdST = smem_u32(smem + P_OFF_DST);
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_expect_tx(bar_load, 4 * 32768);
       tma_load_2d(smem + P_OFF_Q, &tm_qkv, bar_load, h * HD, b * N);
       tma_load_2d(smem + P_OFF_K, &tm_qkv, bar_load, D + h * HD, b * N);

@@ -282,7 +282,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
@@ -317,7 +317,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (single thread) =====================
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc = make_idesc(p.a_mn, p.b_mn);
       int stage = 0;
       uint32_t phase = 0;
@@ -461,7 +461,7 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int w = cluster_id; w < total_work; w += num_clusters) {
@@ -497,7 +497,7 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread of the leader CTA) =====================
-    if (lane == 0 && rank == 0) {
+    if (rank == 0 && elect_one()) {
       const uint32_t idesc = make_idesc_bf16(2 * BLOCK_M, BLOCK_N, p.a_mn, p.b_mn);
       int stage = 0;
       uint32_t phase = 0;

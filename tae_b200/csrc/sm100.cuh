@@ -208,6 +208,21 @@ __device__ __forceinline__ void umma_f16_lo(uint32_t d_tmem, uint32_t a_lo, uint
       : "memory");
 }
 
+// One lane of a CONVERGED warp (elect.sync).  ptxas treats an elect-guarded region as single-threaded, so warp-uniform
+// operands of tcgen05.mma / TMA instructions stay in uniform registers; under a plain `lane == 0` guard every such
+// instruction is wrapped in an ELECT / R2UR / BRA.U.ANY loop that costs the issuing thread ~80 cycles per MMA.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred P;\n"
+      "elect.sync _|P, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, P;\n"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // named barrier among a subset of the CTA's warps
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
