@@ -443,8 +443,9 @@ __device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
 
 __global__ void __launch_bounds__(B_THREADS, 1)
 attn_bwd_tc_pipe(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
-                 const bf16* __restrict__ out, const bf16* __restrict__ dout, const float* __restrict__ lse,
-                 bf16* __restrict__ dqkv, int H, float scale, float sl2, long long* trace) {
+                 const __grid_constant__ CUtensorMap tm_dqkv, const bf16* __restrict__ out,
+                 const bf16* __restrict__ dout, const float* __restrict__ lse, int H, float scale, float sl2,
+                 long long* trace) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P_OFF_BAR);
@@ -459,7 +460,8 @@ attn_bwd_tc_pipe(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
   uint64_t* bar_pfree = bars + 5;   // [2] gradient MMAs that read the P^T/dS^T tile have retired
   uint64_t* bar_g = bars + 7;       // dV/dK (and at the end dQ) accumulators complete
   uint64_t* bar_dfree = bars + 8;   // dV/dK of key tile 0 drained: 256 arrivals
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  uint64_t* bar_load2 = bars + 9;   // V and dO landed (bar_load: K and Q)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
   float* sLse = reinterpret_cast<float*>(smem + P_OFF_LSE);
   float* sDelta = reinterpret_cast<float*>(smem + P_OFF_DELTA);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -469,7 +471,9 @@ attn_bwd_tc_pipe(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_qkv);
     tma_prefetch_desc(&tm_do);
+    tma_prefetch_desc(&tm_dqkv);
     mbar_init(bar_load, 1);
+    mbar_init(bar_load2, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bar_s[i], 1);
       mbar_init(&bar_p[i], 256);
@@ -489,14 +493,12 @@ attn_bwd_tc_pipe(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
 
   if (warp == 0) {
     if (elect_one()) {
-      mbar_expect_tx(bar_load, 4 * 32768);
-      tma_load_2d(smem + P_OFF_Q, &tm_qkv, bar_load, h * HD, b * N);
+      mbar_expect_tx(bar_load, 2 * 32768);
       tma_load_2d(smem + P_OFF_K, &tm_qkv, bar_load, D + h * HD, b * N);
-      tma_load_2d(smem + P_OFF_V, &tm_qkv, bar_load, 2 * D + h * HD, b * N);
-      tma_load_2d(smem + P_OFF_DO, &tm_do, bar_load, h * HD, b * N);
-      mbar_wait(bar_load, 0);
-      tcgen05_fence_after();
-      TRACE_C(0);
+      tma_load_2d(smem + P_OFF_Q, &tm_qkv, bar_load, h * HD, b * N);
+      mbar_expect_tx(bar_load2, 2 * 32768);
+      tma_load_2d(smem + P_OFF_V, &tm_qkv, bar_load2, 2 * D + h * HD, b * N);
+      tma_load_2d(smem + P_OFF_DO, &tm_do, bar_load2, h * HD, b * N);
       const uint32_t id_s = make_idesc_bf16(128, 64, 0, 0);    // S^T, dP^T: [128 keys x 64 q]
       const uint32_t id_kn = make_idesc_bf16(128, 64, 0, 1);   // dV, dK
       const uint32_t id_q = make_idesc_bf16(64, 64, 1, 1);     // dQ: M = 64 queries
@@ -510,8 +512,17 @@ attn_bwd_tc_pipe(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
         const uint32_t ka = k_lo + kt * (16384 >> 4), va = v_lo + kt * (16384 >> 4);
         const uint32_t qb = q_lo + j * (8192 >> 4), ob = do_lo + j * (8192 >> 4);
         const uint32_t ds = tmem + PC_S + buf * 64, dp = tmem + PC_DP + buf * 64;
+        if (blk == 0) {  // S^T needs K and Q only: start as soon as they have landed
+          mbar_wait(bar_load, 0);
+          tcgen05_fence_after();
+        }
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma_f16_lo(ds, ka + k * 2, qb + k * 2, id_s, k > 0);
+        if (blk == 0) {
+          mbar_wait(bar_load2, 0);
+          tcgen05_fence_after();
+          TRACE_C(0);
+        }
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma_f16_lo(dp, va + k * 2, ob + k * 2, id_s, k > 0);
         umma_commit(&bar_s[buf]);
@@ -576,9 +587,23 @@ attn_bwd_tc_pipe(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
       named_bar_sync(1, 256);
     }
     TRACE_E(0);
-    bf16* gd = dqkv + (size_t)b * N * 3 * D + (size_t)h * HD;
-    const size_t ldq = (size_t)3 * D;
     const uint32_t sLseA = smem_u32(sLse), sDeltaA = smem_u32(sDelta);
+    // TMEM accumulator row (64 fp32 columns at `taddr`) -> bf16 -> row `row` of a 128B-swizzled [rows x 64] staging tile
+    auto stage_row = [&](uint32_t taddr, uint32_t tile, int row) {
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t raw[32];
+        tmem_ld_32x32b_x32(taddr + c * 32, raw);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          st_shared_v4(tile + sw128(row, c * 4 + i),
+                       pack_bf16x2(__uint_as_float(raw[i * 8 + 0]), __uint_as_float(raw[i * 8 + 1])),
+                       pack_bf16x2(__uint_as_float(raw[i * 8 + 2]), __uint_as_float(raw[i * 8 + 3])),
+                       pack_bf16x2(__uint_as_float(raw[i * 8 + 4]), __uint_as_float(raw[i * 8 + 5])),
+                       pack_bf16x2(__uint_as_float(raw[i * 8 + 6]), __uint_as_float(raw[i * 8 + 7])));
+      }
+    };
 
 #pragma unroll 1
     for (int blk = 0; blk < 8; ++blk) {
@@ -619,50 +644,36 @@ attn_bwd_tc_pipe(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
       mbar_arrive(&bar_p[buf]);
       TRACE_E(3 + 3 * blk);
       if (j == 3) {
+        // dV_kt (half 0) / dK_kt (half 1).  Every MMA that reads V_kt / K_kt has retired (bar_g), so the accumulator is
+        // staged as bf16 over the dead operand tile and leaves with one coalesced TMA store per tile.
         mbar_wait(bar_g, kt & 1);
         tcgen05_fence_after();
-        const uint32_t tcol = half == 0 ? PC_DV : PC_DK;
-        bf16* dst = gd + (size_t)(kt * 128 + r) * ldq + (half == 0 ? 2 * D : D);
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t raw[32];
-          tmem_ld_32x32b_x32(tlane + tcol + c * 32, raw);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            uint4 o;
-            o.x = pack_bf16x2(__uint_as_float(raw[i * 8 + 0]), __uint_as_float(raw[i * 8 + 1]));
-            o.y = pack_bf16x2(__uint_as_float(raw[i * 8 + 2]), __uint_as_float(raw[i * 8 + 3]));
-            o.z = pack_bf16x2(__uint_as_float(raw[i * 8 + 4]), __uint_as_float(raw[i * 8 + 5]));
-            o.w = pack_bf16x2(__uint_as_float(raw[i * 8 + 6]), __uint_as_float(raw[i * 8 + 7]));
-            *reinterpret_cast<uint4*>(dst + c * 32 + i * 8) = o;
-          }
-        }
+        const int off = (half == 0 ? P_OFF_V : P_OFF_K) + kt * 16384;
+        stage_row(tlane + (half == 0 ? PC_DV : PC_DK), smem_u32(smem + off), r);
         if (kt == 0) {
           tcgen05_fence_before();
           mbar_arrive(bar_dfree);
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(2 + half, 128);
+        if ((warp & 3) == 0 && elect_one()) {
+          tma_store_2d(&tm_dqkv, smem + off, (half == 0 ? 2 * D : D) + h * HD, b * N + kt * 128);
+          tma_store_commit();
         }
       }
     }
     // dQ: M=64 accumulators.  Query block jq lives in columns PC_DQ + (jq>>1)*64 on lanes 16*(jq&1) + {0..15} of every
     // lane quarter; thread (quarter q4, lane l) therefore owns query  (2*half + (l>>4))*64 + 16*q4 + (l&15).
+    // (the final bar_g wait above covers every MMA, so the Q tile is dead and becomes the staging buffer)
     {
       const int qrow = (2 * half + (lane >> 4)) * 64 + 16 * q4 + (lane & 15);
-      bf16* dst = gd + (size_t)qrow * ldq;
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t raw[32];
-        tmem_ld_32x32b_x32(tlane + PC_DQ + half * 64 + c * 32, raw);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          uint4 o;
-          o.x = pack_bf16x2(__uint_as_float(raw[i * 8 + 0]), __uint_as_float(raw[i * 8 + 1]));
-          o.y = pack_bf16x2(__uint_as_float(raw[i * 8 + 2]), __uint_as_float(raw[i * 8 + 3]));
-          o.z = pack_bf16x2(__uint_as_float(raw[i * 8 + 4]), __uint_as_float(raw[i * 8 + 5]));
-          o.w = pack_bf16x2(__uint_as_float(raw[i * 8 + 6]), __uint_as_float(raw[i * 8 + 7]));
-          *reinterpret_cast<uint4*>(dst + c * 32 + i * 8) = o;
-        }
+      stage_row(tlane + PC_DQ + half * 64, sQ, qrow);
+      fence_proxy_async_smem();
+      named_bar_sync(2 + half, 128);  // this half's 128 threads own query rows [half*128, half*128 + 128)
+      if ((warp & 3) == 0 && elect_one()) {
+        tma_store_2d(&tm_dqkv, smem + P_OFF_Q + half * 16384, h * HD, b * N + half * 128);
+        tma_store_commit();
+        tma_store_wait_all();  // smem must stay valid until the bulk stores of this thread have been read
       }
     }
     TRACE_E(28);
@@ -741,7 +752,10 @@ int attention_bwd_tcgen05(const bf16* qkv, const bf16* out, const bf16* dout, co
     static std::once_flag once2;
     rc = set_smem_once(attn_bwd_tc_pipe, P_SMEM, &err2, &once2);
     if (rc) return rc;
-    attn_bwd_tc_pipe<<<B * H, B_THREADS, P_SMEM, stream>>>(tqkv, tdo, out, dout, lse, dqkv, H, scale,
+    CUtensorMap tdq;
+    rc = sm100::make_tmap(&tdq, dqkv, (uint64_t)3 * D, (uint64_t)B * N, (uint64_t)3 * D, 128);
+    if (rc) return rc;
+    attn_bwd_tc_pipe<<<B * H, B_THREADS, P_SMEM, stream>>>(tqkv, tdo, tdq, out, dout, lse, H, scale,
                                                            scale * 1.44269504088896340736f, g_attn_trace);
   }
   TAE_CHECK_LAUNCH();
