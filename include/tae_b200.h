@@ -193,6 +193,39 @@ int tae_cast_f32_to_bf16(const float* src, tae_bf16* dst, size_t n, void* stream
 /* non-finite check + sum of squares over a fp32 arena: found_inf[0] |= any(!isfinite), sq_sum[0] += sum g^2 */
 int tae_grad_stats(const float* g, size_t n, float* sq_sum, int32_t* found_inf, void* stream);
 
+/* ---- fp32 ("no autocast") mode ------------------------------------------------------------------
+ * The reference without autocast keeps every activation in fp32 (tae.py run as plain nn.Module code).  In this
+ * mode the GEMMs still run on the tcgen05 tensor cores: each fp32 operand is split into three bf16 terms
+ * (x = hi + mid + lo, exact), and the six significant cross products are issued as tae_gemm launches that
+ * accumulate into one fp32 output (TAE_EPI_F32_ACC, beta = 1) -> fp32-level error (dropped terms <= 2^-24).
+ * The entry points below are the fp32 element-wise / LayerNorm / attention / loss pieces around those GEMMs
+ * (same reference call sites as their bf16 counterparts above).
+ */
+int tae_split3_bf16(const float* x, tae_bf16* hi, tae_bf16* mid, tae_bf16* lo, size_t n, void* stream);
+/* y[m,n] += bias[n] + resid[m % resid_rows, n] (either may be NULL); act (optional) = gelu_erf(y)  (tae.py:101-104,129-130) */
+int tae_bias_act_f32(float* y, const float* bias, const float* resid, int32_t resid_rows, float* act,
+                     int32_t M, int32_t N, void* stream);
+/* dh = da * gelu_erf'(h) */
+int tae_gelu_bwd_f32(const float* h, const float* da, float* dh, size_t n, void* stream);
+/* out = a + b (b may be NULL) */
+int tae_add_f32(const float* a, const float* b, float* out, size_t n, void* stream);
+int tae_layernorm_fwd_f32(const float* x, const float* gamma, const float* beta, float* y, float* mean,
+                          float* rstd, int32_t rows, int32_t D, float eps, void* stream);
+/* dres_out = dres_in + LN'(dy); dgamma/dbeta (optional) written or accumulated per bit 0/1 of `accumulate` */
+int tae_layernorm_bwd_f32(const float* dy, const float* x, const float* mean, const float* rstd,
+                          const float* gamma, const float* dres_in, float* dres_out, float* dgamma,
+                          float* dbeta, int32_t accumulate, int32_t rows, int32_t D, void* stream);
+/* same tensor layouts as tae_attention_fwd/bwd with fp32 elements; workspace fp32 [2*B*H*N*N] */
+int tae_attention_fwd_f32(const float* qkv, float* out, float* lse, int32_t B, int32_t N, int32_t H,
+                          int32_t hd, void* stream);
+size_t tae_attention_bwd_f32_workspace_floats(int32_t B, int32_t N, int32_t H);
+int tae_attention_bwd_f32(const float* qkv, const float* out, const float* dout, const float* lse,
+                          float* dqkv, float* workspace, int32_t B, int32_t N, int32_t H, int32_t hd,
+                          void* stream);
+int tae_im2col_f32(const float* imgs, float* cols, int32_t B, int32_t S, int32_t p, void* stream);
+int tae_mse_loss_f32(const float* pred, const float* imgs, float* loss_accum, float* dpred,
+                     const float* grad_scale, int32_t B, int32_t S, int32_t p, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -76,6 +76,18 @@ PROTOTYPES = {
     "tae_adamw_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _sz, _f32, _f32, _f32, _f32, _f32, _i32, _f32, _vp, _vp, _vp]),
     "tae_cast_f32_to_bf16": (C.c_int, [_vp, _vp, _sz, _vp]),
     "tae_grad_stats": (C.c_int, [_vp, _sz, _vp, _vp, _vp]),
+    # fp32 ("no autocast") mode
+    "tae_split3_bf16": (C.c_int, [_vp, _vp, _vp, _vp, _sz, _vp]),
+    "tae_bias_act_f32": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _i32, _i32, _vp]),
+    "tae_gelu_bwd_f32": (C.c_int, [_vp, _vp, _vp, _sz, _vp]),
+    "tae_add_f32": (C.c_int, [_vp, _vp, _vp, _sz, _vp]),
+    "tae_layernorm_fwd_f32": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _f32, _vp]),
+    "tae_layernorm_bwd_f32": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp]),
+    "tae_attention_fwd_f32": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+    "tae_attention_bwd_f32_workspace_floats": (C.c_size_t, [_i32, _i32, _i32]),
+    "tae_attention_bwd_f32": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+    "tae_im2col_f32": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp]),
+    "tae_mse_loss_f32": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp]),
 }
 
 _lib = None

@@ -114,90 +114,93 @@ __device__ __forceinline__ void epi_stage_rows(uint32_t stg, uint32_t taddr, int
 // Coalesced phase: lane -> (row = it*4 + lane/8, 4 fp32 columns = chunk lane%8).  Every shared and global load of
 // the step is issued before the first use (8 rows in flight per lane); the bias of the lane's 4 fixed columns is
 // loaded and rounded once per step; the math of the 8 rows is independent, so the scheduler has 32 chains to overlap.
-template <int EPI, int IT0 = 0, int NIT = 8>
-__device__ __forceinline__ void epi_write_coalesced(const Params& p, uint32_t stg, int row_base, int col0, int lane,
-                                                    float4& csum) {
+template <int EPI, int IT0, int NIT, bool FULL>
+__device__ __forceinline__ void epi_write_rows(const Params& p, uint32_t stg, int row_base, int col0, int lane,
+                                               float4& csum, const float4 bias4) {
   const int c = lane & 7, rsub = lane >> 3;
   const int col = col0 + c * 4;
-  const bool col_ok = col < p.N;
   uint4 val[8];
 #pragma unroll
   for (int it = IT0; it < IT0 + NIT; ++it) val[it] = ld_shared_v4(stg + stg_off(it * 4 + rsub, c));
-  if (!col_ok) return;
+  if (!FULL && col >= p.N) return;
+  const int row0 = row_base + rsub;  // this lane's rows are row0 + 4*it
+  // FULL: the whole 32x32 step is inside the matrix, no per-row bounds checks
+  auto row_ok = [&](int it) { return FULL || (row0 + it * 4 < p.M); };
   constexpr bool kSide16 = (EPI == TAE_EPI_F32_RESID || EPI == TAE_EPI_F32_ACC);
   uint4 side[8];
   if (kSide16) {
     const bool want = (EPI == TAE_EPI_F32_RESID) || (p.beta && p.splits <= 1);
+    const float* sbase = (EPI == TAE_EPI_F32_RESID) ? p.resid : reinterpret_cast<const float*>(p.out);
+    const size_t sld = (EPI == TAE_EPI_F32_RESID) ? (size_t)p.ldr : (size_t)p.ldo;
+    const bool wrap = (EPI == TAE_EPI_F32_RESID) && p.resid_rows < p.M;  // pos-embed broadcast over the batch
 #pragma unroll
     for (int it = IT0; it < IT0 + NIT; ++it) {
-      const int grow = row_base + it * 4 + rsub;
       side[it] = make_uint4(0u, 0u, 0u, 0u);
-      if (want && grow < p.M) {
-        if (EPI == TAE_EPI_F32_RESID)
-          side[it] = *reinterpret_cast<const uint4*>(p.resid + (size_t)(grow % p.resid_rows) * p.ldr + col);
-        else
-          side[it] = *reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.out) + (size_t)grow * p.ldo + col);
+      if (want && row_ok(it)) {
+        const int grow = row0 + it * 4;
+        const int srow = wrap ? grow % p.resid_rows : grow;
+        side[it] = *reinterpret_cast<const uint4*>(sbase + (size_t)srow * sld + col);
       }
     }
   } else if (EPI == TAE_EPI_BF16_DGELU) {
+    const bf16* abase = p.aux + (size_t)row0 * p.ldaux + col;
 #pragma unroll
     for (int it = IT0; it < IT0 + NIT; ++it) {
-      const int grow = row_base + it * 4 + rsub;
       side[it] = make_uint4(0u, 0u, 0u, 0u);
-      if (grow < p.M) {
-        const uint2 h = ld_nc_v2(p.aux + (size_t)grow * p.ldaux + col);
+      if (row_ok(it)) {
+        const uint2 h = ld_nc_v2(abase + (size_t)(it * 4) * p.ldaux);
         side[it].x = h.x;
         side[it].y = h.y;
       }
     }
   }
-  float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (EPI != TAE_EPI_F32_ACC && EPI != TAE_EPI_BF16_DGELU && p.bias != nullptr) {
-    // autocast hands the GEMM a bf16 copy of the fp32 bias: same rounding here
-    const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-    bias4 = make_float4(round_bf16(b.x), round_bf16(b.y), round_bf16(b.z), round_bf16(b.w));
-  }
+  constexpr int kOutBytes = (EPI == TAE_EPI_F32_RESID || EPI == TAE_EPI_F32_ACC) ? 4 : 2;
+  const size_t off0 = ((size_t)row0 * p.ldo + col) * kOutBytes;
+  const size_t rstride = (size_t)p.ldo * 4 * kOutBytes;  // 4 rows
+  char* obase = reinterpret_cast<char*>(p.out) + off0;
+  char* obase2 = reinterpret_cast<char*>(p.out2) + off0;
 #pragma unroll
   for (int it = IT0; it < IT0 + NIT; ++it) {
-    const int grow = row_base + it * 4 + rsub;
-    if (grow >= p.M) continue;
+    if (!row_ok(it)) continue;
     const float a0 = __uint_as_float(val[it].x), a1 = __uint_as_float(val[it].y);
     const float a2 = __uint_as_float(val[it].z), a3 = __uint_as_float(val[it].w);
+    char* optr = obase + it * rstride;
     if (EPI == TAE_EPI_BF16) {
-      *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out) + (size_t)grow * p.ldo + col) =
+      *reinterpret_cast<uint2*>(optr) =
           make_uint2(pack_bf16x2(a0 + bias4.x, a1 + bias4.y), pack_bf16x2(a2 + bias4.z, a3 + bias4.w));
     } else if (EPI == TAE_EPI_BF16_GELU) {
       // h = bf16(acc + bias) is the reference's fc1 output; GELU and its derivative are evaluated on that rounded value
       float g[4], gp[4];
-      gelu_and_grad_fast(round_bf16(a0 + bias4.x), g[0], gp[0]);
-      gelu_and_grad_fast(round_bf16(a1 + bias4.y), g[1], gp[1]);
-      gelu_and_grad_fast(round_bf16(a2 + bias4.z), g[2], gp[2]);
-      gelu_and_grad_fast(round_bf16(a3 + bias4.w), g[3], gp[3]);
-      *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out) + (size_t)grow * p.ldo + col) =
-          make_uint2(pack_bf16x2(gp[0], gp[1]), pack_bf16x2(gp[2], gp[3]));
-      *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out2) + (size_t)grow * p.ldo + col) =
-          make_uint2(pack_bf16x2(g[0], g[1]), pack_bf16x2(g[2], g[3]));
+      const float2 h01 = round_bf16x2(a0 + bias4.x, a1 + bias4.y), h23 = round_bf16x2(a2 + bias4.z, a3 + bias4.w);
+      gelu_and_grad_fast(h01.x, g[0], gp[0]);
+      gelu_and_grad_fast(h01.y, g[1], gp[1]);
+      gelu_and_grad_fast(h23.x, g[2], gp[2]);
+      gelu_and_grad_fast(h23.y, g[3], gp[3]);
+      *reinterpret_cast<uint2*>(optr) = make_uint2(pack_bf16x2(gp[0], gp[1]), pack_bf16x2(gp[2], gp[3]));
+      *reinterpret_cast<uint2*>(obase2 + it * rstride) = make_uint2(pack_bf16x2(g[0], g[1]), pack_bf16x2(g[2], g[3]));
     } else if (EPI == TAE_EPI_BF16_DGELU) {
       const float2 m01 = unpack_bf16x2(side[it].x), m23 = unpack_bf16x2(side[it].y);
       // bf16(acc) first: the dgrad GEMM's own output rounding in the reference; aux holds gelu'(h) from the forward
-      const uint32_t o01 = pack_bf16x2(round_bf16(a0) * m01.x, round_bf16(a1) * m01.y);
-      const uint32_t o23 = pack_bf16x2(round_bf16(a2) * m23.x, round_bf16(a3) * m23.y);
-      *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out) + (size_t)grow * p.ldo + col) = make_uint2(o01, o23);
+      const float2 r01 = round_bf16x2(a0, a1), r23 = round_bf16x2(a2, a3);
+      const uint32_t o01 = pack_bf16x2(r01.x * m01.x, r01.y * m01.y);
+      const uint32_t o23 = pack_bf16x2(r23.x * m23.x, r23.y * m23.y);
+      *reinterpret_cast<uint2*>(optr) = make_uint2(o01, o23);
       // column sums of the ROUNDED output (the bias gradient the reference derives from its bf16 dh)
-      const float2 r01 = unpack_bf16x2(o01), r23 = unpack_bf16x2(o23);
-      csum.x += r01.x;
-      csum.y += r01.y;
-      csum.z += r23.x;
-      csum.w += r23.y;
+      const float2 s01 = unpack_bf16x2(o01), s23 = unpack_bf16x2(o23);
+      csum.x += s01.x;
+      csum.y += s01.y;
+      csum.z += s23.x;
+      csum.w += s23.y;
     } else if (EPI == TAE_EPI_F32_RESID) {
+      const float2 r01 = round_bf16x2(a0 + bias4.x, a1 + bias4.y), r23 = round_bf16x2(a2 + bias4.z, a3 + bias4.w);
       float4 o;
-      o.x = __uint_as_float(side[it].x) + round_bf16(a0 + bias4.x);
-      o.y = __uint_as_float(side[it].y) + round_bf16(a1 + bias4.y);
-      o.z = __uint_as_float(side[it].z) + round_bf16(a2 + bias4.z);
-      o.w = __uint_as_float(side[it].w) + round_bf16(a3 + bias4.w);
-      *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (size_t)grow * p.ldo + col) = o;
+      o.x = __uint_as_float(side[it].x) + r01.x;
+      o.y = __uint_as_float(side[it].y) + r01.y;
+      o.z = __uint_as_float(side[it].z) + r23.x;
+      o.w = __uint_as_float(side[it].w) + r23.y;
+      *reinterpret_cast<float4*>(optr) = o;
     } else {  // TAE_EPI_F32_ACC
-      float* dst = reinterpret_cast<float*>(p.out) + (size_t)grow * p.ldo + col;
+      float* dst = reinterpret_cast<float*>(optr);
       if (p.splits > 1) {
         atomicAdd(reinterpret_cast<float4*>(dst), make_float4(a0, a1, a2, a3));
       } else {
@@ -206,6 +209,27 @@ __device__ __forceinline__ void epi_write_coalesced(const Params& p, uint32_t st
       }
     }
   }
+}
+
+template <int EPI, int IT0 = 0, int NIT = 8>
+__device__ __forceinline__ void epi_write_coalesced(const Params& p, uint32_t stg, int row_base, int col0, int lane,
+                                                    float4& csum, const float4 bias4) {
+  if (row_base + 32 <= p.M && col0 + 32 <= p.N)  // warp-uniform
+    epi_write_rows<EPI, IT0, NIT, true>(p, stg, row_base, col0, lane, csum, bias4);
+  else
+    epi_write_rows<EPI, IT0, NIT, false>(p, stg, row_base, col0, lane, csum, bias4);
+}
+
+// The lane's 4 bias columns of a step, rounded to bf16 (autocast hands the GEMM a bf16 copy of the fp32 bias).
+// Issued BEFORE the TMEM load of the step so that its latency hides behind it.
+template <int EPI>
+__device__ __forceinline__ float4 epi_load_bias(const Params& p, int col0, int lane) {
+  const int col = col0 + (lane & 7) * 4;
+  if (EPI == TAE_EPI_F32_ACC || EPI == TAE_EPI_BF16_DGELU || p.bias == nullptr || col >= p.N)
+    return make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+  const float2 lo = round_bf16x2(b.x, b.y), hi = round_bf16x2(b.z, b.w);
+  return make_float4(lo.x, lo.y, hi.x, hi.y);
 }
 
 // Column-sum by-product: lanes {c, c+8, c+16, c+24} hold the partial sums of the same 4 columns over the 32 rows of
@@ -371,10 +395,11 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         const int col0 = it.nt * BLOCK_N + half * 128 + c * COLS;
         if (col0 >= p.N) break;  // warp-uniform
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + half * 128 + c * COLS);
+        const float4 bias4 = epi_load_bias<EPI>(p, col0, lane);
         epi_stage_rows(stg, taddr, lane);
         __syncwarp();
         float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
-        epi_write_coalesced<EPI>(p, stg, row_base, col0, lane, csum);
+        epi_write_coalesced<EPI>(p, stg, row_base, col0, lane, csum, bias4);
         if (EPI == TAE_EPI_BF16_DGELU && p.colsum_part != nullptr) epi_flush_colsum(p, csum, row_base, col0, lane);
         __syncwarp();
       }
@@ -551,14 +576,15 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         if (col0 >= p.N) break;  // warp-uniform
         const uint32_t taddr =
             tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + cg * COLS_PER_WARP + c * EPI_COLS);
+        const float4 bias4 = epi_load_bias<EPI>(p, col0, lane);
         epi_stage_rows(stg, taddr, lane);
         __syncwarp();
         float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
         if (EW == 8) {
-          epi_write_coalesced<EPI, 0, 8>(p, stg, row_base, col0, lane, csum);
+          epi_write_coalesced<EPI, 0, 8>(p, stg, row_base, col0, lane, csum, bias4);
         } else {  // two passes of 16 rows keep the live register set under the 640-thread budget
-          epi_write_coalesced<EPI, 0, 4>(p, stg, row_base, col0, lane, csum);
-          epi_write_coalesced<EPI, 4, 4>(p, stg, row_base, col0, lane, csum);
+          epi_write_coalesced<EPI, 0, 4>(p, stg, row_base, col0, lane, csum, bias4);
+          epi_write_coalesced<EPI, 4, 4>(p, stg, row_base, col0, lane, csum, bias4);
         }
         if (EPI == TAE_EPI_BF16_DGELU && p.colsum_part != nullptr) epi_flush_colsum(p, csum, row_base, col0, lane);
         __syncwarp();

@@ -316,31 +316,36 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const float* __restrict__ x, const fl
   }
 }
 
-// out_k[col] (+)= sum_p partials[p][k][col].  Block = 32 columns x 8 partial-slices (coalesced 128-byte rows),
-// grid = 3*D/32 blocks, so the few hundred partial rows are summed by 8 threads per column in parallel.
-__global__ void __launch_bounds__(256)
+// out_k[col] (+)= sum_p partials[p][k][col].  Block = 32 columns x 32 partial-slices (coalesced 128-byte rows),
+// grid = 3*D/32 blocks; every thread keeps 4 independent loads in flight, so the few hundred partial rows cost
+// ~5 dependent round trips instead of ~40.
+__global__ void __launch_bounds__(1024)
 ln_bwd_finalize_kernel(const float* __restrict__ partials, int num_partials, int D, float* dgamma, float* dbeta,
                        float* dcolsum, int accumulate) {
-  __shared__ float red[8][33];
+  __shared__ float red[32][33];
   const int cx = threadIdx.x & 31, sl = threadIdx.x >> 5;
   const int idx = blockIdx.x * 32 + cx;  // over 3*D
   const int k = idx / D, col = idx - k * D;  // D % 32 == 0: a block never straddles two outputs
   float* out = (k == 0) ? dgamma : (k == 1) ? dbeta : dcolsum;
-  float s0 = 0.f, s1 = 0.f;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
   if (out != nullptr) {
+    const float* src = partials + (size_t)k * D + col;
+    const size_t stride = (size_t)3 * D;
     int p = sl;
-    for (; p + 8 < num_partials; p += 16) {
-      s0 += partials[((size_t)p * 3 + k) * D + col];
-      s1 += partials[((size_t)(p + 8) * 3 + k) * D + col];
+    for (; p + 96 < num_partials; p += 128) {
+      s0 += src[(size_t)p * stride];
+      s1 += src[(size_t)(p + 32) * stride];
+      s2 += src[(size_t)(p + 64) * stride];
+      s3 += src[(size_t)(p + 96) * stride];
     }
-    if (p < num_partials) s0 += partials[((size_t)p * 3 + k) * D + col];
+    for (; p < num_partials; p += 32) s0 += src[(size_t)p * stride];
   }
-  red[sl][cx] = s0 + s1;
+  red[sl][cx] = (s0 + s1) + (s2 + s3);
   __syncthreads();
   if (sl == 0 && out != nullptr) {
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) s += red[i][cx];
+    for (int i = 0; i < 32; ++i) s += red[i][cx];
     out[col] = ((accumulate >> k) & 1) ? out[col] + s : s;
   }
 }
@@ -447,8 +452,7 @@ extern "C" int tae_layernorm_bwd_finalize(const float* partials, int32_t num_par
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   TAE_CHECK_SHAPE(num_partials > 0 && D > 0 && partials != nullptr, "tae_layernorm_bwd_finalize: bad arguments");
   const int total = 3 * D;
-  ln_bwd_finalize_kernel<<<total / 32, 256, 0, stream>>>(partials, num_partials, D, dgamma, dbeta, dcolsum,
-                                                                   accumulate);
+  ln_bwd_finalize_kernel<<<total / 32, 1024, 0, stream>>>(partials, num_partials, D, dgamma, dbeta, dcolsum, accumulate);
   TAE_CHECK_LAUNCH();
   return TAE_OK;
 }

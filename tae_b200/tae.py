@@ -340,6 +340,16 @@ class _MSELossFn(torch.autograd.Function):
         return dpred, None, None
 
 
+def _is_fp32(mod) -> bool:
+    return getattr(mod, "_tae_precision", "bf16") == "fp32"
+
+
+def _fp32():
+    from . import fp32  # deferred: fp32.py imports _sink/_done from this module
+
+    return fp32
+
+
 # ----------------------------------------------------------------------------------------------------
 # Modules (parameter containers with the reference's names)
 # ----------------------------------------------------------------------------------------------------
@@ -369,11 +379,12 @@ class PatchEmbed(nn.Module):
         if x.dtype != torch.float32:
             x = x.float()
         x = x.contiguous()
+        fn = _fp32().PatchEmbedFn if _is_fp32(self) else _PatchEmbedFn
         if pos_embed is None:
             pos_embed = torch.zeros(1, self.num_patches, self.proj.weight.shape[0], device=x.device)
-            return _PatchEmbedFn.apply(x, self.proj.weight, self.proj.bias, pos_embed, self)
+            return fn.apply(x, self.proj.weight, self.proj.bias, pos_embed, self)
         object.__setattr__(self, "_pos_param", pos_embed)
-        return _PatchEmbedFn.apply(x, self.proj.weight, self.proj.bias, pos_embed, self)
+        return fn.apply(x, self.proj.weight, self.proj.bias, pos_embed, self)
 
 
 class Attention(nn.Module):
@@ -426,7 +437,8 @@ class Block(nn.Module):
     def forward(self, x):
         _lib.require_device()
         a, m = self.attn, self.mlp
-        return _BlockFn.apply(x, self.norm1.weight, self.norm1.bias, a.qkv.weight, a.qkv.bias, a.proj.weight, a.proj.bias,
+        fn = _fp32().BlockFn if _is_fp32(self) else _BlockFn
+        return fn.apply(x, self.norm1.weight, self.norm1.bias, a.qkv.weight, a.qkv.bias, a.proj.weight, a.proj.bias,
                               self.norm2.weight, self.norm2.bias, m.fc1.weight, m.fc1.bias, m.fc2.weight, m.fc2.bias, self)
 
 
@@ -481,6 +493,20 @@ class TAE(nn.Module):
         self.invalidate_shadows()
         return out
 
+    def set_precision(self, precision: str):
+        """"bf16" (default): the rounding points of `torch.autocast(dtype=bfloat16)` around the reference — the fast path.
+        "fp32": the reference without autocast; every activation fp32, GEMMs as 3-way bf16 splits on the tensor cores
+        (tae_b200/fp32.py).  Returns self."""
+        if precision not in ("bf16", "fp32"):
+            raise ValueError(f"precision must be 'bf16' or 'fp32', got {precision!r}")
+        for m in self.modules():
+            object.__setattr__(m, "_tae_precision", precision)
+        return self
+
+    @property
+    def precision(self) -> str:
+        return getattr(self, "_tae_precision", "bf16")
+
     # -- integer patch index maps (bit-exact) --
     def patchify(self, imgs):
         """imgs (N, 3, H, W) -> (N, L, patch_size**2 * 3)   (tae.py:196-208)"""
@@ -500,22 +526,30 @@ class TAE(nn.Module):
         x = self.patch_embed(x, self.pos_embed)  # conv-as-GEMM, bias and pos_embed fused in the epilogue
         for blk in self.blocks:
             x = blk(x)
-        return _NormLinearFn.apply(x, self.norm.weight, self.norm.bias, self.dict_proj.weight, self.dict_proj.bias,
-                                   self.norm, self.dict_proj)
+        fn = _fp32().NormLinearFn if _is_fp32(self) else _NormLinearFn
+        return fn.apply(x, self.norm.weight, self.norm.bias, self.dict_proj.weight, self.dict_proj.bias,
+                        self.norm, self.dict_proj)
 
     def forward_decoder(self, x):
         _lib.require_device()
-        x = _EmbedLatentFn.apply(x, self.decoder_embed.weight, self.decoder_embed.bias, self.decoder_pos_embed, self)
+        fp = _is_fp32(self)
+        fn = _fp32().EmbedLatentFn if fp else _EmbedLatentFn
+        x = fn.apply(x, self.decoder_embed.weight, self.decoder_embed.bias, self.decoder_pos_embed, self)
         for blk in self.decoder_blocks:
             x = blk(x)
-        return _NormLinearFn.apply(x, self.decoder_norm.weight, self.decoder_norm.bias, self.decoder_pred.weight,
-                                   self.decoder_pred.bias, self.decoder_norm, self.decoder_pred)
+        fn = _fp32().NormLinearFn if fp else _NormLinearFn
+        return fn.apply(x, self.decoder_norm.weight, self.decoder_norm.bias, self.decoder_pred.weight,
+                        self.decoder_pred.bias, self.decoder_norm, self.decoder_pred)
 
     def forward_loss(self, imgs, pred):
         """imgs [N, 3, H, W], pred [N, L, p*p*3] -> mean squared error per pixel (fp32 scalar)."""
         _lib.require_device()
         if imgs.dtype != torch.float32:
             imgs = imgs.float()
+        if _is_fp32(self):
+            if pred.dtype != torch.float32:
+                pred = pred.float()
+            return _fp32().MSELossFn.apply(pred, imgs.contiguous(), self.patch_embed.patch_size[0])
         if pred.dtype != torch.bfloat16:
             pred = pred.to(torch.bfloat16)
         return _MSELossFn.apply(pred, imgs.contiguous(), self.patch_embed.patch_size[0])

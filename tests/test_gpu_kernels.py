@@ -315,3 +315,108 @@ def test_adamw_matches_oracle_and_torch(n):
     before = p.clone()
     ops.adamw_step(p, g, m, v, pb, lr=1e-3, beta1=0.9, beta2=0.95, eps=1e-8, weight_decay=0.05, step=4, found_inf=flag)
     assert torch.equal(p, before)
+
+
+# ------------------------------------------------------------------------------------------------
+# fp32 mode (csrc/fp32_mode.cu, tae_b200/fp32.py): fp64 PyTorch as the reference of each op, 1e-5-level gates
+# ------------------------------------------------------------------------------------------------
+def _fp32():
+    from tae_b200 import fp32
+
+    return fp32
+
+
+def test_fp32_split3_is_exact():
+    F = _fp32()
+    x = randn(300, 136, dtype=torch.float32, seed=3, scale=7.0)
+    hi, mid, lo = F.split3(x)
+    assert torch.equal(hi.float() + mid.float() + lo.float(), x)  # 3 x 8 mantissa bits: exact reconstruction
+    assert torch.equal(hi, x.to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("M,N,K,a_mn,b_mn", [(300, 136, 264, False, False), (520, 128, 1024, False, True),
+                                             (128, 72, 4104, True, True)])
+def test_fp32_split_gemm(M, N, K, a_mn, b_mn):
+    F = _fp32()
+    A = randn(M, K, dtype=torch.float32, seed=1)
+    Bm = randn(N, K, dtype=torch.float32, seed=2)
+    ref = (A.double() @ Bm.double().t())
+    As = A.t().contiguous() if a_mn else A
+    Bs = Bm.t().contiguous() if b_mn else Bm
+    out = F.gemm_f32(F.split3(As), F.split3(Bs), a_mn=a_mn, b_mn=b_mn)
+    # tensor-core fp32 accumulation truncates: error grows slowly with K (4e-6 at K=4104)
+    assert out.dtype == torch.float32 and rel_err(out, ref) < 1e-5
+    # accumulate form used by the weight gradients
+    out2 = F.gemm_f32(F.split3(As), F.split3(Bs), a_mn=a_mn, b_mn=b_mn, out=out.clone(), beta=1)
+    assert rel_err(out2, 2 * ref) < 1e-5
+    # plain bf16 GEMM on the same data is ~3 orders of magnitude coarser: the split really buys fp32 accuracy
+    coarse = _ops().gemm(As.to(torch.bfloat16), Bs.to(torch.bfloat16), a_mn=a_mn, b_mn=b_mn,
+                         epilogue=3)  # TAE_EPI_F32_ACC
+    assert rel_err(coarse, ref) > 1e-4
+
+
+@pytest.mark.parametrize("rows,D", [(77, 128), (512, 1024), (33, 2560)])
+def test_fp32_layernorm_fwd_bwd(rows, D):
+    F = _fp32()
+    x = randn(rows, D, dtype=torch.float32, seed=4, scale=2.0)
+    w = randn(D, dtype=torch.float32, seed=5) * 0.5 + 1.0
+    b = randn(D, dtype=torch.float32, seed=6)
+    dy = randn(rows, D, dtype=torch.float32, seed=7)
+    dres = randn(rows, D, dtype=torch.float32, seed=8)
+    xr = x.double().requires_grad_(True)
+    wr, br = w.double().requires_grad_(True), b.double().requires_grad_(True)
+    yr = torch.nn.functional.layer_norm(xr, (D,), wr, br, 1e-6)
+    yr.backward(dy.double())
+    y, mean, rstd = F.layernorm_fwd(x, w, b, 1e-6)
+    assert rel_err(y, yr.detach()) < 1e-6
+    dx, dg, db = F.layernorm_bwd(dy, x, mean, rstd, w, dres)
+    assert rel_err(dx, xr.grad + dres.double()) < 1e-5
+    assert rel_err(dg, wr.grad) < 1e-5 and rel_err(db, br.grad) < 1e-5
+    dg2, db2 = dg.clone(), db.clone()
+    F.layernorm_bwd(dy, x, mean, rstd, w, None, dg2, db2, acc_mask=3)
+    assert rel_err(dg2, 2 * wr.grad) < 1e-5 and rel_err(db2, 2 * br.grad) < 1e-5
+
+
+@pytest.mark.parametrize("B,N,H,hd", [(2, 256, 2, 64), (3, 64, 4, 32), (2, 16, 2, 80), (5, 4, 2, 80)])
+def test_fp32_attention_fwd_bwd(B, N, H, hd):
+    F = _fp32()
+    D = H * hd
+    qkv = randn(B * N, 3 * D, dtype=torch.float32, seed=9, scale=0.7)
+    dout = randn(B * N, D, dtype=torch.float32, seed=10)
+    qr = qkv.double().requires_grad_(True)
+    q, k, v = qr.view(B, N, 3, H, hd).permute(2, 0, 3, 1, 4)
+    o = torch.nn.functional.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B * N, D)
+    o.backward(dout.double())
+    out, lse = F.attention_fwd(qkv, B, N, H, hd)
+    assert rel_err(out, o.detach()) < 1e-5
+    lse_ref = torch.logsumexp((q @ k.transpose(-1, -2)) / math.sqrt(hd), dim=-1)
+    assert rel_err(lse, lse_ref.detach()) < 1e-5
+    dqkv = F.attention_bwd(qkv, out, dout, lse, B, N, H, hd)
+    assert rel_err(dqkv, qr.grad) < 2e-5
+
+
+def test_fp32_bias_gelu_loss_im2col():
+    F = _fp32()
+    M, N = 130, 264
+    acc = randn(M, N, dtype=torch.float32, seed=11)
+    bias = randn(N, dtype=torch.float32, seed=12)
+    pos = randn(26, N, dtype=torch.float32, seed=13)
+    y = acc.clone()
+    act = F.bias_act(y, bias, pos, 26, want_act=True)
+    yr = acc.double() + bias.double() + pos.double().repeat(5, 1)
+    assert rel_err(y, yr) < 1e-6 and rel_err(act, torch.nn.functional.gelu(yr)) < 1e-6
+    hr = yr.clone().requires_grad_(True)
+    da = randn(M, N, dtype=torch.float32, seed=14)
+    torch.nn.functional.gelu(hr).backward(da.double())
+    assert rel_err(F.gelu_bwd(y, da), hr.grad) < 1e-5
+    # loss + gradient and im2col against the oracle's restatement
+    imgs = randn(3, 3, 64, 64, dtype=torch.float32, seed=15)
+    pred = randn(3, 16, 768, dtype=torch.float32, seed=16)
+    pr = pred.double().requires_grad_(True)
+    lr = ((pr - O.patchify(imgs.double(), 16)) ** 2).mean()
+    lr.backward()
+    gs = torch.full((1,), 3.0, device="cuda")
+    loss, dpred = F.mse_loss(pred, imgs, 16, want_grad=True, grad_scale=gs)
+    assert abs(float(loss) - float(lr)) < 1e-6 * float(lr) and rel_err(dpred, 3.0 * pr.grad) < 1e-6
+    cols = F.im2col(imgs, 16)
+    assert torch.equal(cols, O.im2col(imgs, 16).reshape(cols.shape))

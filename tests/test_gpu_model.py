@@ -246,3 +246,72 @@ def test_fused_adamw_training_matches_torch_adamw():
     ref = o2.state_dict()
     assert len(sd["state"]) == len(ref["state"]) and [g["params"] for g in sd["param_groups"]] == [g["params"] for g in ref["param_groups"]]
     assert set(sd["state"][0].keys()) == {"step", "exp_avg", "exp_avg_sq"}
+
+
+# ----------------------------------------------------------------------------------------------------
+# fp32 ("no autocast") mode: 1e-4 relative gate of the north star, against the reference's own fp32 results
+# ----------------------------------------------------------------------------------------------------
+FP32_TOL = 1e-4
+
+
+@pytest.mark.parametrize("case", TINY_CASES)
+def test_fp32_mode_matches_reference_fp32(case, golden_meta, golden_tensors):
+    rec = golden_meta[case]
+    kw = rec["kwargs"]
+    t = golden_tensors(case)
+    model = build(kw)
+    sd_cpu = {k: v.clone() for k, v in model.state_dict().items()}
+    model.cuda().train().set_precision("fp32")
+    assert model.precision == "fp32"
+    x = t["input"].cuda()
+    acts = {}
+    hooks = [blk.register_forward_hook(lambda m, a, o, k=f"{pre}.{i}": acts.__setitem__(k, float(o.detach().float().norm())))
+             for pre, blocks in (("blocks", model.blocks), ("decoder_blocks", model.decoder_blocks))
+             for i, blk in enumerate(blocks)]
+    loss, pred, latent = model(x, return_latent=True)
+    for h in hooks:
+        h.remove()
+    assert loss.dtype == pred.dtype == latent.dtype == torch.float32  # the reference's dtypes without autocast
+    loss.backward()
+    torch.cuda.synchronize()
+
+    g = rec["fp32"]
+    # (a) golden fixtures generated by the unmodified reference in fp32
+    assert abs(float(loss) - g["loss"]) < FP32_TOL * abs(g["loss"])
+    assert rel(pred.cpu(), t["fp32.pred"]) < FP32_TOL
+    assert rel(latent.cpu(), t["fp32.latent"]) < FP32_TOL
+    for k, v in g["block_out_norms"].items():  # per-layer activations
+        assert abs(acts[k] - v) < FP32_TOL * v, k
+    for n, p in model.named_parameters():
+        assert p.grad is not None and p.grad.dtype == torch.float32, n
+        gn = float(p.grad.norm())
+        assert abs(gn - g["grad_norm"][n]) < 2e-4 * g["grad_norm"][n] + 1e-9, (n, gn, g["grad_norm"][n])
+        key = f"fp32.grad.{n}"
+        if key in t and float(t[key].norm()) > 1e-6:
+            assert rel(p.grad.cpu(), t[key]) < 2e-4, n
+    gnorm = float(torch.norm(torch.stack([p.grad.norm() for p in model.parameters()])))
+    assert abs(gnorm - g["global_grad_norm"]) < FP32_TOL * g["global_grad_norm"]
+
+    # (b) the oracle in fp32 on the same weights: EVERY gradient tensor
+    sd = {k: v.cuda() for k, v in sd_cpu.items()}
+    lo, po, zo, go = O.forward_backward(sd, x, oracle_cfg(kw), "fp32")
+    assert abs(float(loss) - float(lo)) < FP32_TOL * float(lo)
+    assert rel(pred, po) < FP32_TOL and rel(latent, zo) < FP32_TOL
+    worst = max(((rel(p.grad, go[n]), n) for n, p in model.named_parameters()))
+    assert worst[0] < 2e-4, worst
+
+    # switching back restores the bf16 path on the same module
+    model.set_precision("bf16")
+    model.zero_grad(set_to_none=True)
+    l2, p2 = model(x)
+    assert p2.dtype == torch.bfloat16 and abs(float(l2) - g["loss"]) < BF16_TOL * g["loss"]
+
+
+def test_fp32_mode_encode_decode_no_grad(golden_meta, golden_tensors):
+    case = "tiny_p8_n16_hd32"
+    rec, t = golden_meta[case], golden_tensors(case)
+    model = build(rec["kwargs"]).cuda().eval().set_precision("fp32")
+    with torch.no_grad():
+        z = model.forward_encoder(t["input"].cuda())
+        y = model.forward_decoder(z)
+    assert rel(z.cpu(), t["fp32.latent"]) < FP32_TOL and rel(y.cpu(), t["fp32.pred"]) < FP32_TOL

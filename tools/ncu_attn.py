@@ -1,9 +1,9 @@
-"""ncu target: tcgen05 attention fwd + bwd at the patch16 shape (B=64 keeps replays short)."""
+"""ncu target: tcgen05 attention fwd + bwd at the bench shape (B=256, N=256, H=16, hd=64)."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from tae_b200 import ops
-B, N, H, hd = 64, 256, 16, 64
+B, N, H, hd = 256, 256, 16, 64
 D = H * hd
 qkv = (torch.randn(B * N, 3 * D, device="cuda") * 0.5).to(torch.bfloat16)
 dout = (torch.randn(B * N, D, device="cuda") * 0.5).to(torch.bfloat16)
