@@ -687,6 +687,366 @@ attn_bwd_tc_pipe(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
 #undef TRACE_E
 }
 
+
+// =============================================================================================
+// Backward, PERSISTENT variant (default).  One CTA per SM walks a static list of (image, head) items; the block
+// pipeline of attn_bwd_tc_pipe runs unchanged INSIDE an item, and three things overlap ACROSS items:
+//   * operand prefetch: Q/dO query blocks are re-loaded for the next item as soon as the last MMA that reads them has
+//     retired (during the second key-tile pass), K0/V0 once their dV0/dK0 staging stores have left shared memory, the
+//     rest right after the final MMA — so the next item's first scores are in TMEM before the element-wise warps get
+//     there (the 128 KB operand load, ~8k cycles exposed per item in the one-shot kernel, disappears);
+//   * delta = rowsum(dO*O) and lse of the NEXT item are prepared by three otherwise idle warps into a second buffer;
+//   * the final accumulator drain goes through the (dead) P^T/dS^T tiles, so the operand tiles are free for the
+//     prefetch while the results are still on their way out through TMA stores.
+// Shared memory map = attn_bwd_tc_pipe's, with lse/delta double-buffered.
+// =============================================================================================
+constexpr int S_OFF_LSE = 196608;     // [2][256] fp32
+constexpr int S_OFF_DELTA = 198656;   // [2][256] fp32
+constexpr int S_OFF_BAR = 200704;
+constexpr int S_SMEM = S_OFF_BAR + 256 + 1024;
+
+__global__ void __launch_bounds__(B_THREADS, 1)
+attn_bwd_tc_persist(const __grid_constant__ CUtensorMap tm_qkv,   // box 64 rows x 64 cols over qkv  [B*N, 3D]
+                    const __grid_constant__ CUtensorMap tm_do,    // box 64 rows x 64 cols over dout [B*N, D]
+                    const __grid_constant__ CUtensorMap tm_dqkv,  // box 128 rows x 64 cols over dqkv (stores)
+                    const bf16* __restrict__ out, const bf16* __restrict__ dout, const float* __restrict__ lse,
+                    int H, int num_items, float scale, float sl2) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S_OFF_BAR);
+  uint64_t* bK = bars;               // [2] K tile kt landed                        (TMA, once per item)
+  uint64_t* bV = bars + 2;           // [2] V tile kt landed
+  uint64_t* bQ = bars + 4;           // [4] Q block j landed
+  uint64_t* bdO = bars + 8;          // [4] dO block j landed
+  uint64_t* bar_s = bars + 12;       // [2] S^T/dP^T buffer filled                  (4 per item each)
+  uint64_t* bar_p = bars + 14;       // [2] P^T/dS^T tile written, S/dP drained     (256 arrivals)
+  uint64_t* bar_pfree = bars + 16;   // [2] gradient MMAs reading the tile retired
+  uint64_t* bar_g = bars + 18;       // dV/dK (at the end dQ) complete              (2 per item)
+  uint64_t* bar_dfree = bars + 19;   // dV0/dK0 left TMEM                           (256, once per item)
+  uint64_t* bar_accfree = bars + 20; // dV1/dK1/dQ left TMEM                        (256, once per item)
+  uint64_t* bar_kv0free = bars + 21; // dV0/dK0 staging stores have read K0/V0      (2, once per item)
+  uint64_t* bar_delta = bars + 22;   // [2] lse/delta buffer filled                 (96, every other item each)
+  uint64_t* bar_dbuffree = bars + 24;// [2] lse/delta buffer consumed               (256, every other item each)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
+  float* sLse = reinterpret_cast<float*>(smem + S_OFF_LSE);
+  float* sDelta = reinterpret_cast<float*>(smem + S_OFF_DELTA);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int D = H * HD;
+  // this CTA's items: blockIdx.x, blockIdx.x + gridDim.x, ...
+  const int my_items = (num_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_qkv);
+    tma_prefetch_desc(&tm_do);
+    tma_prefetch_desc(&tm_dqkv);
+    for (int i = 0; i < 12; ++i) mbar_init(&bars[i], 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar_s[i], 1);
+      mbar_init(&bar_p[i], 256);
+      mbar_init(&bar_pfree[i], 1);
+      mbar_init(&bar_delta[i], 96);
+      mbar_init(&bar_dbuffree[i], 256);
+    }
+    mbar_init(bar_g, 1);
+    mbar_init(bar_dfree, 256);
+    mbar_init(bar_accfree, 256);
+    mbar_init(bar_kv0free, 2);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t sQ = smem_u32(smem + P_OFF_Q), sK = smem_u32(smem + P_OFF_K), sV = smem_u32(smem + P_OFF_V);
+  const uint32_t sdO = smem_u32(smem + P_OFF_DO), sPT = smem_u32(smem + P_OFF_PT), sdST = smem_u32(smem + P_OFF_DST);
+
+  if (warp == 0) {
+    if (elect_one()) {
+      // ---------------- TMA producer + MMA issuer ----------------
+      auto item_bh = [&](int it, int& b, int& h) {
+        const int item = (int)blockIdx.x + it * (int)gridDim.x;
+        b = item / H;
+        h = item - b * H;
+      };
+      auto load_q = [&](int it, int j) {  // Q block j and dO block j of item `it`
+        int b, h;
+        item_bh(it, b, h);
+        mbar_expect_tx(&bQ[j], 8192);
+        tma_load_2d(smem + P_OFF_Q + j * 8192, &tm_qkv, &bQ[j], h * HD, b * N + j * 64);
+        mbar_expect_tx(&bdO[j], 8192);
+        tma_load_2d(smem + P_OFF_DO + j * 8192, &tm_do, &bdO[j], h * HD, b * N + j * 64);
+      };
+      auto load_kv = [&](int it, int kt) {
+        int b, h;
+        item_bh(it, b, h);
+        mbar_expect_tx(&bK[kt], 16384);
+        tma_load_2d(smem + P_OFF_K + kt * 16384, &tm_qkv, &bK[kt], D + h * HD, b * N + kt * 128);
+        tma_load_2d(smem + P_OFF_K + kt * 16384 + 8192, &tm_qkv, &bK[kt], D + h * HD, b * N + kt * 128 + 64);
+        mbar_expect_tx(&bV[kt], 16384);
+        tma_load_2d(smem + P_OFF_V + kt * 16384, &tm_qkv, &bV[kt], 2 * D + h * HD, b * N + kt * 128);
+        tma_load_2d(smem + P_OFF_V + kt * 16384 + 8192, &tm_qkv, &bV[kt], 2 * D + h * HD, b * N + kt * 128 + 64);
+      };
+      const uint32_t id_s = make_idesc_bf16(128, 64, 0, 0);    // S^T, dP^T: [128 keys x 64 q]
+      const uint32_t id_kn = make_idesc_bf16(128, 64, 0, 1);   // dV, dK
+      const uint32_t id_q = make_idesc_bf16(64, 64, 1, 1);     // dQ: M = 64 queries
+      const uint32_t q_lo = desc_lo(sQ), k_lo = desc_lo(sK), v_lo = desc_lo(sV), do_lo = desc_lo(sdO);
+      const uint32_t pt_lo = desc_lo(sPT), dst_lo = desc_lo(sdST);
+      const uint32_t qmn_lo = desc_lo(sQ, 8192), kmn_lo = desc_lo(sK, 8192), domn_lo = desc_lo(sdO, 8192);
+      const uint32_t dstmn_lo = desc_lo(sdST, 8192);
+      // scores of block `blk` of item `it`: S^T = K_kt Q_j^T, dP^T = V_kt dO_j^T into S/dP buffer (blk & 1)
+      auto issue_scores = [&](int it, int blk) {
+        const int kt = blk >> 2, j = blk & 3, buf = blk & 1;
+        const uint32_t par = (uint32_t)(it & 1);
+        const uint32_t ka = k_lo + kt * (16384 >> 4), va = v_lo + kt * (16384 >> 4);
+        const uint32_t qb = q_lo + j * (8192 >> 4), ob = do_lo + j * (8192 >> 4);
+        const uint32_t ds = tmem + PC_S + buf * 64, dp = tmem + PC_DP + buf * 64;
+        mbar_wait(&bK[kt], par);
+        mbar_wait(&bQ[j], par);
+        tcgen05_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16_lo(ds, ka + k * 2, qb + k * 2, id_s, k > 0);
+        mbar_wait(&bV[kt], par);
+        mbar_wait(&bdO[j], par);
+        tcgen05_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16_lo(dp, va + k * 2, ob + k * 2, id_s, k > 0);
+        umma_commit(&bar_s[buf]);
+      };
+      if (my_items > 0) {
+        load_kv(0, 0);
+        load_q(0, 0);
+        load_q(0, 1);
+        load_q(0, 2);
+        load_q(0, 3);
+        load_kv(0, 1);
+        issue_scores(0, 0);
+        issue_scores(0, 1);
+      }
+#pragma unroll 1
+      for (int it = 0; it < my_items; ++it) {
+        const bool has_next = it + 1 < my_items;
+#pragma unroll 1
+        for (int blk = 0; blk < 8; ++blk) {
+          const int kt = blk >> 2, j = blk & 3, buf = blk & 1;
+          const int g = it * 8 + blk;  // running block index: barrier phases are counted over the whole CTA lifetime
+          mbar_wait(&bar_p[buf], (uint32_t)((g >> 1) & 1));
+          tcgen05_fence_after();
+          if (blk == 0 && it > 0) {  // dV1/dK1/dQ of the previous item must have left TMEM before they are overwritten
+            mbar_wait(bar_accfree, (uint32_t)((it - 1) & 1));
+            tcgen05_fence_after();
+          }
+          if (blk == 4) {  // dV0/dK0 must have left TMEM
+            mbar_wait(bar_dfree, (uint32_t)(it & 1));
+            tcgen05_fence_after();
+          }
+          const uint32_t a_pt = pt_lo + buf * (16384 >> 4), a_dst = dst_lo + buf * (16384 >> 4);
+          const uint32_t b_do = domn_lo + j * (8192 >> 4), b_q = qmn_lo + j * (8192 >> 4);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {  // 16 queries per instruction
+            umma_f16_lo(tmem + PC_DV, a_pt + k * 2, b_do + k * (2048 >> 4), id_kn, (j > 0 || k > 0));
+            umma_f16_lo(tmem + PC_DK, a_dst + k * 2, b_q + k * (2048 >> 4), id_kn, (j > 0 || k > 0));
+          }
+          const uint32_t dq_addr = tmem + PC_DQ + (j >> 1) * 64 + ((uint32_t)((j & 1) * 16) << 16);
+          const uint32_t a_ds = dstmn_lo + buf * (16384 >> 4), b_k = kmn_lo + kt * (16384 >> 4);
+#pragma unroll
+          for (int k = 0; k < 8; ++k)  // 16 keys per instruction; A = dS^T tile read MN-major (64 queries contiguous)
+            umma_f16_lo(dq_addr, a_ds + k * (2048 >> 4), b_k + k * (2048 >> 4), id_q, (kt > 0 || k > 0));
+          umma_commit(&bar_pfree[buf]);
+          if (j == 3) umma_commit(bar_g);
+          if (blk < 6) {
+            issue_scores(it, blk + 2);
+          } else if (has_next) {
+            // E arrived on bar_p(blk) only after bar_pfree(blk-2): every MMA of block blk-2 = (kt 1, j = blk-6) has
+            // retired, and it was the last reader of Q/dO block j = blk-6 of this item.
+            if (blk == 6) {
+              mbar_wait(bar_kv0free, (uint32_t)(it & 1));  // dV0/dK0 staging stores are done with K0/V0
+              load_kv(it + 1, 0);
+              load_q(it + 1, 0);
+            } else {
+              load_q(it + 1, 1);
+              issue_scores(it + 1, 0);
+            }
+          }
+        }
+        if (has_next) {
+          // everything of this item has retired once bar_g completes for its second key tile
+          mbar_wait(bar_g, (uint32_t)((it * 2 + 1) & 1));
+          tcgen05_fence_after();
+          load_q(it + 1, 2);
+          load_q(it + 1, 3);
+          load_kv(it + 1, 1);
+          issue_scores(it + 1, 1);
+        }
+      }
+    }
+  } else if (warp < 4) {
+    // ---------------- helper warps 1-3: delta = rowsum(dO * O) and lse (exp2 domain) of item `it` ----------------
+    const int te = threadIdx.x - 32;  // 0..95
+#pragma unroll 1
+    for (int it = 0; it < my_items; ++it) {
+      const int item = (int)blockIdx.x + it * (int)gridDim.x;
+      const int b = item / H, h = item - b * H;
+      const int dbuf = it & 1;
+      if (it >= 2) mbar_wait(&bar_dbuffree[dbuf], (uint32_t)(((it >> 1) - 1) & 1));
+      const bf16* go = out + (size_t)b * N * D + (size_t)h * HD;
+      const bf16* gdo = dout + (size_t)b * N * D + (size_t)h * HD;
+      float* dl = sDelta + dbuf * 256;
+      float* ls = sLse + dbuf * 256;
+      // 3 chunks of 96 rows; all 16 loads of a chunk are in flight before the first use (3 round trips per item)
+#pragma unroll 1
+      for (int c0 = 0; c0 < 288; c0 += 96) {
+        uint4 dv[8], ov[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int row = c0 + u * 12 + (te >> 3), ch = te & 7;
+          dv[u] = make_uint4(0u, 0u, 0u, 0u);
+          ov[u] = make_uint4(0u, 0u, 0u, 0u);
+          if (row < 256) {
+            dv[u] = ld_nc_v4(gdo + (size_t)row * D + ch * 8);
+            ov[u] = ld_nc_v4(go + (size_t)row * D + ch * 8);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int row = c0 + u * 12 + (te >> 3), ch = te & 7;
+          const uint32_t dw[4] = {dv[u].x, dv[u].y, dv[u].z, dv[u].w}, ow[4] = {ov[u].x, ov[u].y, ov[u].z, ov[u].w};
+          float acc = 0.f;
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            const float2 d2 = unpack_bf16x2(dw[jj]), o2 = unpack_bf16x2(ow[jj]);
+            acc += d2.x * o2.x + d2.y * o2.y;
+          }
+          acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+          acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+          acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+          if (ch == 0 && row < 256) dl[row] = acc;
+        }
+      }
+      for (int i = te; i < 256; i += 96) ls[i] = lse[((size_t)b * H + h) * N + i] * 1.44269504088896340736f;
+      mbar_arrive(&bar_delta[dbuf]);  // release: the smem writes above are visible to whoever acquires the phase
+    }
+  } else {
+    // ---------------- element-wise warps 4-11 ----------------
+    const int q4 = warp & 3;
+    const int half = (warp - 4) >> 2;   // which 32 query columns of the 64-wide block
+    const int r = q4 * 32 + lane;       // key row inside the key tile == TMEM lane
+    const uint32_t tlane = tmem + ((uint32_t)(q4 * 32) << 16);
+    const bool storer_warp = (warp & 3) == 0;
+    // TMEM accumulator row (64 fp32 columns at `taddr`) -> bf16 -> row `row` of a 128B-swizzled [rows x 64] staging tile
+    auto stage_row = [&](uint32_t taddr, uint32_t tile, int row) {
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t raw[32];
+        tmem_ld_32x32b_x32(taddr + c * 32, raw);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          st_shared_v4(tile + sw128(row, c * 4 + i),
+                       pack_bf16x2(__uint_as_float(raw[i * 8 + 0]), __uint_as_float(raw[i * 8 + 1])),
+                       pack_bf16x2(__uint_as_float(raw[i * 8 + 2]), __uint_as_float(raw[i * 8 + 3])),
+                       pack_bf16x2(__uint_as_float(raw[i * 8 + 4]), __uint_as_float(raw[i * 8 + 5])),
+                       pack_bf16x2(__uint_as_float(raw[i * 8 + 6]), __uint_as_float(raw[i * 8 + 7])));
+      }
+    };
+    bool kv0_pending = false;  // this warp's storer still owes bar_kv0free an arrival for the current item
+#pragma unroll 1
+    for (int it = 0; it < my_items; ++it) {
+      const int item = (int)blockIdx.x + it * (int)gridDim.x;
+      const int b = item / H, h = item - b * H;
+      const int dbuf = it & 1;
+      mbar_wait(&bar_delta[dbuf], (uint32_t)((it >> 1) & 1));
+      const uint32_t sLseA = smem_u32(sLse + dbuf * 256), sDeltaA = smem_u32(sDelta + dbuf * 256);
+#pragma unroll 1
+      for (int blk = 0; blk < 8; ++blk) {
+        const int kt = blk >> 2, j = blk & 3, buf = blk & 1;
+        const int g = it * 8 + blk;
+        if (kv0_pending && blk == 5) {
+          // the dV0/dK0 stores were issued a block ago: by now they have read their staging tiles (K0/V0)
+          if (storer_warp && elect_one()) {
+            tma_store_wait_read();
+            mbar_arrive(bar_kv0free);
+          }
+          kv0_pending = false;
+        }
+        mbar_wait(&bar_s[buf], (uint32_t)((g >> 1) & 1));
+        tcgen05_fence_after();
+        uint32_t sraw[32], draw[32];
+        tmem_ld_32x32b_x32(tlane + PC_S + buf * 64 + half * 32, sraw);
+        tmem_ld_32x32b_x32(tlane + PC_DP + buf * 64 + half * 32, draw);
+        tmem_ld_wait();
+        const int qcol = j * 64 + half * 32;
+        uint32_t pk[16], dk[16];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 lv = ld_shared_f4(sLseA + (qcol + 4 * i) * 4), dl = ld_shared_f4(sDeltaA + (qcol + 4 * i) * 4);
+          const float p0 = ex2_approx(fmaf(__uint_as_float(sraw[4 * i + 0]), sl2, -lv.x));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(sraw[4 * i + 1]), sl2, -lv.y));
+          const float p2 = ex2_approx(fmaf(__uint_as_float(sraw[4 * i + 2]), sl2, -lv.z));
+          const float p3 = ex2_approx(fmaf(__uint_as_float(sraw[4 * i + 3]), sl2, -lv.w));
+          pk[2 * i] = pack_bf16x2(p0, p1);
+          pk[2 * i + 1] = pack_bf16x2(p2, p3);
+          dk[2 * i] = pack_bf16x2(p0 * (__uint_as_float(draw[4 * i + 0]) - dl.x) * scale,
+                                  p1 * (__uint_as_float(draw[4 * i + 1]) - dl.y) * scale);
+          dk[2 * i + 1] = pack_bf16x2(p2 * (__uint_as_float(draw[4 * i + 2]) - dl.z) * scale,
+                                      p3 * (__uint_as_float(draw[4 * i + 3]) - dl.w) * scale);
+        }
+        if (g >= 2) mbar_wait(&bar_pfree[buf], (uint32_t)(((g >> 1) - 1) & 1));  // MMAs of block g-2 are done with this tile
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t off = (uint32_t)buf * 16384u + sw128(r, half * 4 + i);
+          st_shared_v4(sPT + off, pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+          st_shared_v4(sdST + off, dk[4 * i], dk[4 * i + 1], dk[4 * i + 2], dk[4 * i + 3]);
+        }
+        fence_proxy_async_smem();
+        tcgen05_fence_before();
+        mbar_arrive(&bar_p[buf]);
+        if (blk == 7) mbar_arrive(&bar_dbuffree[dbuf]);  // last read of this item's lse/delta buffer
+        if (blk == 3) {
+          // dV0 (half 0) / dK0 (half 1): every MMA that reads V0 / K0 has retired (bar_g), so the accumulator is staged
+          // as bf16 over the dead operand tile and leaves with one coalesced TMA store.
+          mbar_wait(bar_g, (uint32_t)((it * 2) & 1));
+          tcgen05_fence_after();
+          const int off = half == 0 ? P_OFF_V : P_OFF_K;
+          stage_row(tlane + (half == 0 ? PC_DV : PC_DK), smem_u32(smem + off), r);
+          tcgen05_fence_before();
+          mbar_arrive(bar_dfree);
+          fence_proxy_async_smem();
+          named_bar_sync(2 + half, 128);
+          if (storer_warp && elect_one()) {
+            tma_store_2d(&tm_dqkv, smem + off, (half == 0 ? 2 * D : D) + h * HD, b * N);
+            tma_store_commit();
+          }
+          kv0_pending = true;
+        }
+      }
+      // ---- final drain of the item: dV1 -> P^T[0], dK1 -> P^T[1], dQ -> dS^T[0..1] (all dead once bar_g completes) ----
+      mbar_wait(bar_g, (uint32_t)((it * 2 + 1) & 1));
+      tcgen05_fence_after();
+      stage_row(tlane + (half == 0 ? PC_DV : PC_DK), sPT + half * 16384, r);
+      // dQ: M=64 accumulators; thread (quarter q4, lane l) owns query (2*half + (l>>4))*64 + 16*q4 + (l&15)
+      const int qrow = (2 * half + (lane >> 4)) * 64 + 16 * q4 + (lane & 15);
+      stage_row(tlane + PC_DQ + half * 64, sdST, qrow);
+      tcgen05_fence_before();
+      mbar_arrive(bar_accfree);
+      fence_proxy_async_smem();
+      named_bar_sync(2 + half, 128);  // this half's threads own dV1 or dK1 and query rows [half*128, half*128 + 128)
+      if (storer_warp && elect_one()) {
+        tma_store_2d(&tm_dqkv, smem + P_OFF_PT + half * 16384, (half == 0 ? 2 * D : D) + h * HD, b * N + 128);
+        tma_store_2d(&tm_dqkv, smem + P_OFF_DST + half * 16384, h * HD, b * N + half * 128);
+        tma_store_commit();
+        tma_store_wait_read();  // the staging tiles are P^T/dS^T of the next item's first blocks
+      }
+      named_bar_sync(1, 256);
+    }
+    if (storer_warp && elect_one()) tma_store_wait_all();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
 }  // namespace attn_tc
 long long* g_attn_trace = nullptr;  // debug: device buffer of 64 int64 set through tae_debug_set_attn_trace
 namespace attn_tc {
@@ -738,16 +1098,16 @@ int attention_bwd_tcgen05(const bf16* qkv, const bf16* out, const bf16* dout, co
   rc = sm100::make_tmap(&tdo, dout, (uint64_t)D, (uint64_t)B * N, (uint64_t)D, 256);
   if (rc) return rc;
   const float scale = 1.0f / sqrtf((float)HD);
-  // TAE_ATTN_BWD_V1=1 selects the unpipelined kernel (A/B testing)
-  static int v1 = -1;
-  if (v1 < 0) {
-    const char* e = getenv("TAE_ATTN_BWD_V1");
-    v1 = (e != nullptr && e[0] == '1') ? 1 : 0;
+  // TAE_ATTN_BWD = persist (default) | pipe | v1 selects the kernel generation (A/B testing)
+  static int variant = -1;
+  if (variant < 0) {
+    const char* e = getenv("TAE_ATTN_BWD");
+    variant = (e == nullptr) ? 2 : (e[0] == 'v' ? 0 : (e[0] == 'p' && e[1] == 'i' ? 1 : 2));
   }
-  if (v1) {
-    attn_bwd_tc<<<B * H, B_THREADS, B_SMEM, stream>>>(tqkv, tdo, out, dout, lse, dqkv, H, scale,
-                                                      scale * 1.44269504088896340736f);
-  } else {
+  const float sl2 = scale * 1.44269504088896340736f;
+  if (variant == 0) {
+    attn_bwd_tc<<<B * H, B_THREADS, B_SMEM, stream>>>(tqkv, tdo, out, dout, lse, dqkv, H, scale, sl2);
+  } else if (variant == 1) {
     static cudaError_t err2 = cudaSuccess;
     static std::once_flag once2;
     rc = set_smem_once(attn_bwd_tc_pipe, P_SMEM, &err2, &once2);
@@ -755,8 +1115,24 @@ int attention_bwd_tcgen05(const bf16* qkv, const bf16* out, const bf16* dout, co
     CUtensorMap tdq;
     rc = sm100::make_tmap(&tdq, dqkv, (uint64_t)3 * D, (uint64_t)B * N, (uint64_t)3 * D, 128);
     if (rc) return rc;
-    attn_bwd_tc_pipe<<<B * H, B_THREADS, P_SMEM, stream>>>(tqkv, tdo, tdq, out, dout, lse, H, scale,
-                                                           scale * 1.44269504088896340736f, g_attn_trace);
+    attn_bwd_tc_pipe<<<B * H, B_THREADS, P_SMEM, stream>>>(tqkv, tdo, tdq, out, dout, lse, H, scale, sl2, g_attn_trace);
+  } else {
+    static cudaError_t err3 = cudaSuccess;
+    static std::once_flag once3;
+    rc = set_smem_once(attn_bwd_tc_persist, S_SMEM, &err3, &once3);
+    if (rc) return rc;
+    CUtensorMap tq64, tdo64, tdq;
+    rc = sm100::make_tmap(&tq64, qkv, (uint64_t)3 * D, (uint64_t)B * N, (uint64_t)3 * D, 64);
+    if (rc) return rc;
+    rc = sm100::make_tmap(&tdo64, dout, (uint64_t)D, (uint64_t)B * N, (uint64_t)D, 64);
+    if (rc) return rc;
+    rc = sm100::make_tmap(&tdq, dqkv, (uint64_t)3 * D, (uint64_t)B * N, (uint64_t)3 * D, 128);
+    if (rc) return rc;
+    const int sms = num_sms();
+    if (sms <= 0) return TAE_ERR_CUDA;
+    const int items = B * H;
+    const int grid = items < sms ? items : sms;
+    attn_bwd_tc_persist<<<grid, B_THREADS, S_SMEM, stream>>>(tq64, tdo64, tdq, out, dout, lse, H, items, scale, sl2);
   }
   TAE_CHECK_LAUNCH();
   return TAE_OK;
