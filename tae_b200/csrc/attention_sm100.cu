@@ -710,10 +710,14 @@ attn_bwd_tc_persist(const __grid_constant__ CUtensorMap tm_qkv,   // box 64 rows
                     const __grid_constant__ CUtensorMap tm_do,    // box 64 rows x 64 cols over dout [B*N, D]
                     const __grid_constant__ CUtensorMap tm_dqkv,  // box 128 rows x 64 cols over dqkv (stores)
                     const bf16* __restrict__ out, const bf16* __restrict__ dout, const float* __restrict__ lse,
-                    int H, int num_items, float scale, float sl2) {
+                    int H, int num_items, float scale, float sl2, long long* trace) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S_OFF_BAR);
+  // debug timeline (tools/attn_trace.py): CTA gridDim.x/2 stamps clock64() at the milestones of its 6th item
+  const bool trc = trace != nullptr && blockIdx.x == gridDim.x / 2;
+#define TRACE_C(i) do { if (trc && it == 5) trace[(i)] = clock64(); } while (0)
+#define TRACE_E(i) do { if (trc && it == 5 && threadIdx.x == 128) trace[32 + (i)] = clock64(); } while (0)
   uint64_t* bK = bars;               // [2] K tile kt landed                        (TMA, once per item)
   uint64_t* bV = bars + 2;           // [2] V tile kt landed
   uint64_t* bQ = bars + 4;           // [4] Q block j landed
@@ -832,6 +836,7 @@ attn_bwd_tc_persist(const __grid_constant__ CUtensorMap tm_qkv,   // box 64 rows
           const int g = it * 8 + blk;  // running block index: barrier phases are counted over the whole CTA lifetime
           mbar_wait(&bar_p[buf], (uint32_t)((g >> 1) & 1));
           tcgen05_fence_after();
+          TRACE_C(1 + 2 * blk);
           if (blk == 0 && it > 0) {  // dV1/dK1/dQ of the previous item must have left TMEM before they are overwritten
             mbar_wait(bar_accfree, (uint32_t)((it - 1) & 1));
             tcgen05_fence_after();
@@ -868,6 +873,7 @@ attn_bwd_tc_persist(const __grid_constant__ CUtensorMap tm_qkv,   // box 64 rows
               issue_scores(it + 1, 0);
             }
           }
+          TRACE_C(2 + 2 * blk);
         }
         if (has_next) {
           // everything of this item has retired once bar_g completes for its second key tile
@@ -877,6 +883,7 @@ attn_bwd_tc_persist(const __grid_constant__ CUtensorMap tm_qkv,   // box 64 rows
           load_q(it + 1, 3);
           load_kv(it + 1, 1);
           issue_scores(it + 1, 1);
+          TRACE_C(17);
         }
       }
     }
@@ -955,7 +962,9 @@ attn_bwd_tc_persist(const __grid_constant__ CUtensorMap tm_qkv,   // box 64 rows
       const int item = (int)blockIdx.x + it * (int)gridDim.x;
       const int b = item / H, h = item - b * H;
       const int dbuf = it & 1;
+      TRACE_E(29);
       mbar_wait(&bar_delta[dbuf], (uint32_t)((it >> 1) & 1));
+      TRACE_E(0);
       const uint32_t sLseA = smem_u32(sLse + dbuf * 256), sDeltaA = smem_u32(sDelta + dbuf * 256);
 #pragma unroll 1
       for (int blk = 0; blk < 8; ++blk) {
@@ -971,6 +980,7 @@ attn_bwd_tc_persist(const __grid_constant__ CUtensorMap tm_qkv,   // box 64 rows
         }
         mbar_wait(&bar_s[buf], (uint32_t)((g >> 1) & 1));
         tcgen05_fence_after();
+        TRACE_E(1 + 3 * blk);
         uint32_t sraw[32], draw[32];
         tmem_ld_32x32b_x32(tlane + PC_S + buf * 64 + half * 32, sraw);
         tmem_ld_32x32b_x32(tlane + PC_DP + buf * 64 + half * 32, draw);
@@ -991,6 +1001,7 @@ attn_bwd_tc_persist(const __grid_constant__ CUtensorMap tm_qkv,   // box 64 rows
           dk[2 * i + 1] = pack_bf16x2(p2 * (__uint_as_float(draw[4 * i + 2]) - dl.z) * scale,
                                       p3 * (__uint_as_float(draw[4 * i + 3]) - dl.w) * scale);
         }
+        TRACE_E(2 + 3 * blk);
         if (g >= 2) mbar_wait(&bar_pfree[buf], (uint32_t)(((g >> 1) - 1) & 1));  // MMAs of block g-2 are done with this tile
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -1001,6 +1012,7 @@ attn_bwd_tc_persist(const __grid_constant__ CUtensorMap tm_qkv,   // box 64 rows
         fence_proxy_async_smem();
         tcgen05_fence_before();
         mbar_arrive(&bar_p[buf]);
+        TRACE_E(3 + 3 * blk);
         if (blk == 7) mbar_arrive(&bar_dbuffree[dbuf]);  // last read of this item's lse/delta buffer
         if (blk == 3) {
           // dV0 (half 0) / dK0 (half 1): every MMA that reads V0 / K0 has retired (bar_g), so the accumulator is staged
@@ -1023,12 +1035,14 @@ attn_bwd_tc_persist(const __grid_constant__ CUtensorMap tm_qkv,   // box 64 rows
       // ---- final drain of the item: dV1 -> P^T[0], dK1 -> P^T[1], dQ -> dS^T[0..1] (all dead once bar_g completes) ----
       mbar_wait(bar_g, (uint32_t)((it * 2 + 1) & 1));
       tcgen05_fence_after();
+      TRACE_E(25);
       stage_row(tlane + (half == 0 ? PC_DV : PC_DK), sPT + half * 16384, r);
       // dQ: M=64 accumulators; thread (quarter q4, lane l) owns query (2*half + (l>>4))*64 + 16*q4 + (l&15)
       const int qrow = (2 * half + (lane >> 4)) * 64 + 16 * q4 + (lane & 15);
       stage_row(tlane + PC_DQ + half * 64, sdST, qrow);
       tcgen05_fence_before();
       mbar_arrive(bar_accfree);
+      TRACE_E(26);
       fence_proxy_async_smem();
       named_bar_sync(2 + half, 128);  // this half's threads own dV1 or dK1 and query rows [half*128, half*128 + 128)
       if (storer_warp && elect_one()) {
@@ -1038,6 +1052,7 @@ attn_bwd_tc_persist(const __grid_constant__ CUtensorMap tm_qkv,   // box 64 rows
         tma_store_wait_read();  // the staging tiles are P^T/dS^T of the next item's first blocks
       }
       named_bar_sync(1, 256);
+      TRACE_E(27);
     }
     if (storer_warp && elect_one()) tma_store_wait_all();
   }
@@ -1045,6 +1060,8 @@ attn_bwd_tc_persist(const __grid_constant__ CUtensorMap tm_qkv,   // box 64 rows
   __syncthreads();
   tcgen05_fence_after();
   if (warp == 0) tmem_dealloc(tmem, 512);
+#undef TRACE_C
+#undef TRACE_E
 }
 
 }  // namespace attn_tc
@@ -1132,7 +1149,8 @@ int attention_bwd_tcgen05(const bf16* qkv, const bf16* out, const bf16* dout, co
     if (sms <= 0) return TAE_ERR_CUDA;
     const int items = B * H;
     const int grid = items < sms ? items : sms;
-    attn_bwd_tc_persist<<<grid, B_THREADS, S_SMEM, stream>>>(tq64, tdo64, tdq, out, dout, lse, H, items, scale, sl2);
+    attn_bwd_tc_persist<<<grid, B_THREADS, S_SMEM, stream>>>(tq64, tdo64, tdq, out, dout, lse, H, items, scale, sl2,
+                                                              g_attn_trace);
   }
   TAE_CHECK_LAUNCH();
   return TAE_OK;

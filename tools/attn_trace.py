@@ -18,12 +18,12 @@ ops.attention_bwd(qkv, out, dout, lse, B, N, H, hd)
 torch.cuda.synchronize()
 L.tae_debug_set_attn_trace(0)
 t = tr.tolist()
-t0 = t[63]
-print("CTA start 0; end", t[62] - t0)
-print("C: loaded", t[0] - t0)
+t0 = t[32 + 29]
+print("persistent kernel, 6th item of CTA grid/2; t=0 at the element-wise warps' entry into the item")
+print("E: delta ready", t[32] - t0)
 for b in range(8):
     print(f"C blk{b}: bar_p seen {t[1+2*b]-t0:7d}  issued {t[2+2*b]-t0:7d}")
-print("E: prologue done", t[32] - t0)
+print("C: tail prefetch issued", t[17] - t0)
 for b in range(8):
     print(f"E blk{b}: bar_s seen {t[32+1+3*b]-t0:7d}  computed {t[32+2+3*b]-t0:7d}  arrived {t[32+3+3*b]-t0:7d}")
-print("E done", t[32 + 28] - t0)
+print("E: final bar_g seen", t[32 + 25] - t0, " accumulators drained", t[32 + 26] - t0, " item done", t[32 + 27] - t0)
