@@ -152,6 +152,11 @@ int tae_patchify(const void* imgs, void* out, int32_t B, int32_t S, int32_t p, i
 /* TAE.unpatchify (tae.py:210-222): exact inverse of tae_patchify */
 int tae_unpatchify(const void* x, void* imgs, int32_t B, int32_t S, int32_t p, int32_t elem_size, void* stream);
 
+/* C-channel variants for the downstream segmentation head: VITForSegmentation.unpatchify (tae.py:391-403),
+ * out[b, c, h*p+i, w*p+j] = x[b, h*g+w, (i*p+j)*C + c], and its adjoint (the gradient's path back). */
+int tae_patchify_c(const void* imgs, void* out, int32_t B, int32_t S, int32_t p, int32_t C, int32_t elem_size, void* stream);
+int tae_unpatchify_c(const void* x, void* imgs, int32_t B, int32_t S, int32_t p, int32_t C, int32_t elem_size, void* stream);
+
 /* ---- Loss ---------------------------------------------------------------------------------
  * TAE.forward_loss (tae.py:256-265) with patchify folded into the indexing:
  *   loss = mean over all B*N*3p^2 elements of (float(pred) - patchify(imgs))^2      (fp32)
@@ -174,6 +179,11 @@ int tae_colsum_f32(const float* x, int32_t R, int32_t N, float* out, int32_t acc
 /* out[r, :] (+)= sum_b x[b*R + r, :],  x fp32 [B*R, D].  pos_embed / decoder_pos_embed gradients. */
 int tae_batch_sum_f32(const float* x, int32_t B, int32_t R, int32_t D, float* out, int32_t accumulate,
                       void* stream);
+
+/* global average pooling over tokens, VITForRecognition.forward_head (tae.py:333): out[b,:] = mean_n x[b*N+n,:],
+ * and its gradient dx[b*N+n,:] = dy[b,:] / N.  fp32, D % 4 == 0. */
+int tae_token_mean_f32(const float* x, float* out, int32_t B, int32_t N, int32_t D, void* stream);
+int tae_token_mean_bwd_f32(const float* dy, float* dx, int32_t B, int32_t N, int32_t D, void* stream);
 
 /* ---- Optimizer ------------------------------------------------------------------------------
  * torch.optim.AdamW(fused=True) (train.py:109) over a flat fp32 arena, one launch per call:

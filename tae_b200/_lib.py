@@ -76,6 +76,10 @@ PROTOTYPES = {
     "tae_adamw_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _sz, _f32, _f32, _f32, _f32, _f32, _i32, _f32, _vp, _vp, _vp]),
     "tae_cast_f32_to_bf16": (C.c_int, [_vp, _vp, _sz, _vp]),
     "tae_grad_stats": (C.c_int, [_vp, _sz, _vp, _vp, _vp]),
+    "tae_patchify_c": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "tae_unpatchify_c": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "tae_token_mean_f32": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp]),
+    "tae_token_mean_bwd_f32": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp]),
     # fp32 ("no autocast") mode
     "tae_split3_bf16": (C.c_int, [_vp, _vp, _vp, _vp, _sz, _vp]),
     "tae_bias_act_f32": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _i32, _i32, _vp]),

@@ -44,22 +44,22 @@ __global__ void im2col_kernel(const float* __restrict__ imgs, bf16* __restrict__
 // patchify / unpatchify: out[b, h*g+w, (i*p+j)*3+c] <-> imgs[b, c, h*p+i, w*p+j]
 // ---------------------------------------------------------------------------------------------
 template <typename T, bool kUnpatchify>
-__global__ void patch_permute_kernel(const T* __restrict__ src, T* __restrict__ dst, int B, int S, int p) {
+__global__ void patch_permute_kernel(const T* __restrict__ src, T* __restrict__ dst, int B, int S, int p, int C) {
   const int g = S / p;
-  const size_t per_img = (size_t)3 * S * S;
+  const size_t per_img = (size_t)C * S * S;
   const size_t total = (size_t)B * per_img;
-  const int Kp = 3 * p * p;
+  const int Kp = C * p * p;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
     // idx enumerates the patch layout [b][n][(i*p+j)*3+c]
     const int b = (int)(idx / per_img);
     const size_t r = idx - (size_t)b * per_img;
     const int n = (int)(r / Kp);
     const int e = (int)(r - (size_t)n * Kp);
-    const int c = e % 3;
-    const int ij = e / 3;
+    const int c = e % C;
+    const int ij = e / C;
     const int i = ij / p, j = ij - i * p;
     const int h = n / g, w = n - h * g;
-    const size_t img_off = (((size_t)b * 3 + c) * S + (size_t)h * p + i) * S + (size_t)w * p + j;
+    const size_t img_off = (((size_t)b * C + c) * S + (size_t)h * p + i) * S + (size_t)w * p + j;
     if (kUnpatchify)
       dst[img_off] = src[idx];
     else
@@ -224,6 +224,36 @@ __global__ void __launch_bounds__(512) colsum_f32_kernel(const float* __restrict
   }
 }
 
+// out[b, :] = mean_n x[b*N + n, :]   (global average pooling over tokens, tae.py:333)
+__global__ void token_mean_kernel(const float* __restrict__ x, float* __restrict__ out, int B, int N, int D) {
+  const int d4 = blockIdx.x * blockDim.x + threadIdx.x;  // float4 column
+  const int b = blockIdx.y;
+  if (d4 * 4 >= D) return;
+  const float4* src = reinterpret_cast<const float4*>(x + (size_t)b * N * D) + d4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int n = 0; n < N; ++n) {
+    const float4 v = src[(size_t)n * (D / 4)];
+    acc.x += v.x;
+    acc.y += v.y;
+    acc.z += v.z;
+    acc.w += v.w;
+  }
+  const float inv = 1.0f / (float)N;
+  reinterpret_cast<float4*>(out + (size_t)b * D)[d4] = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+}
+// dx[b*N + n, :] = dy[b, :] / N
+__global__ void token_mean_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, int B, int N, int D) {
+  const size_t total = (size_t)B * N * (D / 4);
+  const float inv = 1.0f / (float)N;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int d4 = (int)(idx % (D / 4));
+    const size_t row = idx / (D / 4);
+    const int b = (int)(row / N);
+    const float4 v = reinterpret_cast<const float4*>(dy + (size_t)b * D)[d4];
+    reinterpret_cast<float4*>(dx)[idx] = make_float4(v.x * inv, v.y * inv, v.z * inv, v.w * inv);
+  }
+}
+
 // out[r, :] (+)= sum_b x[b*R + r, :]
 __global__ void batch_sum_kernel(const float* __restrict__ x, int B, int R, int D, float* out, int accumulate) {
   const int d4 = D / 4;
@@ -286,24 +316,25 @@ extern "C" int tae_im2col_bf16(const float* imgs, tae_bf16* cols, int32_t B, int
 }
 
 static int patch_permute(const void* src, void* dst, int32_t B, int32_t S, int32_t p, int32_t elem_size, bool unpatchify,
-                         void* stream_) {
+                         void* stream_, int32_t C = 3) {
   using namespace tae;
   using namespace tae::ew;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   TAE_CHECK_SHAPE(B > 0 && S > 0 && p > 0 && S % p == 0, "patchify/unpatchify: need S %% p == 0 (S=%d p=%d)", S, p);
   TAE_CHECK_SHAPE(elem_size == 2 || elem_size == 4, "patchify/unpatchify: elem_size must be 2 or 4");
-  const size_t total = (size_t)B * 3 * S * S;
+  TAE_CHECK_SHAPE(C > 0, "patchify/unpatchify: channels must be positive");
+  const size_t total = (size_t)B * C * S * S;
   const int grid = stream_grid(total, 256);
   if (elem_size == 4) {
     if (unpatchify)
-      patch_permute_kernel<uint32_t, true><<<grid, 256, 0, stream>>>((const uint32_t*)src, (uint32_t*)dst, B, S, p);
+      patch_permute_kernel<uint32_t, true><<<grid, 256, 0, stream>>>((const uint32_t*)src, (uint32_t*)dst, B, S, p, C);
     else
-      patch_permute_kernel<uint32_t, false><<<grid, 256, 0, stream>>>((const uint32_t*)src, (uint32_t*)dst, B, S, p);
+      patch_permute_kernel<uint32_t, false><<<grid, 256, 0, stream>>>((const uint32_t*)src, (uint32_t*)dst, B, S, p, C);
   } else {
     if (unpatchify)
-      patch_permute_kernel<uint16_t, true><<<grid, 256, 0, stream>>>((const uint16_t*)src, (uint16_t*)dst, B, S, p);
+      patch_permute_kernel<uint16_t, true><<<grid, 256, 0, stream>>>((const uint16_t*)src, (uint16_t*)dst, B, S, p, C);
     else
-      patch_permute_kernel<uint16_t, false><<<grid, 256, 0, stream>>>((const uint16_t*)src, (uint16_t*)dst, B, S, p);
+      patch_permute_kernel<uint16_t, false><<<grid, 256, 0, stream>>>((const uint16_t*)src, (uint16_t*)dst, B, S, p, C);
   }
   TAE_CHECK_LAUNCH();
   return TAE_OK;
@@ -314,6 +345,16 @@ extern "C" int tae_patchify(const void* imgs, void* out, int32_t B, int32_t S, i
 }
 extern "C" int tae_unpatchify(const void* x, void* imgs, int32_t B, int32_t S, int32_t p, int32_t elem_size, void* stream) {
   return patch_permute(x, imgs, B, S, p, elem_size, true, stream);
+}
+
+/* C-channel variants: VITForSegmentation.unpatchify (tae.py:391-403) and its adjoint */
+extern "C" int tae_patchify_c(const void* imgs, void* out, int32_t B, int32_t S, int32_t p, int32_t C, int32_t elem_size,
+                              void* stream) {
+  return patch_permute(imgs, out, B, S, p, elem_size, false, stream, C);
+}
+extern "C" int tae_unpatchify_c(const void* x, void* imgs, int32_t B, int32_t S, int32_t p, int32_t C, int32_t elem_size,
+                                void* stream) {
+  return patch_permute(x, imgs, B, S, p, elem_size, true, stream, C);
 }
 
 extern "C" int tae_mse_loss(const tae_bf16* pred, const float* imgs, float* loss_accum, tae_bf16* dpred,
@@ -363,6 +404,26 @@ extern "C" int tae_colsum_f32(const float* x, int32_t R, int32_t N, float* out, 
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   TAE_CHECK_SHAPE(R > 0 && N > 0 && x != nullptr && out != nullptr, "tae_colsum_f32: bad arguments");
   colsum_f32_kernel<<<(N + 31) / 32, 512, 0, stream>>>(x, R, N, out, accumulate);
+  TAE_CHECK_LAUNCH();
+  return TAE_OK;
+}
+
+extern "C" int tae_token_mean_f32(const float* x, float* out, int32_t B, int32_t N, int32_t D, void* stream_) {
+  using namespace tae;
+  using namespace tae::ew;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  TAE_CHECK_SHAPE(B > 0 && N > 0 && D > 0 && D % 4 == 0 && x && out, "tae_token_mean_f32: bad shape B=%d N=%d D=%d", B, N, D);
+  dim3 grid((D / 4 + 127) / 128, B);
+  token_mean_kernel<<<grid, 128, 0, stream>>>(x, out, B, N, D);
+  TAE_CHECK_LAUNCH();
+  return TAE_OK;
+}
+extern "C" int tae_token_mean_bwd_f32(const float* dy, float* dx, int32_t B, int32_t N, int32_t D, void* stream_) {
+  using namespace tae;
+  using namespace tae::ew;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  TAE_CHECK_SHAPE(B > 0 && N > 0 && D > 0 && D % 4 == 0 && dy && dx, "tae_token_mean_bwd_f32: bad shape B=%d N=%d D=%d", B, N, D);
+  token_mean_bwd_kernel<<<stream_grid((size_t)B * N * (D / 4), 256), 256, 0, stream>>>(dy, dx, B, N, D);
   TAE_CHECK_LAUNCH();
   return TAE_OK;
 }

@@ -221,6 +221,54 @@ def unpatchify(x: torch.Tensor, p: int) -> torch.Tensor:
     return imgs
 
 
+def unpatchify_c(x: torch.Tensor, p: int, C: int) -> torch.Tensor:
+    """VITForSegmentation.unpatchify (tae.py:391-403): [B, L, p*p*C] -> [B, C, S, S]."""
+    if not x.is_cuda:
+        raise _lib.TaeError("unpatchify_c: expected a CUDA tensor (tae_b200 has no CPU fallback)")
+    g = int(x.shape[1] ** .5)
+    assert g * g == x.shape[1] and x.shape[2] == C * p * p
+    x = x.contiguous()
+    es = x.element_size()
+    assert es in (2, 4)
+    B, S = x.shape[0], g * p
+    imgs = torch.empty((B, C, S, S), dtype=x.dtype, device=x.device)
+    check(_L().tae_unpatchify_c(x.data_ptr(), imgs.data_ptr(), B, S, p, C, es, _stream()), "tae_unpatchify_c")
+    return imgs
+
+
+def patchify_c(imgs: torch.Tensor, p: int) -> torch.Tensor:
+    """Adjoint / inverse of unpatchify_c: [B, C, S, S] -> [B, (S/p)^2, p*p*C]."""
+    if not imgs.is_cuda:
+        raise _lib.TaeError("patchify_c: expected a CUDA tensor (tae_b200 has no CPU fallback)")
+    imgs = imgs.contiguous()
+    es = imgs.element_size()
+    assert es in (2, 4)
+    B, Cc, S, _ = imgs.shape
+    g = S // p
+    out = torch.empty((B, g * g, Cc * p * p), dtype=imgs.dtype, device=imgs.device)
+    check(_L().tae_patchify_c(imgs.data_ptr(), out.data_ptr(), B, S, p, Cc, es, _stream()), "tae_patchify_c")
+    return out
+
+
+def token_mean(x: torch.Tensor, B: int, N: int) -> torch.Tensor:
+    """fp32 [B*N, D] -> fp32 [B, D]: mean over the tokens of each image (tae.py:333)."""
+    _req(x, f32, "token_mean x")
+    assert x.is_contiguous()
+    D = x.shape[-1]
+    out = torch.empty((B, D), dtype=f32, device=x.device)
+    check(_L().tae_token_mean_f32(x.data_ptr(), out.data_ptr(), B, N, D, _stream()), "tae_token_mean_f32")
+    return out
+
+
+def token_mean_bwd(dy: torch.Tensor, B: int, N: int) -> torch.Tensor:
+    _req(dy, f32, "token_mean_bwd dy")
+    dy = dy.contiguous()
+    D = dy.shape[-1]
+    dx = torch.empty((B * N, D), dtype=f32, device=dy.device)
+    check(_L().tae_token_mean_bwd_f32(dy.data_ptr(), dx.data_ptr(), B, N, D, _stream()), "tae_token_mean_bwd_f32")
+    return dx
+
+
 def mse_loss(pred: torch.Tensor, imgs: torch.Tensor, p: int, *, want_grad: bool = False,
              grad_scale: torch.Tensor | None = None):
     """forward_loss (tae.py:256-265).  Returns (loss fp32 0-dim, dpred bf16 | None)."""

@@ -568,6 +568,250 @@ class TAE(nn.Module):
 
 
 # ----------------------------------------------------------------------------------------------------
+# Downstream consumers of the same Block: VITForRecognition (tae.py:274-342), VITForSegmentation (tae.py:345-429)
+# (SURVEY.md §8f.2).  They reuse the TAE decoder's autograd functions unchanged; the new pieces are a standalone
+# LayerNorm, mean-pool + head, and the C-channel unpatchify.
+# ----------------------------------------------------------------------------------------------------
+class _NormFn(torch.autograd.Function):
+    """decoder_norm on its own (tae.py:329): fp32 in, fp32 out (LayerNorm stays fp32 under autocast)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, norm):
+        from . import fp32 as F
+
+        B, N, D = x.shape
+        x2 = _as_f32_2d(x, D)
+        y, mean, rstd = F.layernorm_fwd(x2, w.detach(), b.detach(), norm.eps)
+        ctx.norm, ctx.dims = norm, (B, N, D)
+        ctx.save_for_backward(x2, mean, rstd)
+        return y.view(B, N, D)
+
+    @staticmethod
+    def backward(ctx, dy):
+        from . import fp32 as F
+
+        x2, mean, rstd = ctx.saved_tensors
+        norm = ctx.norm
+        B, N, D = ctx.dims
+        t_g, a_g = _sink(norm.weight)
+        t_b, a_b = _sink(norm.bias)
+        dx, dg, db = F.layernorm_bwd(_as_f32_2d(dy, D), x2, mean, rstd, norm.weight.detach(), None, t_g, t_b,
+                                     a_g | (a_b << 1))
+        return dx.view(B, N, D), _done(norm.weight, dg), _done(norm.bias, db), None
+
+
+def _pad8(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
+class _MeanHeadFn(torch.autograd.Function):
+    """forward_head (tae.py:332-335): global average pool over tokens (fp32) -> head Linear (bf16 out under autocast).
+    Class counts and batch sizes that are not multiples of 8 are zero-padded to the GEMM's granularity."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, head, fp32_mode):
+        B, N, D = x.shape
+        pooled = ops.token_mean(_as_f32_2d(x, D), B, N)  # fp32 [B, D]
+        C = w.shape[0]
+        Bp, Cp = _pad8(B), _pad8(C)
+        if fp32_mode:
+            from . import fp32 as F
+
+            pp = pooled if Bp == B else torch.cat([pooled, pooled.new_zeros(Bp - B, D)])
+            wp = w.detach() if Cp == C else torch.cat([w.detach(), w.new_zeros(Cp - C, D)])
+            y = F.gemm_f32(F.split3(pp), F.split3(wp))
+            if b is not None:
+                bp = b.detach() if Cp == C else torch.cat([b.detach(), b.new_zeros(Cp - C)])
+                F.bias_act(y, bp)
+        else:
+            pp = torch.zeros((Bp, D), dtype=torch.bfloat16, device=x.device)
+            ops.cast_bf16(pooled, pp[:B])
+            wb = shadow_bf16(w)
+            if Cp != C:
+                wb = torch.cat([wb, wb.new_zeros(Cp - C, D)])
+            bp = None
+            if b is not None:
+                bp = b.detach() if Cp == C else torch.cat([b.detach(), b.new_zeros(Cp - C)])
+            y = ops.gemm(pp, wb, epilogue=EPI_BF16, bias=bp)
+        ctx.head, ctx.dims, ctx.fp32_mode = head, (B, N, D, C, Bp, Cp), fp32_mode
+        ctx.save_for_backward(pp)
+        return y[:B, :C]
+
+    @staticmethod
+    def backward(ctx, dy):
+        (pp,) = ctx.saved_tensors
+        head = ctx.head
+        B, N, D, C, Bp, Cp = ctx.dims
+        need = ctx.needs_input_grad
+        w, b = head.weight, head.bias
+        dyp = torch.zeros((Bp, Cp), dtype=torch.float32 if ctx.fp32_mode else torch.bfloat16, device=dy.device)
+        dyp[:B, :C] = dy
+        g_b = None
+        if b is not None and need[2]:
+            t, acc = _sink(b)
+            full = ops.colsum_f32(dyp) if ctx.fp32_mode else ops.colsum(dyp)
+            if t is None:
+                g_b = full[:C].clone()
+            else:
+                t.add_(full[:C]) if acc else t.copy_(full[:C])
+            g_b = _done(b, g_b)
+        g_w = None
+        if ctx.fp32_mode:
+            from . import fp32 as F
+
+            dy3 = F.split3(dyp)
+            gw_full = F.gemm_f32(dy3, F.split3(pp), a_mn=True, b_mn=True) if need[1] else None
+            wp = w.detach() if Cp == C else torch.cat([w.detach(), w.new_zeros(Cp - C, D)])
+            dpooled = F.gemm_f32(dy3, F.split3(wp), b_mn=True)[:B] if need[0] else None
+        else:
+            gw_full = ops.gemm(dyp, pp, a_mn=True, b_mn=True, epilogue=EPI_F32_ACC, splits=1) if need[1] else None
+            wb = shadow_bf16(w)
+            if Cp != C:
+                wb = torch.cat([wb, wb.new_zeros(Cp - C, D)])
+            dpooled = ops.gemm(dyp, wb, b_mn=True, epilogue=EPI_F32_ACC, splits=1)[:B] if need[0] else None
+        if need[1]:
+            t, acc = _sink(w)
+            if t is None:
+                g_w = gw_full[:C].contiguous()
+            else:
+                tv = t.view(C, D)
+                tv.add_(gw_full[:C]) if acc else tv.copy_(gw_full[:C])
+            g_w = _done(w, g_w)
+        dx = ops.token_mean_bwd(dpooled.contiguous(), B, N).view(B, N, D) if need[0] else None
+        return dx, g_w, g_b, None, None
+
+
+class _UnpatchifyCFn(torch.autograd.Function):
+    """VITForSegmentation.unpatchify (tae.py:391-403): a pure permutation, so its adjoint is the inverse permutation."""
+
+    @staticmethod
+    def forward(ctx, x, p, C):
+        ctx.p = p
+        return ops.unpatchify_c(x, p, C)
+
+    @staticmethod
+    def backward(ctx, dimgs):
+        return ops.patchify_c(dimgs, ctx.p), None, None
+
+
+class _ViTBase(nn.Module):
+    def initialize_weights(self):
+        torch.nn.init.trunc_normal_(self.decoder_pos_embed, std=0.02)
+        self.apply(self._init_weights)
+
+    def _init_weights(self, m):
+        if isinstance(m, nn.Linear):
+            torch.nn.init.xavier_uniform_(m.weight)
+            if m.bias is not None:
+                nn.init.constant_(m.bias, 0)
+        elif isinstance(m, nn.LayerNorm):
+            nn.init.constant_(m.bias, 0)
+            nn.init.constant_(m.weight, 1.0)
+
+    set_precision = TAE.set_precision
+    precision = TAE.precision
+    invalidate_shadows = TAE.invalidate_shadows
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self.invalidate_shadows()
+        return out
+
+    def _embed(self, x):
+        _lib.require_device()
+        fn = _fp32().EmbedLatentFn if _is_fp32(self) else _EmbedLatentFn
+        return fn.apply(x, self.decoder_embed.weight, self.decoder_embed.bias, self.decoder_pos_embed, self)
+
+
+class VITForRecognition(_ViTBase):
+    """PatchEmbed-less ViT classifier over TAE latents (tae.py:274-342): same constructor, attributes and state_dict."""
+
+    def __init__(self, num_patches=256, vocab_size=16, decoder_embed_dim=512, decoder_depth=8, decoder_num_heads=16,
+                 mlp_ratio=4., norm_layer=nn.LayerNorm, num_classes=None):
+        super().__init__()
+        self.decoder_embed = nn.Linear(vocab_size, decoder_embed_dim, bias=True)
+        self.decoder_pos_embed = nn.Parameter(torch.zeros(1, num_patches, decoder_embed_dim))
+        self.decoder_blocks = nn.ModuleList([Block(decoder_embed_dim, decoder_num_heads, mlp_ratio, qkv_bias=True,
+                                                   norm_layer=norm_layer) for _ in range(decoder_depth)])
+        self.decoder_norm = norm_layer(decoder_embed_dim)
+        self.head = nn.Linear(decoder_embed_dim, num_classes, bias=True) if num_classes is not None else nn.Identity()
+        self.initialize_weights()
+
+    def forward_features(self, x):
+        x = self._embed(x)
+        for blk in self.decoder_blocks:
+            x = blk(x)
+        return _NormFn.apply(x, self.decoder_norm.weight, self.decoder_norm.bias, self.decoder_norm)
+
+    def forward_head(self, x):
+        if isinstance(self.head, nn.Identity):
+            B, N, D = x.shape
+            return _MeanOnlyFn.apply(x)
+        return _MeanHeadFn.apply(x, self.head.weight, self.head.bias, self.head, _is_fp32(self))
+
+    def forward(self, x):
+        return self.forward_head(self.forward_features(x))
+
+
+class _MeanOnlyFn(torch.autograd.Function):
+    """x.mean(dim=1) when the classifier has no head (num_classes=None)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        B, N, D = x.shape
+        ctx.dims = (B, N, D)
+        return ops.token_mean(_as_f32_2d(x, D), B, N)
+
+    @staticmethod
+    def backward(ctx, dy):
+        B, N, D = ctx.dims
+        return ops.token_mean_bwd(_as_f32_2d(dy, D), B, N).view(B, N, D)
+
+
+class VITForSegmentation(_ViTBase):
+    """PatchEmbed-less ViT segmenter over TAE latents with an auxiliary head at 3/4 depth (tae.py:345-429)."""
+
+    def __init__(self, num_patches=256, patch_size=16, vocab_size=16, decoder_embed_dim=512, decoder_depth=8,
+                 decoder_num_heads=16, mlp_ratio=4., norm_layer=nn.LayerNorm, num_classes=None):
+        super().__init__()
+        self.aux_depth = int(decoder_depth * 0.75)
+        self.patch_size = patch_size
+        self.num_classes = num_classes
+        self.decoder_embed = nn.Linear(vocab_size, decoder_embed_dim, bias=True)
+        self.decoder_pos_embed = nn.Parameter(torch.zeros(1, num_patches, decoder_embed_dim))
+        self.decoder_blocks = nn.ModuleList([Block(decoder_embed_dim, decoder_num_heads, mlp_ratio, qkv_bias=True,
+                                                   norm_layer=norm_layer) for _ in range(decoder_depth)])
+        self.decoder_norm = norm_layer(decoder_embed_dim)
+        self.aux_decoder_norm = norm_layer(decoder_embed_dim)
+        self.head = nn.Linear(decoder_embed_dim, patch_size ** 2 * num_classes, bias=True)
+        self.aux_head = nn.Linear(decoder_embed_dim, patch_size ** 2 * num_classes, bias=True)
+        self.initialize_weights()
+
+    def unpatchify(self, x):
+        """x (N, L, patch_size**2 * C) -> (N, C, H, W)   (tae.py:391-403)"""
+        h = int(x.shape[1] ** .5)
+        assert h * h == x.shape[1]
+        return _UnpatchifyCFn.apply(x, self.patch_size, x.shape[2] // (self.patch_size ** 2))
+
+    def _norm_head(self, x, norm, lin):
+        fn = _fp32().NormLinearFn if _is_fp32(self) else _NormLinearFn
+        return fn.apply(x, norm.weight, norm.bias, lin.weight, lin.bias, norm, lin)
+
+    def forward(self, x):
+        x = self._embed(x)
+        result = collections.OrderedDict()
+        aux = None
+        for i, blk in enumerate(self.decoder_blocks):
+            x = blk(x)
+            if i + 1 == self.aux_depth:
+                aux = self.unpatchify(self._norm_head(x, self.aux_decoder_norm, self.aux_head))
+        x = self.unpatchify(self._norm_head(x, self.decoder_norm, self.head))
+        result["out"] = x
+        result["aux"] = aux
+        return result
+
+
+# ----------------------------------------------------------------------------------------------------
 # Model zoo (tae.py:431-483): same names, zero arguments
 # ----------------------------------------------------------------------------------------------------
 _ZOO = {
@@ -598,3 +842,28 @@ for _p, (_dim, _depth, _heads, _vocabs) in _ZOO.items():
         globals()[_f.__name__] = _f
         MODEL_NAMES.append(_f.__name__)
 del _p, _dim, _depth, _heads, _vocabs, _v, _f
+
+
+# ************** RECOGNITION / SEGMENTATION (tae.py:485-587): ViT-Base over TAE latents **************
+_VIT_ZOO = {256: (16, 64, 256), 64: (64, 256, 1024), 16: (256, 1024, 4096), 4: (1024, 4096, 16384)}
+
+
+def _make_vit_factory(kind, cls, num_patches, vocab):
+    def factory(num_classes=None):
+        return cls(num_patches=num_patches, vocab_size=vocab, decoder_embed_dim=768, decoder_depth=12, decoder_num_heads=12,
+                   mlp_ratio=4, norm_layer=partial(nn.LayerNorm, eps=1e-6), num_classes=num_classes)
+
+    factory.__name__ = f"vit_{kind}_numpatches{num_patches}_vocab{vocab}_base"
+    factory.__qualname__ = factory.__name__
+    factory.__doc__ = f"ViT-Base {kind} model over {num_patches}-token, width-{vocab} TAE latents (reference tae.py:485-587)."
+    return factory
+
+
+VIT_MODEL_NAMES = []
+for _kind, _cls in (("recognition", VITForRecognition), ("segmentation", VITForSegmentation)):
+    for _np, _vocabs in _VIT_ZOO.items():
+        for _v in _vocabs:
+            _f = _make_vit_factory(_kind, _cls, _np, _v)
+            globals()[_f.__name__] = _f
+            VIT_MODEL_NAMES.append(_f.__name__)
+del _kind, _cls, _np, _vocabs, _v, _f
