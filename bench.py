@@ -355,7 +355,8 @@ def encode_throughput(torch, dist, engine, model_name, B, dev, world, iters=10, 
 
 
 def gemm_roofline(torch, ops, step_fn, peaks):
-    """Per-launch CUDA-event timing of every tae_gemm launch during 2 instrumented training steps."""
+    """Per-launch CUDA-event timing of every kernel family during 2 instrumented training steps (after the timed
+    regions).  Returns (roofline of the dominant kernel = the tcgen05 GEMM, per-family detail)."""
     records = []
     orig = ops.gemm
 
@@ -367,24 +368,61 @@ def gemm_roofline(torch, ops, step_fn, peaks):
         K = A.shape[0] if kw.get("a_mn") else A.shape[1]
         M = A.shape[1] if kw.get("a_mn") else A.shape[0]
         N = B.shape[1] if kw.get("b_mn") else B.shape[0]
-        records.append((kw.get("epilogue", 0), 2.0 * M * N * K, s, e))
+        epi = kw.get("epilogue", 0)
+        # algorithmic bytes: both operands once + every output / side input the epilogue touches once
+        by = 2.0 * (M * K + N * K) + {0: 2.0, 1: 4.0, 2: 8.0, 3: 4.0 + (4.0 if kw.get("beta") else 0.0), 4: 4.0}[epi] * M * N
+        records.append((epi, 2.0 * M * N * K, s, e, by))
         return out
 
-    import tae_b200.tae as model_mod
+    # the other kernels of the step: name -> [kind, algorithmic bytes or flops, events, calls]
+    other = {}
 
+    def wrap(name, unit_fn, kind):
+        fn = getattr(ops, name)
+
+        def timed(*a, **kw):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            out = fn(*a, **kw)
+            e.record()
+            rec = other.setdefault(name, [kind, 0.0, [], 0])
+            rec[1] += unit_fn(*a, **kw)
+            rec[2].append((s, e))
+            rec[3] += 1
+            return out
+
+        setattr(ops, name, timed)
+        return fn
+
+    saved = {
+        # LayerNorm fwd: read fp32 x, write bf16 y (6 B/elem)
+        "layernorm_fwd": wrap("layernorm_fwd", lambda x, *a, **k: 6.0 * x.numel(), "hbm"),
+        # LayerNorm bwd: dy bf16 + x fp32 + dres_in fp32 -> dres_out fp32 + bf16 copy (16 B/elem; 12 without dres_in)
+        "layernorm_bwd": wrap("layernorm_bwd",
+                              lambda dy, x, m, r, g, dres, **k: (16.0 if dres is not None else 12.0) * x.numel(), "hbm"),
+        "colsum": wrap("colsum", lambda x, *a, **k: 2.0 * x.numel(), "hbm"),
+        # AdamW: p,g,m,v read + p,m,v write + bf16 shadow write = 30 B/param
+        "adamw_step": wrap("adamw_step", lambda p, *a, **k: 30.0 * p.numel(), "hbm"),
+        # loss: pred bf16 + imgs fp32 (+ dpred bf16)
+        "mse_loss": wrap("mse_loss", lambda pred, imgs, p, **k: (8.0 if k.get("want_grad") else 6.0) * pred.numel(), "hbm"),
+        "im2col": wrap("im2col", lambda imgs, p: 6.0 * imgs.numel(), "hbm"),
+        # attention: 4 N^2 hd flops per (image, head) forward; backward counted algorithmically as 2.5x (5 GEMMs vs 2)
+        "attention_fwd": wrap("attention_fwd", lambda qkv, B, N, H, hd: 4.0 * B * H * N * N * hd, "tensor"),
+        "attention_bwd": wrap("attention_bwd", lambda qkv, o, do, lse, B, N, H, hd: 10.0 * B * H * N * N * hd, "tensor"),
+    }
     ops.gemm = timed_gemm
-    model_mod.ops.gemm = timed_gemm
     try:
         for i in range(2):
             step_fn(i)
         torch.cuda.synchronize()
     finally:
         ops.gemm = orig
-        model_mod.ops.gemm = orig
+        for name, fn in saved.items():
+            setattr(ops, name, fn)
     names = {0: "bf16", 1: "bf16_gelu", 2: "f32_resid", 3: "f32_acc(wgrad)", 4: "bf16_dgelu"}
     per = {}
-    tot_fl = tot_ms = 0.0
-    for epi, fl, s, e in records:
+    tot_fl = tot_ms = tot_by = 0.0
+    for epi, fl, s, e, by in records:
         ms = s.elapsed_time(e)
         d = per.setdefault(names[epi], [0.0, 0.0, 0])
         d[0] += fl
@@ -392,15 +430,39 @@ def gemm_roofline(torch, ops, step_fn, peaks):
         d[2] += 1
         tot_fl += fl
         tot_ms += ms
+        tot_by += by
     achieved = tot_fl / (tot_ms * 1e-3) / 1e12
     peak = peaks["bf16_tflops_sustained"]
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(tpath):  # committed ncu evidence (dram__bytes_read.sum + dram__bytes_write.sum per launch)
+        with open(tpath) as f:
+            tj = json.load(f)
+        k = tj["kernels"].get("gemm_bf16_tcgen05")
+        if k:
+            traffic, traffic_src = k["dram_bytes_per_launch"], "profiles/r1_traffic.json: " + tj["source"]
     roof = {"bound": "tensor", "kernel": "gemm_bf16_tcgen05 (all epilogue instantiations)", "achieved": achieved,
-            "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+            "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
             "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a long step)",
             "launches": len(records), "avg_launch_ms": tot_ms / max(1, len(records)),
-            "algorithmic_flops_per_launch": tot_fl / max(1, len(records))}
+            "algorithmic_flops_per_launch": tot_fl / max(1, len(records)),
+            "algorithmic_bytes_per_launch": tot_by / max(1, len(records)), "traffic_source": traffic_src}
     detail = {k: {"tflops": v[0] / (v[1] * 1e-3) / 1e12, "ms_per_step": v[1] / 2, "launches_per_step": v[2] // 2}
               for k, v in per.items()}
+    # memory-bound kernels against the measured HBM copy bandwidth; attention against the tensor peak
+    hbm = peaks.get("hbm_gbs")
+    for name, (kind, units, evs, calls) in other.items():
+        ms = sum(s.elapsed_time(e) for s, e in evs)
+        if ms <= 0:
+            continue
+        if kind == "hbm":
+            gbs = units / (ms * 1e-3) / 1e9
+            detail[name] = {"GB/s": gbs, "frac_of_hbm_peak": gbs / hbm if hbm else None, "ms_per_step": ms / 2,
+                            "calls_per_step": calls // 2, "bound": "hbm"}
+        else:
+            tf = units / (ms * 1e-3) / 1e12
+            detail[name] = {"tflops": tf, "frac_of_bf16_peak": tf / peak, "ms_per_step": ms / 2, "calls_per_step": calls // 2,
+                            "bound": "tensor (exp/MUFU- and HBM-limited, see DESIGN.md)"}
     return roof, detail
 
 

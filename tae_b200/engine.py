@@ -6,11 +6,15 @@
   HostBatchFeeder   train.py:134 / encode.py:82   pinned-host -> device copies, double-buffered on a copy stream
                     (the synchronous 201 MB H2D per step is the adjacent host overhead)
   shard_for_rank    batch sharding for multi-GPU encode / evaluate (no communication; rank r takes slice r)
+  LatentWriter      encode.py:87,93-100   asynchronous device->host ring + background writer for the extracted latents
+                    (the reference .cpu()-s every batch synchronously and concatenates at the end)
 """
 from __future__ import annotations
 
 import math
+import queue
 import sys
+import threading
 
 import torch
 
@@ -110,3 +114,87 @@ class HostBatchFeeder:
         slot = self.i % self.depth
         self.freed[slot].record(torch.cuda.current_stream(self.device))
         self.i += 1
+
+
+class LatentWriter:
+    """Streams encoded latents off the device without stalling the encoder (encode.py:87,93-100).
+
+    The reference does `latents.append(latent.cpu())` per batch (a synchronous D2H copy on the compute stream) and one
+    `torch.save({"latents", "targets"})` at the end.  Here `put()` enqueues the copy on a dedicated stream into a ring
+    of pinned host buffers and returns immediately; a background thread waits for each copy's event, moves the rows
+    into pageable storage and frees the ring slot.  `close()` writes the SAME file layout as the reference
+    (`{"latents": [n, N, V], "targets": [n]}`, encode.py:97-100), so downstream loaders are unaffected; with
+    `shard_rows` the rows are written as `path.partNNNNN` files of that many rows instead (same dict per part)."""
+
+    def __init__(self, path: str, device="cuda", depth: int = 3, shard_rows: int | None = None):
+        self.path, self.device, self.depth, self.shard_rows = path, torch.device(device), depth, shard_rows
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.pinned = [None] * depth
+        self.copied = [torch.cuda.Event() for _ in range(depth)]
+        self.free = [threading.Semaphore(1) for _ in range(depth)]
+        self.q: queue.Queue = queue.Queue()
+        self.lat, self.tgt, self.parts, self.rows_pending = [], [], [], 0
+        self.i = 0
+        self.bytes_copied = 0
+        self.err = None
+        self.worker = threading.Thread(target=self._drain, daemon=True)
+        self.worker.start()
+
+    def put(self, latent: torch.Tensor, targets: torch.Tensor | None = None):
+        """latent: device tensor [b, N, V] produced on the current stream; targets: host or device tensor [b] or None."""
+        if self.err is not None:
+            raise self.err
+        slot = self.i % self.depth
+        self.i += 1
+        self.free[slot].acquire()  # blocks only when the host writer is `depth` batches behind
+        buf = self.pinned[slot]
+        if buf is None or buf.shape[1:] != latent.shape[1:] or buf.shape[0] < latent.shape[0] or buf.dtype != latent.dtype:
+            buf = torch.empty(latent.shape, dtype=latent.dtype, pin_memory=True)
+            self.pinned[slot] = buf
+        produced = torch.cuda.Event()
+        produced.record(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(produced)
+            buf[:latent.shape[0]].copy_(latent, non_blocking=True)
+            self.copied[slot].record(self.stream)
+        latent.record_stream(self.stream)
+        self.bytes_copied += latent.numel() * latent.element_size()
+        self.q.put((slot, latent.shape[0], None if targets is None else targets.detach().cpu()))
+
+    def _flush_part(self, final: bool):
+        if not self.lat:
+            return
+        out = {"latents": torch.cat(self.lat), "targets": torch.cat(self.tgt) if self.tgt else torch.empty(0, dtype=torch.long)}
+        name = self.path if (final and not self.parts and self.shard_rows is None) else f"{self.path}.part{len(self.parts):05d}"
+        torch.save(out, name)
+        self.parts.append(name)
+        self.lat, self.tgt, self.rows_pending = [], [], 0
+
+    def _drain(self):
+        try:
+            while True:
+                item = self.q.get()
+                if item is None:
+                    break
+                slot, rows, tg = item
+                self.copied[slot].synchronize()
+                self.lat.append(self.pinned[slot][:rows].clone())
+                self.free[slot].release()
+                if tg is not None:
+                    self.tgt.append(tg)
+                self.rows_pending += rows
+                if self.shard_rows is not None and self.rows_pending >= self.shard_rows:
+                    self._flush_part(False)
+            self._flush_part(True)
+        except Exception as e:  # surfaced by the next put()/close()
+            self.err = e
+            for s in self.free:
+                s.release()
+
+    def close(self):
+        """Waits for every copy and write; returns the list of files written."""
+        self.q.put(None)
+        self.worker.join()
+        if self.err is not None:
+            raise self.err
+        return list(self.parts)

@@ -315,3 +315,33 @@ def test_fp32_mode_encode_decode_no_grad(golden_meta, golden_tensors):
         z = model.forward_encoder(t["input"].cuda())
         y = model.forward_decoder(z)
     assert rel(z.cpu(), t["fp32.latent"]) < FP32_TOL and rel(y.cpu(), t["fp32.pred"]) < FP32_TOL
+
+
+def test_latent_writer_matches_synchronous_reference_layout(tmp_path, golden_meta, golden_tensors):
+    """encode.py:80-100 restated: the asynchronous writer produces the reference's file layout with identical contents."""
+    from tae_b200 import engine
+
+    case = "tiny_p8_n16_hd32"
+    rec, t = golden_meta[case], golden_tensors(case)
+    model = build(rec["kwargs"]).cuda().eval()
+    xs = [torch.randn(5, 3, 32, 32, generator=torch.Generator().manual_seed(s)).cuda() for s in range(7)]
+    ys = [torch.arange(5) + 5 * s for s in range(7)]
+    ref_lat, ref_tgt = [], []
+    w = engine.LatentWriter(str(tmp_path / "lat.pth"), depth=2)
+    w2 = engine.LatentWriter(str(tmp_path / "shards.pth"), depth=3, shard_rows=10)
+    for x, y in zip(xs, ys):
+        z = engine.encode_batch(model, x)
+        w.put(z, y)
+        w2.put(z, y)
+        ref_lat.append(z.cpu())  # what the reference does (synchronous)
+        ref_tgt.append(y)
+    files = w.close()
+    assert files == [str(tmp_path / "lat.pth")]
+    d = torch.load(files[0])
+    assert set(d) == {"latents", "targets"}
+    assert torch.equal(d["latents"], torch.cat(ref_lat)) and torch.equal(d["targets"], torch.cat(ref_tgt))
+    parts = w2.close()
+    assert len(parts) == 4  # 35 rows in parts of >= 10
+    cat = torch.cat([torch.load(p)["latents"] for p in parts])
+    assert torch.equal(cat, torch.cat(ref_lat))
+    assert w.bytes_copied == sum(z.numel() * z.element_size() for z in ref_lat)

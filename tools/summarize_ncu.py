@@ -79,5 +79,33 @@ def full(path):
         print(f"| {n} | `{short(r[ik])}` | " + " | ".join(vals) + " |")
 
 
+def traffic(*paths):
+    """Average DRAM bytes (read + write) per launch and kernel family -> JSON for bench.py's `roofline.traffic`."""
+    import json
+
+    fam = OrderedDict()
+    for path in paths:
+        out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(out.splitlines()))
+        hdr, units = rows[0], rows[1]
+        ik, ir, iw = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        it = hdr.index("gpu__time_duration.sum")
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        tscale = {"ns": 1e-3, "us": 1.0, "ms": 1e3}
+        for r in rows[2:]:
+            name = short(r[ik])
+            key = "gemm_bf16_tcgen05" if "gemm_bf16_tcgen05" in name else name.split("<")[0]
+            b = float(r[ir]) * scale[units[ir]] + float(r[iw]) * scale[units[iw]]
+            d = fam.setdefault(key, {"launches": 0, "dram_bytes": 0.0, "time_us": 0.0})
+            d["launches"] += 1
+            d["dram_bytes"] += b
+            d["time_us"] += float(r[it]) * tscale[units[it]]
+    res = {k: {"launches_profiled": v["launches"], "dram_bytes_per_launch": v["dram_bytes"] / v["launches"],
+               "avg_time_us": v["time_us"] / v["launches"]} for k, v in fam.items()}
+    print(json.dumps({"source": "ncu --set full (tools/gpu_profile.sh); dram__bytes_read.sum + dram__bytes_write.sum per launch, "
+                                "averaged over the profiled launches of each kernel family at the bench shapes",
+                      "kernels": res}, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](*sys.argv[2:])
