@@ -316,6 +316,99 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const float* __restrict__ x, const fl
   }
 }
 
+// Backward, warp-per-row variant (D = NV*128 <= 1024).  A warp owns whole rows, so the two row statistics are shuffle
+// reductions and the kernel has no block-level barrier; a lane owns the same 4*NV columns for every row its warp
+// visits, so dgamma / dbeta / colsum accumulate in registers.  One partial row per WARP.
+template <int NV>
+__global__ void __launch_bounds__(256, 1)
+ln_bwd_warp_kernel(const bf16* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
+                   const float* __restrict__ rstd, const float* __restrict__ gamma, const float* dres_in,
+                   float* dres_out, bf16* __restrict__ dres_out_b, float* __restrict__ partials, int rows) {
+  constexpr int D = NV * 128;
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int gw = blockIdx.x * wpb + (threadIdx.x >> 5);
+  const int nw = gridDim.x * wpb;
+  float4 g[NV], acc_dg[NV], acc_db[NV], acc_cs[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    g[i] = __ldg(reinterpret_cast<const float4*>(gamma + (i * 32 + lane) * 4));
+    acc_dg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    acc_db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    acc_cs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const float invD = 1.0f / (float)D;
+#pragma unroll 1
+  for (int row = gw; row < rows; row += nw) {
+    const size_t base = (size_t)row * D;
+    float4 xh[NV], gy[NV], din[NV];
+    uint2 draw[NV];
+    const float mu = __ldg(mean + row), rs = __ldg(rstd + row);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const size_t off = base + (i * 32 + lane) * 4;
+      xh[i] = ld_nc_f4(x + off);
+      draw[i] = ld_nc_v2(dy + off);
+      din[i] = dres_in != nullptr ? *reinterpret_cast<const float4*>(dres_in + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float2 d01 = unpack_bf16x2(draw[i].x), d23 = unpack_bf16x2(draw[i].y);
+      const float4 d = make_float4(d01.x, d01.y, d23.x, d23.y);
+      const float4 h = make_float4((xh[i].x - mu) * rs, (xh[i].y - mu) * rs, (xh[i].z - mu) * rs, (xh[i].w - mu) * rs);
+      xh[i] = h;
+      acc_dg[i].x += d.x * h.x;
+      acc_dg[i].y += d.y * h.y;
+      acc_dg[i].z += d.z * h.z;
+      acc_dg[i].w += d.w * h.w;
+      acc_db[i].x += d.x;
+      acc_db[i].y += d.y;
+      acc_db[i].z += d.z;
+      acc_db[i].w += d.w;
+      const float4 t = make_float4(d.x * g[i].x, d.y * g[i].y, d.z * g[i].z, d.w * g[i].w);
+      gy[i] = t;
+      s1 += (t.x + t.y) + (t.z + t.w);
+      s2 += (t.x * h.x + t.y * h.y) + (t.z * h.z + t.w * h.w);
+    }
+    const float c1 = warp_sum(s1) * invD, c2 = warp_sum(s2) * invD;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const size_t off = base + (i * 32 + lane) * 4;
+      float4 o;
+      o.x = rs * (gy[i].x - c1 - xh[i].x * c2) + din[i].x;
+      o.y = rs * (gy[i].y - c1 - xh[i].y * c2) + din[i].y;
+      o.z = rs * (gy[i].z - c1 - xh[i].z * c2) + din[i].z;
+      o.w = rs * (gy[i].w - c1 - xh[i].w * c2) + din[i].w;
+      *reinterpret_cast<float4*>(dres_out + off) = o;
+      const uint32_t p01 = pack_bf16x2(o.x, o.y), p23 = pack_bf16x2(o.z, o.w);
+      if (dres_out_b != nullptr) *reinterpret_cast<uint2*>(dres_out_b + off) = make_uint2(p01, p23);
+      const float2 r01 = unpack_bf16x2(p01), r23 = unpack_bf16x2(p23);
+      acc_cs[i].x += r01.x;
+      acc_cs[i].y += r01.y;
+      acc_cs[i].z += r23.x;
+      acc_cs[i].w += r23.y;
+    }
+  }
+  float* pbase = partials + (size_t)gw * 3 * D;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int col = (i * 32 + lane) * 4;
+    *reinterpret_cast<float4*>(pbase + col) = acc_dg[i];
+    *reinterpret_cast<float4*>(pbase + D + col) = acc_db[i];
+    *reinterpret_cast<float4*>(pbase + 2 * D + col) = acc_cs[i];
+  }
+}
+
+// warp-per-row backward: which widths, and how many partial rows (= warps) it produces
+static bool bwd_warp_ok(int D) { return D % 128 == 0 && D / 128 <= 8 && (D / 128 == 1 || D / 128 == 2 || D / 128 == 6 || D / 128 == 8); }
+static int bwd_warp_grid(int rows) {
+  const int sms = num_sms() > 0 ? num_sms() : 148;
+  int grid = (rows + 7) / 8;
+  if (grid > sms) grid = sms;
+  return grid < 1 ? 1 : grid;
+}
+
 // out_k[col] (+)= sum_p partials[p][k][col].  Block = 32 columns x 32 partial-slices (coalesced 128-byte rows),
 // grid = 3*D/32 blocks; every thread keeps 4 independent loads in flight, so the few hundred partial rows cost
 // ~5 dependent round trips instead of ~40.
@@ -419,6 +512,7 @@ extern "C" int tae_layernorm_bwd_num_partials(int32_t rows, int32_t D) {
   using namespace tae::ln;
   int vpt, threads;
   if (rows <= 0 || !pick_config(D, &vpt, &threads)) return TAE_ERR_SHAPE;
+  if (bwd_warp_ok(D)) return bwd_warp_grid(rows) * 8;
   return grid_for(rows, threads, true);
 }
 
@@ -435,6 +529,17 @@ extern "C" int tae_layernorm_bwd(const tae_bf16* dy, const float* x, const float
   const int grid = grid_for(rows, threads, true);
   const bf16* dyy = reinterpret_cast<const bf16*>(dy);
   bf16* ob = reinterpret_cast<bf16*>(dres_out_bf16);
+  if (bwd_warp_ok(D)) {
+    const int wg = bwd_warp_grid(rows);
+    switch (D / 128) {
+      case 1: ln_bwd_warp_kernel<1><<<wg, 256, 0, stream>>>(dyy, x, mean, rstd, gamma, dres_in, dres_out, ob, partials, rows); break;
+      case 2: ln_bwd_warp_kernel<2><<<wg, 256, 0, stream>>>(dyy, x, mean, rstd, gamma, dres_in, dres_out, ob, partials, rows); break;
+      case 6: ln_bwd_warp_kernel<6><<<wg, 256, 0, stream>>>(dyy, x, mean, rstd, gamma, dres_in, dres_out, ob, partials, rows); break;
+      default: ln_bwd_warp_kernel<8><<<wg, 256, 0, stream>>>(dyy, x, mean, rstd, gamma, dres_in, dres_out, ob, partials, rows); break;
+    }
+    TAE_CHECK_LAUNCH();
+    return TAE_OK;
+  }
   switch (vpt) {
     case 1: ln_bwd_kernel<1><<<grid, threads, 0, stream>>>(dyy, x, mean, rstd, gamma, dres_in, dres_out, ob, partials, rows, D); break;
     case 2: ln_bwd_kernel<2><<<grid, threads, 0, stream>>>(dyy, x, mean, rstd, gamma, dres_in, dres_out, ob, partials, rows, D); break;
