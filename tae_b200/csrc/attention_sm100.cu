@@ -700,12 +700,15 @@ attn_bwd_tc_pipe(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
 //     prefetch while the results are still on their way out through TMA stores.
 // Shared memory map = attn_bwd_tc_pipe's, with lse/delta double-buffered.
 // =============================================================================================
-constexpr int S_OFF_LSE = 196608;     // [2][256] fp32
-constexpr int S_OFF_DELTA = 198656;   // [2][256] fp32
-constexpr int S_OFF_BAR = 200704;
+constexpr int S_OFF_Q0ALT = 196608;   // second home of Q block 0 (odd items), 8 KB
+constexpr int S_OFF_DO0ALT = 204800;  // second home of dO block 0 (odd items), 8 KB
+constexpr int S_OFF_LSE = 212992;     // [2][256] fp32
+constexpr int S_OFF_DELTA = 215040;   // [2][256] fp32
+constexpr int S_OFF_BAR = 217088;
 constexpr int S_SMEM = S_OFF_BAR + 256 + 1024;
+constexpr int S_THREADS = 512;  // warp 0: MMA issue; 1: TMA producer; 2-3: delta/lse of the next item; 4-11: element-wise; 12-15: drains
 
-__global__ void __launch_bounds__(B_THREADS, 1)
+__global__ void __launch_bounds__(S_THREADS, 1)
 attn_bwd_tc_persist(const __grid_constant__ CUtensorMap tm_qkv,   // box 64 rows x 64 cols over qkv  [B*N, 3D]
                     const __grid_constant__ CUtensorMap tm_do,    // box 64 rows x 64 cols over dout [B*N, D]
                     const __grid_constant__ CUtensorMap tm_dqkv,  // box 128 rows x 64 cols over dqkv (stores)
@@ -726,12 +729,16 @@ attn_bwd_tc_persist(const __grid_constant__ CUtensorMap tm_qkv,   // box 64 rows
   uint64_t* bar_p = bars + 14;       // [2] P^T/dS^T tile written, S/dP drained     (256 arrivals)
   uint64_t* bar_pfree = bars + 16;   // [2] gradient MMAs reading the tile retired
   uint64_t* bar_g = bars + 18;       // dV/dK (at the end dQ) complete              (2 per item)
-  uint64_t* bar_dfree = bars + 19;   // dV0/dK0 left TMEM                           (256, once per item)
-  uint64_t* bar_accfree = bars + 20; // dV1/dK1/dQ left TMEM                        (256, once per item)
-  uint64_t* bar_kv0free = bars + 21; // dV0/dK0 staging stores have read K0/V0      (2, once per item)
-  uint64_t* bar_delta = bars + 22;   // [2] lse/delta buffer filled                 (96, every other item each)
+  uint64_t* bar_dfree = bars + 19;   // dV0/dK0 left TMEM                           (128 drain threads, once per item)
+  uint64_t* bar_accfree = bars + 20; // dV1/dK1/dQ left TMEM                        (128, once per item)
+  uint64_t* bar_kv0free = bars + 21; // dV0/dK0 staging stores have read K0/V0      (1, once per item)
+  uint64_t* bar_tailfree = bars + 27;// final staging stores have read K1/V1/Q2-3/dO2-3 (1, once per item)
+  uint64_t* bQalt = bars + 28;       // Q block 0 landed in its second home            (TMA, every other item)
+  uint64_t* bdOalt = bars + 29;      // dO block 0 landed in its second home
+  uint64_t* bar_qfree = bars + 30;   // [1] is used: the last MMA reading Q/dO block 1 of the item retired (commit, once per item)
+  uint64_t* bar_delta = bars + 22;   // [2] lse/delta buffer filled                 (64, every other item each)
   uint64_t* bar_dbuffree = bars + 24;// [2] lse/delta buffer consumed               (256, every other item each)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);  // (bars + 27 is bar_tailfree)
   float* sLse = reinterpret_cast<float*>(smem + S_OFF_LSE);
   float* sDelta = reinterpret_cast<float*>(smem + S_OFF_DELTA);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -748,13 +755,18 @@ attn_bwd_tc_persist(const __grid_constant__ CUtensorMap tm_qkv,   // box 64 rows
       mbar_init(&bar_s[i], 1);
       mbar_init(&bar_p[i], 256);
       mbar_init(&bar_pfree[i], 1);
-      mbar_init(&bar_delta[i], 96);
+      mbar_init(&bar_delta[i], 64);
       mbar_init(&bar_dbuffree[i], 256);
     }
     mbar_init(bar_g, 1);
-    mbar_init(bar_dfree, 256);
-    mbar_init(bar_accfree, 256);
-    mbar_init(bar_kv0free, 2);
+    mbar_init(bar_dfree, 128);
+    mbar_init(bar_accfree, 128);
+    mbar_init(bar_kv0free, 1);
+    mbar_init(bar_tailfree, 1);
+    mbar_init(bQalt, 1);
+    mbar_init(bdOalt, 1);
+    mbar_init(&bar_qfree[0], 1);
+    mbar_init(&bar_qfree[1], 1);
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, 512);
@@ -765,21 +777,25 @@ attn_bwd_tc_persist(const __grid_constant__ CUtensorMap tm_qkv,   // box 64 rows
   const uint32_t sQ = smem_u32(smem + P_OFF_Q), sK = smem_u32(smem + P_OFF_K), sV = smem_u32(smem + P_OFF_V);
   const uint32_t sdO = smem_u32(smem + P_OFF_DO), sPT = smem_u32(smem + P_OFF_PT), sdST = smem_u32(smem + P_OFF_DST);
 
-  if (warp == 0) {
+  if (warp == 1) {
     if (elect_one()) {
-      // ---------------- TMA producer + MMA issuer ----------------
+      // ---------------- TMA producer: every operand piece of item it+1 as soon as its home is dead ----------------
       auto item_bh = [&](int it, int& b, int& h) {
         const int item = (int)blockIdx.x + it * (int)gridDim.x;
         b = item / H;
         h = item - b * H;
       };
-      auto load_q = [&](int it, int j) {  // Q block j and dO block j of item `it`
+      auto load_q = [&](int it, int j) {  // Q block j and dO block j of item `it` (block 0 alternates between two homes)
         int b, h;
         item_bh(it, b, h);
-        mbar_expect_tx(&bQ[j], 8192);
-        tma_load_2d(smem + P_OFF_Q + j * 8192, &tm_qkv, &bQ[j], h * HD, b * N + j * 64);
-        mbar_expect_tx(&bdO[j], 8192);
-        tma_load_2d(smem + P_OFF_DO + j * 8192, &tm_do, &bdO[j], h * HD, b * N + j * 64);
+        // each home of block 0 has its own barrier (it completes every other item); blocks 1-3 complete every item
+        const bool alt = (j == 0) && (it & 1);
+        uint64_t* bq = alt ? bQalt : &bQ[j];
+        uint64_t* bo = alt ? bdOalt : &bdO[j];
+        mbar_expect_tx(bq, 8192);
+        tma_load_2d(smem + (alt ? S_OFF_Q0ALT : P_OFF_Q + j * 8192), &tm_qkv, bq, h * HD, b * N + j * 64);
+        mbar_expect_tx(bo, 8192);
+        tma_load_2d(smem + (alt ? S_OFF_DO0ALT : P_OFF_DO + j * 8192), &tm_do, bo, h * HD, b * N + j * 64);
       };
       auto load_kv = [&](int it, int kt) {
         int b, h;
@@ -791,32 +807,6 @@ attn_bwd_tc_persist(const __grid_constant__ CUtensorMap tm_qkv,   // box 64 rows
         tma_load_2d(smem + P_OFF_V + kt * 16384, &tm_qkv, &bV[kt], 2 * D + h * HD, b * N + kt * 128);
         tma_load_2d(smem + P_OFF_V + kt * 16384 + 8192, &tm_qkv, &bV[kt], 2 * D + h * HD, b * N + kt * 128 + 64);
       };
-      const uint32_t id_s = make_idesc_bf16(128, 64, 0, 0);    // S^T, dP^T: [128 keys x 64 q]
-      const uint32_t id_kn = make_idesc_bf16(128, 64, 0, 1);   // dV, dK
-      const uint32_t id_q = make_idesc_bf16(64, 64, 1, 1);     // dQ: M = 64 queries
-      const uint32_t q_lo = desc_lo(sQ), k_lo = desc_lo(sK), v_lo = desc_lo(sV), do_lo = desc_lo(sdO);
-      const uint32_t pt_lo = desc_lo(sPT), dst_lo = desc_lo(sdST);
-      const uint32_t qmn_lo = desc_lo(sQ, 8192), kmn_lo = desc_lo(sK, 8192), domn_lo = desc_lo(sdO, 8192);
-      const uint32_t dstmn_lo = desc_lo(sdST, 8192);
-      // scores of block `blk` of item `it`: S^T = K_kt Q_j^T, dP^T = V_kt dO_j^T into S/dP buffer (blk & 1)
-      auto issue_scores = [&](int it, int blk) {
-        const int kt = blk >> 2, j = blk & 3, buf = blk & 1;
-        const uint32_t par = (uint32_t)(it & 1);
-        const uint32_t ka = k_lo + kt * (16384 >> 4), va = v_lo + kt * (16384 >> 4);
-        const uint32_t qb = q_lo + j * (8192 >> 4), ob = do_lo + j * (8192 >> 4);
-        const uint32_t ds = tmem + PC_S + buf * 64, dp = tmem + PC_DP + buf * 64;
-        mbar_wait(&bK[kt], par);
-        mbar_wait(&bQ[j], par);
-        tcgen05_fence_after();
-#pragma unroll
-        for (int k = 0; k < 4; ++k) umma_f16_lo(ds, ka + k * 2, qb + k * 2, id_s, k > 0);
-        mbar_wait(&bV[kt], par);
-        mbar_wait(&bdO[j], par);
-        tcgen05_fence_after();
-#pragma unroll
-        for (int k = 0; k < 4; ++k) umma_f16_lo(dp, va + k * 2, ob + k * 2, id_s, k > 0);
-        umma_commit(&bar_s[buf]);
-      };
       if (my_items > 0) {
         load_kv(0, 0);
         load_q(0, 0);
@@ -824,6 +814,61 @@ attn_bwd_tc_persist(const __grid_constant__ CUtensorMap tm_qkv,   // box 64 rows
         load_q(0, 2);
         load_q(0, 3);
         load_kv(0, 1);
+      }
+#pragma unroll 1
+      for (int it = 0; it + 1 < my_items; ++it) {
+        const uint32_t par = (uint32_t)(it & 1);
+        // Q/dO block 0 goes to its OTHER home, last read by item it-1: all of that item had retired when its
+        // bar_tailfree (waited at the end of the previous iteration) completed
+        load_q(it + 1, 0);
+        // K0/V0: the drain warps' dV0/dK0 staging stores of this item have read them
+        mbar_wait(bar_kv0free, par);
+        load_kv(it + 1, 0);
+        // Q/dO block 1: its last reader of this item (block 5) has retired
+        mbar_wait(&bar_qfree[1], par);
+        load_q(it + 1, 1);
+        // K1/V1 and Q/dO blocks 2-3 are the drain warps' final staging tiles until their stores have read them
+        mbar_wait(bar_tailfree, par);
+        load_q(it + 1, 2);
+        load_q(it + 1, 3);
+        load_kv(it + 1, 1);
+      }
+    }
+  } else if (warp == 0) {
+    if (elect_one()) {
+      // ---------------- MMA issuer ----------------
+      const uint32_t id_s = make_idesc_bf16(128, 64, 0, 0);    // S^T, dP^T: [128 keys x 64 q]
+      const uint32_t id_kn = make_idesc_bf16(128, 64, 0, 1);   // dV, dK
+      const uint32_t id_q = make_idesc_bf16(64, 64, 1, 1);     // dQ: M = 64 queries
+      const uint32_t q_lo = desc_lo(sQ), k_lo = desc_lo(sK), v_lo = desc_lo(sV), do_lo = desc_lo(sdO);
+      const uint32_t pt_lo = desc_lo(sPT), dst_lo = desc_lo(sdST);
+      const uint32_t qmn_lo = desc_lo(sQ, 8192), kmn_lo = desc_lo(sK, 8192), domn_lo = desc_lo(sdO, 8192);
+      const uint32_t dstmn_lo = desc_lo(sdST, 8192);
+      const uint32_t sQalt = smem_u32(smem + S_OFF_Q0ALT), sdOalt = smem_u32(smem + S_OFF_DO0ALT);
+      const uint32_t qalt_lo = desc_lo(sQalt), doalt_lo = desc_lo(sdOalt);
+      const uint32_t qaltmn_lo = desc_lo(sQalt, 8192), doaltmn_lo = desc_lo(sdOalt, 8192);
+      // scores of block `blk` of item `it`: S^T = K_kt Q_j^T, dP^T = V_kt dO_j^T into S/dP buffer (blk & 1)
+      auto issue_scores = [&](int it, int blk) {
+        const int kt = blk >> 2, j = blk & 3, buf = blk & 1;
+        const uint32_t par = (uint32_t)(it & 1);
+        const uint32_t ka = k_lo + kt * (16384 >> 4), va = v_lo + kt * (16384 >> 4);
+        const bool alt = (j == 0) && (it & 1);
+        const uint32_t qb = alt ? qalt_lo : q_lo + j * (8192 >> 4), ob = alt ? doalt_lo : do_lo + j * (8192 >> 4);
+        const uint32_t ds = tmem + PC_S + buf * 64, dp = tmem + PC_DP + buf * 64;
+        const uint32_t parq = j == 0 ? (uint32_t)((it >> 1) & 1) : par;
+        mbar_wait(&bK[kt], par);
+        mbar_wait(alt ? bQalt : &bQ[j], parq);
+        tcgen05_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16_lo(ds, ka + k * 2, qb + k * 2, id_s, k > 0);
+        mbar_wait(&bV[kt], par);
+        mbar_wait(alt ? bdOalt : &bdO[j], parq);
+        tcgen05_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16_lo(dp, va + k * 2, ob + k * 2, id_s, k > 0);
+        umma_commit(&bar_s[buf]);
+      };
+      if (my_items > 0) {
         issue_scores(0, 0);
         issue_scores(0, 1);
       }
@@ -846,7 +891,9 @@ attn_bwd_tc_persist(const __grid_constant__ CUtensorMap tm_qkv,   // box 64 rows
             tcgen05_fence_after();
           }
           const uint32_t a_pt = pt_lo + buf * (16384 >> 4), a_dst = dst_lo + buf * (16384 >> 4);
-          const uint32_t b_do = domn_lo + j * (8192 >> 4), b_q = qmn_lo + j * (8192 >> 4);
+          const bool alt = (j == 0) && (it & 1);
+          const uint32_t b_do = alt ? doaltmn_lo : domn_lo + j * (8192 >> 4);
+          const uint32_t b_q = alt ? qaltmn_lo : qmn_lo + j * (8192 >> 4);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {  // 16 queries per instruction
             umma_f16_lo(tmem + PC_DV, a_pt + k * 2, b_do + k * (2048 >> 4), id_kn, (j > 0 || k > 0));
@@ -859,37 +906,20 @@ attn_bwd_tc_persist(const __grid_constant__ CUtensorMap tm_qkv,   // box 64 rows
             umma_f16_lo(dq_addr, a_ds + k * (2048 >> 4), b_k + k * (2048 >> 4), id_q, (kt > 0 || k > 0));
           umma_commit(&bar_pfree[buf]);
           if (j == 3) umma_commit(bar_g);
+          if (blk == 5) umma_commit(&bar_qfree[1]);  // block 5 = (kt 1, j 1) is the last reader of Q/dO block 1
+          // scores run two blocks ahead, across the item boundary (S/dP buffer blk&1 was drained by block blk)
           if (blk < 6) {
             issue_scores(it, blk + 2);
           } else if (has_next) {
-            // E arrived on bar_p(blk) only after bar_pfree(blk-2): every MMA of block blk-2 = (kt 1, j = blk-6) has
-            // retired, and it was the last reader of Q/dO block j = blk-6 of this item.
-            if (blk == 6) {
-              mbar_wait(bar_kv0free, (uint32_t)(it & 1));  // dV0/dK0 staging stores are done with K0/V0
-              load_kv(it + 1, 0);
-              load_q(it + 1, 0);
-            } else {
-              load_q(it + 1, 1);
-              issue_scores(it + 1, 0);
-            }
+            issue_scores(it + 1, blk - 6);
           }
           TRACE_C(2 + 2 * blk);
-        }
-        if (has_next) {
-          // everything of this item has retired once bar_g completes for its second key tile
-          mbar_wait(bar_g, (uint32_t)((it * 2 + 1) & 1));
-          tcgen05_fence_after();
-          load_q(it + 1, 2);
-          load_q(it + 1, 3);
-          load_kv(it + 1, 1);
-          issue_scores(it + 1, 1);
-          TRACE_C(17);
         }
       }
     }
   } else if (warp < 4) {
-    // ---------------- helper warps 1-3: delta = rowsum(dO * O) and lse (exp2 domain) of item `it` ----------------
-    const int te = threadIdx.x - 32;  // 0..95
+    // ---------------- helper warps 2-3: delta = rowsum(dO * O) and lse (exp2 domain) of item `it` ----------------
+    const int te = threadIdx.x - 64;  // 0..63
 #pragma unroll 1
     for (int it = 0; it < my_items; ++it) {
       const int item = (int)blockIdx.x + it * (int)gridDim.x;
@@ -900,13 +930,13 @@ attn_bwd_tc_persist(const __grid_constant__ CUtensorMap tm_qkv,   // box 64 rows
       const bf16* gdo = dout + (size_t)b * N * D + (size_t)h * HD;
       float* dl = sDelta + dbuf * 256;
       float* ls = sLse + dbuf * 256;
-      // 3 chunks of 96 rows; all 16 loads of a chunk are in flight before the first use (3 round trips per item)
+      // 4 chunks of 64 rows; all 16 loads of a chunk are in flight before the first use (4 round trips per item)
 #pragma unroll 1
-      for (int c0 = 0; c0 < 288; c0 += 96) {
+      for (int c0 = 0; c0 < 256; c0 += 64) {
         uint4 dv[8], ov[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-          const int row = c0 + u * 12 + (te >> 3), ch = te & 7;
+          const int row = c0 + u * 8 + (te >> 3), ch = te & 7;
           dv[u] = make_uint4(0u, 0u, 0u, 0u);
           ov[u] = make_uint4(0u, 0u, 0u, 0u);
           if (row < 256) {
@@ -916,7 +946,7 @@ attn_bwd_tc_persist(const __grid_constant__ CUtensorMap tm_qkv,   // box 64 rows
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-          const int row = c0 + u * 12 + (te >> 3), ch = te & 7;
+          const int row = c0 + u * 8 + (te >> 3), ch = te & 7;
           const uint32_t dw[4] = {dv[u].x, dv[u].y, dv[u].z, dv[u].w}, ow[4] = {ov[u].x, ov[u].y, ov[u].z, ov[u].w};
           float acc = 0.f;
 #pragma unroll
@@ -930,33 +960,15 @@ attn_bwd_tc_persist(const __grid_constant__ CUtensorMap tm_qkv,   // box 64 rows
           if (ch == 0 && row < 256) dl[row] = acc;
         }
       }
-      for (int i = te; i < 256; i += 96) ls[i] = lse[((size_t)b * H + h) * N + i] * 1.44269504088896340736f;
+      for (int i = te; i < 256; i += 64) ls[i] = lse[((size_t)b * H + h) * N + i] * 1.44269504088896340736f;
       mbar_arrive(&bar_delta[dbuf]);  // release: the smem writes above are visible to whoever acquires the phase
     }
-  } else {
+  } else if (warp < 12) {
     // ---------------- element-wise warps 4-11 ----------------
     const int q4 = warp & 3;
     const int half = (warp - 4) >> 2;   // which 32 query columns of the 64-wide block
     const int r = q4 * 32 + lane;       // key row inside the key tile == TMEM lane
     const uint32_t tlane = tmem + ((uint32_t)(q4 * 32) << 16);
-    const bool storer_warp = (warp & 3) == 0;
-    // TMEM accumulator row (64 fp32 columns at `taddr`) -> bf16 -> row `row` of a 128B-swizzled [rows x 64] staging tile
-    auto stage_row = [&](uint32_t taddr, uint32_t tile, int row) {
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t raw[32];
-        tmem_ld_32x32b_x32(taddr + c * 32, raw);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          st_shared_v4(tile + sw128(row, c * 4 + i),
-                       pack_bf16x2(__uint_as_float(raw[i * 8 + 0]), __uint_as_float(raw[i * 8 + 1])),
-                       pack_bf16x2(__uint_as_float(raw[i * 8 + 2]), __uint_as_float(raw[i * 8 + 3])),
-                       pack_bf16x2(__uint_as_float(raw[i * 8 + 4]), __uint_as_float(raw[i * 8 + 5])),
-                       pack_bf16x2(__uint_as_float(raw[i * 8 + 6]), __uint_as_float(raw[i * 8 + 7])));
-      }
-    };
-    bool kv0_pending = false;  // this warp's storer still owes bar_kv0free an arrival for the current item
 #pragma unroll 1
     for (int it = 0; it < my_items; ++it) {
       const int item = (int)blockIdx.x + it * (int)gridDim.x;
@@ -970,14 +982,6 @@ attn_bwd_tc_persist(const __grid_constant__ CUtensorMap tm_qkv,   // box 64 rows
       for (int blk = 0; blk < 8; ++blk) {
         const int kt = blk >> 2, j = blk & 3, buf = blk & 1;
         const int g = it * 8 + blk;
-        if (kv0_pending && blk == 5) {
-          // the dV0/dK0 stores were issued a block ago: by now they have read their staging tiles (K0/V0)
-          if (storer_warp && elect_one()) {
-            tma_store_wait_read();
-            mbar_arrive(bar_kv0free);
-          }
-          kv0_pending = false;
-        }
         mbar_wait(&bar_s[buf], (uint32_t)((g >> 1) & 1));
         tcgen05_fence_after();
         TRACE_E(1 + 3 * blk);
@@ -1014,47 +1018,73 @@ attn_bwd_tc_persist(const __grid_constant__ CUtensorMap tm_qkv,   // box 64 rows
         mbar_arrive(&bar_p[buf]);
         TRACE_E(3 + 3 * blk);
         if (blk == 7) mbar_arrive(&bar_dbuffree[dbuf]);  // last read of this item's lse/delta buffer
-        if (blk == 3) {
-          // dV0 (half 0) / dK0 (half 1): every MMA that reads V0 / K0 has retired (bar_g), so the accumulator is staged
-          // as bf16 over the dead operand tile and leaves with one coalesced TMA store.
-          mbar_wait(bar_g, (uint32_t)((it * 2) & 1));
-          tcgen05_fence_after();
-          const int off = half == 0 ? P_OFF_V : P_OFF_K;
-          stage_row(tlane + (half == 0 ? PC_DV : PC_DK), smem_u32(smem + off), r);
-          tcgen05_fence_before();
-          mbar_arrive(bar_dfree);
-          fence_proxy_async_smem();
-          named_bar_sync(2 + half, 128);
-          if (storer_warp && elect_one()) {
-            tma_store_2d(&tm_dqkv, smem + off, (half == 0 ? 2 * D : D) + h * HD, b * N);
-            tma_store_commit();
-          }
-          kv0_pending = true;
-        }
       }
-      // ---- final drain of the item: dV1 -> P^T[0], dK1 -> P^T[1], dQ -> dS^T[0..1] (all dead once bar_g completes) ----
+    }
+  } else {
+    // ---------------- drain warps 12-15: accumulators -> bf16 -> swizzled staging tile -> TMA store ----------------
+    const int q4 = warp & 3;
+    const int r = q4 * 32 + lane;       // TMEM lane == key row inside the key tile
+    const uint32_t tlane = tmem + ((uint32_t)(q4 * 32) << 16);
+    // TMEM accumulator row (64 fp32 columns at `taddr`) -> bf16 -> row `row` of a 128B-swizzled [rows x 64] staging tile
+    auto stage_row = [&](uint32_t taddr, uint32_t tile, int row) {
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t raw[32];
+        tmem_ld_32x32b_x32(taddr + c * 32, raw);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          st_shared_v4(tile + sw128(row, c * 4 + i),
+                       pack_bf16x2(__uint_as_float(raw[i * 8 + 0]), __uint_as_float(raw[i * 8 + 1])),
+                       pack_bf16x2(__uint_as_float(raw[i * 8 + 2]), __uint_as_float(raw[i * 8 + 3])),
+                       pack_bf16x2(__uint_as_float(raw[i * 8 + 4]), __uint_as_float(raw[i * 8 + 5])),
+                       pack_bf16x2(__uint_as_float(raw[i * 8 + 6]), __uint_as_float(raw[i * 8 + 7])));
+      }
+    };
+#pragma unroll 1
+    for (int it = 0; it < my_items; ++it) {
+      const int item = (int)blockIdx.x + it * (int)gridDim.x;
+      const int b = item / H, h = item - b * H;
+      // key tile 0: every MMA that reads K0 / V0 has retired (bar_g), so dK0 / dV0 are staged over those dead tiles
+      mbar_wait(bar_g, (uint32_t)((it * 2) & 1));
+      tcgen05_fence_after();
+      stage_row(tlane + PC_DV, sV, r);
+      stage_row(tlane + PC_DK, sK, r);
+      tcgen05_fence_before();
+      mbar_arrive(bar_dfree);
+      fence_proxy_async_smem();
+      named_bar_sync(2, 128);
+      if (warp == 12 && elect_one()) {
+        tma_store_2d(&tm_dqkv, smem + P_OFF_V, 2 * D + h * HD, b * N);
+        tma_store_2d(&tm_dqkv, smem + P_OFF_K, D + h * HD, b * N);
+        tma_store_commit();
+        tma_store_wait_read();
+        mbar_arrive(bar_kv0free);  // the producer may overwrite K0/V0 with the next item's tiles
+      }
+      // end of the item: dV1 -> V1, dK1 -> K1, dQ -> the Q / dO blocks 2-3 (two [128 x 64] tiles), all dead by now
       mbar_wait(bar_g, (uint32_t)((it * 2 + 1) & 1));
       tcgen05_fence_after();
-      TRACE_E(25);
-      stage_row(tlane + (half == 0 ? PC_DV : PC_DK), sPT + half * 16384, r);
-      // dQ: M=64 accumulators; thread (quarter q4, lane l) owns query (2*half + (l>>4))*64 + 16*q4 + (l&15)
-      const int qrow = (2 * half + (lane >> 4)) * 64 + 16 * q4 + (lane & 15);
-      stage_row(tlane + PC_DQ + half * 64, sdST, qrow);
+      stage_row(tlane + PC_DV, sV + 16384, r);
+      stage_row(tlane + PC_DK, sK + 16384, r);
+      // dQ: M=64 accumulators; (quarter q4, lane l) of column group c2 owns query (2*c2 + (l>>4))*64 + 16*q4 + (l&15)
+      const int qlo = (lane >> 4) * 64 + 16 * q4 + (lane & 15);  // row inside a 128-query tile
+      stage_row(tlane + PC_DQ, sQ + 16384, qlo);
+      stage_row(tlane + PC_DQ + 64, sdO + 16384, qlo);
       tcgen05_fence_before();
       mbar_arrive(bar_accfree);
-      TRACE_E(26);
       fence_proxy_async_smem();
-      named_bar_sync(2 + half, 128);  // this half's threads own dV1 or dK1 and query rows [half*128, half*128 + 128)
-      if (storer_warp && elect_one()) {
-        tma_store_2d(&tm_dqkv, smem + P_OFF_PT + half * 16384, (half == 0 ? 2 * D : D) + h * HD, b * N + 128);
-        tma_store_2d(&tm_dqkv, smem + P_OFF_DST + half * 16384, h * HD, b * N + half * 128);
+      named_bar_sync(2, 128);
+      if (warp == 12 && elect_one()) {
+        tma_store_2d(&tm_dqkv, smem + P_OFF_V + 16384, 2 * D + h * HD, b * N + 128);
+        tma_store_2d(&tm_dqkv, smem + P_OFF_K + 16384, D + h * HD, b * N + 128);
+        tma_store_2d(&tm_dqkv, smem + P_OFF_Q + 16384, h * HD, b * N);
+        tma_store_2d(&tm_dqkv, smem + P_OFF_DO + 16384, h * HD, b * N + 128);
         tma_store_commit();
-        tma_store_wait_read();  // the staging tiles are P^T/dS^T of the next item's first blocks
+        tma_store_wait_read();
+        mbar_arrive(bar_tailfree);
       }
-      named_bar_sync(1, 256);
-      TRACE_E(27);
     }
-    if (storer_warp && elect_one()) tma_store_wait_all();
+    if (warp == 12 && elect_one()) tma_store_wait_all();
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -1149,7 +1179,7 @@ int attention_bwd_tcgen05(const bf16* qkv, const bf16* out, const bf16* dout, co
     if (sms <= 0) return TAE_ERR_CUDA;
     const int items = B * H;
     const int grid = items < sms ? items : sms;
-    attn_bwd_tc_persist<<<grid, B_THREADS, S_SMEM, stream>>>(tq64, tdo64, tdq, out, dout, lse, H, items, scale, sl2,
+    attn_bwd_tc_persist<<<grid, S_THREADS, S_SMEM, stream>>>(tq64, tdo64, tdq, out, dout, lse, H, items, scale, sl2,
                                                               g_attn_trace);
   }
   TAE_CHECK_LAUNCH();
