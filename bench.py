@@ -370,7 +370,7 @@ def gemm_roofline(torch, ops, step_fn, peaks):
         N = B.shape[1] if kw.get("b_mn") else B.shape[0]
         epi = kw.get("epilogue", 0)
         # algorithmic bytes: both operands once + every output / side input the epilogue touches once
-        by = 2.0 * (M * K + N * K) + {0: 2.0, 1: 4.0, 2: 8.0, 3: 4.0 + (4.0 if kw.get("beta") else 0.0), 4: 4.0}[epi] * M * N
+        by = 2.0 * (M * K + N * K) + {0: 2.0, 1: 4.0, 2: 8.0, 3: 4.0 + (4.0 if kw.get("beta") else 0.0), 4: 4.0, 5: 4.0}[epi] * M * N
         records.append((epi, 2.0 * M * N * K, s, e, by))
         return out
 
@@ -408,7 +408,7 @@ def gemm_roofline(torch, ops, step_fn, peaks):
         "im2col": wrap("im2col", lambda imgs, p: 6.0 * imgs.numel(), "hbm"),
         # attention: 4 N^2 hd flops per (image, head) forward; backward counted algorithmically as 2.5x (5 GEMMs vs 2)
         "attention_fwd": wrap("attention_fwd", lambda qkv, B, N, H, hd: 4.0 * B * H * N * N * hd, "tensor"),
-        "attention_bwd": wrap("attention_bwd", lambda qkv, o, do, lse, B, N, H, hd: 10.0 * B * H * N * N * hd, "tensor"),
+        "attention_bwd": wrap("attention_bwd", lambda qkv, o, do, lse, B, N, H, hd, **k: 10.0 * B * H * N * N * hd, "tensor"),
     }
     ops.gemm = timed_gemm
     try:
@@ -419,7 +419,7 @@ def gemm_roofline(torch, ops, step_fn, peaks):
         ops.gemm = orig
         for name, fn in saved.items():
             setattr(ops, name, fn)
-    names = {0: "bf16", 1: "bf16_gelu", 2: "f32_resid", 3: "f32_acc(wgrad)", 4: "bf16_dgelu"}
+    names = {0: "bf16", 1: "bf16_gelu", 2: "f32_resid", 3: "f32_acc(wgrad)", 4: "bf16_dgelu", 5: "bf16_rowdot"}
     per = {}
     tot_fl = tot_ms = tot_by = 0.0
     for epi, fl, s, e, by in records:

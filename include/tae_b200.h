@@ -74,7 +74,12 @@ enum tae_gemm_epilogue {
   TAE_EPI_F32_ACC = 3,
   /* out(bf16)[m,n] = bf16( float(bf16(acc)) * aux[m,n] ),  aux = gelu_erf'(h) saved by TAE_EPI_BF16_GELU:
    * GELU backward fused into the fc2 dgrad */
-  TAE_EPI_BF16_DGELU = 4
+  TAE_EPI_BF16_DGELU = 4,
+  /* out(bf16)[m,n] = acc + bias[n] (as TAE_EPI_BF16), and in the same pass
+   *   rowdot[b, h, t] = sum_{n in head h} float(out[m,n]) * float(aux[m,n]),   m = b*rowdot_tokens + t, head = 64 columns:
+   * the attention backward's delta = rowsum(dO * O) emitted by the GEMM that produces dO (attn.proj dgrad, tae.py:81),
+   * so the attention kernel never re-reads O and dO for it.  N % 64 == 0. */
+  TAE_EPI_BF16_ROWDOT = 5
 };
 
 typedef struct tae_gemm_args {
@@ -98,6 +103,8 @@ typedef struct tae_gemm_args {
   float* colsum_partials;  /* TAE_EPI_BF16_DGELU, optional: fp32 [ceil(M/32), N]; row r receives the column sums of output
                             * rows 32r..32r+31 (of the bf16-rounded values).  tae_colsum_f32 reduces it to the bias
                             * gradient without re-reading the [M, N] output */
+  float* rowdot;           /* TAE_EPI_BF16_ROWDOT: fp32 [M / rowdot_tokens, N / 64, rowdot_tokens]; aux/ldaux give the multiplier */
+  int32_t rowdot_tokens;   /* tokens per image (M % rowdot_tokens == 0) */
 } tae_gemm_args;
 
 int tae_gemm(const tae_gemm_args* args, void* stream);
@@ -137,7 +144,10 @@ int tae_layernorm_bwd_finalize(const float* partials, int32_t num_partials, int3
  */
 int tae_attention_fwd(const tae_bf16* qkv, tae_bf16* out, float* lse, int32_t B, int32_t N,
                       int32_t H, int32_t hd, void* stream);
-/* dqkv bf16 [B*N, 3*H*hd] from dout bf16 [B*N, H*hd] */
+/* dqkv bf16 [B*N, 3*H*hd] from dout bf16 [B*N, H*hd].  tae_attention_bwd_delta takes delta = rowsum(dout * out) per
+ * (image, head, token) as fp32 [B, H, N] (e.g. from a TAE_EPI_BF16_ROWDOT GEMM) instead of `out`. */
+int tae_attention_bwd_delta(const tae_bf16* qkv, const tae_bf16* dout, const float* lse, const float* delta,
+                            tae_bf16* dqkv, int32_t B, int32_t N, int32_t H, int32_t hd, void* stream);
 int tae_attention_bwd(const tae_bf16* qkv, const tae_bf16* out, const tae_bf16* dout,
                       const float* lse, tae_bf16* dqkv, int32_t B, int32_t N, int32_t H, int32_t hd,
                       void* stream);

@@ -13,7 +13,7 @@ _PKG_DIR = Path(__file__).resolve().parent
 LIB_PATH = _PKG_DIR / "libtae_b200.so"
 
 TAE_OK = 0
-EPI_BF16, EPI_BF16_GELU, EPI_F32_RESID, EPI_F32_ACC, EPI_BF16_DGELU = range(5)
+EPI_BF16, EPI_BF16_GELU, EPI_F32_RESID, EPI_F32_ACC, EPI_BF16_DGELU, EPI_BF16_ROWDOT = range(6)
 
 
 class TaeError(RuntimeError):
@@ -46,6 +46,8 @@ class GemmArgs(C.Structure):
         ("beta", C.c_int32),
         ("splits", C.c_int32),
         ("colsum_partials", C.c_void_p),
+        ("rowdot", C.c_void_p),
+        ("rowdot_tokens", C.c_int32),
     ]
 
 
@@ -65,6 +67,7 @@ PROTOTYPES = {
     "tae_layernorm_bwd_finalize": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp, _i32, _vp]),
     "tae_attention_fwd": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "tae_attention_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+    "tae_attention_bwd_delta": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "tae_im2col_bf16": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp]),
     "tae_patchify": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "tae_unpatchify": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),

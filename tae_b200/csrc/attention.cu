@@ -20,8 +20,8 @@ namespace tae {
 
 // tcgen05 path for the 256-token grid (attention_sm100.cu)
 int attention_fwd_tcgen05(const bf16* qkv, bf16* out, float* lse, int B, int H, cudaStream_t stream);
-int attention_bwd_tcgen05(const bf16* qkv, const bf16* out, const bf16* dout, const float* lse, bf16* dqkv, int B, int H,
-                          cudaStream_t stream);
+int attention_bwd_tcgen05(const bf16* qkv, const bf16* out, const bf16* dout, const float* lse, const float* delta,
+                          bf16* dqkv, int B, int H, cudaStream_t stream);
 
 namespace attn {
 
@@ -600,7 +600,7 @@ extern "C" int tae_attention_bwd(const tae_bf16* qkv_, const tae_bf16* out_, con
   TAE_CHECK_SHAPE(B > 0 && N > 0 && H > 0 && hd > 0, "tae_attention_bwd: non-positive dims");
   TAE_CHECK_SHAPE(hd % 8 == 0 && hd <= 128, "tae_attention_bwd: hd=%d unsupported", hd);
   const float scale = 1.0f / sqrtf((float)hd);
-  if (hd == HD && N == 256 && use_tcgen05()) return attention_bwd_tcgen05(qkv, out, dout, lse, dqkv, B, H, stream);
+  if (hd == HD && N == 256 && use_tcgen05()) return attention_bwd_tcgen05(qkv, out, dout, lse, nullptr, dqkv, B, H, stream);
   if (hd == HD && (N == 64 || N == 256)) {
     const float sl2 = scale * 1.44269504088896340736f;
     const int smem = 4 * N * LDS * 2 + 2 * N * 4;
@@ -625,4 +625,15 @@ extern "C" int tae_attention_bwd(const tae_bf16* qkv_, const tae_bf16* out_, con
   attn_bwd_simt<<<(BH + wpc - 1) / wpc, wpc * 32, smem, stream>>>(qkv, dout, lse, dqkv, BH, N, H, hd, scale, pw);
   TAE_CHECK_LAUNCH();
   return TAE_OK;
+}
+
+extern "C" int tae_attention_bwd_delta(const tae_bf16* qkv_, const tae_bf16* dout_, const float* lse, const float* delta,
+                                       tae_bf16* dqkv_, int32_t B, int32_t N, int32_t H, int32_t hd, void* stream_) {
+  using namespace tae;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  TAE_CHECK_SHAPE(qkv_ && dout_ && lse && delta && dqkv_, "tae_attention_bwd_delta: NULL argument");
+  TAE_CHECK_SHAPE(B > 0 && H > 0 && N == 256 && hd == 64,
+                  "tae_attention_bwd_delta: only the tcgen05 path (N=256, hd=64) takes a precomputed delta (got N=%d hd=%d)", N, hd);
+  return attention_bwd_tcgen05(reinterpret_cast<const bf16*>(qkv_), nullptr, reinterpret_cast<const bf16*>(dout_), lse, delta,
+                               reinterpret_cast<bf16*>(dqkv_), B, H, stream);
 }

@@ -713,6 +713,7 @@ attn_bwd_tc_persist(const __grid_constant__ CUtensorMap tm_qkv,   // box 64 rows
                     const __grid_constant__ CUtensorMap tm_do,    // box 64 rows x 64 cols over dout [B*N, D]
                     const __grid_constant__ CUtensorMap tm_dqkv,  // box 128 rows x 64 cols over dqkv (stores)
                     const bf16* __restrict__ out, const bf16* __restrict__ dout, const float* __restrict__ lse,
+                    const float* __restrict__ delta_in,  // optional [B, H, N]: rowsum(dO * O) from the GEMM that made dO
                     int H, int num_items, float scale, float sl2, long long* trace) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -930,6 +931,16 @@ attn_bwd_tc_persist(const __grid_constant__ CUtensorMap tm_qkv,   // box 64 rows
       const bf16* gdo = dout + (size_t)b * N * D + (size_t)h * HD;
       float* dl = sDelta + dbuf * 256;
       float* ls = sLse + dbuf * 256;
+      if (delta_in != nullptr) {
+        // delta came with dO: two 1 KB rows to copy per item
+        const float4 d4 = __ldg(reinterpret_cast<const float4*>(delta_in + ((size_t)b * H + h) * N) + te);
+        const float4 l4 = __ldg(reinterpret_cast<const float4*>(lse + ((size_t)b * H + h) * N) + te);
+        constexpr float kL2e = 1.44269504088896340736f;
+        reinterpret_cast<float4*>(dl)[te] = d4;
+        reinterpret_cast<float4*>(ls)[te] = make_float4(l4.x * kL2e, l4.y * kL2e, l4.z * kL2e, l4.w * kL2e);
+        mbar_arrive(&bar_delta[dbuf]);
+        continue;
+      }
       // 4 chunks of 64 rows; all 16 loads of a chunk are in flight before the first use (4 round trips per item)
 #pragma unroll 1
       for (int c0 = 0; c0 < 256; c0 += 64) {
@@ -1131,8 +1142,8 @@ int attention_fwd_tcgen05(const bf16* qkv, bf16* out, float* lse, int B, int H, 
   return TAE_OK;
 }
 
-int attention_bwd_tcgen05(const bf16* qkv, const bf16* out, const bf16* dout, const float* lse, bf16* dqkv, int B, int H,
-                          cudaStream_t stream) {
+int attention_bwd_tcgen05(const bf16* qkv, const bf16* out, const bf16* dout, const float* lse, const float* delta,
+                          bf16* dqkv, int B, int H, cudaStream_t stream) {
   using namespace attn_tc;
   static cudaError_t err = cudaSuccess;
   static std::once_flag once;
@@ -1150,6 +1161,10 @@ int attention_bwd_tcgen05(const bf16* qkv, const bf16* out, const bf16* dout, co
   if (variant < 0) {
     const char* e = getenv("TAE_ATTN_BWD");
     variant = (e == nullptr) ? 2 : (e[0] == 'v' ? 0 : (e[0] == 'p' && e[1] == 'i' ? 1 : 2));
+  }
+  if (delta != nullptr && variant != 2) {
+    set_error("tae_attention_bwd_delta: a precomputed delta needs the persistent kernel (unset TAE_ATTN_BWD)");
+    return TAE_ERR_UNSUPPORTED;
   }
   const float sl2 = scale * 1.44269504088896340736f;
   if (variant == 0) {
@@ -1179,7 +1194,7 @@ int attention_bwd_tcgen05(const bf16* qkv, const bf16* out, const bf16* dout, co
     if (sms <= 0) return TAE_ERR_CUDA;
     const int items = B * H;
     const int grid = items < sms ? items : sms;
-    attn_bwd_tc_persist<<<grid, S_THREADS, S_SMEM, stream>>>(tq64, tdo64, tdq, out, dout, lse, H, items, scale, sl2,
+    attn_bwd_tc_persist<<<grid, S_THREADS, S_SMEM, stream>>>(tq64, tdo64, tdq, out, dout, lse, delta, H, items, scale, sl2,
                                                               g_attn_trace);
   }
   TAE_CHECK_LAUNCH();

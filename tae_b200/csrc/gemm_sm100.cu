@@ -58,6 +58,8 @@ struct Params {
   int ldaux;
   int beta;
   float* colsum_part;  // optional [ceil(M/32), N] fp32: per-32-row column sums of the bf16 output (bias gradients)
+  float* rowdot;       // TAE_EPI_BF16_ROWDOT: fp32 [M / rd_tokens, N / 64, rd_tokens]
+  int rd_tokens;
 };
 
 // K-major tile [rows x 64] (128 B per row, 8-row swizzle atoms of 1024 B): SBO = 1024 between 8-row groups;
@@ -116,7 +118,7 @@ __device__ __forceinline__ void epi_stage_rows(uint32_t stg, uint32_t taddr, int
 // loaded and rounded once per step; the math of the 8 rows is independent, so the scheduler has 32 chains to overlap.
 template <int EPI, int IT0, int NIT, bool FULL>
 __device__ __forceinline__ void epi_write_rows(const Params& p, uint32_t stg, int row_base, int col0, int lane,
-                                               float4& csum, const float4 bias4) {
+                                               float4& csum, const float4 bias4, float (&rdot)[8]) {
   const int c = lane & 7, rsub = lane >> 3;
   const int col = col0 + c * 4;
   uint4 val[8];
@@ -142,7 +144,7 @@ __device__ __forceinline__ void epi_write_rows(const Params& p, uint32_t stg, in
         side[it] = *reinterpret_cast<const uint4*>(sbase + (size_t)srow * sld + col);
       }
     }
-  } else if (EPI == TAE_EPI_BF16_DGELU) {
+  } else if (EPI == TAE_EPI_BF16_DGELU || EPI == TAE_EPI_BF16_ROWDOT) {
     const bf16* abase = p.aux + (size_t)row0 * p.ldaux + col;
 #pragma unroll
     for (int it = IT0; it < IT0 + NIT; ++it) {
@@ -168,6 +170,13 @@ __device__ __forceinline__ void epi_write_rows(const Params& p, uint32_t stg, in
     if (EPI == TAE_EPI_BF16) {
       *reinterpret_cast<uint2*>(optr) =
           make_uint2(pack_bf16x2(a0 + bias4.x, a1 + bias4.y), pack_bf16x2(a2 + bias4.z, a3 + bias4.w));
+    } else if (EPI == TAE_EPI_BF16_ROWDOT) {
+      const uint32_t o01 = pack_bf16x2(a0 + bias4.x, a1 + bias4.y), o23 = pack_bf16x2(a2 + bias4.z, a3 + bias4.w);
+      *reinterpret_cast<uint2*>(optr) = make_uint2(o01, o23);
+      // dot product of the ROUNDED outputs with aux over this lane's 4 columns (the attention kernel sees those values)
+      const float2 r01 = unpack_bf16x2(o01), r23 = unpack_bf16x2(o23);
+      const float2 m01 = unpack_bf16x2(side[it].x), m23 = unpack_bf16x2(side[it].y);
+      rdot[it] += (r01.x * m01.x + r01.y * m01.y) + (r23.x * m23.x + r23.y * m23.y);
     } else if (EPI == TAE_EPI_BF16_GELU) {
       // h = bf16(acc + bias) is the reference's fc1 output; GELU and its derivative are evaluated on that rounded value
       float g[4], gp[4];
@@ -213,11 +222,30 @@ __device__ __forceinline__ void epi_write_rows(const Params& p, uint32_t stg, in
 
 template <int EPI, int IT0 = 0, int NIT = 8>
 __device__ __forceinline__ void epi_write_coalesced(const Params& p, uint32_t stg, int row_base, int col0, int lane,
-                                                    float4& csum, const float4 bias4) {
+                                                    float4& csum, const float4 bias4, float (&rdot)[8]) {
   if (row_base + 32 <= p.M && col0 + 32 <= p.N)  // warp-uniform
-    epi_write_rows<EPI, IT0, NIT, true>(p, stg, row_base, col0, lane, csum, bias4);
+    epi_write_rows<EPI, IT0, NIT, true>(p, stg, row_base, col0, lane, csum, bias4, rdot);
   else
-    epi_write_rows<EPI, IT0, NIT, false>(p, stg, row_base, col0, lane, csum, bias4);
+    epi_write_rows<EPI, IT0, NIT, false>(p, stg, row_base, col0, lane, csum, bias4, rdot);
+}
+
+// Row-dot by-product (TAE_EPI_BF16_ROWDOT): after the second 32-column step of a 64-column head, fold the 8 lanes that
+// share a row (3 shuffles) and let lane c == 0 write rowdot[image, head, token] for its 8 rows.
+__device__ __forceinline__ void epi_flush_rowdot(const Params& p, float (&rdot)[8], int row_base, int col0, int lane) {
+  const int head = col0 >> 6;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    float v = rdot[it];
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    const int grow = row_base + it * 4 + (lane >> 3);
+    if ((lane & 7) == 0 && grow < p.M) {
+      const int img = grow / p.rd_tokens, tok = grow - img * p.rd_tokens;
+      p.rowdot[((size_t)img * (p.N >> 6) + head) * p.rd_tokens + tok] = v;
+    }
+    rdot[it] = 0.f;
+  }
 }
 
 // The lane's 4 bias columns of a step, rounded to bf16 (autocast hands the GEMM a bf16 copy of the fp32 bias).
@@ -390,6 +418,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       tcgen05_fence_after();
       const int row_base = it.mt * BLOCK_M + q * 32;
       constexpr int COLS = EPI_COLS;
+      float rdot[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
       for (int c = 0; c < 128 / COLS; ++c) {
         const int col0 = it.nt * BLOCK_N + half * 128 + c * COLS;
@@ -399,8 +428,9 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         epi_stage_rows(stg, taddr, lane);
         __syncwarp();
         float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
-        epi_write_coalesced<EPI>(p, stg, row_base, col0, lane, csum, bias4);
+        epi_write_coalesced<EPI>(p, stg, row_base, col0, lane, csum, bias4, rdot);
         if (EPI == TAE_EPI_BF16_DGELU && p.colsum_part != nullptr) epi_flush_colsum(p, csum, row_base, col0, lane);
+        if (EPI == TAE_EPI_BF16_ROWDOT && (c & 1)) epi_flush_rowdot(p, rdot, row_base, col0, lane);
         __syncwarp();
       }
       tcgen05_fence_before();
@@ -570,6 +600,7 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tcgen05_fence_after();
       const int row_base = it.mt * (2 * BLOCK_M) + (int)rank * BLOCK_M + q * 32;
+      float rdot[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
       for (int c = 0; c < COLS_PER_WARP / EPI_COLS; ++c) {
         const int col0 = it.nt * BLOCK_N + cg * COLS_PER_WARP + c * EPI_COLS;
@@ -581,12 +612,13 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         __syncwarp();
         float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
         if (EW == 8) {
-          epi_write_coalesced<EPI, 0, 8>(p, stg, row_base, col0, lane, csum, bias4);
+          epi_write_coalesced<EPI, 0, 8>(p, stg, row_base, col0, lane, csum, bias4, rdot);
         } else {  // two passes of 16 rows keep the live register set under the 640-thread budget
-          epi_write_coalesced<EPI, 0, 4>(p, stg, row_base, col0, lane, csum, bias4);
-          epi_write_coalesced<EPI, 4, 4>(p, stg, row_base, col0, lane, csum, bias4);
+          epi_write_coalesced<EPI, 0, 4>(p, stg, row_base, col0, lane, csum, bias4, rdot);
+          epi_write_coalesced<EPI, 4, 4>(p, stg, row_base, col0, lane, csum, bias4, rdot);
         }
         if (EPI == TAE_EPI_BF16_DGELU && p.colsum_part != nullptr) epi_flush_colsum(p, csum, row_base, col0, lane);
+        if (EPI == TAE_EPI_BF16_ROWDOT && (c & 1)) epi_flush_rowdot(p, rdot, row_base, col0, lane);
         __syncwarp();
       }
       tcgen05_fence_before();
@@ -644,7 +676,8 @@ static int launch_2sm_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const Pa
 template <int EPI>
 static int launch_2sm(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, int clusters, cudaStream_t stream) {
   // epilogue-heavy: GELU always; residual / GELU' epilogues when the main loop per tile is short (K <= 2048)
-  const bool heavy = (EPI == TAE_EPI_BF16_GELU) || ((EPI == TAE_EPI_F32_RESID || EPI == TAE_EPI_BF16_DGELU) && p.K <= 2048);
+  const bool heavy = (EPI == TAE_EPI_BF16_GELU) ||
+                     ((EPI == TAE_EPI_F32_RESID || EPI == TAE_EPI_BF16_DGELU || EPI == TAE_EPI_BF16_ROWDOT) && p.K <= 2048);
   if (heavy) return launch_2sm_cfg<EPI, 16>(ta, tb, p, clusters, stream);
   return launch_2sm_cfg<EPI, 8>(ta, tb, p, clusters, stream);
 }
@@ -675,7 +708,7 @@ extern "C" int tae_gemm(const tae_gemm_args* a, void* stream_) {
                       (reinterpret_cast<uintptr_t>(a->out) & 15) == 0,
                   "tae_gemm: A, B and out must be 16-byte aligned");
   TAE_CHECK_SHAPE(a->out != nullptr && a->A != nullptr && a->B != nullptr, "tae_gemm: NULL operand");
-  TAE_CHECK_SHAPE(a->epilogue >= TAE_EPI_BF16 && a->epilogue <= TAE_EPI_BF16_DGELU, "tae_gemm: bad epilogue %d", a->epilogue);
+  TAE_CHECK_SHAPE(a->epilogue >= TAE_EPI_BF16 && a->epilogue <= TAE_EPI_BF16_ROWDOT, "tae_gemm: bad epilogue %d", a->epilogue);
   const bool out_f32 = (a->epilogue == TAE_EPI_F32_RESID || a->epilogue == TAE_EPI_F32_ACC);
   TAE_CHECK_SHAPE(a->ldo % (out_f32 ? 4 : 8) == 0 && a->ldo >= a->N, "tae_gemm: bad ldo %d", a->ldo);
   if (a->epilogue == TAE_EPI_BF16_GELU)
@@ -683,9 +716,12 @@ extern "C" int tae_gemm(const tae_gemm_args* a, void* stream_) {
   if (a->epilogue == TAE_EPI_F32_RESID)
     TAE_CHECK_SHAPE(a->resid != nullptr && a->resid_rows > 0 && a->ldr % 4 == 0 && (reinterpret_cast<uintptr_t>(a->resid) & 15) == 0,
                     "tae_gemm: RESID epilogue needs resid/resid_rows/ldr");
-  if (a->epilogue == TAE_EPI_BF16_DGELU)
+  if (a->epilogue == TAE_EPI_BF16_ROWDOT)
+    TAE_CHECK_SHAPE(a->rowdot != nullptr && a->rowdot_tokens > 0 && a->M % a->rowdot_tokens == 0 && a->N % 64 == 0,
+                    "tae_gemm: ROWDOT epilogue needs rowdot, M %% rowdot_tokens == 0 and N %% 64 == 0");
+  if (a->epilogue == TAE_EPI_BF16_DGELU || a->epilogue == TAE_EPI_BF16_ROWDOT)
     TAE_CHECK_SHAPE(a->aux != nullptr && a->ldaux % 8 == 0 && (reinterpret_cast<uintptr_t>(a->aux) & 15) == 0,
-                    "tae_gemm: DGELU epilogue needs aux/ldaux");
+                    "tae_gemm: DGELU / ROWDOT epilogues need aux/ldaux");
   if (a->colsum_partials)
     TAE_CHECK_SHAPE(a->epilogue == TAE_EPI_BF16_DGELU && (reinterpret_cast<uintptr_t>(a->colsum_partials) & 15) == 0,
                     "tae_gemm: colsum_partials is only produced by the TAE_EPI_BF16_DGELU epilogue (16-byte aligned)");
@@ -743,6 +779,8 @@ extern "C" int tae_gemm(const tae_gemm_args* a, void* stream_) {
   p.ldaux = a->ldaux;
   p.beta = a->beta;
   p.colsum_part = a->colsum_partials;
+  p.rowdot = a->rowdot;
+  p.rd_tokens = a->rowdot_tokens > 0 ? a->rowdot_tokens : 1;
 
   if (a->epilogue == TAE_EPI_F32_ACC && p.splits > 1 && !a->beta) {
     // split-K partial sums are accumulated with red.global.add: start from zero
@@ -771,6 +809,7 @@ extern "C" int tae_gemm(const tae_gemm_args* a, void* stream_) {
       case TAE_EPI_F32_RESID: return launch_2sm<TAE_EPI_F32_RESID>(ta, tb, p, clusters, stream);
       case TAE_EPI_F32_ACC: return launch_2sm<TAE_EPI_F32_ACC>(ta, tb, p, clusters, stream);
       case TAE_EPI_BF16_DGELU: return launch_2sm<TAE_EPI_BF16_DGELU>(ta, tb, p, clusters, stream);
+      case TAE_EPI_BF16_ROWDOT: return launch_2sm<TAE_EPI_BF16_ROWDOT>(ta, tb, p, clusters, stream);
     }
     return TAE_ERR_SHAPE;
   }
@@ -781,6 +820,7 @@ extern "C" int tae_gemm(const tae_gemm_args* a, void* stream_) {
     case TAE_EPI_F32_RESID: return launch<TAE_EPI_F32_RESID>(ta, tb, p, grid, stream);
     case TAE_EPI_F32_ACC: return launch<TAE_EPI_F32_ACC>(ta, tb, p, grid, stream);
     case TAE_EPI_BF16_DGELU: return launch<TAE_EPI_BF16_DGELU>(ta, tb, p, grid, stream);
+    case TAE_EPI_BF16_ROWDOT: return launch<TAE_EPI_BF16_ROWDOT>(ta, tb, p, grid, stream);
   }
   return TAE_ERR_SHAPE;
 }

@@ -7,11 +7,12 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os as _os
 
 import torch
 
 from . import _lib
-from ._lib import (EPI_BF16, EPI_BF16_DGELU, EPI_BF16_GELU, EPI_F32_ACC, EPI_F32_RESID, GemmArgs, check)
+from ._lib import (EPI_BF16, EPI_BF16_DGELU, EPI_BF16_GELU, EPI_BF16_ROWDOT, EPI_F32_ACC, EPI_F32_RESID, GemmArgs, check)
 
 bf16 = torch.bfloat16
 f32 = torch.float32
@@ -42,7 +43,7 @@ def _req(t: torch.Tensor, dtype, name: str) -> None:
 def gemm(A: torch.Tensor, B: torch.Tensor, *, a_mn: bool = False, b_mn: bool = False, epilogue: int = EPI_BF16,
          out: torch.Tensor | None = None, out2: torch.Tensor | None = None, bias: torch.Tensor | None = None,
          resid: torch.Tensor | None = None, resid_rows: int = 0, aux: torch.Tensor | None = None, beta: int = 0,
-         splits: int = 0, colsum_partials: torch.Tensor | None = None):
+         splits: int = 0, colsum_partials: torch.Tensor | None = None, rowdot_tokens: int = 0):
     """D[M,N] = sum_k A(m,k) B(n,k) on the tcgen05 tensor cores; see include/tae_b200.h for the conventions.
 
     A: [M,K] (or [K,M] if a_mn); B: [N,K] (or [K,N] if b_mn); 2-D bf16, inner stride 1.
@@ -87,7 +88,12 @@ def gemm(A: torch.Tensor, B: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
         assert resid.dim() == 2 and resid.shape[1] == N and resid.stride(1) == 1
         a.resid, a.ldr = resid.data_ptr(), resid.stride(0)
         a.resid_rows = resid_rows if resid_rows > 0 else resid.shape[0]
-    if epilogue == EPI_BF16_DGELU:
+    rowdot = None
+    if epilogue == EPI_BF16_ROWDOT:
+        assert rowdot_tokens > 0 and M % rowdot_tokens == 0 and N % 64 == 0
+        rowdot = torch.empty((M // rowdot_tokens, N // 64, rowdot_tokens), dtype=f32, device=A.device)
+        a.rowdot, a.rowdot_tokens = rowdot.data_ptr(), rowdot_tokens
+    if epilogue in (EPI_BF16_DGELU, EPI_BF16_ROWDOT):
         _req(aux, bf16, "gemm aux")
         assert aux.shape == (M, N) and aux.stride(1) == 1
         a.aux, a.ldaux = aux.data_ptr(), aux.stride(0)
@@ -100,6 +106,8 @@ def gemm(A: torch.Tensor, B: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
     check(_L().tae_gemm(C.byref(a), _stream()), "tae_gemm")
     if epilogue == EPI_BF16_GELU:
         return out, out2
+    if epilogue == EPI_BF16_ROWDOT:
+        return out, rowdot
     return out
 
 
@@ -167,10 +175,21 @@ def attention_fwd(qkv: torch.Tensor, B: int, N: int, H: int, hd: int):
     return out, lse
 
 
-def attention_bwd(qkv, out, dout, lse, B: int, N: int, H: int, hd: int):
+def attention_takes_delta(N: int, hd: int) -> bool:
+    """True when attention_bwd accepts delta = rowsum(dout * out) precomputed by a TAE_EPI_BF16_ROWDOT GEMM."""
+    return N == 256 and hd == 64 and _os.environ.get("TAE_ATTN_BWD") is None and _os.environ.get("TAE_ATTN_LEGACY") != "1"
+
+
+def attention_bwd(qkv, out, dout, lse, B: int, N: int, H: int, hd: int, delta: torch.Tensor | None = None):
     _req(dout, bf16, "attention dout")
-    assert dout.is_contiguous() and qkv.is_contiguous() and out.is_contiguous()
+    assert dout.is_contiguous() and qkv.is_contiguous() and (out is None or out.is_contiguous())
     dqkv = torch.empty_like(qkv)
+    if delta is not None:
+        _req(delta, f32, "attention delta")
+        assert delta.is_contiguous() and delta.shape == (B, H, N)
+        check(_L().tae_attention_bwd_delta(qkv.data_ptr(), dout.data_ptr(), lse.data_ptr(), delta.data_ptr(), dqkv.data_ptr(),
+                                           B, N, H, hd, _stream()), "tae_attention_bwd_delta")
+        return dqkv
     check(_L().tae_attention_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), dqkv.data_ptr(), B, N,
                                  H, hd, _stream()), "tae_attention_bwd")
     return dqkv

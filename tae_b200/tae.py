@@ -26,7 +26,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib, ops
-from ._lib import EPI_BF16, EPI_BF16_DGELU, EPI_BF16_GELU, EPI_F32_ACC, EPI_F32_RESID
+from ._lib import EPI_BF16, EPI_BF16_DGELU, EPI_BF16_GELU, EPI_BF16_ROWDOT, EPI_F32_ACC, EPI_F32_RESID
 
 
 def _pair(x):
@@ -224,8 +224,15 @@ class _BlockFn(torch.autograd.Function):
         # ---- attention branch: y = proj(sdpa(qkv(norm1(x)))) ----
         g_pb = _bgrad(attn.proj.bias, precomputed=csum2) if (attn.proj.bias is not None and need[6]) else None
         g_pw = _wgrad(attn.proj.weight, dres2_b, att) if need[5] else None
-        datt = ops.gemm(dres2_b, shadow_bf16(attn.proj.weight), b_mn=True, epilogue=EPI_BF16)
-        dqkv = ops.attention_bwd(qkv, att, datt, lse, B, N, H, hd)
+        if ops.attention_takes_delta(N, hd):
+            # the proj dgrad epilogue also emits delta = rowsum(dO * O) per (image, head, token): the attention kernel
+            # then never re-reads O and dO for it
+            datt, delta = ops.gemm(dres2_b, shadow_bf16(attn.proj.weight), b_mn=True, epilogue=EPI_BF16_ROWDOT, aux=att,
+                                   rowdot_tokens=N)
+            dqkv = ops.attention_bwd(qkv, None, datt, lse, B, N, H, hd, delta=delta)
+        else:
+            datt = ops.gemm(dres2_b, shadow_bf16(attn.proj.weight), b_mn=True, epilogue=EPI_BF16)
+            dqkv = ops.attention_bwd(qkv, att, datt, lse, B, N, H, hd)
         del datt
         g_qb = _bgrad(attn.qkv.bias, dy_b=dqkv) if (attn.qkv.bias is not None and need[4]) else None
         g_qw = _wgrad(attn.qkv.weight, dqkv, ln1) if need[3] else None

@@ -420,3 +420,32 @@ def test_fp32_bias_gelu_loss_im2col():
     assert abs(float(loss) - float(lr)) < 1e-6 * float(lr) and rel_err(dpred, 3.0 * pr.grad) < 1e-6
     cols = F.im2col(imgs, 16)
     assert torch.equal(cols, O.im2col(imgs, 16).reshape(cols.shape))
+
+
+# ------------------------------------------------------------------------------------------------
+# ROWDOT epilogue (delta = rowsum(dO * O) emitted by the proj dgrad) and attention backward fed with it
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,K,tokens", [(512, 128, 264, 256), (1024, 1024, 1024, 256), (300, 64, 4104, 100)])
+def test_gemm_rowdot_epilogue(M, N, K, tokens):
+    ops = _ops()
+    A, W = randn(M, K, seed=21, scale=0.5), randn(K, N, seed=22, scale=0.5)   # dgrad layout: B is [K, N] (b_mn)
+    aux = randn(M, N, seed=23)
+    out, rd = ops.gemm(A, W, b_mn=True, epilogue=5, aux=aux, rowdot_tokens=tokens)
+    ref = (A.float() @ W.float()).to(torch.bfloat16)
+    assert max_err_scaled(out.float(), ref.float()) < 1e-2
+    # the row-dot is taken over the ROUNDED outputs the kernel wrote
+    want = (out.float() * aux.float()).view(M // tokens, tokens, N // 64, 64).sum(-1).permute(0, 2, 1).contiguous()
+    assert rd.shape == (M // tokens, N // 64, tokens) and rel_err(rd, want) < 1e-5
+
+
+def test_attention_bwd_with_precomputed_delta():
+    ops = _ops()
+    B, N, H, hd = 5, 256, 3, 64
+    D = H * hd
+    qkv = randn(B * N, 3 * D, seed=24, scale=0.7)
+    dout = randn(B * N, D, seed=25)
+    out, lse = ops.attention_fwd(qkv, B, N, H, hd)
+    ref = ops.attention_bwd(qkv, out, dout, lse, B, N, H, hd)
+    delta = (dout.float() * out.float()).view(B, N, H, hd).sum(-1).permute(0, 2, 1).contiguous()
+    got = ops.attention_bwd(qkv, None, dout, lse, B, N, H, hd, delta=delta)
+    assert max_err_scaled(got.float(), ref.float()) < 2e-3

@@ -45,28 +45,32 @@ __global__ void __launch_bounds__(128, 1) bench(const Cfg* cfgs, int ncfg, long 
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem = slot;
-  if (threadIdx.x == 0) {
-    uint32_t phase = 0;
-    const uint32_t sA = smem_u32(smem), sB = smem_u32(smem + 65536);
-    for (int c = 0; c < ncfg; ++c) {
-      const Cfg cf = cfgs[c];
-      const uint32_t idesc = make_idesc_bf16(cf.m, cf.n, cf.a_mn, cf.b_mn);
-      for (int rep = 0; rep < 3; ++rep) {
-        const long long t0 = clock64();
-        for (int i = 0; i < cf.count; ++i) {
-          const int k = i & 3;
-          const uint64_t ad = cf.a_mn ? make_smem_desc(sA + k * 2048, 8192, 1024) : make_smem_desc(sA + k * 32, 0, 1024);
-          const uint64_t bd = cf.b_mn ? make_smem_desc(sB + k * 2048, 8192, 1024) : make_smem_desc(sB + k * 32, 0, 1024);
-          if (cf.a_tmem)
-            umma_f16_ts(tmem, tmem + 256 + k * 8, bd, idesc, 1);
-          else
-            umma_f16(tmem, ad, bd, idesc, 1);
+  if (threadIdx.x < 32) {
+    if (elect_one()) {
+      uint32_t phase = 0;
+      const uint32_t sA = smem_u32(smem), sB = smem_u32(smem + 65536);
+      for (int c = 0; c < ncfg; ++c) {
+        const Cfg cf = cfgs[c];
+        const uint32_t idesc = make_idesc_bf16(cf.m, cf.n, cf.a_mn, cf.b_mn);
+        const uint32_t a_lo = cf.a_mn ? desc_lo(sA, 8192) : desc_lo(sA), b_lo = cf.b_mn ? desc_lo(sB, 8192) : desc_lo(sB);
+        const uint32_t a_st = cf.a_mn ? (2048 >> 4) : 2, b_st = cf.b_mn ? (2048 >> 4) : 2;
+        for (int rep = 0; rep < 3; ++rep) {
+          const long long t0 = clock64();
+          for (int i = 0; i < cf.count; i += 8) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              if (cf.a_tmem)
+                umma_f16_ts(tmem, tmem + 256 + (k & 3) * 8, make_smem_desc(sB + (k & 3) * 32, 0, 1024), idesc, 1);
+              else
+                umma_f16_lo(tmem, a_lo + (k & 3) * a_st, b_lo + (k & 3) * b_st, idesc, 1);
+            }
+          }
+          umma_commit(&bar);
+          mbar_wait(&bar, phase);
+          phase ^= 1;
+          const long long t1 = clock64();
+          if (blockIdx.x == 0) out[c * 3 + rep] = t1 - t0;
         }
-        umma_commit(&bar);
-        mbar_wait(&bar, phase);
-        phase ^= 1;
-        const long long t1 = clock64();
-        if (blockIdx.x == 0) out[c * 3 + rep] = t1 - t0;
       }
     }
   }
@@ -82,7 +86,7 @@ int main() {
       {128, 64, 0, 1, 0, 64},  {128, 64, 1, 1, 0, 64},  {64, 64, 1, 1, 0, 64},  {64, 64, 0, 0, 0, 64},
       {128, 128, 0, 1, 0, 64}, {128, 128, 1, 1, 0, 64}, {128, 256, 1, 1, 0, 64}, {64, 128, 0, 0, 0, 64},
       {64, 256, 0, 0, 0, 64},  {128, 64, 0, 0, 1, 64},  {128, 64, 0, 1, 1, 64},  {128, 128, 0, 0, 1, 64},
-      {128, 256, 0, 0, 1, 64}, {128, 64, 0, 0, 0, 8},   {128, 64, 0, 0, 0, 1},   {128, 256, 0, 0, 0, 1},
+      {128, 256, 0, 0, 1, 64}, {128, 64, 0, 0, 0, 8},   {128, 64, 0, 0, 0, 16},   {128, 256, 0, 0, 0, 8},
   };
   const int n = sizeof(h) / sizeof(h[0]);
   Cfg* d;
