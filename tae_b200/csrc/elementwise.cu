@@ -28,7 +28,7 @@ __global__ void im2col_kernel(const float* __restrict__ imgs, bf16* __restrict__
     const int b = (int)(r / 3);
     const int x = xq * 8;
     const float* src = imgs + (((size_t)b * 3 + c) * S + y) * S + x;
-    const float4 v0 = ld_nc_f4(src), v1 = ld_nc_f4(src + 4);
+    const float4 v0 = __ldg(reinterpret_cast<const float4*>(src)), v1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
     const int h = y / p, i = y - h * p, w = x / p, j = x - w * p;
     bf16* dst = cols + ((size_t)b * g * g + (size_t)h * g + w) * Kp + (size_t)c * p * p + i * p + j;
     uint4 o;
@@ -37,6 +37,28 @@ __global__ void im2col_kernel(const float* __restrict__ imgs, bf16* __restrict__
     o.z = pack_bf16x2(v1.x, v1.y);
     o.w = pack_bf16x2(v1.z, v1.w);
     *reinterpret_cast<uint4*>(dst) = o;
+  }
+}
+
+// p % 16 == 0: threads enumerate the OUTPUT in 16-element (32-byte) pieces, so a warp writes 1 KB contiguous; each
+// piece is 64 contiguous bytes of one image row.
+__global__ void im2col16_kernel(const float* __restrict__ imgs, bf16* __restrict__ cols, int B, int S, int p) {
+  const int g = S / p;
+  const int Kp = 3 * p * p;
+  const int pieces = Kp / 16;                      // per patch
+  const size_t total = (size_t)B * g * g * pieces;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int e = (int)(idx % pieces) * 16;        // element offset inside the patch row: c*p*p + i*p + j
+    const size_t row = idx / pieces;               // b*g*g + h*g + w
+    const int c = e / (p * p), ij = e - c * p * p, i = ij / p, j = ij - i * p;
+    const int n = (int)(row % (g * g));
+    const int b = (int)(row / (g * g));
+    const int h = n / g, w = n - h * g;
+    const float4* src = reinterpret_cast<const float4*>(imgs + (((size_t)b * 3 + c) * S + (size_t)h * p + i) * S + (size_t)w * p + j);
+    const float4 v0 = __ldg(src), v1 = __ldg(src + 1), v2 = __ldg(src + 2), v3 = __ldg(src + 3);
+    uint4* dst = reinterpret_cast<uint4*>(cols + row * Kp + e);
+    dst[0] = make_uint4(pack_bf16x2(v0.x, v0.y), pack_bf16x2(v0.z, v0.w), pack_bf16x2(v1.x, v1.y), pack_bf16x2(v1.z, v1.w));
+    dst[1] = make_uint4(pack_bf16x2(v2.x, v2.y), pack_bf16x2(v2.z, v2.w), pack_bf16x2(v3.x, v3.y), pack_bf16x2(v3.z, v3.w));
   }
 }
 
@@ -91,7 +113,9 @@ mse_loss_kernel(const bf16* __restrict__ pred, const float* __restrict__ imgs, f
     const int h = n / g, w = n - h * g;
     const int j0 = jq * 8;
     const size_t poff = ((size_t)b * g * g + n) * Kp + (size_t)(i * p + j0) * 3;
-    const uint4 pr0 = ld_nc_v4(pred + poff), pr1 = ld_nc_v4(pred + poff + 8), pr2 = ld_nc_v4(pred + poff + 16);
+    // L1-allocating loads: the three 16-byte pieces of a lane's 48 bytes share sectors with its neighbours' pieces
+    const uint4* pp = reinterpret_cast<const uint4*>(pred + poff);
+    const uint4 pr0 = __ldg(pp), pr1 = __ldg(pp + 1), pr2 = __ldg(pp + 2);
     const uint32_t pw[12] = {pr0.x, pr0.y, pr0.z, pr0.w, pr1.x, pr1.y, pr1.z, pr1.w, pr2.x, pr2.y, pr2.z, pr2.w};
     float pv[24];
 #pragma unroll
@@ -104,7 +128,7 @@ mse_loss_kernel(const bf16* __restrict__ pred, const float* __restrict__ imgs, f
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       const float* src = imgs + (((size_t)b * 3 + c) * S + (size_t)h * p + i) * S + (size_t)w * p + j0;
-      const float4 a = ld_nc_f4(src), bq = ld_nc_f4(src + 4);
+      const float4 a = __ldg(reinterpret_cast<const float4*>(src)), bq = __ldg(reinterpret_cast<const float4*>(src) + 1);
       tv[c][0] = a.x; tv[c][1] = a.y; tv[c][2] = a.z; tv[c][3] = a.w;
       tv[c][4] = bq.x; tv[c][5] = bq.y; tv[c][6] = bq.z; tv[c][7] = bq.w;
     }
@@ -309,6 +333,12 @@ extern "C" int tae_im2col_bf16(const float* imgs, tae_bf16* cols, int32_t B, int
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   TAE_CHECK_SHAPE(B > 0 && S > 0 && p > 0 && S % p == 0, "tae_im2col_bf16: need S %% p == 0 (S=%d p=%d)", S, p);
   TAE_CHECK_SHAPE(p % 8 == 0, "tae_im2col_bf16: patch size must be a multiple of 8 (p=%d)", p);
+  if (p % 16 == 0) {
+    const size_t total16 = (size_t)B * 3 * S * (S / 16);
+    im2col16_kernel<<<stream_grid(total16, 256), 256, 0, stream>>>(imgs, reinterpret_cast<bf16*>(cols), B, S, p);
+    TAE_CHECK_LAUNCH();
+    return TAE_OK;
+  }
   const size_t total = (size_t)B * 3 * S * (S / 8);
   im2col_kernel<<<stream_grid(total, 256), 256, 0, stream>>>(imgs, reinterpret_cast<bf16*>(cols), B, S, p);
   TAE_CHECK_LAUNCH();

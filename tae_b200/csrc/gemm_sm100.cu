@@ -232,20 +232,32 @@ __device__ __forceinline__ void epi_write_coalesced(const Params& p, uint32_t st
 // Row-dot by-product (TAE_EPI_BF16_ROWDOT): after the second 32-column step of a 64-column head, fold the 8 lanes that
 // share a row (3 shuffles) and let lane c == 0 write rowdot[image, head, token] for its 8 rows.
 __device__ __forceinline__ void epi_flush_rowdot(const Params& p, float (&rdot)[8], int row_base, int col0, int lane) {
-  const int head = col0 >> 6;
+  // 8 partial sums (one per row iteration) on each of the 8 lanes c = lane & 7 that share rows: a halving butterfly
+  // (4 + 2 + 1 shuffles) leaves lane c with the complete sum of row iteration it = c.
+  const int c = lane & 7;
+  float a[4], b[2];
 #pragma unroll
-  for (int it = 0; it < 8; ++it) {
-    float v = rdot[it];
-    v += __shfl_xor_sync(0xffffffffu, v, 1);
-    v += __shfl_xor_sync(0xffffffffu, v, 2);
-    v += __shfl_xor_sync(0xffffffffu, v, 4);
-    const int grow = row_base + it * 4 + (lane >> 3);
-    if ((lane & 7) == 0 && grow < p.M) {
-      const int img = grow / p.rd_tokens, tok = grow - img * p.rd_tokens;
-      p.rowdot[((size_t)img * (p.N >> 6) + head) * p.rd_tokens + tok] = v;
-    }
-    rdot[it] = 0.f;
+  for (int i = 0; i < 4; ++i) {  // exchange across bit 2 of c: keep its[0..3] if bit clear, its[4..7] if set
+    const float keep = (c & 4) ? rdot[4 + i] : rdot[i];
+    const float send = (c & 4) ? rdot[i] : rdot[4 + i];
+    a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
   }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {  // bit 1
+    const float keep = (c & 2) ? a[2 + i] : a[i];
+    const float send = (c & 2) ? a[i] : a[2 + i];
+    b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  const float keep = (c & 1) ? b[1] : b[0];
+  const float send = (c & 1) ? b[0] : b[1];
+  const float v = keep + __shfl_xor_sync(0xffffffffu, send, 1);  // row iteration it == c
+  const int grow = row_base + c * 4 + (lane >> 3);
+  if (grow < p.M) {
+    const int img = grow / p.rd_tokens, tok = grow - img * p.rd_tokens;
+    p.rowdot[((size_t)img * (p.N >> 6) + (col0 >> 6)) * p.rd_tokens + tok] = v;
+  }
+#pragma unroll
+  for (int it = 0; it < 8; ++it) rdot[it] = 0.f;
 }
 
 // The lane's 4 bias columns of a step, rounded to bf16 (autocast hands the GEMM a bf16 copy of the fp32 bias).
