@@ -40,28 +40,6 @@ __global__ void im2col_kernel(const float* __restrict__ imgs, bf16* __restrict__
   }
 }
 
-// p % 16 == 0: threads enumerate the OUTPUT in 16-element (32-byte) pieces, so a warp writes 1 KB contiguous; each
-// piece is 64 contiguous bytes of one image row.
-__global__ void im2col16_kernel(const float* __restrict__ imgs, bf16* __restrict__ cols, int B, int S, int p) {
-  const int g = S / p;
-  const int Kp = 3 * p * p;
-  const int pieces = Kp / 16;                      // per patch
-  const size_t total = (size_t)B * g * g * pieces;
-  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-    const int e = (int)(idx % pieces) * 16;        // element offset inside the patch row: c*p*p + i*p + j
-    const size_t row = idx / pieces;               // b*g*g + h*g + w
-    const int c = e / (p * p), ij = e - c * p * p, i = ij / p, j = ij - i * p;
-    const int n = (int)(row % (g * g));
-    const int b = (int)(row / (g * g));
-    const int h = n / g, w = n - h * g;
-    const float4* src = reinterpret_cast<const float4*>(imgs + (((size_t)b * 3 + c) * S + (size_t)h * p + i) * S + (size_t)w * p + j);
-    const float4 v0 = __ldg(src), v1 = __ldg(src + 1), v2 = __ldg(src + 2), v3 = __ldg(src + 3);
-    uint4* dst = reinterpret_cast<uint4*>(cols + row * Kp + e);
-    dst[0] = make_uint4(pack_bf16x2(v0.x, v0.y), pack_bf16x2(v0.z, v0.w), pack_bf16x2(v1.x, v1.y), pack_bf16x2(v1.z, v1.w));
-    dst[1] = make_uint4(pack_bf16x2(v2.x, v2.y), pack_bf16x2(v2.z, v2.w), pack_bf16x2(v3.x, v3.y), pack_bf16x2(v3.z, v3.w));
-  }
-}
-
 // ---------------------------------------------------------------------------------------------
 // patchify / unpatchify: out[b, h*g+w, (i*p+j)*3+c] <-> imgs[b, c, h*p+i, w*p+j]
 // ---------------------------------------------------------------------------------------------
@@ -333,12 +311,6 @@ extern "C" int tae_im2col_bf16(const float* imgs, tae_bf16* cols, int32_t B, int
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   TAE_CHECK_SHAPE(B > 0 && S > 0 && p > 0 && S % p == 0, "tae_im2col_bf16: need S %% p == 0 (S=%d p=%d)", S, p);
   TAE_CHECK_SHAPE(p % 8 == 0, "tae_im2col_bf16: patch size must be a multiple of 8 (p=%d)", p);
-  if (p % 16 == 0) {
-    const size_t total16 = (size_t)B * 3 * S * (S / 16);
-    im2col16_kernel<<<stream_grid(total16, 256), 256, 0, stream>>>(imgs, reinterpret_cast<bf16*>(cols), B, S, p);
-    TAE_CHECK_LAUNCH();
-    return TAE_OK;
-  }
   const size_t total = (size_t)B * 3 * S * (S / 8);
   im2col_kernel<<<stream_grid(total, 256), 256, 0, stream>>>(imgs, reinterpret_cast<bf16*>(cols), B, S, p);
   TAE_CHECK_LAUNCH();
