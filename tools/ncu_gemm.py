@@ -21,7 +21,7 @@ for rep in range(2):
     dw1 = ops.gemm(dh, x, a_mn=True, b_mn=True, epilogue=EPI_F32_ACC)        # 7 fc1 wgrad
     dx = ops.gemm(dh, w1, b_mn=True, epilogue=EPI_BF16)                      # 8 fc1 dgrad
     dwp = ops.gemm(x, x, a_mn=True, b_mn=True, epilogue=EPI_F32_ACC)         # 9 proj wgrad
-    da = ops.gemm(x, wp, b_mn=True, epilogue=EPI_BF16)                       # 10 proj dgrad
+    da, dl2 = ops.gemm(x, wp, b_mn=True, epilogue=EPI_BF16_ROWDOT, aux=x, rowdot_tokens=256)  # 10 proj dgrad (+delta)
     dwq = ops.gemm(qkv, x, a_mn=True, b_mn=True, epilogue=EPI_F32_ACC)       # 11 qkv wgrad
     dl = ops.gemm(qkv, wq, b_mn=True, epilogue=EPI_BF16)                     # 12 qkv dgrad
 torch.cuda.synchronize()
