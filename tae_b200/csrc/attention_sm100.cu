@@ -107,10 +107,11 @@ attn_fwd_tc(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CU
       mbar_wait(bar_p, 0);
       tcgen05_fence_after();
       const uint32_t idesc2 = make_idesc_bf16(128, 64, 0, 1);
-      const uint32_t p_lo = desc_lo(sP), v_lo = desc_lo(sV, 8192);
+      // O = P V with P read from TENSOR MEMORY (bf16 pairs written by the softmax threads over the dead S columns:
+      // keys 0-127 in columns 0-63, keys 128-255 in columns 128-191); the accumulator goes to columns 64-127.
 #pragma unroll
-      for (int j = 0; j < 16; ++j)  // 16 keys per instruction
-        umma_f16_lo(tmem, p_lo + (j >> 2) * (16384 >> 4) + (j & 3) * 2, v_lo + j * (2048 >> 4), idesc2, j > 0);
+      for (int j = 0; j < 16; ++j)  // 16 keys = 8 TMEM columns of P per instruction
+        umma_f16_ts(tmem + 64, tmem + (j >> 3) * 128 + (j & 7) * 8, make_smem_desc(sV + j * 2048, 8192, 1024), idesc2, j > 0);
       umma_commit(bar_o);
     }
   } else {
@@ -150,13 +151,11 @@ attn_fwd_tc(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CU
         l += p0 + p1;
         pk[i] = pack_bf16x2(p0, p1);
       }
-      const uint32_t base = sP + (half * 2 + (c >> 1)) * 16384;  // k-block of 64 keys
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-        st_shared_v4(base + sw128(r, (c & 1) * 4 + i), pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+      // P chunk c (32 keys = 16 packed cells) over S columns this thread has already consumed
+      tmem_st_32x32b_x16(tcol + c * 16, pk);
     }
     s_sum[half * 128 + r] = l;
-    fence_proxy_async_smem();
+    tmem_st_wait();
     tcgen05_fence_before();
     mbar_arrive(bar_p);
     // ---- epilogue: each thread normalises 32 of the row's 64 output columns ----
@@ -168,7 +167,7 @@ attn_fwd_tc(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CU
     const float inv = 1.0f / l;
     {
       uint32_t raw[32];
-      tmem_ld_32x32b_x32(taddr + half * 32, raw);
+      tmem_ld_32x32b_x32(taddr + 64 + half * 32, raw);
       tmem_ld_wait();
 #pragma unroll
       for (int i = 0; i < 4; ++i) {

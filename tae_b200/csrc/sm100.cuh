@@ -186,6 +186,31 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta)
       : "memory");
 }
 
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand is read from tensor memory.  Layout (probed, tools/tmem_a_probe.cu): TMEM
+// lane = row m, 32-bit cell c of the operand = (A[m][2c] in the low half, A[m][2c+1] in the high half), so one K=16
+// instruction consumes 8 consecutive columns.  46 cycles at 128x64x16 against 78 with A in shared memory.
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 16 consecutive 32-bit TMEM columns of this thread's lane <- 16 registers (warp-collective, lane = TMEM lane)
+__device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // Cheap descriptor path for single-thread MMA issue loops.  Every tile in this library uses SBO = 1024 and the
 // 128B-swizzle layout, so the upper descriptor word is a constant and a descriptor is just a 32-bit `lo` word
 // (start address >> 4 | LBO >> 4 << 16) that advances by (byte offset >> 4).
