@@ -193,6 +193,216 @@ attn_fwd_tc(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CU
 }
 
 // =============================================================================================
+// Forward, PERSISTENT variant (default): one CTA per SM walks (image, head) items with two items' operands resident
+// (2 x 96 KB) and the two 128-query tiles of an item handled by two independent softmax groups, so loads, the S and PV
+// MMAs, the exp2 work (MUFU) and the output stores of neighbouring tiles / items overlap instead of running as one
+// serial chain per CTA.
+//   warp 0   MMA issue: S_t = Q_t K^T (128x256x64) and O_t = P_t V (P read from TENSOR MEMORY)
+//   warp 1   TMA producer: K, Q, V of item i+1 (+2) into the other operand buffer as soon as it is free
+//   warps 4-11 / 12-19   softmax + epilogue of query tile 0 / 1: two threads per row, P written back over the dead S
+//            columns with tcgen05.st, O normalised and staged over the dead Q tile, TMA store
+//   TMEM: tile t owns columns [256t, 256t+256): S, then P in +0..63 / +128..191 and the O accumulator in +64..127.
+// =============================================================================================
+constexpr int G_BUF = 98304;                 // one item's operands: Q 32 KB | K 32 KB | V 32 KB
+constexpr int G_OFF_RED = 2 * G_BUF;         // [2 tiles][max, sum][2 halves][128] fp32 = 4 KB
+constexpr int G_OFF_BAR = G_OFF_RED + 4096;
+constexpr int G_SMEM = G_OFF_BAR + 256 + 1024;
+constexpr int G_THREADS = 640;
+
+__global__ void __launch_bounds__(G_THREADS, 1)
+attn_fwd_tc_persist(const __grid_constant__ CUtensorMap tm_qkv,  // box 256 rows x 64 cols over qkv [B*N, 3D]
+                    const __grid_constant__ CUtensorMap tm_o,    // box 128 rows x 64 cols over out [B*N, D]
+                    float* __restrict__ lse, int H, int num_items, float scale, float sl2) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G_OFF_BAR);
+  uint64_t* bar_kq = bars;          // [2 buffers] K and Q landed                      (TMA, every other item)
+  uint64_t* bar_v = bars + 2;       // [2 buffers] V landed
+  uint64_t* bar_buffree = bars + 4; // [2 buffers] both tiles' output stores have read the buffer (2 arrivals)
+  uint64_t* bar_s = bars + 6;       // [2 tiles] S_t in TMEM                            (commit, every item)
+  uint64_t* bar_p = bars + 8;       // [2 tiles] P_t written to TMEM                    (256 arrivals)
+  uint64_t* bar_o = bars + 10;      // [2 tiles] O_t accumulated                        (commit)
+  uint64_t* bar_tfree = bars + 12;  // [2 tiles] O_t read out of TMEM: the tile's columns may be overwritten (256)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int D = H * HD;
+  const int my_items = (num_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_qkv);
+    tma_prefetch_desc(&tm_o);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar_kq[i], 1);
+      mbar_init(&bar_v[i], 1);
+      mbar_init(&bar_buffree[i], 2);
+      mbar_init(&bar_s[i], 1);
+      mbar_init(&bar_p[i], 256);
+      mbar_init(&bar_o[i], 1);
+      mbar_init(&bar_tfree[i], 256);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 1) {
+    if (elect_one()) {
+      // ---------------- TMA producer ----------------
+#pragma unroll 1
+      for (int it = 0; it < my_items; ++it) {
+        const int item = (int)blockIdx.x + it * (int)gridDim.x;
+        const int b = item / H, h = item - b * H;
+        const int s = it & 1;
+        if (it >= 2) mbar_wait(&bar_buffree[s], (uint32_t)(((it >> 1) - 1) & 1));
+        uint8_t* buf = smem + s * G_BUF;
+        mbar_expect_tx(&bar_kq[s], 65536);
+        tma_load_2d(buf + 32768, &tm_qkv, &bar_kq[s], D + h * HD, b * N);
+        tma_load_2d(buf, &tm_qkv, &bar_kq[s], h * HD, b * N);
+        mbar_expect_tx(&bar_v[s], 32768);
+        tma_load_2d(buf + 65536, &tm_qkv, &bar_v[s], 2 * D + h * HD, b * N);
+      }
+    }
+  } else if (warp == 0) {
+    if (elect_one()) {
+      // ---------------- MMA issuer ----------------
+      const uint32_t idesc1 = make_idesc_bf16(128, 256, 0, 0);
+      const uint32_t idesc2 = make_idesc_bf16(128, 64, 0, 1);
+      auto issue_s = [&](int it, int t) {
+        const int s = it & 1;
+        const uint32_t base = smem_u32(smem + s * G_BUF);
+        mbar_wait(&bar_kq[s], (uint32_t)((it >> 1) & 1));
+        if (it >= 1) mbar_wait(&bar_tfree[t], (uint32_t)((it - 1) & 1));
+        tcgen05_fence_after();
+        const uint32_t q_lo = desc_lo(base + t * 16384), k_lo = desc_lo(base + 32768);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16_lo(tmem + t * 256, q_lo + k * 2, k_lo + k * 2, idesc1, k > 0);
+        umma_commit(&bar_s[t]);
+      };
+      auto issue_pv = [&](int it, int t) {
+        const int s = it & 1;
+        const uint32_t sV = smem_u32(smem + s * G_BUF + 65536);
+        mbar_wait(&bar_v[s], (uint32_t)((it >> 1) & 1));
+        mbar_wait(&bar_p[t], (uint32_t)(it & 1));
+        tcgen05_fence_after();
+        const uint32_t tt = tmem + t * 256;
+#pragma unroll
+        for (int j = 0; j < 16; ++j)  // 16 keys = 8 TMEM columns of P per instruction
+          umma_f16_ts(tt + 64, tt + (j >> 3) * 128 + (j & 7) * 8, make_smem_desc(sV + j * 2048, 8192, 1024), idesc2, j > 0);
+        umma_commit(&bar_o[t]);
+      };
+      if (my_items > 0) {
+        issue_s(0, 0);
+        issue_s(0, 1);
+      }
+#pragma unroll 1
+      for (int it = 0; it < my_items; ++it) {
+        issue_pv(it, 0);
+        issue_pv(it, 1);
+        if (it + 1 < my_items) {  // each waits until that tile's O has been read out of TMEM
+          issue_s(it + 1, 0);
+          issue_s(it + 1, 1);
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ---------------- softmax + epilogue groups ----------------
+    const int t = (warp - 4) >> 3;               // query tile of this group
+    const int wg = (warp - 4) & 7;               // warp inside the group
+    const int q = warp & 3;                      // TMEM lane quarter (== warp % 4)
+    const int half = wg >> 2;                    // which 128 score columns of the row
+    const int r = q * 32 + lane;                 // query row inside the tile == TMEM lane
+    const uint32_t taddr = tmem + t * 256 + ((uint32_t)(q * 32) << 16);
+    const uint32_t tcol = taddr + half * 128;
+    float* s_max = reinterpret_cast<float*>(smem + G_OFF_RED) + t * 512;  // [2 halves][128]
+    float* s_sum = s_max + 256;
+    const bool storer = (wg == 0);
+#pragma unroll 1
+    for (int it = 0; it < my_items; ++it) {
+      const int item = (int)blockIdx.x + it * (int)gridDim.x;
+      const int b = item / H, h = item - b * H;
+      const int s = it & 1;
+      const uint32_t par = (uint32_t)(it & 1);
+      mbar_wait(&bar_s[t], par);
+      tcgen05_fence_after();
+      // pass 1: row max over this thread's 128 columns (TMEM loads software-pipelined one chunk ahead)
+      uint32_t buf[2][32];
+      float mx = -INFINITY;
+      tmem_ld_32x32b_x32(tcol, buf[0]);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        tmem_ld_wait_regs(buf[c & 1]);
+        if (c + 1 < 4) tmem_ld_32x32b_x32(tcol + (c + 1) * 32, buf[(c + 1) & 1]);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(buf[c & 1][i]));
+      }
+      s_max[half * 128 + r] = mx;
+      tmem_ld_32x32b_x32(tcol, buf[0]);  // first chunk of pass 2 in flight across the barrier
+      named_bar_sync(1 + t, 256);
+      mx = fmaxf(mx, s_max[(half ^ 1) * 128 + r]);
+      const float m2 = mx * sl2;
+      float l = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        tmem_ld_wait_regs(buf[c & 1]);
+        if (c + 1 < 4) tmem_ld_32x32b_x32(tcol + (c + 1) * 32, buf[(c + 1) & 1]);
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float p0 = ex2_approx(fmaf(__uint_as_float(buf[c & 1][2 * i]), sl2, -m2));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(buf[c & 1][2 * i + 1]), sl2, -m2));
+          l += p0 + p1;
+          pk[i] = pack_bf16x2(p0, p1);
+        }
+        tmem_st_32x32b_x16(tcol + c * 16, pk);  // P chunk c over S columns this thread has already consumed
+      }
+      s_sum[half * 128 + r] = l;
+      tmem_st_wait();
+      tcgen05_fence_before();
+      mbar_arrive(&bar_p[t]);
+      // ---- epilogue: each thread normalises 32 of the row's 64 output columns ----
+      named_bar_sync(1 + t, 256);  // partner's s_sum write is ordered before this read (and s_max reads are done)
+      mbar_wait(&bar_o[t], par);
+      tcgen05_fence_after();
+      l += s_sum[(half ^ 1) * 128 + r];
+      if (half == 0) lse[((size_t)b * H + h) * N + t * 128 + r] = mx * scale + __logf(l);
+      const float inv = 1.0f / l;
+      const uint32_t stage = smem_u32(smem + s * G_BUF + t * 16384);  // the item's dead Q tile
+      {
+        uint32_t raw[32];
+        tmem_ld_32x32b_x32(taddr + 64 + half * 32, raw);
+        tmem_ld_wait();
+        tcgen05_fence_before();
+        mbar_arrive(&bar_tfree[t]);  // this tile's TMEM columns may take the next item's S
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint32_t o[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            o[j] = pack_bf16x2(__uint_as_float(raw[i * 8 + 2 * j]) * inv, __uint_as_float(raw[i * 8 + 2 * j + 1]) * inv);
+          st_shared_v4(stage + sw128(r, half * 4 + i), o[0], o[1], o[2], o[3]);
+        }
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(1 + t, 256);
+      if (storer && elect_one()) {
+        tma_store_2d(&tm_o, smem + s * G_BUF + t * 16384, h * HD, b * N + t * 128);
+        tma_store_commit();
+        tma_store_wait_read();
+        mbar_arrive(&bar_buffree[s]);  // (with the other tile's arrival) the producer may refill this buffer
+      }
+    }
+    if (storer && elect_one()) tma_store_wait_all();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// =============================================================================================
 // Backward
 // =============================================================================================
 constexpr int B_OFF_Q = 0;
@@ -1123,11 +1333,37 @@ static int set_smem_once(K kernel, int bytes, cudaError_t* cached, std::once_fla
 // entry points used by attention.cu's dispatcher (N == 256, hd == 64)
 int attention_fwd_tcgen05(const bf16* qkv, bf16* out, float* lse, int B, int H, cudaStream_t stream) {
   using namespace attn_tc;
+  const int D = H * HD;
+  const float scale = 1.0f / sqrtf((float)HD);
+  // TAE_ATTN_FWD=v1 selects the one-shot kernel (A/B testing); default is the persistent kernel
+  static int variant = -1;
+  if (variant < 0) {
+    const char* e = getenv("TAE_ATTN_FWD");
+    variant = (e != nullptr && e[0] == 'v') ? 0 : 1;
+  }
+  int rc;
+  if (variant == 1) {
+    static cudaError_t err2 = cudaSuccess;
+    static std::once_flag once2;
+    rc = set_smem_once(attn_fwd_tc_persist, G_SMEM, &err2, &once2);
+    if (rc) return rc;
+    CUtensorMap tkv, to;
+    rc = sm100::make_tmap(&tkv, qkv, (uint64_t)3 * D, (uint64_t)B * N, (uint64_t)3 * D, 256);
+    if (rc) return rc;
+    rc = sm100::make_tmap(&to, out, (uint64_t)D, (uint64_t)B * N, (uint64_t)D, 128);
+    if (rc) return rc;
+    const int sms = num_sms();
+    if (sms <= 0) return TAE_ERR_CUDA;
+    const int items = B * H;
+    attn_fwd_tc_persist<<<items < sms ? items : sms, G_THREADS, G_SMEM, stream>>>(tkv, to, lse, H, items, scale,
+                                                                                  scale * 1.44269504088896340736f);
+    TAE_CHECK_LAUNCH();
+    return TAE_OK;
+  }
   static cudaError_t err = cudaSuccess;
   static std::once_flag once;
-  int rc = set_smem_once(attn_fwd_tc, F_SMEM, &err, &once);
+  rc = set_smem_once(attn_fwd_tc, F_SMEM, &err, &once);
   if (rc) return rc;
-  const int D = H * HD;
   CUtensorMap tq, tkv, to;
   rc = sm100::make_tmap(&tq, qkv, (uint64_t)3 * D, (uint64_t)B * N, (uint64_t)3 * D, 128);
   if (rc) return rc;
@@ -1135,7 +1371,6 @@ int attention_fwd_tcgen05(const bf16* qkv, bf16* out, float* lse, int B, int H, 
   if (rc) return rc;
   rc = sm100::make_tmap(&to, out, (uint64_t)D, (uint64_t)B * N, (uint64_t)D, 128);
   if (rc) return rc;
-  const float scale = 1.0f / sqrtf((float)HD);
   attn_fwd_tc<<<B * H * 2, F_THREADS, F_SMEM, stream>>>(tq, tkv, to, lse, H, scale, scale * 1.44269504088896340736f);
   TAE_CHECK_LAUNCH();
   return TAE_OK;
