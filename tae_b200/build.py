@@ -7,6 +7,7 @@ Each csrc/*.cu is compiled to an object (in parallel), then linked into tae_b200
 from __future__ import annotations
 
 import argparse
+import fcntl
 import hashlib
 import os
 import subprocess
@@ -39,7 +40,9 @@ def _fingerprint() -> str:
     for f in sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + [INCLUDE_DIR / "tae_b200.h"]):
         h.update(f.name.encode())
         h.update(f.read_bytes())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    # flags WITHOUT the checkout's absolute include path: the same sources must hash the same wherever the repo lives
+    # (the GPU box runs a copy under another path and must not rebuild a library that is already current)
+    h.update(" ".join(f for f in NVCC_FLAGS if f != str(INCLUDE_DIR)).encode())
     return h.hexdigest()
 
 
@@ -53,7 +56,20 @@ def build(force: bool = False, verbose: bool = False) -> Path:
             return LIB_PATH  # GPU box without a toolchain change: use the prebuilt library
         raise RuntimeError(f"nvcc not found at {NVCC} and {LIB_PATH} is missing")
     BUILD_DIR.mkdir(parents=True, exist_ok=True)
+    # One builder at a time (torchrun starts one process per GPU, all of which import the package): the others block
+    # on the lock, re-check the stamp and return.  The library is linked under a temporary name and renamed into
+    # place, so a concurrent dlopen never sees a half-written file.
+    with open(BUILD_DIR / ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and LIB_PATH.exists() and stamp.exists() and stamp.read_text() == fp:
+                return LIB_PATH
+            return _build_locked(fp, stamp, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
 
+
+def _build_locked(fp: str, stamp: Path, verbose: bool) -> Path:
     def compile_one(src: Path) -> Path:
         obj = BUILD_DIR / (src.stem + ".o")
         cmd = [NVCC, *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
@@ -70,10 +86,12 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
         objs = list(ex.map(compile_one, _sources()))
-    cmd = [NVCC, "-shared", "-o", str(LIB_PATH), *[str(o) for o in objs], "-lcudart"]
+    tmp = LIB_PATH.with_suffix(f".so.tmp{os.getpid()}")
+    cmd = [NVCC, "-shared", "-o", str(tmp), *[str(o) for o in objs], "-lcudart"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")
+    os.replace(tmp, LIB_PATH)
     stamp.write_text(fp)
     return LIB_PATH
 

@@ -170,3 +170,26 @@ def test_pos_embed_interpolation_and_load_model(tmp_path):
     big = {"pos_embed": torch.randn(1, 64, 128)}
     misc.interpolate_pos_embed(dst, big)
     assert big["pos_embed"].shape == (1, 16, 128)
+
+
+def test_build_fingerprint_is_location_independent(tmp_path):
+    """The GPU box runs a copy of the repo under another path: the prebuilt library must be recognised as current there
+    (a rebuild by 8 torchrun ranks at once is how a half-written .so gets dlopen'ed)."""
+    import importlib.util
+    import shutil
+
+    from tae_b200 import build as here
+
+    root = tmp_path / "elsewhere"
+    (root / "tae_b200").mkdir(parents=True)
+    shutil.copytree(here.CSRC, root / "tae_b200" / "csrc", ignore=shutil.ignore_patterns("build"))
+    shutil.copytree(here.INCLUDE_DIR, root / "include")
+    shutil.copy(here.PKG_DIR / "build.py", root / "tae_b200" / "build.py")
+    spec = importlib.util.spec_from_file_location("build_elsewhere", root / "tae_b200" / "build.py")
+    there = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(there)
+    assert there.INCLUDE_DIR != here.INCLUDE_DIR
+    assert there._fingerprint() == here._fingerprint()
+    stamp = here.BUILD_DIR / "fingerprint.txt"
+    if here.LIB_PATH.exists() and stamp.exists():
+        assert stamp.read_text() == here._fingerprint(), "in-tree library is stale: run python -m tae_b200.build"
