@@ -449,3 +449,31 @@ def test_attention_bwd_with_precomputed_delta():
     delta = (dout.float() * out.float()).view(B, N, H, hd).sum(-1).permute(0, 2, 1).contiguous()
     got = ops.attention_bwd(qkv, None, dout, lse, B, N, H, hd, delta=delta)
     assert max_err_scaled(got.float(), ref.float()) < 2e-3
+
+
+@pytest.mark.parametrize("B,H", [(41, 16), (300, 1)])
+def test_attention_persistent_kernels_many_items_per_cta(B, H):
+    """The tcgen05 attention kernels are persistent: with more (image, head) items than SMs every CTA walks several
+    items, which exercises the cross-item operand prefetch, the double-buffered lse/delta and operand homes and the
+    barrier phase bookkeeping (item counts per CTA differ: 656 and 300 items over 148 CTAs)."""
+    ops = _ops()
+    N, hd = 256, 64
+    D = H * hd
+    qkv = randn(B * N, 3 * D, seed=40 + H, scale=0.8)
+    dout = randn(B * N, D, seed=41 + H)
+    out, lse = ops.attention_fwd(qkv, B, N, H, hd)
+    oref, lref, dref = _attn_ref(qkv, B, N, H, hd, dout)
+    assert rel_err(out.float(), oref) < 8e-3 and max_err_scaled(out.float(), oref) < 1.5e-2
+    assert float((lse - lref).abs().max()) < 2e-3
+    # per-image error: a wrong item mapping or a stale operand buffer would show up in single images
+    per_img = ((out.float() - oref).view(B, -1).norm(dim=1) / oref.view(B, -1).norm(dim=1)).max()
+    assert float(per_img) < 1e-2
+    for kw in ({}, {"delta": (dout.float() * out.float()).view(B, N, H, hd).sum(-1).permute(0, 2, 1).contiguous()}):
+        dqkv = ops.attention_bwd(qkv, None if kw else out, dout, lse, B, N, H, hd, **kw)
+        assert rel_err(dqkv.float(), dref) < 1.5e-2 and max_err_scaled(dqkv.float(), dref) < 2e-2
+        per_img = ((dqkv.float() - dref).view(B, -1).norm(dim=1) / dref.view(B, -1).norm(dim=1)).max()
+        assert float(per_img) < 2e-2
+    # determinism: the kernels use no atomics
+    out2, lse2 = ops.attention_fwd(qkv, B, N, H, hd)
+    assert torch.equal(out2, out) and torch.equal(lse2, lse)
+    assert torch.equal(ops.attention_bwd(qkv, out, dout, lse, B, N, H, hd), ops.attention_bwd(qkv, out, dout, lse, B, N, H, hd))
