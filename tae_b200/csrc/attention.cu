@@ -403,15 +403,33 @@ __device__ __forceinline__ void load_head_f32(float* s, const bf16* g, size_t ld
   }
 }
 
-// per-warp smem floats: fwd 3*N*ldp + N*(N+1); bwd 4*N*ldp + 2*N*(N+1) + N
+// per-warp smem floats: fwd 3*N*ldp + N*(N+1); bwd 4*N*ldp + 2*N*(N+1) + N, with ldp = hd + 4: rows are 16-byte
+// aligned so every dot product runs on 128-bit shared loads (the scalar version was LDS-bound: 2 loads per FMA), and
+// the 4-float skew keeps the 8 rows a quarter-warp touches on distinct banks (hd = 80: starts 0,20,8,28,16,4,24,12).
+__device__ __forceinline__ float dot4(const float4 a, const float4 b, float acc) {
+  acc = fmaf(a.x, b.x, acc);
+  acc = fmaf(a.y, b.y, acc);
+  acc = fmaf(a.z, b.z, acc);
+  return fmaf(a.w, b.w, acc);
+}
+__device__ __forceinline__ void axpy4(float4& acc, float s, const float4 v) {
+  acc.x = fmaf(s, v.x, acc.x);
+  acc.y = fmaf(s, v.y, acc.y);
+  acc.z = fmaf(s, v.z, acc.z);
+  acc.w = fmaf(s, v.w, acc.w);
+}
+__device__ __forceinline__ void store_bf16x4(bf16* dst, const float4 v) {
+  *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+}
+
 __global__ void attn_fwd_simt(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* __restrict__ lse, int BH,
                               int N, int H, int hd, float scale, int per_warp_floats) {
-  extern __shared__ float smem_f[];
+  extern __shared__ __align__(16) float smem_f[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int wg = blockIdx.x * (blockDim.x >> 5) + warp;
   if (wg >= BH) return;  // no CTA-wide barriers below
   const int b = wg / H, h = wg % H;
-  const int D = H * hd, ldp = hd + 1, ldn = N + 1;
+  const int D = H * hd, ldp = hd + 4, ldn = N + 1, h4 = hd >> 2;
   const size_t ldq = (size_t)3 * D;
   float* sq = smem_f + (size_t)warp * per_warp_floats;
   float* sk = sq + N * ldp;
@@ -424,11 +442,16 @@ __global__ void attn_fwd_simt(const bf16* __restrict__ qkv, bf16* __restrict__ o
   __syncwarp();
   for (int e = lane; e < N * N; e += 32) {
     const int i = e / N, j = e - i * N;
-    const float* a = sq + i * ldp;
-    const float* c = sk + j * ldp;
-    float acc = 0.f;
-    for (int d = 0; d < hd; ++d) acc = fmaf(a[d], c[d], acc);
-    sp[i * ldn + j] = acc * scale;
+    const float4* a = reinterpret_cast<const float4*>(sq + i * ldp);
+    const float4* c = reinterpret_cast<const float4*>(sk + j * ldp);
+    float acc0 = 0.f, acc1 = 0.f;
+    int d = 0;
+    for (; d + 1 < h4; d += 2) {
+      acc0 = dot4(a[d], c[d], acc0);
+      acc1 = dot4(a[d + 1], c[d + 1], acc1);
+    }
+    if (d < h4) acc0 = dot4(a[d], c[d], acc0);
+    sp[i * ldn + j] = (acc0 + acc1) * scale;
   }
   __syncwarp();
   for (int i = lane; i < N; i += 32) {
@@ -447,23 +470,23 @@ __global__ void attn_fwd_simt(const bf16* __restrict__ qkv, bf16* __restrict__ o
   }
   __syncwarp();
   bf16* go = out + (size_t)b * N * D + (size_t)h * hd;
-  for (int e = lane; e < N * hd; e += 32) {
-    const int i = e / hd, d = e - i * hd;
+  for (int e = lane; e < N * h4; e += 32) {  // 4 output columns per lane: one scalar + one 128-bit load per 4 FMAs
+    const int i = e / h4, d4 = e - i * h4;
     const float* p = sp + i * ldn;
-    float acc = 0.f;
-    for (int j = 0; j < N; ++j) acc = fmaf(p[j], sv[j * ldp + d], acc);
-    go[(size_t)i * D + d] = __float2bfloat16_rn(acc);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < N; ++j) axpy4(acc, p[j], reinterpret_cast<const float4*>(sv + j * ldp)[d4]);
+    store_bf16x4(go + (size_t)i * D + d4 * 4, acc);
   }
 }
 
 __global__ void attn_bwd_simt(const bf16* __restrict__ qkv, const bf16* __restrict__ dout, const float* __restrict__ lse,
                               bf16* __restrict__ dqkv, int BH, int N, int H, int hd, float scale, int per_warp_floats) {
-  extern __shared__ float smem_f[];
+  extern __shared__ __align__(16) float smem_f[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int wg = blockIdx.x * (blockDim.x >> 5) + warp;
   if (wg >= BH) return;
   const int b = wg / H, h = wg % H;
-  const int D = H * hd, ldp = hd + 1, ldn = N + 1;
+  const int D = H * hd, ldp = hd + 4, ldn = N + 1, h4 = hd >> 2;
   const size_t ldq = (size_t)3 * D;
   float* sq = smem_f + (size_t)warp * per_warp_floats;
   float* sk = sq + N * ldp;
@@ -481,14 +504,14 @@ __global__ void attn_bwd_simt(const bf16* __restrict__ qkv, const bf16* __restri
   const float* lrow = lse + ((size_t)b * H + h) * N;
   for (int e = lane; e < N * N; e += 32) {
     const int i = e / N, j = e - i * N;
-    const float* qa = sq + i * ldp;
-    const float* ka = sk + j * ldp;
-    const float* da = sdo + i * ldp;
-    const float* va = sv + j * ldp;
+    const float4* qa = reinterpret_cast<const float4*>(sq + i * ldp);
+    const float4* ka = reinterpret_cast<const float4*>(sk + j * ldp);
+    const float4* da = reinterpret_cast<const float4*>(sdo + i * ldp);
+    const float4* va = reinterpret_cast<const float4*>(sv + j * ldp);
     float s = 0.f, dp = 0.f;
-    for (int d = 0; d < hd; ++d) {
-      s = fmaf(qa[d], ka[d], s);
-      dp = fmaf(da[d], va[d], dp);
+    for (int d = 0; d < h4; ++d) {
+      s = dot4(qa[d], ka[d], s);
+      dp = dot4(da[d], va[d], dp);
     }
     sp[i * ldn + j] = __expf(s * scale - lrow[i]);
     sds[i * ldn + j] = dp;
@@ -506,25 +529,26 @@ __global__ void attn_bwd_simt(const bf16* __restrict__ qkv, const bf16* __restri
   }
   __syncwarp();
   bf16* gdq = dqkv + (size_t)b * N * ldq + (size_t)h * hd;
-  for (int e = lane; e < N * hd; e += 32) {
-    const int r = e / hd, d = e - r * hd;
-    float aq = 0.f, ak = 0.f, av = 0.f;
+  for (int e = lane; e < N * h4; e += 32) {
+    const int r = e / h4, d4 = e - r * h4;
+    float4 aq = make_float4(0.f, 0.f, 0.f, 0.f), ak = aq, av = aq;
     for (int j = 0; j < N; ++j) {
-      aq = fmaf(sds[r * ldn + j], sk[j * ldp + d], aq);   // dQ[r] = sum_j dS[r,j] K[j]
-      ak = fmaf(sds[j * ldn + r], sq[j * ldp + d], ak);   // dK[r] = sum_i dS[i,r] Q[i]
-      av = fmaf(sp[j * ldn + r], sdo[j * ldp + d], av);   // dV[r] = sum_i P[i,r] dO[i]
+      axpy4(aq, sds[r * ldn + j], reinterpret_cast<const float4*>(sk + j * ldp)[d4]);   // dQ[r] = sum_j dS[r,j] K[j]
+      axpy4(ak, sds[j * ldn + r], reinterpret_cast<const float4*>(sq + j * ldp)[d4]);   // dK[r] = sum_i dS[i,r] Q[i]
+      axpy4(av, sp[j * ldn + r], reinterpret_cast<const float4*>(sdo + j * ldp)[d4]);   // dV[r] = sum_i P[i,r] dO[i]
     }
-    gdq[(size_t)r * ldq + d] = __float2bfloat16_rn(aq);
-    gdq[(size_t)r * ldq + D + d] = __float2bfloat16_rn(ak);
-    gdq[(size_t)r * ldq + 2 * D + d] = __float2bfloat16_rn(av);
+    bf16* dst = gdq + (size_t)r * ldq + d4 * 4;
+    store_bf16x4(dst, aq);
+    store_bf16x4(dst + D, ak);
+    store_bf16x4(dst + 2 * D, av);
   }
 }
 
 constexpr int SIMT_MAX_SMEM = 200 * 1024;
 
 static int simt_config(int N, int hd, bool bwd, int* wpc, int* per_warp_floats) {
-  const int ldp = hd + 1, ldn = N + 1;
-  const int pw = bwd ? (4 * N * ldp + 2 * N * ldn + N) : (3 * N * ldp + N * ldn);
+  const int ldp = hd + 4, ldn = N + 1;
+  const int pw = ((bwd ? (4 * N * ldp + 2 * N * ldn + N) : (3 * N * ldp + N * ldn)) + 3) & ~3;  // 16-byte multiple
   const int bytes = pw * 4;
   if (bytes > SIMT_MAX_SMEM) return -1;
   int w = SIMT_MAX_SMEM / bytes;
