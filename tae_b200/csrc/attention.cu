@@ -385,6 +385,273 @@ attn_bwd_mma(const bf16* __restrict__ qkv, const bf16* __restrict__ out, const b
 }
 
 // =============================================================================================
+// Tiny grids (N <= 16 tokens: patch64 / patch128 models, hd = 80): ONE WARP per (image, head), tensor-core math
+// (mma.sync m16n8k16) on a 16x16 score tile.  Rows / keys >= N are zero-padded and masked.  The fp32 shared-memory
+// version of this case was bound by shared-memory bandwidth (110 us forward at B=256, H=32, N=16 against a 13 us HBM
+// floor).  The backward needs no saved output: delta = rowsum(dO * O) = rowsum(P * dP).
+// =============================================================================================
+__device__ __forceinline__ uint32_t movmatrix_t(uint32_t a) {
+  uint32_t d;
+  asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(d) : "r"(a));
+  return d;
+}
+
+template <int HDT>
+struct Small {
+  static constexpr int LD = HDT + 8;      // padded row (hd = 80: 176 B -> 8 ldmatrix rows on distinct banks)
+  static constexpr int KS = HDT / 16;     // k-steps over the head dimension
+  static constexpr int NT8 = HDT / 8;     // 8-wide n-tiles over the head dimension
+  static constexpr int TILE = 16 * LD;    // elements of one [16 x HDT] tile
+  __device__ static uint32_t a_addr(uint32_t base, int k0, int lane) {  // A: rows 0..15, k0..k0+15 of [row][k]
+    return base + (uint32_t)(((lane & 7) + ((lane >> 3) & 1) * 8) * LD + k0 + (lane >> 4) * 8) * 2u;
+  }
+  __device__ static uint32_t b_addr(uint32_t base, int k0, int lane) {  // B from [n][k]: n 0..15 (two n-tiles), k0..
+    return base + (uint32_t)(((lane & 7) + (lane >> 4) * 8) * LD + k0 + ((lane >> 3) & 1) * 8) * 2u;
+  }
+  __device__ static uint32_t bt_addr(uint32_t base, int n0, int lane) {  // B from [k][n] (.trans): k 0..15, n0..n0+15
+    return base + (uint32_t)(((lane & 7) + ((lane >> 3) & 1) * 8) * LD + n0 + (lane >> 4) * 8) * 2u;
+  }
+  // [N x HDT] rows of global (row stride ld_g) -> padded smem tile, rows >= N zeroed
+  __device__ static void load_tile(bf16* s, const bf16* g, size_t ld_g, int N, int lane) {
+    constexpr int CPR = HDT / 8;
+    for (int c = lane; c < 16 * CPR; c += 32) {
+      const int row = c / CPR, ch = c - row * CPR;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (row < N) v = ld_nc_v4(g + (size_t)row * ld_g + ch * 8);
+      *reinterpret_cast<uint4*>(s + row * LD + ch * 8) = v;
+    }
+  }
+};
+
+// S (exp2 domain, masked) of one 16x16 tile: s[nt][0..3] = rows (g, g+8), keys nt*8 + 2t + {0,1}
+template <int HDT>
+__device__ __forceinline__ void small_scores(float (&s)[2][4], uint32_t bQ, uint32_t bK, int N, float scale_log2, int lane) {
+  using C = Small<HDT>;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < C::KS; ++ks) {
+    uint32_t qa[4], kb[4];
+    ldsm_x4(qa, C::a_addr(bQ, ks * 16, lane));
+    ldsm_x4(kb, C::b_addr(bK, ks * 16, lane));
+    mma16816(s[0], qa, kb[0], kb[1]);
+    mma16816(s[1], qa, kb[2], kb[3]);
+  }
+  const int t = lane & 3;
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt) {
+    const int j0 = nt * 8 + 2 * t;
+    s[nt][0] = j0 < N ? s[nt][0] * scale_log2 : -INFINITY;
+    s[nt][2] = j0 < N ? s[nt][2] * scale_log2 : -INFINITY;
+    s[nt][1] = j0 + 1 < N ? s[nt][1] * scale_log2 : -INFINITY;
+    s[nt][3] = j0 + 1 < N ? s[nt][3] * scale_log2 : -INFINITY;
+  }
+}
+__device__ __forceinline__ float quad_max(float v) {
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+  return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+}
+__device__ __forceinline__ float quad_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v + __shfl_xor_sync(0xffffffffu, v, 2);
+}
+
+template <int HDT>
+__global__ void __launch_bounds__(128)
+attn_fwd_small(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* __restrict__ lse, int BH, int N, int H,
+               float scale_log2) {
+  using C = Small<HDT>;
+  extern __shared__ uint4 smem_u4[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wg = blockIdx.x * 4 + warp;
+  if (wg >= BH) return;  // no CTA-wide barriers below
+  const int b = wg / H, h = wg - b * H;
+  const int D = H * HDT;
+  const size_t ldq = (size_t)3 * D;
+  bf16* sQ = reinterpret_cast<bf16*>(smem_u4) + (size_t)warp * 3 * C::TILE;
+  bf16* sK = sQ + C::TILE;
+  bf16* sV = sK + C::TILE;
+  const bf16* gq = qkv + (size_t)b * N * ldq + (size_t)h * HDT;
+  C::load_tile(sQ, gq, ldq, N, lane);
+  C::load_tile(sK, gq + D, ldq, N, lane);
+  C::load_tile(sV, gq + 2 * D, ldq, N, lane);
+  __syncwarp();
+  const uint32_t bQ = smem_u32(sQ), bK = smem_u32(sK), bV = smem_u32(sV);
+  float s[2][4];
+  small_scores<HDT>(s, bQ, bK, N, scale_log2, lane);
+  const float m0 = quad_max(fmaxf(fmaxf(s[0][0], s[0][1]), fmaxf(s[1][0], s[1][1])));
+  const float m1 = quad_max(fmaxf(fmaxf(s[0][2], s[0][3]), fmaxf(s[1][2], s[1][3])));
+  float p[2][4];
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt) {
+    p[nt][0] = exp2f(s[nt][0] - m0);
+    p[nt][1] = exp2f(s[nt][1] - m0);
+    p[nt][2] = exp2f(s[nt][2] - m1);
+    p[nt][3] = exp2f(s[nt][3] - m1);
+  }
+  const float l0 = quad_sum(p[0][0] + p[0][1] + p[1][0] + p[1][1]);
+  const float l1 = quad_sum(p[0][2] + p[0][3] + p[1][2] + p[1][3]);
+  // C fragments of the two key n-tiles are the A fragment of the single 16-key k-step of P V
+  const uint32_t pa[4] = {pack_bf16x2(p[0][0], p[0][1]), pack_bf16x2(p[0][2], p[0][3]), pack_bf16x2(p[1][0], p[1][1]),
+                          pack_bf16x2(p[1][2], p[1][3])};
+  const int g = lane >> 2, t = lane & 3;
+  const float inv0 = 1.f / l0, inv1 = 1.f / l1;
+  if (t == 0) {
+    float* lrow = lse + ((size_t)b * H + h) * N;
+    if (g < N) lrow[g] = (m0 + log2f(l0)) * 0.69314718055994530942f;
+    if (g + 8 < N) lrow[g + 8] = (m1 + log2f(l1)) * 0.69314718055994530942f;
+  }
+  bf16* go = out + (size_t)b * N * D + (size_t)h * HDT;
+#pragma unroll
+  for (int dp = 0; dp < C::NT8 / 2; ++dp) {
+    uint32_t vb[4];
+    ldsm_x4_t(vb, C::bt_addr(bV, dp * 16, lane));
+    float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f};
+    mma16816(o0, pa, vb[0], vb[1]);
+    mma16816(o1, pa, vb[2], vb[3]);
+    const int col = dp * 16 + 2 * t;
+    if (g < N) {
+      *reinterpret_cast<uint32_t*>(go + (size_t)g * D + col) = pack_bf16x2(o0[0] * inv0, o0[1] * inv0);
+      *reinterpret_cast<uint32_t*>(go + (size_t)g * D + col + 8) = pack_bf16x2(o1[0] * inv0, o1[1] * inv0);
+    }
+    if (g + 8 < N) {
+      *reinterpret_cast<uint32_t*>(go + (size_t)(g + 8) * D + col) = pack_bf16x2(o0[2] * inv1, o0[3] * inv1);
+      *reinterpret_cast<uint32_t*>(go + (size_t)(g + 8) * D + col + 8) = pack_bf16x2(o1[2] * inv1, o1[3] * inv1);
+    }
+  }
+}
+
+template <int HDT>
+__global__ void __launch_bounds__(128)
+attn_bwd_small(const bf16* __restrict__ qkv, const bf16* __restrict__ dout, const float* __restrict__ lse,
+               bf16* __restrict__ dqkv, int BH, int N, int H, float scale, float scale_log2) {
+  using C = Small<HDT>;
+  extern __shared__ uint4 smem_u4[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wg = blockIdx.x * 4 + warp;
+  if (wg >= BH) return;
+  const int b = wg / H, h = wg - b * H;
+  const int D = H * HDT;
+  const size_t ldq = (size_t)3 * D;
+  bf16* sQ = reinterpret_cast<bf16*>(smem_u4) + (size_t)warp * 4 * C::TILE;
+  bf16* sK = sQ + C::TILE;
+  bf16* sV = sK + C::TILE;
+  bf16* sdO = sV + C::TILE;
+  const bf16* gq = qkv + (size_t)b * N * ldq + (size_t)h * HDT;
+  C::load_tile(sQ, gq, ldq, N, lane);
+  C::load_tile(sK, gq + D, ldq, N, lane);
+  C::load_tile(sV, gq + 2 * D, ldq, N, lane);
+  C::load_tile(sdO, dout + (size_t)b * N * D + (size_t)h * HDT, (size_t)D, N, lane);
+  __syncwarp();
+  const uint32_t bQ = smem_u32(sQ), bK = smem_u32(sK), bV = smem_u32(sV), bdO = smem_u32(sdO);
+  const int g = lane >> 2, t = lane & 3;
+  // P = exp2(S * c - lse2[row])   (masked keys give exp2(-inf) = 0; padded rows are discarded at the stores)
+  float s[2][4];
+  small_scores<HDT>(s, bQ, bK, N, scale_log2, lane);
+  const float* lrow = lse + ((size_t)b * H + h) * N;
+  const float ls0 = g < N ? lrow[g] * 1.44269504088896340736f : 0.f;
+  const float ls1 = g + 8 < N ? lrow[g + 8] * 1.44269504088896340736f : 0.f;
+  float p[2][4], dp[2][4];
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt) {
+    p[nt][0] = exp2f(s[nt][0] - ls0);
+    p[nt][1] = exp2f(s[nt][1] - ls0);
+    p[nt][2] = exp2f(s[nt][2] - ls1);
+    p[nt][3] = exp2f(s[nt][3] - ls1);
+    dp[nt][0] = dp[nt][1] = dp[nt][2] = dp[nt][3] = 0.f;
+  }
+  // dP = dO V^T
+#pragma unroll
+  for (int ks = 0; ks < C::KS; ++ks) {
+    uint32_t da[4], vb[4];
+    ldsm_x4(da, C::a_addr(bdO, ks * 16, lane));
+    ldsm_x4(vb, C::b_addr(bV, ks * 16, lane));
+    mma16816(dp[0], da, vb[0], vb[1]);
+    mma16816(dp[1], da, vb[2], vb[3]);
+  }
+  // delta = rowsum(P * dP)  (== rowsum(dO * O));  dS = P (dP - delta) * scale
+  const float dl0 = quad_sum(p[0][0] * dp[0][0] + p[0][1] * dp[0][1] + p[1][0] * dp[1][0] + p[1][1] * dp[1][1]);
+  const float dl1 = quad_sum(p[0][2] * dp[0][2] + p[0][3] * dp[0][3] + p[1][2] * dp[1][2] + p[1][3] * dp[1][3]);
+  float ds[2][4];
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt) {
+    ds[nt][0] = p[nt][0] * (dp[nt][0] - dl0) * scale;
+    ds[nt][1] = p[nt][1] * (dp[nt][1] - dl0) * scale;
+    ds[nt][2] = p[nt][2] * (dp[nt][2] - dl1) * scale;
+    ds[nt][3] = p[nt][3] * (dp[nt][3] - dl1) * scale;
+  }
+  // A fragments: dS [q x key] for dQ; dS^T and P^T [key x q] (8x8 blocks transposed with movmatrix) for dK and dV
+  const uint32_t dsa[4] = {pack_bf16x2(ds[0][0], ds[0][1]), pack_bf16x2(ds[0][2], ds[0][3]), pack_bf16x2(ds[1][0], ds[1][1]),
+                           pack_bf16x2(ds[1][2], ds[1][3])};
+  const uint32_t pa[4] = {pack_bf16x2(p[0][0], p[0][1]), pack_bf16x2(p[0][2], p[0][3]), pack_bf16x2(p[1][0], p[1][1]),
+                          pack_bf16x2(p[1][2], p[1][3])};
+  const uint32_t dst_[4] = {movmatrix_t(dsa[0]), movmatrix_t(dsa[2]), movmatrix_t(dsa[1]), movmatrix_t(dsa[3])};
+  const uint32_t pt_[4] = {movmatrix_t(pa[0]), movmatrix_t(pa[2]), movmatrix_t(pa[1]), movmatrix_t(pa[3])};
+  bf16* gd = dqkv + (size_t)b * N * ldq + (size_t)h * HDT;
+#pragma unroll
+  for (int dpi = 0; dpi < C::NT8 / 2; ++dpi) {
+    uint32_t kb[4], qb[4], ob[4];
+    ldsm_x4_t(kb, C::bt_addr(bK, dpi * 16, lane));    // K  [key][d]
+    ldsm_x4_t(qb, C::bt_addr(bQ, dpi * 16, lane));    // Q  [q][d]
+    ldsm_x4_t(ob, C::bt_addr(bdO, dpi * 16, lane));   // dO [q][d]
+    float q0[4] = {0.f, 0.f, 0.f, 0.f}, q1[4] = {0.f, 0.f, 0.f, 0.f};
+    float k0[4] = {0.f, 0.f, 0.f, 0.f}, k1[4] = {0.f, 0.f, 0.f, 0.f};
+    float v0[4] = {0.f, 0.f, 0.f, 0.f}, v1[4] = {0.f, 0.f, 0.f, 0.f};
+    mma16816(q0, dsa, kb[0], kb[1]);   // dQ = dS K
+    mma16816(q1, dsa, kb[2], kb[3]);
+    mma16816(k0, dst_, qb[0], qb[1]);  // dK = dS^T Q
+    mma16816(k1, dst_, qb[2], qb[3]);
+    mma16816(v0, pt_, ob[0], ob[1]);   // dV = P^T dO
+    mma16816(v1, pt_, ob[2], ob[3]);
+    const int col = dpi * 16 + 2 * t;
+    if (g < N) {
+      bf16* r = gd + (size_t)g * ldq + col;
+      *reinterpret_cast<uint32_t*>(r) = pack_bf16x2(q0[0], q0[1]);
+      *reinterpret_cast<uint32_t*>(r + 8) = pack_bf16x2(q1[0], q1[1]);
+      *reinterpret_cast<uint32_t*>(r + D) = pack_bf16x2(k0[0], k0[1]);
+      *reinterpret_cast<uint32_t*>(r + D + 8) = pack_bf16x2(k1[0], k1[1]);
+      *reinterpret_cast<uint32_t*>(r + 2 * D) = pack_bf16x2(v0[0], v0[1]);
+      *reinterpret_cast<uint32_t*>(r + 2 * D + 8) = pack_bf16x2(v1[0], v1[1]);
+    }
+    if (g + 8 < N) {
+      bf16* r = gd + (size_t)(g + 8) * ldq + col;
+      *reinterpret_cast<uint32_t*>(r) = pack_bf16x2(q0[2], q0[3]);
+      *reinterpret_cast<uint32_t*>(r + 8) = pack_bf16x2(q1[2], q1[3]);
+      *reinterpret_cast<uint32_t*>(r + D) = pack_bf16x2(k0[2], k0[3]);
+      *reinterpret_cast<uint32_t*>(r + D + 8) = pack_bf16x2(k1[2], k1[3]);
+      *reinterpret_cast<uint32_t*>(r + 2 * D) = pack_bf16x2(v0[2], v0[3]);
+      *reinterpret_cast<uint32_t*>(r + 2 * D + 8) = pack_bf16x2(v1[2], v1[3]);
+    }
+  }
+}
+
+template <int HDT>
+static int launch_small(bool bwd, const bf16* qkv, const bf16* dout, bf16* out_or_dqkv, const float* lse_in, float* lse_out,
+                        int B, int N, int H, float scale, cudaStream_t stream) {
+  const int BH = B * H;
+  const int smem = 4 * (bwd ? 4 : 3) * Small<HDT>::TILE * 2;  // 4 warps per CTA
+  const float sl2 = scale * 1.44269504088896340736f;
+  if (!bwd) {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(attn_fwd_small<HDT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    attn_fwd_small<HDT><<<(BH + 3) / 4, 128, smem, stream>>>(qkv, out_or_dqkv, lse_out, BH, N, H, sl2);
+  } else {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(attn_bwd_small<HDT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    attn_bwd_small<HDT><<<(BH + 3) / 4, 128, smem, stream>>>(qkv, dout, lse_in, out_or_dqkv, BH, N, H, scale, sl2);
+  }
+  TAE_CHECK_LAUNCH();
+  return TAE_OK;
+}
+static bool force_simt();
+// N <= 16 and a head dimension the tensor-core kernels are instantiated for
+static bool small_ok(int N, int hd) { return N <= 16 && (hd == 32 || hd == 64 || hd == 80); }
+static int dispatch_small(bool bwd, const bf16* qkv, const bf16* dout, bf16* o, const float* lse_in, float* lse_out, int B,
+                          int N, int H, int hd, float scale, cudaStream_t stream) {
+  if (hd == 32) return launch_small<32>(bwd, qkv, dout, o, lse_in, lse_out, B, N, H, scale, stream);
+  if (hd == 64) return launch_small<64>(bwd, qkv, dout, o, lse_in, lse_out, B, N, H, scale, stream);
+  return launch_small<80>(bwd, qkv, dout, o, lse_in, lse_out, B, N, H, scale, stream);
+}
+
+// =============================================================================================
 // Generic path: one warp per (image, head), fp32 math in shared memory
 // =============================================================================================
 __device__ __forceinline__ void load_head_f32(float* s, const bf16* g, size_t ld_g, int N, int hd, int ldp, int lane) {
@@ -544,6 +811,16 @@ __global__ void attn_bwd_simt(const bf16* __restrict__ qkv, const bf16* __restri
   }
 }
 
+// TAE_ATTN_SIMT=1 forces the fp32 shared-memory kernels for N <= 16 (A/B testing of the tensor-core small-grid kernels)
+static bool force_simt() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TAE_ATTN_SIMT");
+    v = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
 constexpr int SIMT_MAX_SMEM = 200 * 1024;
 
 static int simt_config(int N, int hd, bool bwd, int* wpc, int* per_warp_floats) {
@@ -601,6 +878,7 @@ extern "C" int tae_attention_fwd(const tae_bf16* qkv_, tae_bf16* out_, float* ls
     TAE_CHECK_LAUNCH();
     return TAE_OK;
   }
+  if (small_ok(N, hd) && !force_simt()) return dispatch_small(false, qkv, nullptr, out, nullptr, lse, B, N, H, hd, scale, stream);
   int wpc, pw;
   TAE_CHECK_SHAPE(simt_config(N, hd, false, &wpc, &pw) == 0, "tae_attention_fwd: N=%d hd=%d does not fit shared memory", N, hd);
   const int smem = wpc * pw * 4;
@@ -640,6 +918,7 @@ extern "C" int tae_attention_bwd(const tae_bf16* qkv_, const tae_bf16* out_, con
     TAE_CHECK_LAUNCH();
     return TAE_OK;
   }
+  if (small_ok(N, hd) && !force_simt()) return dispatch_small(true, qkv, dout, dqkv, lse, nullptr, B, N, H, hd, scale, stream);
   int wpc, pw;
   TAE_CHECK_SHAPE(simt_config(N, hd, true, &wpc, &pw) == 0, "tae_attention_bwd: N=%d hd=%d does not fit shared memory", N, hd);
   const int smem = wpc * pw * 4;
