@@ -150,7 +150,7 @@ def run_reference(args):
         return
     steps, warmup = max(1, args.steps), max(0, args.warmup)
     # bounded: each step is `cpu_batch` images of the same workload; cap the number of CPU steps to stay in minutes
-    steps_run, warm_run = min(steps, 3), min(warmup, 1)
+    steps_run, warm_run = min(steps, 12), min(warmup, 2)  # ~10-15 s of CPU work at ~0.9 s per 2-image step
     ips, cores, sec = cpu_reference_step_time(args.model, args.cpu_batch, steps_run, warm_run)
     line = {
         "impl": "reference", "metric": "train images/sec at px256 patch16", "value": ips, "unit": "images/s",
@@ -299,9 +299,9 @@ def run_b200(args):
     if enc is not None:
         line["encode"] = enc
     if not args.no_cpu_baseline and world == 1:
-        cips, cores, csec = cpu_reference_step_time(args.model, args.cpu_batch, 2, 1)
+        cips, cores, csec = cpu_reference_step_time(args.model, args.cpu_batch, 10, 1)  # ~10 s of CPU work
         line["cpu_baseline"] = {"value": cips, "unit": "images/s", "cores": cores, "kind": "port",
-                                "sample": f"2 timed steps x {args.cpu_batch} images of the same training step, fp32, oracle port, "
+                                "sample": f"10 timed steps x {args.cpu_batch} images of the same training step, fp32, oracle port, "
                                           f"{cores} threads ({csec:.1f} s/step)"}
     print(json.dumps(line), flush=True)
     if world > 1:

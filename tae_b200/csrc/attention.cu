@@ -87,23 +87,66 @@ __device__ __forceinline__ void load_rows(bf16* s, const bf16* g, size_t ld_g, i
   }
 }
 
+// asynchronous variant (LDGSTS): the rows land in shared memory without passing through registers
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void* g) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int PENDING>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory"); }
+template <int N, int NTHREADS>
+__device__ __forceinline__ void load_rows_async(bf16* s, const bf16* g, size_t ld_g, int tid) {
+  for (int c = tid; c < N * 8; c += NTHREADS) {
+    const int row = c >> 3, ch = c & 7;
+    cp_async16(smem_u32(s + row * LDS + ch * 8), g + (size_t)row * ld_g + ch * 8);
+  }
+}
+
+// Persistent over (image, head) items; for N = 64 the operands are double-buffered (cp.async of item i+1 while item i
+// computes), which is what the short grid needs: per-item work is a few microseconds and the one-shot version spent
+// most of it waiting for its own loads.
 template <int N>
 __global__ void __launch_bounds__(N * 2, 1)
-attn_fwd_mma(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* __restrict__ lse, int H, float scale_log2) {
+attn_fwd_mma(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* __restrict__ lse, int H, int BH,
+             float scale_log2) {
   constexpr int NT = N * 2;  // threads: one warp per 16 queries
+  constexpr int NBUF = N <= 64 ? 2 : 1;
+  constexpr int BUF = 3 * N * LDS;  // elements of one operand buffer (Q | K | V)
   extern __shared__ uint4 smem_u4[];
-  bf16* sQ = reinterpret_cast<bf16*>(smem_u4);
-  bf16* sK = sQ + N * LDS;
-  bf16* sV = sK + N * LDS;
+  bf16* sbase = reinterpret_cast<bf16*>(smem_u4);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int b = blockIdx.x / H, h = blockIdx.x % H;
   const int D = H * HD;
   const size_t ldq = (size_t)3 * D;
-  const bf16* gq = qkv + (size_t)b * N * ldq + (size_t)h * HD;
-  load_rows<N, NT>(sQ, gq, ldq, tid);
-  load_rows<N, NT>(sK, gq + D, ldq, tid);
-  load_rows<N, NT>(sV, gq + 2 * D, ldq, tid);
+  auto issue = [&](int item, int st) {
+    const int b = item / H, h = item - b * H;
+    const bf16* gq = qkv + (size_t)b * N * ldq + (size_t)h * HD;
+    bf16* q = sbase + st * BUF;
+    load_rows_async<N, NT>(q, gq, ldq, tid);
+    load_rows_async<N, NT>(q + N * LDS, gq + D, ldq, tid);
+    load_rows_async<N, NT>(q + 2 * N * LDS, gq + 2 * D, ldq, tid);
+  };
+  int stage = 0;
+  if (NBUF == 2 && (int)blockIdx.x < BH) {
+    issue(blockIdx.x, 0);
+    cp_async_commit();
+  }
+#pragma unroll 1
+  for (int item = blockIdx.x; item < BH; item += gridDim.x) {
+  if (NBUF == 2) {
+    const int nxt = item + gridDim.x;
+    if (nxt < BH) issue(nxt, stage ^ 1);
+    cp_async_commit();  // (possibly empty) keeps one group per iteration
+    cp_async_wait<1>();
+  } else {
+    issue(item, 0);
+    cp_async_commit();
+    cp_async_wait<0>();
+  }
   __syncthreads();
+  bf16* sQ = sbase + stage * BUF;
+  bf16* sK = sQ + N * LDS;
+  bf16* sV = sK + N * LDS;
+  const int b = item / H, h = item - b * H;
 
   const uint32_t bQ = smem_u32(sQ), bK = smem_u32(sK), bV = smem_u32(sV);
   const int q0 = warp * 16;
@@ -207,6 +250,9 @@ attn_fwd_mma(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* __rest
   for (int c = lane; c < 16 * 8; c += 32) {
     const int row = q0 + (c >> 3), ch = c & 7;
     *reinterpret_cast<uint4*>(go + (size_t)row * D + ch * 8) = *reinterpret_cast<const uint4*>(sQ + row * LDS + ch * 8);
+  }
+  __syncthreads();  // every warp is done with this buffer before the next iteration's loads overwrite it
+  if (NBUF == 2) stage ^= 1;
   }
 }
 
@@ -869,11 +915,14 @@ extern "C" int tae_attention_fwd(const tae_bf16* qkv_, tae_bf16* out_, float* ls
     if (N == 256) {
       int rc = set_smem(attn_fwd_mma<256>, smem);
       if (rc) return rc;
-      attn_fwd_mma<256><<<B * H, 512, smem, stream>>>(qkv, out, lse, H, sl2);
+      attn_fwd_mma<256><<<B * H, 512, smem, stream>>>(qkv, out, lse, H, B * H, sl2);
     } else {
-      int rc = set_smem(attn_fwd_mma<64>, smem);
+      const int smem2 = 2 * smem;  // double-buffered operands
+      int rc = set_smem(attn_fwd_mma<64>, smem2);
       if (rc) return rc;
-      attn_fwd_mma<64><<<B * H, 128, smem, stream>>>(qkv, out, lse, H, sl2);
+      const int sms = num_sms() > 0 ? num_sms() : 148;
+      const int grid = B * H < sms * 3 ? B * H : sms * 3;  // 3 resident CTAs per SM (140 registers, 54 KB each)
+      attn_fwd_mma<64><<<grid, 128, smem2, stream>>>(qkv, out, lse, H, B * H, sl2);
     }
     TAE_CHECK_LAUNCH();
     return TAE_OK;
