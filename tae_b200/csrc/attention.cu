@@ -259,31 +259,56 @@ attn_fwd_mma(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* __rest
 template <int N>
 __global__ void __launch_bounds__(N * 2, 1)
 attn_bwd_mma(const bf16* __restrict__ qkv, const bf16* __restrict__ out, const bf16* __restrict__ dout,
-             const float* __restrict__ lse, bf16* __restrict__ dqkv, int H, float scale, float scale_log2) {
+             const float* __restrict__ lse, bf16* __restrict__ dqkv, int H, int BH, float scale, float scale_log2) {
   constexpr int NT = N * 2;
+  constexpr int NBUF = N <= 64 ? 2 : 1;      // N = 64: operands of item i+1 arrive (cp.async) while item i computes
+  constexpr int BUF = 5 * N * LDS;           // elements of one operand buffer: Q | K | V | dO | O
   extern __shared__ uint4 smem_u4[];
-  bf16* sQ = reinterpret_cast<bf16*>(smem_u4);
+  bf16* sbase = reinterpret_cast<bf16*>(smem_u4);
+  float* sLse = reinterpret_cast<float*>(sbase + NBUF * BUF);  // lse * log2(e)
+  float* sDelta = sLse + N;                                    // rowsum(dO * O)
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int D = H * HD;
+  const size_t ldq = (size_t)3 * D;
+  auto issue = [&](int item, int st) {
+    const int b = item / H, h = item - b * H;
+    const bf16* gq = qkv + (size_t)b * N * ldq + (size_t)h * HD;
+    bf16* q = sbase + st * BUF;
+    load_rows_async<N, NT>(q, gq, ldq, tid);
+    load_rows_async<N, NT>(q + N * LDS, gq + D, ldq, tid);
+    load_rows_async<N, NT>(q + 2 * N * LDS, gq + 2 * D, ldq, tid);
+    load_rows_async<N, NT>(q + 3 * N * LDS, dout + (size_t)b * N * D + (size_t)h * HD, (size_t)D, tid);
+    load_rows_async<N, NT>(q + 4 * N * LDS, out + (size_t)b * N * D + (size_t)h * HD, (size_t)D, tid);
+  };
+  int stage = 0;
+  if (NBUF == 2 && (int)blockIdx.x < BH) {
+    issue(blockIdx.x, 0);
+    cp_async_commit();
+  }
+#pragma unroll 1
+  for (int item = blockIdx.x; item < BH; item += gridDim.x) {
+  if (NBUF == 2) {
+    const int nxt = item + gridDim.x;
+    if (nxt < BH) issue(nxt, stage ^ 1);
+    cp_async_commit();
+    cp_async_wait<1>();
+  } else {
+    issue(item, 0);
+    cp_async_commit();
+    cp_async_wait<0>();
+  }
+  __syncthreads();
+  bf16* sQ = sbase + stage * BUF;
   bf16* sK = sQ + N * LDS;
   bf16* sV = sK + N * LDS;
   bf16* sdO = sV + N * LDS;
-  float* sLse = reinterpret_cast<float*>(sdO + N * LDS);  // lse * log2(e)
-  float* sDelta = sLse + N;                               // rowsum(dO * O)
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int b = blockIdx.x / H, h = blockIdx.x % H;
-  const int D = H * HD;
-  const size_t ldq = (size_t)3 * D;
-  const bf16* gq = qkv + (size_t)b * N * ldq + (size_t)h * HD;
-  const bf16* go = out + (size_t)b * N * D + (size_t)h * HD;
-  const bf16* gdo = dout + (size_t)b * N * D + (size_t)h * HD;
-  load_rows<N, NT>(sQ, gq, ldq, tid);
-  load_rows<N, NT>(sK, gq + D, ldq, tid);
-  load_rows<N, NT>(sV, gq + 2 * D, ldq, tid);
-  // dO rows + delta = rowsum(dO * O): 8 consecutive lanes own the 8 16-byte chunks of one row
+  const bf16* sO = sdO + N * LDS;
+  const int b = item / H, h = item - b * H;
+  // delta = rowsum(dO * O) out of shared memory: 8 consecutive lanes own the 8 16-byte chunks of one row
   for (int c = tid; c < N * 8; c += NT) {
     const int row = c >> 3, ch = c & 7;
-    const uint4 dv = ld_nc_v4(gdo + (size_t)row * D + ch * 8);
-    const uint4 ov = ld_nc_v4(go + (size_t)row * D + ch * 8);
-    *reinterpret_cast<uint4*>(sdO + row * LDS + ch * 8) = dv;
+    const uint4 dv = *reinterpret_cast<const uint4*>(sdO + row * LDS + ch * 8);
+    const uint4 ov = *reinterpret_cast<const uint4*>(sO + row * LDS + ch * 8);
     const uint32_t dw[4] = {dv.x, dv.y, dv.z, dv.w}, ow[4] = {ov.x, ov.y, ov.z, ov.w};
     float acc = 0.f;
 #pragma unroll
@@ -427,6 +452,9 @@ attn_bwd_mma(const bf16* __restrict__ qkv, const bf16* __restrict__ out, const b
       *reinterpret_cast<uint32_t*>(gdq + (size_t)(i0 + g) * ldq + col) = pack_bf16x2(dq[i][0] * scale, dq[i][1] * scale);
       *reinterpret_cast<uint32_t*>(gdq + (size_t)(i0 + g + 8) * ldq + col) = pack_bf16x2(dq[i][2] * scale, dq[i][3] * scale);
     }
+  }
+  __syncthreads();  // every warp is done with this buffer (and lse/delta) before the next iteration overwrites them
+  if (NBUF == 2) stage ^= 1;
   }
 }
 
@@ -954,15 +982,18 @@ extern "C" int tae_attention_bwd(const tae_bf16* qkv_, const tae_bf16* out_, con
   if (hd == HD && N == 256 && use_tcgen05()) return attention_bwd_tcgen05(qkv, out, dout, lse, nullptr, dqkv, B, H, stream);
   if (hd == HD && (N == 64 || N == 256)) {
     const float sl2 = scale * 1.44269504088896340736f;
-    const int smem = 4 * N * LDS * 2 + 2 * N * 4;
     if (N == 256) {
+      const int smem = 5 * N * LDS * 2 + 2 * N * 4;
       int rc = set_smem(attn_bwd_mma<256>, smem);
       if (rc) return rc;
-      attn_bwd_mma<256><<<B * H, 512, smem, stream>>>(qkv, out, dout, lse, dqkv, H, scale, sl2);
+      attn_bwd_mma<256><<<B * H, 512, smem, stream>>>(qkv, out, dout, lse, dqkv, H, B * H, scale, sl2);
     } else {
+      const int smem = 2 * 5 * N * LDS * 2 + 2 * N * 4;  // double-buffered operands
       int rc = set_smem(attn_bwd_mma<64>, smem);
       if (rc) return rc;
-      attn_bwd_mma<64><<<B * H, 128, smem, stream>>>(qkv, out, dout, lse, dqkv, H, scale, sl2);
+      const int sms = num_sms() > 0 ? num_sms() : 148;
+      const int grid = B * H < sms * 2 ? B * H : sms * 2;  // 2 resident CTAs per SM (93 KB each)
+      attn_bwd_mma<64><<<grid, 128, smem, stream>>>(qkv, out, dout, lse, dqkv, H, B * H, scale, sl2);
     }
     TAE_CHECK_LAUNCH();
     return TAE_OK;
