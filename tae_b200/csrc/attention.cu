@@ -699,6 +699,9 @@ attn_bwd_small(const bf16* __restrict__ qkv, const bf16* __restrict__ dout, cons
   }
 }
 
+template <typename K>
+static int set_smem(K kernel, int bytes);
+
 template <int HDT>
 static int launch_small(bool bwd, const bf16* qkv, const bf16* dout, bf16* out_or_dqkv, const float* lse_in, float* lse_out,
                         int B, int N, int H, float scale, cudaStream_t stream) {
@@ -706,10 +709,12 @@ static int launch_small(bool bwd, const bf16* qkv, const bf16* dout, bf16* out_o
   const int smem = 4 * (bwd ? 4 : 3) * Small<HDT>::TILE * 2;  // 4 warps per CTA
   const float sl2 = scale * 1.44269504088896340736f;
   if (!bwd) {
-    if (smem > 48 * 1024) cudaFuncSetAttribute(attn_fwd_small<HDT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    const int rc = set_smem(attn_fwd_small<HDT>, smem);
+    if (rc) return rc;
     attn_fwd_small<HDT><<<(BH + 3) / 4, 128, smem, stream>>>(qkv, out_or_dqkv, lse_out, BH, N, H, sl2);
   } else {
-    if (smem > 48 * 1024) cudaFuncSetAttribute(attn_bwd_small<HDT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    const int rc = set_smem(attn_bwd_small<HDT>, smem);
+    if (rc) return rc;
     attn_bwd_small<HDT><<<(BH + 3) / 4, 128, smem, stream>>>(qkv, dout, lse_in, out_or_dqkv, BH, N, H, scale, sl2);
   }
   TAE_CHECK_LAUNCH();
