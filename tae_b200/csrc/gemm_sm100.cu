@@ -39,7 +39,7 @@ constexpr int NUM_ACC = 2;                            // TMEM accumulator double
 constexpr int TMEM_COLS = NUM_ACC * BLOCK_N;          // 512
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_THREADS = 128 + NUM_EPI_WARPS * 32;  // 384
-constexpr int SMEM_BARRIER_BYTES = 256;
+constexpr int SMEM_BARRIER_BYTES = 512;
 constexpr int SMEM_STAGING_BYTES = NUM_EPI_WARPS * 32 * 128;  // 4 KB transpose tile per epilogue warp
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + SMEM_BARRIER_BYTES + SMEM_STAGING_BYTES + 1024;  // +1024: alignment slack
 
@@ -60,6 +60,7 @@ struct Params {
   float* colsum_part;  // optional [ceil(M/32), N] fp32: per-32-row column sums of the bf16 output (bias gradients)
   float* rowdot;       // TAE_EPI_BF16_ROWDOT: fp32 [M / rd_tokens, N / 64, rd_tokens]
   int rd_tokens;
+  int* sched;          // dynamic tile scheduler: {next work item, clusters done}; NULL = static round-robin
 };
 
 // K-major tile [rows x 64] (128 B per row, 8-row swizzle atoms of 1024 B): SBO = 1024 between 8-row groups;
@@ -498,12 +499,27 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
   uint64_t* tmem_full_bar = bars + 2 * STAGES2;               // [NUM_ACC]  (both CTAs, multicast commit)
   uint64_t* tmem_empty_bar = bars + 2 * STAGES2 + NUM_ACC;    // [NUM_ACC]  (leader's copy, 16 arrivals)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES2 + 2 * NUM_ACC);
+  // Dynamic tile scheduler.  A persistent kernel with a STATIC tile list doubles its run time as soon as one cluster
+  // cannot become resident (e.g. NCCL's all-reduce CTAs hold a few SMs during the DDP backward): that cluster starts
+  // when the others have finished and then works through its whole share alone.  Here the leader's producer thread
+  // draws work items from a global counter and publishes them to both CTAs through a 16-deep ring (index + mbarrier
+  // per slot, filled at cluster scope); a cluster that starts late simply finds the counter exhausted.
+  constexpr int SCHED_RING = 16;  // > the producer's maximum lead over the epilogue (6 smem stages + 2 accumulators)
+  uint64_t* sched_full = bars + 2 * STAGES2 + 2 * NUM_ACC + 1;              // [SCHED_RING]
+  volatile int* sched_ring = reinterpret_cast<volatile int*>(sched_full + SCHED_RING);  // [SCHED_RING]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
   const int total_work = p.m_tiles * p.n_tiles * p.splits;  // m_tiles counts 256-row tiles here
+  const bool dynamic = p.sched != nullptr;
+  // i-th work item of this cluster, as seen by a CONSUMER role (MMA issuer, epilogue warps, the peer's producer)
+  auto work_at = [&](int i) -> int {
+    if (!dynamic) return cluster_id + i * num_clusters;
+    mbar_wait_acquire_cluster(&sched_full[i & (SCHED_RING - 1)], (uint32_t)((i / SCHED_RING) & 1));
+    return sched_ring[i & (SCHED_RING - 1)];
+  };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -518,6 +534,7 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       mbar_init(&tmem_full_bar[a], 1);
       mbar_init(&tmem_empty_bar[a], 2 * NUM_EPI_WARPS2);
     }
+    for (int r = 0; r < SCHED_RING; ++r) mbar_init(&sched_full[r], 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc_2sm(tmem_slot, TMEM_COLS);
@@ -531,7 +548,23 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int w = cluster_id; w < total_work; w += num_clusters) {
+      // the leader draws work items ONE AHEAD: the atomic's round trip to L2 overlaps the loads of the current tile
+      int w_ahead = (dynamic && rank == 0) ? atomicAdd(p.sched, 1) : 0;
+      for (int i = 0;; ++i) {
+        int w;
+        if (dynamic && rank == 0) {
+          // publish the item to both CTAs of the pair, then request the next one
+          w = w_ahead;
+          if (w < total_work) w_ahead = atomicAdd(p.sched, 1);
+          const int slot = i & (SCHED_RING - 1);
+          sched_ring[slot] = w;
+          st_shared_cluster_u32(const_cast<int*>(&sched_ring[slot]), 1, (uint32_t)w);
+          mbar_arrive_release_cluster(&sched_full[slot], 0);
+          mbar_arrive_release_cluster(&sched_full[slot], 1);
+        } else {
+          w = work_at(i);
+        }
+        if (w >= total_work) break;
         const WorkItem it = decode_work(p, w);
         const int m0 = it.mt * (2 * BLOCK_M) + (int)rank * BLOCK_M;
         const int n0 = it.nt * BLOCK_N + (int)rank * (BLOCK_N / 2);
@@ -561,6 +594,15 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
           }
         }
       }
+      if (dynamic && rank == 0) {
+        // every cluster has drawn its last (out-of-range) item before it counts itself done: the last one re-arms the
+        // counters for the next launch that uses this slot
+        if (atomicAdd(p.sched + 1, 1) == num_clusters - 1) {
+          p.sched[0] = 0;
+          p.sched[1] = 0;
+          __threadfence();
+        }
+      }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread of the leader CTA) =====================
@@ -570,7 +612,9 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int w = cluster_id; w < total_work; w += num_clusters) {
+      for (int i = 0;; ++i) {
+        const int w = work_at(i);
+        if (w >= total_work) break;
         const WorkItem it = decode_work(p, w);
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);
         tcgen05_fence_after();
@@ -607,7 +651,9 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     const uint32_t stg = smem_u32(smem + STAGES2 * STAGE2_BYTES + SMEM_BARRIER_BYTES + ew * STG_BYTES_PER_WARP);
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int w = cluster_id; w < total_work; w += num_clusters) {
+    for (int i = 0;; ++i) {
+      const int w = work_at(i);
+      if (w >= total_work) break;
       const WorkItem it = decode_work(p, w);
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tcgen05_fence_after();
@@ -692,6 +738,28 @@ static int launch_2sm(const CUtensorMap& ta, const CUtensorMap& tb, const Params
                      ((EPI == TAE_EPI_F32_RESID || EPI == TAE_EPI_BF16_DGELU || EPI == TAE_EPI_BF16_ROWDOT) && p.K <= 2048);
   if (heavy) return launch_2sm_cfg<EPI, 16>(ta, tb, p, clusters, stream);
   return launch_2sm_cfg<EPI, 8>(ta, tb, p, clusters, stream);
+}
+
+// Counter slots of the dynamic tile scheduler: a ring of {next item, clusters done} pairs in device memory, zeroed once;
+// every launch takes the next slot and the kernel re-arms it when its last cluster finishes.  TAE_GEMM_STATIC=1 turns
+// the scheduler off (static round-robin tile lists).
+static int* sched_slot() {
+  constexpr int kSlots = 256;
+  static int* base = nullptr;
+  static std::once_flag once;
+  static std::atomic<unsigned> seq{0};
+  static bool enabled = true;
+  std::call_once(once, []() {
+    const char* e = getenv("TAE_GEMM_STATIC");
+    enabled = !(e != nullptr && e[0] == '1');
+    if (!enabled) return;
+    if (cudaMalloc(&base, kSlots * 2 * sizeof(int)) != cudaSuccess || cudaMemset(base, 0, kSlots * 2 * sizeof(int)) != cudaSuccess) {
+      base = nullptr;
+      (void)cudaGetLastError();
+    }
+  });
+  if (!enabled || base == nullptr) return nullptr;
+  return base + 2 * (seq.fetch_add(1, std::memory_order_relaxed) % kSlots);
 }
 
 // TAE_GEMM_1SM=1 forces the single-CTA kernel (A/B testing)
@@ -815,6 +883,7 @@ extern "C" int tae_gemm(const tae_gemm_args* a, void* stream_) {
   const int total = p.m_tiles * p.n_tiles * p.splits;
   if (use2) {
     const int clusters = total < units ? total : units;
+    p.sched = total > clusters ? sched_slot() : nullptr;  // one item per cluster needs no scheduler
     switch (a->epilogue) {
       case TAE_EPI_BF16: return launch_2sm<TAE_EPI_BF16>(ta, tb, p, clusters, stream);
       case TAE_EPI_BF16_GELU: return launch_2sm<TAE_EPI_BF16_GELU>(ta, tb, p, clusters, stream);

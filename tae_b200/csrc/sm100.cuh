@@ -211,6 +211,48 @@ __device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// ---- cluster-scope signalling with data (dynamic tile scheduler of the CTA-pair GEMM) ------------------------------
+// arrive (release at CLUSTER scope) on the barrier at the same smem offset in CTA `cta` of the cluster (may be this CTA)
+__device__ __forceinline__ void mbar_arrive_release_cluster(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n"
+      ".reg .b32 remaddr;\n"
+      "mapa.shared::cluster.u32 remaddr, %0, %1;\n"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [remaddr];\n"
+      "}"
+      ::"r"(smem_u32(bar)), "r"(cta)
+      : "memory");
+}
+// 32-bit store into the same smem offset of CTA `cta` of the cluster
+__device__ __forceinline__ void st_shared_cluster_u32(void* ptr, uint32_t cta, uint32_t v) {
+  asm volatile(
+      "{\n"
+      ".reg .b32 remaddr;\n"
+      "mapa.shared::cluster.u32 remaddr, %0, %1;\n"
+      "st.shared::cluster.u32 [remaddr], %2;\n"
+      "}"
+      ::"r"(smem_u32(ptr)), "r"(cta), "r"(v)
+      : "memory");
+}
+// bounded wait with acquire at CLUSTER scope (pairs with mbar_arrive_release_cluster)
+__device__ __forceinline__ void mbar_wait_acquire_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (++spins > (1u << 26)) __trap();
+  }
+}
+
 // Cheap descriptor path for single-thread MMA issue loops.  Every tile in this library uses SBO = 1024 and the
 // 128B-swizzle layout, so the upper descriptor word is a constant and a descriptor is just a 32-bit `lo` word
 // (start address >> 4 | LBO >> 4 << 16) that advances by (byte offset >> 4).
