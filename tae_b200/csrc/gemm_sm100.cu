@@ -753,7 +753,9 @@ static int* sched_slot() {
     const char* e = getenv("TAE_GEMM_STATIC");
     enabled = !(e != nullptr && e[0] == '1');
     if (!enabled) return;
-    if (cudaMalloc(&base, kSlots * 2 * sizeof(int)) != cudaSuccess || cudaMemset(base, 0, kSlots * 2 * sizeof(int)) != cudaSuccess) {
+    // one-time setup: the synchronize orders the memset (null stream) before the first launch on ANY stream
+    if (cudaMalloc(&base, kSlots * 2 * sizeof(int)) != cudaSuccess || cudaMemset(base, 0, kSlots * 2 * sizeof(int)) != cudaSuccess ||
+        cudaDeviceSynchronize() != cudaSuccess) {
       base = nullptr;
       (void)cudaGetLastError();
     }
