@@ -740,30 +740,6 @@ static int launch_2sm(const CUtensorMap& ta, const CUtensorMap& tb, const Params
   return launch_2sm_cfg<EPI, 8>(ta, tb, p, clusters, stream);
 }
 
-// Counter slots of the dynamic tile scheduler: a ring of {next item, clusters done} pairs in device memory, zeroed once;
-// every launch takes the next slot and the kernel re-arms it when its last cluster finishes.  TAE_GEMM_STATIC=1 turns
-// the scheduler off (static round-robin tile lists).
-static int* sched_slot() {
-  constexpr int kSlots = 256;
-  static int* base = nullptr;
-  static std::once_flag once;
-  static std::atomic<unsigned> seq{0};
-  static bool enabled = true;
-  std::call_once(once, []() {
-    const char* e = getenv("TAE_GEMM_STATIC");
-    enabled = !(e != nullptr && e[0] == '1');
-    if (!enabled) return;
-    // one-time setup: the synchronize orders the memset (null stream) before the first launch on ANY stream
-    if (cudaMalloc(&base, kSlots * 2 * sizeof(int)) != cudaSuccess || cudaMemset(base, 0, kSlots * 2 * sizeof(int)) != cudaSuccess ||
-        cudaDeviceSynchronize() != cudaSuccess) {
-      base = nullptr;
-      (void)cudaGetLastError();
-    }
-  });
-  if (!enabled || base == nullptr) return nullptr;
-  return base + 2 * (seq.fetch_add(1, std::memory_order_relaxed) % kSlots);
-}
-
 // TAE_GEMM_1SM=1 forces the single-CTA kernel (A/B testing)
 static bool allow_2sm() {
   static int v = -1;
@@ -885,7 +861,7 @@ extern "C" int tae_gemm(const tae_gemm_args* a, void* stream_) {
   const int total = p.m_tiles * p.n_tiles * p.splits;
   if (use2) {
     const int clusters = total < units ? total : units;
-    p.sched = total > clusters ? sched_slot() : nullptr;  // one item per cluster needs no scheduler
+    p.sched = total > clusters ? sched_counter_slot() : nullptr;  // one item per cluster needs no scheduler
     switch (a->epilogue) {
       case TAE_EPI_BF16: return launch_2sm<TAE_EPI_BF16>(ta, tb, p, clusters, stream);
       case TAE_EPI_BF16_GELU: return launch_2sm<TAE_EPI_BF16_GELU>(ta, tb, p, clusters, stream);

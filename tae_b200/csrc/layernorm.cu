@@ -323,8 +323,9 @@ template <int NV>
 __global__ void __launch_bounds__(256, 1)
 ln_bwd_warp_kernel(const bf16* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
                    const float* __restrict__ rstd, const float* __restrict__ gamma, const float* dres_in,
-                   float* dres_out, bf16* __restrict__ dres_out_b, float* __restrict__ partials, int rows) {
+                   float* dres_out, bf16* __restrict__ dres_out_b, float* __restrict__ partials, int rows, int* sched) {
   constexpr int D = NV * 128;
+  constexpr int CHUNK = 1;  // rows per dynamically scheduled work item (1 keeps concurrent warps on consecutive rows)
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   const int gw = blockIdx.x * wpb + (threadIdx.x >> 5);
@@ -338,8 +339,29 @@ ln_bwd_warp_kernel(const bf16* __restrict__ dy, const float* __restrict__ x, con
     acc_cs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   const float invD = 1.0f / (float)D;
+  // Work list: static row striding, or (sched != NULL) chunks of CHUNK rows drawn from a global counter one ahead, so a
+  // CTA that starts late (its SM held by another kernel, e.g. NCCL) does not leave its whole share for the end.
+  int next_chunk = 0;
+  if (sched != nullptr) {
+    if (lane == 0) next_chunk = atomicAdd(sched, 1);
+    next_chunk = __shfl_sync(0xffffffffu, next_chunk, 0);
+  }
 #pragma unroll 1
-  for (int row = gw; row < rows; row += nw) {
+  for (int it = 0;; ++it) {
+    int row_begin, row_end;
+    if (sched != nullptr) {
+      row_begin = next_chunk * CHUNK;
+      if (row_begin >= rows) break;
+      row_end = min(rows, row_begin + CHUNK);
+      if (lane == 0) next_chunk = atomicAdd(sched, 1);
+      next_chunk = __shfl_sync(0xffffffffu, next_chunk, 0);
+    } else {
+      row_begin = gw + it * nw;
+      if (row_begin >= rows) break;
+      row_end = row_begin + 1;
+    }
+#pragma unroll 1
+  for (int row = row_begin; row < row_end; ++row) {
     const size_t base = (size_t)row * D;
     float4 xh[NV], gy[NV], din[NV];
     uint2 draw[NV];
@@ -388,6 +410,15 @@ ln_bwd_warp_kernel(const bf16* __restrict__ dy, const float* __restrict__ x, con
       acc_cs[i].y += r01.y;
       acc_cs[i].z += r23.x;
       acc_cs[i].w += r23.y;
+    }
+  }
+  }
+  if (sched != nullptr && lane == 0) {
+    // every warp has drawn its last (out-of-range) chunk before it counts itself done: the last one re-arms the slot
+    if (atomicAdd(sched + 1, 1) == nw - 1) {
+      sched[0] = 0;
+      sched[1] = 0;
+      __threadfence();
     }
   }
   float* pbase = partials + (size_t)gw * 3 * D;
@@ -531,11 +562,12 @@ extern "C" int tae_layernorm_bwd(const tae_bf16* dy, const float* x, const float
   bf16* ob = reinterpret_cast<bf16*>(dres_out_bf16);
   if (bwd_warp_ok(D)) {
     const int wg = bwd_warp_grid(rows);
+    int* sched = rows > wg * 8 ? sched_counter_slot() : nullptr;  // more rows than warps: dynamic row chunks
     switch (D / 128) {
-      case 1: ln_bwd_warp_kernel<1><<<wg, 256, 0, stream>>>(dyy, x, mean, rstd, gamma, dres_in, dres_out, ob, partials, rows); break;
-      case 2: ln_bwd_warp_kernel<2><<<wg, 256, 0, stream>>>(dyy, x, mean, rstd, gamma, dres_in, dres_out, ob, partials, rows); break;
-      case 6: ln_bwd_warp_kernel<6><<<wg, 256, 0, stream>>>(dyy, x, mean, rstd, gamma, dres_in, dres_out, ob, partials, rows); break;
-      default: ln_bwd_warp_kernel<8><<<wg, 256, 0, stream>>>(dyy, x, mean, rstd, gamma, dres_in, dres_out, ob, partials, rows); break;
+      case 1: ln_bwd_warp_kernel<1><<<wg, 256, 0, stream>>>(dyy, x, mean, rstd, gamma, dres_in, dres_out, ob, partials, rows, sched); break;
+      case 2: ln_bwd_warp_kernel<2><<<wg, 256, 0, stream>>>(dyy, x, mean, rstd, gamma, dres_in, dres_out, ob, partials, rows, sched); break;
+      case 6: ln_bwd_warp_kernel<6><<<wg, 256, 0, stream>>>(dyy, x, mean, rstd, gamma, dres_in, dres_out, ob, partials, rows, sched); break;
+      default: ln_bwd_warp_kernel<8><<<wg, 256, 0, stream>>>(dyy, x, mean, rstd, gamma, dres_in, dres_out, ob, partials, rows, sched); break;
     }
     TAE_CHECK_LAUNCH();
     return TAE_OK;

@@ -1,5 +1,6 @@
 // lib.cu — library-level entry points of libtae_b200.so: version, error string, device capability cache.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -42,6 +43,30 @@ int num_sms() {
   std::call_once(g_dev_once, query_device);
   if (g_sms <= 0) set_error("no CUDA device available");
   return g_sms;
+}
+
+// Why dynamic work lists: a persistent kernel with a static list doubles its run time as soon as one of its CTAs cannot
+// become resident (NCCL's all-reduce CTAs hold a few SMs during the DDP backward): that CTA starts when the others have
+// finished and then works through its whole share alone.
+int* sched_counter_slot() {
+  constexpr int kSlots = 256;
+  static int* base = nullptr;
+  static std::once_flag once;
+  static std::atomic<unsigned> seq{0};
+  static bool enabled = true;
+  std::call_once(once, []() {
+    const char* e = getenv("TAE_GEMM_STATIC");
+    enabled = !(e != nullptr && e[0] == '1');
+    if (!enabled) return;
+    // one-time setup: the synchronize orders the memset (null stream) before the first launch on ANY stream
+    if (cudaMalloc(&base, kSlots * 2 * sizeof(int)) != cudaSuccess || cudaMemset(base, 0, kSlots * 2 * sizeof(int)) != cudaSuccess ||
+        cudaDeviceSynchronize() != cudaSuccess) {
+      base = nullptr;
+      (void)cudaGetLastError();
+    }
+  });
+  if (!enabled || base == nullptr) return nullptr;
+  return base + 2 * (seq.fetch_add(1, std::memory_order_relaxed) % kSlots);
 }
 
 }  // namespace tae
