@@ -41,6 +41,11 @@ int tae_version(void);                       /* ABI version, currently 1 */
 const char* tae_last_error_string(void);     /* thread-local, never NULL */
 int tae_device_check(void);                  /* 0 iff current device is sm_100 (B200) */
 int tae_num_sms(void);                       /* SM count of the current device (148 on B200), <0 on error */
+/* Work scheduling of the persistent kernels (GEMM tiles, LayerNorm-backward rows).  Static lists (default) are ~0.5 %
+ * faster when the GPU is not shared; dynamic lists (a global counter per launch) keep a kernel from doubling its run
+ * time when some of its CTAs cannot become resident, e.g. while NCCL's all-reduce kernels hold SMs during a
+ * data-parallel backward — tae_b200.ddp turns them on for world_size > 1.  Returns the previous setting (-1 = unset). */
+int tae_set_dynamic_scheduling(int enable);
 /* number of kernel launches issued through this library since process start (all threads) */
 uint64_t tae_launch_count(void);
 

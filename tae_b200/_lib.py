@@ -60,6 +60,7 @@ PROTOTYPES = {
     "tae_device_check": (C.c_int, []),
     "tae_num_sms": (C.c_int, []),
     "tae_launch_count": (C.c_uint64, []),
+    "tae_set_dynamic_scheduling": (C.c_int, [C.c_int]),
     "tae_gemm": (C.c_int, [C.POINTER(GemmArgs), _vp]),
     "tae_layernorm_fwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _f32, _vp]),
     "tae_layernorm_bwd_num_partials": (C.c_int, [_i32, _i32]),

@@ -50,8 +50,10 @@ inline void count_launch(int n = 1) { g_launch_count.fetch_add((uint64_t)n, std:
 int num_sms();  // cached per process (current device)
 // Work counters for dynamically scheduled persistent kernels: returns a zeroed {next item, workers done} pair in device
 // memory (a ring of slots, one per launch; the kernel re-arms its slot when its last worker finishes), or NULL when
-// TAE_GEMM_STATIC=1 / allocation failed (callers then use their static work lists).
+// dynamic scheduling is off (the default: tae_set_dynamic_scheduling / TAE_GEMM_DYNAMIC=1 turn it on) or allocation
+// failed; callers then use their static work lists.
 int* sched_counter_slot();
+int set_dynamic_scheduling(int enable);
 
 // ---- device helpers -----------------------------------------------------------------------
 #ifdef __CUDACC__

@@ -48,16 +48,26 @@ int num_sms() {
 // Why dynamic work lists: a persistent kernel with a static list doubles its run time as soon as one of its CTAs cannot
 // become resident (NCCL's all-reduce CTAs hold a few SMs during the DDP backward): that CTA starts when the others have
 // finished and then works through its whole share alone.
+// -1: not decided yet (TAE_GEMM_DYNAMIC=1 / TAE_GEMM_STATIC=1 decide at first use, default static); 0 static; 1 dynamic
+static std::atomic<int> g_dynamic{-1};
+
+int set_dynamic_scheduling(int enable) { return g_dynamic.exchange(enable ? 1 : 0); }
+
 int* sched_counter_slot() {
   constexpr int kSlots = 256;
   static int* base = nullptr;
   static std::once_flag once;
   static std::atomic<unsigned> seq{0};
-  static bool enabled = true;
+  int dyn = g_dynamic.load(std::memory_order_relaxed);
+  if (dyn < 0) {
+    const char* e = getenv("TAE_GEMM_DYNAMIC");
+    dyn = (e != nullptr && e[0] == '1') ? 1 : 0;
+    int expected = -1;
+    g_dynamic.compare_exchange_strong(expected, dyn);
+    dyn = g_dynamic.load(std::memory_order_relaxed);
+  }
+  if (dyn != 1) return nullptr;
   std::call_once(once, []() {
-    const char* e = getenv("TAE_GEMM_STATIC");
-    enabled = !(e != nullptr && e[0] == '1');
-    if (!enabled) return;
     // one-time setup: the synchronize orders the memset (null stream) before the first launch on ANY stream
     if (cudaMalloc(&base, kSlots * 2 * sizeof(int)) != cudaSuccess || cudaMemset(base, 0, kSlots * 2 * sizeof(int)) != cudaSuccess ||
         cudaDeviceSynchronize() != cudaSuccess) {
@@ -65,7 +75,7 @@ int* sched_counter_slot() {
       (void)cudaGetLastError();
     }
   });
-  if (!enabled || base == nullptr) return nullptr;
+  if (base == nullptr) return nullptr;
   return base + 2 * (seq.fetch_add(1, std::memory_order_relaxed) % kSlots);
 }
 
@@ -89,5 +99,7 @@ extern "C" int tae_device_check(void) {
   }
   return TAE_OK;
 }
+
+extern "C" int tae_set_dynamic_scheduling(int enable) { return tae::set_dynamic_scheduling(enable); }
 
 extern "C" uint64_t tae_launch_count(void) { return tae::g_launch_count.load(std::memory_order_relaxed); }

@@ -65,6 +65,13 @@ class DistributedDataParallel(nn.Module):
         self._launched = []
         self._optimizer = optimizer
         self._needs_broadcast = broadcast and self.world_size > 1
+        if self.world_size > 1 and next(module.parameters()).is_cuda:
+            # NCCL's all-reduce CTAs will hold SMs while the weight-gradient GEMMs run: a persistent kernel with a static
+            # work list doubles its run time when one of its CTAs cannot become resident, so switch the library to
+            # dynamic work lists (patch32_v1024 at 8 GPUs: 9666 -> 10400 img/s; ~0.5 % slower on an unshared GPU)
+            from . import ops
+
+            ops.set_dynamic_scheduling(True)
         if optimizer is not None:
             self.attach(optimizer)
 

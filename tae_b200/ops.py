@@ -368,5 +368,10 @@ def grad_stats(g: torch.Tensor, sq_sum: torch.Tensor | None, found_inf: torch.Te
     check(_L().tae_grad_stats(g.data_ptr(), g.numel(), _ptr(sq_sum), _ptr(found_inf), _stream()), "tae_grad_stats")
 
 
+def set_dynamic_scheduling(enable: bool) -> int:
+    """Dynamic work lists for the persistent kernels (see include/tae_b200.h); returns the previous setting."""
+    return int(_L().tae_set_dynamic_scheduling(int(bool(enable))))
+
+
 def launch_count() -> int:
     return int(_L().tae_launch_count())
