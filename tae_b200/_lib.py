@@ -106,6 +106,15 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
+    override = os.environ.get("TAE_B200_LIB")  # developer A/B builds (tae_b200.build --variant); never a fallback
+    if override:
+        lib = C.CDLL(os.fspath(Path(override).resolve(strict=True)))
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+        return lib
     if build_if_missing:
         # no-op when the in-tree library matches the sources' fingerprint; rebuilds (nvcc) when csrc/ changed
         from . import build as _build

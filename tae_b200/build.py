@@ -96,10 +96,40 @@ def _build_locked(fp: str, stamp: Path, verbose: bool) -> Path:
     return LIB_PATH
 
 
+def build_variant(name: str, defines: list[str], verbose: bool = False) -> Path:
+    """Developer A/B builds: the same sources with extra -D flags, linked as tae_b200/libtae_b200.<name>.so (objects
+    under csrc/build/<name>/).  `TAE_B200_LIB=<path>` makes `tae_b200._lib` load it instead of the default library."""
+    out_dir = BUILD_DIR / name
+    out_dir.mkdir(parents=True, exist_ok=True)
+    lib = PKG_DIR / f"libtae_b200.{name}.so"
+
+    def compile_one(src: Path) -> Path:
+        obj = out_dir / (src.stem + ".o")
+        cmd = [NVCC, *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-c", str(src), "-o", str(obj)]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {src.name}:\n{res.stdout}\n{res.stderr}")
+        if verbose:
+            print(" ".join(cmd), res.stderr, flush=True)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        objs = list(ex.map(compile_one, _sources()))
+    res = subprocess.run([NVCC, "-shared", "-o", str(lib), *[str(o) for o in objs], "-lcudart"], capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")
+    return lib
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--force", action="store_true")
     ap.add_argument("--verbose", action="store_true")
+    ap.add_argument("--variant", default=None, help="A/B build name: writes libtae_b200.<name>.so")
+    ap.add_argument("-D", dest="defines", action="append", default=[], help="extra macro for a --variant build")
     a = ap.parse_args()
-    print(build(force=a.force, verbose=a.verbose))
+    if a.variant:
+        print(build_variant(a.variant, a.defines, verbose=a.verbose))
+    else:
+        print(build(force=a.force, verbose=a.verbose))
     sys.exit(0)

@@ -138,6 +138,68 @@ __device__ __forceinline__ float2 round_bf16x2(float a, float b) {
   return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
 }
 
+// ---- packed fp32 pairs (sm_100 FFMA2 / FMUL2 / FADD2: two lanes of fp32 math per issued instruction) -------------
+// A pair lives in one 64-bit register; ptxas keeps the halves in an aligned register pair, so pack/unpack are free.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 f2_pack(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(f32x2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 f2_bcast(float c) { return f2_pack(c, c); }
+__device__ __forceinline__ f32x2 f2_fma(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2 f2_mul(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 f2_add(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
+// gelu_and_grad_fast on a PAIR, starting from the raw accumulator and bias pairs: h = bf16(acc + bias), then the same
+// formulas and roundings as the scalar version (bit-identical results), with every FMA-pipe instruction packed: 13.5
+// issued instructions per element instead of 20.5 (the GELU epilogue of the fc1 GEMM is issue/FMA-pipe bound).
+// Returns bf16x2 bit patterns of gelu(h) and gelu'(h).
+__device__ __forceinline__ void gelu_and_grad_pair(f32x2 acc, f32x2 bias, uint32_t& g_bf16x2, uint32_t& gp_bf16x2) {
+  float s0, s1;
+  f2_unpack(f2_add(acc, bias), s0, s1);
+  const uint32_t hb = pack_bf16x2(s0, s1);
+  const float h0 = __uint_as_float(hb << 16), h1 = __uint_as_float(hb & 0xffff0000u);
+  const f32x2 h = f2_pack(h0, h1);
+  float d0, d1, t0, t1, a0, a1, e0, e1;
+  f2_unpack(f2_fma(f2_pack(fabsf(h0), fabsf(h1)), f2_bcast(0.3275911f * 0.70710678118654752440f), f2_bcast(1.0f)), d0, d1);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(d0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(d1));
+  f2_unpack(f2_mul(f2_mul(h, f2_bcast(-0.72134752044448170368f)), h), a0, a1);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(a0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(a1));
+  const f32x2 t = f2_pack(t0, t1), e = f2_pack(e0, e1);
+  f32x2 poly = f2_fma(t, f2_bcast(0.5f * 1.061405429f), f2_bcast(0.5f * -1.453152027f));
+  poly = f2_fma(t, poly, f2_bcast(0.5f * 1.421413741f));
+  poly = f2_fma(t, poly, f2_bcast(0.5f * -0.284496736f));
+  poly = f2_fma(t, poly, f2_bcast(0.5f * 0.254829592f));
+  const f32x2 q = f2_mul(f2_mul(poly, t), e);
+  float q0, q1, o0, o1;
+  f2_unpack(q, q0, q1);
+  f2_unpack(f2_fma(q, f2_bcast(-1.0f), f2_bcast(1.0f)), o0, o1);
+  const f32x2 cdf = f2_pack(h0 > 0.f ? o0 : q0, h1 > 0.f ? o1 : q1);
+  float g0, g1, p0, p1;
+  f2_unpack(f2_mul(h, cdf), g0, g1);
+  f2_unpack(f2_fma(f2_mul(h, f2_bcast(0.39894228040143267794f)), e, cdf), p0, p1);
+  g_bf16x2 = pack_bf16x2(g0, g1);
+  gp_bf16x2 = pack_bf16x2(p0, p1);
+}
+
 // 128-bit streaming loads/stores (read-once data: do not allocate in L1)
 __device__ __forceinline__ uint4 ld_nc_v4(const void* p) {
   uint4 r;

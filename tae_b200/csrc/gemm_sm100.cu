@@ -180,6 +180,14 @@ __device__ __forceinline__ void epi_write_rows(const Params& p, uint32_t stg, in
       rdot[it] += (r01.x * m01.x + r01.y * m01.y) + (r23.x * m23.x + r23.y * m23.y);
     } else if (EPI == TAE_EPI_BF16_GELU) {
       // h = bf16(acc + bias) is the reference's fc1 output; GELU and its derivative are evaluated on that rounded value
+#ifndef TAE_GELU_SCALAR
+      // packed-pair evaluation (FFMA2/FMUL2): same values as the scalar path, 2/3 of its issue slots
+      uint32_t g01, gp01, g23, gp23;
+      gelu_and_grad_pair(f2_pack(a0, a1), f2_pack(bias4.x, bias4.y), g01, gp01);
+      gelu_and_grad_pair(f2_pack(a2, a3), f2_pack(bias4.z, bias4.w), g23, gp23);
+      *reinterpret_cast<uint2*>(optr) = make_uint2(gp01, gp23);
+      *reinterpret_cast<uint2*>(obase2 + it * rstride) = make_uint2(g01, g23);
+#else
       float g[4], gp[4];
       const float2 h01 = round_bf16x2(a0 + bias4.x, a1 + bias4.y), h23 = round_bf16x2(a2 + bias4.z, a3 + bias4.w);
       gelu_and_grad_fast(h01.x, g[0], gp[0]);
@@ -188,6 +196,7 @@ __device__ __forceinline__ void epi_write_rows(const Params& p, uint32_t stg, in
       gelu_and_grad_fast(h23.y, g[3], gp[3]);
       *reinterpret_cast<uint2*>(optr) = make_uint2(pack_bf16x2(gp[0], gp[1]), pack_bf16x2(gp[2], gp[3]));
       *reinterpret_cast<uint2*>(obase2 + it * rstride) = make_uint2(pack_bf16x2(g[0], g[1]), pack_bf16x2(g[2], g[3]));
+#endif
     } else if (EPI == TAE_EPI_BF16_DGELU) {
       const float2 m01 = unpack_bf16x2(side[it].x), m23 = unpack_bf16x2(side[it].y);
       // bf16(acc) first: the dgrad GEMM's own output rounding in the reference; aux holds gelu'(h) from the forward

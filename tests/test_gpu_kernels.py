@@ -477,3 +477,50 @@ def test_attention_persistent_kernels_many_items_per_cta(B, H):
     out2, lse2 = ops.attention_fwd(qkv, B, N, H, hd)
     assert torch.equal(out2, out) and torch.equal(lse2, lse)
     assert torch.equal(ops.attention_bwd(qkv, out, dout, lse, B, N, H, hd), ops.attention_bwd(qkv, out, dout, lse, B, N, H, hd))
+
+
+def test_dynamic_scheduling_matches_static():
+    """tae_set_dynamic_scheduling: the persistent kernels draw their work (GEMM tiles, LayerNorm-backward rows) from a
+    global counter instead of static round-robin lists (tae_b200.ddp turns this on for world_size > 1).  Which CTA
+    computes a tile must not change any value: every per-element result is bit-identical (only sums
+    whose order follows the work assignment — split-K atomics, LayerNorm parameter-gradient partials — may differ in the
+    last bits)."""
+    ops = _ops()
+    from tae_b200._lib import EPI_BF16, EPI_BF16_GELU, EPI_F32_ACC
+
+    A, W = randn(8192, 1024, seed=50), randn(2048, 1024, seed=51, scale=0.05)
+    bias = randn(2048, dtype=torch.float32, seed=52)
+    dY, X = randn(8192, 640, seed=53, scale=0.1), randn(8192, 384, seed=54)
+    x = randn(5000, 1024, dtype=torch.float32, seed=55) * 2 + 0.5
+    w = randn(1024, dtype=torch.float32, seed=56) * 0.2 + 1
+    dy, dres = randn(5000, 1024, seed=57), randn(5000, 1024, dtype=torch.float32, seed=58)
+    _, mean, rstd = ops.layernorm_fwd(x, w, torch.zeros_like(w), 1e-6)
+
+    def run():
+        plain = ops.gemm(A, W, epilogue=EPI_BF16, bias=bias)
+        gp, g = ops.gemm(A, W, epilogue=EPI_BF16_GELU, bias=bias)
+        dw = ops.gemm(dY, X, a_mn=True, b_mn=True, epilogue=EPI_F32_ACC, splits=1)
+        dw_split = ops.gemm(dY, X, a_mn=True, b_mn=True, epilogue=EPI_F32_ACC, splits=0)
+        ln = ops.layernorm_bwd(dy, x, mean, rstd, w, dres)
+        torch.cuda.synchronize()
+        # exact: per-element results; approx: sums whose order follows the row -> CTA assignment or the split-K atomics
+        return [plain, gp, g, dw, ln[0], ln[1]], [dw_split, *[t for t in ln[2:] if t is not None]]
+
+    prev = ops.set_dynamic_scheduling(False)
+    try:
+        static, static_sums = run()
+        assert ops.set_dynamic_scheduling(True) == 0
+        for _ in range(3):  # several launches: the counter slots are re-armed by the kernels themselves
+            dynamic, dynamic_sums = run()
+            for s, d in zip(static, dynamic):
+                assert torch.equal(s, d)
+            for s, d in zip(static_sums, dynamic_sums):
+                assert rel_err(d, s) < 1e-5
+        assert ops.set_dynamic_scheduling(False) == 1
+    finally:
+        if prev >= 0:
+            ops.set_dynamic_scheduling(bool(prev))
+        else:
+            ops.set_dynamic_scheduling(False)
+    ref = (A.float() @ W.float().t() + bias.to(torch.bfloat16).float())
+    assert max_err_scaled(static[0].float(), ref) < 1e-2

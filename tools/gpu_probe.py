@@ -42,6 +42,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--attn-only", action="store_true")
+    ap.add_argument("--gemm-only", action="store_true")
     args = ap.parse_args()
     hbm, tf, how = peaks()
     dev = "cuda"
@@ -87,6 +88,8 @@ def main():
         print(f"gemm {name[:4]} wgrad: {med:.3f} ms  {fl / med / 1e9:.0f} TFLOP/s ({fl / med / 1e9 / tf:.2f})")
         del A, W, dY, dW
 
+    if args.gemm_only:
+        return
     # ---- attention (patch16: N=256, hd=64, H=16) ----
     B = M // 256
     qkv = rnd(M, 3 * D)
