@@ -21,6 +21,16 @@
 
 #include "sm100.cuh"
 
+// TAE_GELU_TMA_EPI=1: the GELU epilogue of the CTA-pair kernel is evaluated in the accumulator's ROW layout (the layout
+// tcgen05.ld delivers) and leaves through TMA stores, instead of the fp32 transpose through shared memory + coalesced
+// st.global of the generic epilogue.  TAE_GELU_TMA_SWZ64: 64-byte swizzle of the staging boxes (bank-conflict-free).
+#ifndef TAE_GELU_TMA_EPI
+#define TAE_GELU_TMA_EPI 0
+#endif
+#ifndef TAE_GELU_TMA_SWZ64
+#define TAE_GELU_TMA_SWZ64 1
+#endif
+
 namespace tae {
 namespace gemm {
 
@@ -100,6 +110,24 @@ __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
   uint4 r;
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr) : "memory");
   return r;
+}
+
+// [32 rows x 32 bf16] TMA-store staging box (64 B per row); with CU_TENSOR_MAP_SWIZZLE_64B the 16-byte chunk index is
+// XORed with address bits 7-8, i.e. (row >> 1) & 3 for 64-byte rows
+__device__ __forceinline__ uint32_t stg64_off(int row, int chunk) {
+#if TAE_GELU_TMA_SWZ64
+  return (uint32_t)(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4));
+#else
+  return (uint32_t)(row * 64 + (chunk << 4));
+#endif
+}
+__device__ __forceinline__ void st_shared_u16(uint32_t addr, unsigned short v) {
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d_sa(const CUtensorMap* tmap, uint32_t smem_addr, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tmap), "r"(smem_addr),
+               "r"(c0), "r"(c1)
+               : "memory");
 }
 
 constexpr int EPI_COLS = 32;  // accumulator columns per staging step (32 fp32 = one 128-byte row segment)
@@ -489,15 +517,18 @@ struct Cfg2 {
   static constexpr int kStages = EW == 8 ? 6 : 5;
   static constexpr int kThreads = 128 + EW * 32;
   static constexpr int kStagingBytes = EW * 32 * 128;
-  static constexpr int kSmemBytes = kStages * STAGE2_BYTES + SMEM_BARRIER_BYTES + kStagingBytes + 1024;
+  static constexpr int kBiasBytes = (TAE_GELU_TMA_EPI && EW == 16) ? EW * 64 : 0;  // bf16[32] per epilogue warp
+  static constexpr int kSmemBytes = kStages * STAGE2_BYTES + SMEM_BARRIER_BYTES + kStagingBytes + kBiasBytes + 1024;
   static constexpr int kColsPerWarp = 256 / (EW / 4);
 };
 
 template <int EPI, int EW>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg2<EW>::kThreads, 1)
 gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                      const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ CUtensorMap tmap_o2,
                       const Params p) {
   constexpr int STAGES2 = Cfg2<EW>::kStages;
+  constexpr bool kGeluTma = TAE_GELU_TMA_EPI && EPI == TAE_EPI_BF16_GELU && EW == 16;
   constexpr int NUM_EPI_WARPS2 = EW;
   constexpr int COLS_PER_WARP = Cfg2<EW>::kColsPerWarp;
   extern __shared__ uint8_t smem_raw[];
@@ -667,6 +698,72 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tcgen05_fence_after();
       const int row_base = it.mt * (2 * BLOCK_M) + (int)rank * BLOCK_M + q * 32;
+      if constexpr (kGeluTma) {
+        // Row-layout GELU: thread = accumulator row, 32 consecutive columns per step.  gelu(h) and gelu'(h) are packed
+        // to bf16 straight from the tcgen05.ld registers into two [32 rows x 32 cols] staging boxes (64 B per row,
+        // 16-byte chunks XOR-swizzled) and leave through two TMA stores per step, which also clip the M / N edges.
+        // The accumulator buffer is handed back to the MMA issuer as soon as the tile's last tcgen05.ld has landed.
+        const uint32_t bias_sa = smem_u32(smem + STAGES2 * STAGE2_BYTES + SMEM_BARRIER_BYTES + Cfg2<EW>::kStagingBytes) +
+                                 (uint32_t)ew * 64u;
+        constexpr int NSTEP = COLS_PER_WARP / EPI_COLS;
+        bool released = false;
+#pragma unroll 1
+        for (int c = 0; c < NSTEP; ++c) {
+          const int col0 = it.nt * BLOCK_N + cg * COLS_PER_WARP + c * EPI_COLS;
+          if (col0 >= p.N) break;  // warp-uniform
+          const bool last = (c == NSTEP - 1) || (col0 + EPI_COLS >= p.N);
+          const uint32_t taddr =
+              tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + cg * COLS_PER_WARP + c * EPI_COLS);
+          // the step's 32 bias values are warp-uniform: lane j fetches and rounds column col0 + j, the warp shares them
+          // through 64 bytes of shared memory (autocast hands the GEMM a bf16 copy of the fp32 bias)
+          float bv = 0.f;
+          if (p.bias != nullptr && col0 + lane < p.N) bv = __ldg(p.bias + col0 + lane);
+          uint32_t raw[32];
+          tmem_ld_32x32b_x32(taddr, raw);
+          st_shared_u16(bias_sa + (uint32_t)lane * 2u, __bfloat16_as_ushort(__float2bfloat16_rn(bv)));
+          tmem_ld_wait();
+          if (last) tcgen05_fence_before();
+          if (elect_one()) tma_store_wait_read();  // the previous step's TMA stores have finished reading the boxes
+          __syncwarp();
+          if (last) {
+            if (lane == 0) mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
+            released = true;
+          }
+          uint4 bq[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) bq[k] = ld_shared_v4(bias_sa + (uint32_t)k * 16u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {  // 8 columns = one 16-byte chunk of each output row
+            const uint32_t bw[4] = {bq[k].x, bq[k].y, bq[k].z, bq[k].w};
+            uint32_t gw[4], pw[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int e = 8 * k + 2 * j;
+              gelu_and_grad_pair(f2_pack(__uint_as_float(raw[e]), __uint_as_float(raw[e + 1])),
+                                 f2_pack(__uint_as_float(bw[j] << 16), __uint_as_float(bw[j] & 0xffff0000u)), gw[j], pw[j]);
+            }
+            st_shared_v4(stg + stg64_off(lane, k), gw[0], gw[1], gw[2], gw[3]);          // gelu(h)  -> out2
+            st_shared_v4(stg + 2048u + stg64_off(lane, k), pw[0], pw[1], pw[2], pw[3]);  // gelu'(h) -> out
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (row_base < p.M && elect_one()) {
+            tma_store_2d_sa(&tmap_o2, stg, col0, row_base);
+            tma_store_2d_sa(&tmap_o, stg + 2048u, col0, row_base);
+            tma_store_commit();
+          }
+        }
+        if (!released) {  // this warp's columns lie outside the matrix
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
+        }
+        if (++acc == NUM_ACC) {
+          acc = 0;
+          acc_phase ^= 1u;
+        }
+        continue;
+      }
       float rdot[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
       for (int c = 0; c < COLS_PER_WARP / EPI_COLS; ++c) {
@@ -696,6 +793,9 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         acc_phase ^= 1u;
       }
     }
+    if constexpr (kGeluTma) {
+      if (elect_one()) tma_store_wait_all();  // shared memory must outlive the last TMA store's reads
+    }
   }
 
   tcgen05_fence_before();
@@ -724,7 +824,8 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p,
 }
 
 template <int EPI, int EW>
-static int launch_2sm_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, int clusters, cudaStream_t stream) {
+static int launch_2sm_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& to2,
+                          const Params& p, int clusters, cudaStream_t stream) {
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, []() {
@@ -735,18 +836,19 @@ static int launch_2sm_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const Pa
     set_error("cudaFuncSetAttribute(smem=%d) failed: %s", Cfg2<EW>::kSmemBytes, cudaGetErrorString(attr_err));
     return TAE_ERR_CUDA;
   }
-  gemm_bf16_tcgen05_2sm<EPI, EW><<<2 * clusters, Cfg2<EW>::kThreads, Cfg2<EW>::kSmemBytes, stream>>>(ta, tb, p);
+  gemm_bf16_tcgen05_2sm<EPI, EW><<<2 * clusters, Cfg2<EW>::kThreads, Cfg2<EW>::kSmemBytes, stream>>>(ta, tb, to, to2, p);
   TAE_CHECK_LAUNCH();
   return TAE_OK;
 }
 
 template <int EPI>
-static int launch_2sm(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, int clusters, cudaStream_t stream) {
+static int launch_2sm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& to2,
+                      const Params& p, int clusters, cudaStream_t stream) {
   // epilogue-heavy: GELU always; residual / GELU' epilogues when the main loop per tile is short (K <= 2048)
   const bool heavy = (EPI == TAE_EPI_BF16_GELU) ||
                      ((EPI == TAE_EPI_F32_RESID || EPI == TAE_EPI_BF16_DGELU || EPI == TAE_EPI_BF16_ROWDOT) && p.K <= 2048);
-  if (heavy) return launch_2sm_cfg<EPI, 16>(ta, tb, p, clusters, stream);
-  return launch_2sm_cfg<EPI, 8>(ta, tb, p, clusters, stream);
+  if (heavy) return launch_2sm_cfg<EPI, 16>(ta, tb, to, to2, p, clusters, stream);
+  return launch_2sm_cfg<EPI, 8>(ta, tb, to, to2, p, clusters, stream);
 }
 
 // TAE_GEMM_1SM=1 forces the single-CTA kernel (A/B testing)
@@ -868,16 +970,26 @@ extern "C" int tae_gemm(const tae_gemm_args* a, void* stream_) {
   if (rc) return rc;
 
   const int total = p.m_tiles * p.n_tiles * p.splits;
+  CUtensorMap to{}, to2{};  // output maps: only the TMA-store GELU epilogue reads them
+#if TAE_GELU_TMA_EPI
+  if (use2 && a->epilogue == TAE_EPI_BF16_GELU) {
+    const CUtensorMapSwizzle swz = TAE_GELU_TMA_SWZ64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE;
+    rc = make_tmap_box(&to, a->out, (uint64_t)a->N, (uint64_t)a->M, (uint64_t)a->ldo, 32, 32, swz);
+    if (rc) return rc;
+    rc = make_tmap_box(&to2, a->out2, (uint64_t)a->N, (uint64_t)a->M, (uint64_t)a->ldo, 32, 32, swz);
+    if (rc) return rc;
+  }
+#endif
   if (use2) {
     const int clusters = total < units ? total : units;
     p.sched = total > clusters ? sched_counter_slot() : nullptr;  // one item per cluster needs no scheduler
     switch (a->epilogue) {
-      case TAE_EPI_BF16: return launch_2sm<TAE_EPI_BF16>(ta, tb, p, clusters, stream);
-      case TAE_EPI_BF16_GELU: return launch_2sm<TAE_EPI_BF16_GELU>(ta, tb, p, clusters, stream);
-      case TAE_EPI_F32_RESID: return launch_2sm<TAE_EPI_F32_RESID>(ta, tb, p, clusters, stream);
-      case TAE_EPI_F32_ACC: return launch_2sm<TAE_EPI_F32_ACC>(ta, tb, p, clusters, stream);
-      case TAE_EPI_BF16_DGELU: return launch_2sm<TAE_EPI_BF16_DGELU>(ta, tb, p, clusters, stream);
-      case TAE_EPI_BF16_ROWDOT: return launch_2sm<TAE_EPI_BF16_ROWDOT>(ta, tb, p, clusters, stream);
+      case TAE_EPI_BF16: return launch_2sm<TAE_EPI_BF16>(ta, tb, to, to2, p, clusters, stream);
+      case TAE_EPI_BF16_GELU: return launch_2sm<TAE_EPI_BF16_GELU>(ta, tb, to, to2, p, clusters, stream);
+      case TAE_EPI_F32_RESID: return launch_2sm<TAE_EPI_F32_RESID>(ta, tb, to, to2, p, clusters, stream);
+      case TAE_EPI_F32_ACC: return launch_2sm<TAE_EPI_F32_ACC>(ta, tb, to, to2, p, clusters, stream);
+      case TAE_EPI_BF16_DGELU: return launch_2sm<TAE_EPI_BF16_DGELU>(ta, tb, to, to2, p, clusters, stream);
+      case TAE_EPI_BF16_ROWDOT: return launch_2sm<TAE_EPI_BF16_ROWDOT>(ta, tb, to, to2, p, clusters, stream);
     }
     return TAE_ERR_SHAPE;
   }

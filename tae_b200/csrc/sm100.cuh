@@ -331,6 +331,30 @@ inline EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+// 2-D bf16 tensor map over a row-major matrix [outer, inner] with an explicit box [box_outer, box_inner] and swizzle
+// mode (box_inner * 2 bytes must equal the swizzle span, or be a multiple of 16 bytes without swizzle)
+inline int make_tmap_box(CUtensorMap* tm, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld_elems,
+                         uint32_t box_inner, uint32_t box_outer, CUtensorMapSwizzle swizzle) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return TAE_ERR_CUDA;
+  }
+  cuuint64_t gdim[2] = {inner, outer};
+  cuuint64_t gstride[1] = {ld_elems * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (inner=%llu outer=%llu ld=%llu box=%ux%u ptr=%p)", (int)r,
+              (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld_elems, box_outer, box_inner, ptr);
+    return TAE_ERR_CUDA;
+  }
+  return TAE_OK;
+}
+
 // 2-D bf16 tensor map over a row-major matrix [outer, inner] (inner contiguous), box [box_outer, 64], 128B swizzle
 inline int make_tmap(CUtensorMap* tm, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld_elems,
                      uint32_t box_outer) {

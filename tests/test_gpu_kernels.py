@@ -64,11 +64,13 @@ def test_gemm_majors(M, N, K, a_mn, b_mn):
     assert rel_err(out.float(), ref) < 5e-3
 
 
-def test_gemm_epilogue_bias_gelu():
+@pytest.mark.parametrize("M,N,K", [(640, 512, 256), (1000, 264, 72), (300, 4096, 64), (2048, 1032, 128), (96, 256, 64)])
+def test_gemm_epilogue_bias_gelu(M, N, K):
+    """fc1 + GELU epilogue, including ragged edges: N % 32 != 0 (a partly out-of-range 32-column step), M % 32 != 0,
+    epilogue warps whose 32 rows lie entirely outside the matrix, and the single-CTA kernel (M <= 128)."""
     ops = _ops()
     from tae_b200._lib import EPI_BF16, EPI_BF16_GELU
 
-    M, N, K = 640, 512, 256
     A, B = randn(M, K, seed=3), randn(N, K, seed=4, scale=0.1)
     bias = randn(N, dtype=torch.float32, seed=5)
     acc = A.float() @ B.float().t() + bias.to(torch.bfloat16).float()
@@ -80,6 +82,13 @@ def test_gemm_epilogue_bias_gelu():
     gpref = 0.5 * (1 + torch.erf(hf / math.sqrt(2))) + hf * torch.exp(-0.5 * hf * hf) / math.sqrt(2 * math.pi)
     assert max_err_scaled(a.float(), aref) < 1e-2 and rel_err(a.float(), aref) < 4e-3
     assert max_err_scaled(gp.float(), gpref) < 1e-2 and rel_err(gp.float(), gpref) < 4e-3
+    # the two outputs are views into larger buffers in the model (leading dimension > N): nothing outside [M, N] is touched
+    big = torch.full((M + 8, N + 64), 7.0, dtype=torch.bfloat16, device="cuda")
+    big2 = torch.full((M + 8, N + 64), 7.0, dtype=torch.bfloat16, device="cuda")
+    ops.gemm(A, B, epilogue=EPI_BF16_GELU, bias=bias, out=big[:M, :N], out2=big2[:M, :N])
+    assert torch.equal(big[:M, :N], gp) and torch.equal(big2[:M, :N], a)
+    assert bool((big[M:] == 7).all()) and bool((big[:, N:] == 7).all())
+    assert bool((big2[M:] == 7).all()) and bool((big2[:, N:] == 7).all())
 
 
 def test_gemm_epilogue_residual_and_posembed():
