@@ -21,14 +21,33 @@
 
 #include "sm100.cuh"
 
-// TAE_GELU_TMA_EPI=1: the GELU epilogue of the CTA-pair kernel is evaluated in the accumulator's ROW layout (the layout
-// tcgen05.ld delivers) and leaves through TMA stores, instead of the fp32 transpose through shared memory + coalesced
-// st.global of the generic epilogue.  TAE_GELU_TMA_SWZ64: 64-byte swizzle of the staging boxes (bank-conflict-free).
+// Build-time switches of the CTA-pair kernel's epilogues (A/B variants: `python -m tae_b200.build --variant NAME -D...`).
+// TAE_GELU_TMA_EPI (default 1): the GELU epilogue is evaluated in the accumulator's ROW layout, the layout tcgen05.ld
+//   delivers, and leaves through TMA stores of swizzled bf16 staging boxes, instead of the fp32 transpose through shared
+//   memory + coalesced st.global of the generic epilogue.  With it 8 epilogue warps carry the GELU work, which frees
+//   the shared memory for a 6th pipeline stage.  Measured on B200 (fc1 of patch16, M=65536 N=4096 K=1024): generic
+//   epilogue with 16 warps 0.488 ms, with 8 warps 0.531 ms; row-layout/TMA with 16 warps 0.494 ms, with 8 warps
+//   0.465 ms; in the training step 998 -> 1092 TFLOP/s.  Dropping the second output (diagnostic) gives 0.43-0.44 ms:
+//   the two output streams, not the GELU arithmetic, are what separates this GEMM from the plain one (0.39 ms).
+// TAE_GELU_TMA_SWZ64: 64-byte swizzle of the staging boxes (bank-conflict-free st.shared); 0 = linear boxes.
+// TAE_GELU_EW: epilogue warps for the GELU epilogue, 8 (6 pipeline stages) or 16 (5 stages).
+// TAE_BF16_TMA_EPI (default 0): the same row-layout / TMA-store path for the plain bf16(+bias) epilogue.  Parity-green
+//   but not faster (in-step 1311 vs 1319 TFLOP/s), so the generic epilogue stays.
+// TAE_DIAG_GELU_ONE_OUT: diagnostic only (results are WRONG): drops the gelu(h) store.
 #ifndef TAE_GELU_TMA_EPI
-#define TAE_GELU_TMA_EPI 0
+#define TAE_GELU_TMA_EPI 1
 #endif
 #ifndef TAE_GELU_TMA_SWZ64
 #define TAE_GELU_TMA_SWZ64 1
+#endif
+#ifndef TAE_BF16_TMA_EPI
+#define TAE_BF16_TMA_EPI 0
+#endif
+#ifndef TAE_GELU_EW
+#define TAE_GELU_EW 8
+#endif
+#ifndef TAE_DIAG_GELU_ONE_OUT
+#define TAE_DIAG_GELU_ONE_OUT 0
 #endif
 
 namespace tae {
@@ -214,6 +233,9 @@ __device__ __forceinline__ void epi_write_rows(const Params& p, uint32_t stg, in
       gelu_and_grad_pair(f2_pack(a0, a1), f2_pack(bias4.x, bias4.y), g01, gp01);
       gelu_and_grad_pair(f2_pack(a2, a3), f2_pack(bias4.z, bias4.w), g23, gp23);
       *reinterpret_cast<uint2*>(optr) = make_uint2(gp01, gp23);
+#if TAE_DIAG_GELU_ONE_OUT
+      if (g01 == 0x12345678u && g23 == 0x9abcdef0u)  // keeps the math alive, never true in practice
+#endif
       *reinterpret_cast<uint2*>(obase2 + it * rstride) = make_uint2(g01, g23);
 #else
       float g[4], gp[4];
@@ -510,14 +532,15 @@ constexpr int B2_STAGE_BYTES = (BLOCK_N / 2) * BLOCK_K * 2;          // 16 KB: t
 constexpr int STAGE2_BYTES = A_STAGE_BYTES + B2_STAGE_BYTES;         // 32 KB
 
 // Two shapes of the kernel: EW = 8 epilogue warps (128 columns each, 32 KB of transpose staging, 6 pipeline stages) for
-// main-loop-bound GEMMs, EW = 16 (64 columns each, 64 KB staging, 5 stages) when the epilogue carries the work
-// (GELU, short-K residual GEMMs).
+// main-loop-bound GEMMs and the row-layout GELU epilogue, EW = 16 (64 columns each, 64 KB staging, 5 stages) when the
+// generic epilogue carries the work (GELU', row-dot and residual epilogues of short-K GEMMs).
 template <int EW>
 struct Cfg2 {
   static constexpr int kStages = EW == 8 ? 6 : 5;
   static constexpr int kThreads = 128 + EW * 32;
   static constexpr int kStagingBytes = EW * 32 * 128;
-  static constexpr int kBiasBytes = (TAE_GELU_TMA_EPI && EW == 16) ? EW * 64 : 0;  // bf16[32] per epilogue warp
+  static constexpr int kBiasBytes =  // bf16[32] per epilogue warp (row-layout epilogues)
+      ((TAE_GELU_TMA_EPI && EW == TAE_GELU_EW) || (TAE_BF16_TMA_EPI && EW == 8)) ? EW * 64 : 0;
   static constexpr int kSmemBytes = kStages * STAGE2_BYTES + SMEM_BARRIER_BYTES + kStagingBytes + kBiasBytes + 1024;
   static constexpr int kColsPerWarp = 256 / (EW / 4);
 };
@@ -528,7 +551,9 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                       const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ CUtensorMap tmap_o2,
                       const Params p) {
   constexpr int STAGES2 = Cfg2<EW>::kStages;
-  constexpr bool kGeluTma = TAE_GELU_TMA_EPI && EPI == TAE_EPI_BF16_GELU && EW == 16;
+  constexpr bool kGeluTma = TAE_GELU_TMA_EPI && EPI == TAE_EPI_BF16_GELU && EW == TAE_GELU_EW;
+  constexpr bool kPlainTma = TAE_BF16_TMA_EPI && EPI == TAE_EPI_BF16 && EW == 8;
+  constexpr bool kRowTma = kGeluTma || kPlainTma;
   constexpr int NUM_EPI_WARPS2 = EW;
   constexpr int COLS_PER_WARP = Cfg2<EW>::kColsPerWarp;
   extern __shared__ uint8_t smem_raw[];
@@ -698,8 +723,8 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tcgen05_fence_after();
       const int row_base = it.mt * (2 * BLOCK_M) + (int)rank * BLOCK_M + q * 32;
-      if constexpr (kGeluTma) {
-        // Row-layout GELU: thread = accumulator row, 32 consecutive columns per step.  gelu(h) and gelu'(h) are packed
+      if constexpr (kRowTma) {
+        // Row-layout epilogue: thread = accumulator row, 32 consecutive columns per step.  gelu(h) and gelu'(h) are packed
         // to bf16 straight from the tcgen05.ld registers into two [32 rows x 32 cols] staging boxes (64 B per row,
         // 16-byte chunks XOR-swizzled) and leave through two TMA stores per step, which also clip the M / N edges.
         // The accumulator buffer is handed back to the MMA issuer as soon as the tile's last tcgen05.ld has landed.
@@ -723,7 +748,11 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
           st_shared_u16(bias_sa + (uint32_t)lane * 2u, __bfloat16_as_ushort(__float2bfloat16_rn(bv)));
           tmem_ld_wait();
           if (last) tcgen05_fence_before();
-          if (elect_one()) tma_store_wait_read();  // the previous step's TMA stores have finished reading the boxes
+          // the staging boxes about to be overwritten are no longer being read: GELU rewrites both boxes every step,
+          // the plain epilogue alternates between its two boxes (one store may stay in flight)
+          if (elect_one()) {
+            if constexpr (kGeluTma) tma_store_wait_read(); else tma_store_wait_read_le1();
+          }
           __syncwarp();
           if (last) {
             if (lane == 0) mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
@@ -732,6 +761,30 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
           uint4 bq[4];
 #pragma unroll
           for (int k = 0; k < 4; ++k) bq[k] = ld_shared_v4(bias_sa + (uint32_t)k * 16u);
+          if constexpr (kPlainTma) {
+            const uint32_t box = stg + (uint32_t)(c & 1) * 2048u;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint32_t bw[4] = {bq[k].x, bq[k].y, bq[k].z, bq[k].w};
+              uint32_t ow[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int e = 8 * k + 2 * j;
+                float s0, s1;
+                f2_unpack(f2_add(f2_pack(__uint_as_float(raw[e]), __uint_as_float(raw[e + 1])),
+                                 f2_pack(__uint_as_float(bw[j] << 16), __uint_as_float(bw[j] & 0xffff0000u))), s0, s1);
+                ow[j] = pack_bf16x2(s0, s1);
+              }
+              st_shared_v4(box + stg64_off(lane, k), ow[0], ow[1], ow[2], ow[3]);
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (row_base < p.M && elect_one()) {
+              tma_store_2d_sa(&tmap_o, box, col0, row_base);
+              tma_store_commit();
+            }
+            continue;
+          }
 #pragma unroll
           for (int k = 0; k < 4; ++k) {  // 8 columns = one 16-byte chunk of each output row
             const uint32_t bw[4] = {bq[k].x, bq[k].y, bq[k].z, bq[k].w};
@@ -748,7 +801,9 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
           fence_proxy_async_smem();
           __syncwarp();
           if (row_base < p.M && elect_one()) {
+#if !TAE_DIAG_GELU_ONE_OUT
             tma_store_2d_sa(&tmap_o2, stg, col0, row_base);
+#endif
             tma_store_2d_sa(&tmap_o, stg + 2048u, col0, row_base);
             tma_store_commit();
           }
@@ -793,7 +848,7 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         acc_phase ^= 1u;
       }
     }
-    if constexpr (kGeluTma) {
+    if constexpr (kRowTma) {
       if (elect_one()) tma_store_wait_all();  // shared memory must outlive the last TMA store's reads
     }
   }
@@ -845,7 +900,7 @@ template <int EPI>
 static int launch_2sm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& to2,
                       const Params& p, int clusters, cudaStream_t stream) {
   // epilogue-heavy: GELU always; residual / GELU' epilogues when the main loop per tile is short (K <= 2048)
-  const bool heavy = (EPI == TAE_EPI_BF16_GELU) ||
+  const bool heavy = (EPI == TAE_EPI_BF16_GELU && TAE_GELU_EW == 16) ||
                      ((EPI == TAE_EPI_F32_RESID || EPI == TAE_EPI_BF16_DGELU || EPI == TAE_EPI_BF16_ROWDOT) && p.K <= 2048);
   if (heavy) return launch_2sm_cfg<EPI, 16>(ta, tb, to, to2, p, clusters, stream);
   return launch_2sm_cfg<EPI, 8>(ta, tb, to, to2, p, clusters, stream);
@@ -971,13 +1026,15 @@ extern "C" int tae_gemm(const tae_gemm_args* a, void* stream_) {
 
   const int total = p.m_tiles * p.n_tiles * p.splits;
   CUtensorMap to{}, to2{};  // output maps: only the TMA-store GELU epilogue reads them
-#if TAE_GELU_TMA_EPI
-  if (use2 && a->epilogue == TAE_EPI_BF16_GELU) {
+#if TAE_GELU_TMA_EPI || TAE_BF16_TMA_EPI
+  if (use2 && ((TAE_GELU_TMA_EPI && a->epilogue == TAE_EPI_BF16_GELU) || (TAE_BF16_TMA_EPI && a->epilogue == TAE_EPI_BF16))) {
     const CUtensorMapSwizzle swz = TAE_GELU_TMA_SWZ64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE;
     rc = make_tmap_box(&to, a->out, (uint64_t)a->N, (uint64_t)a->M, (uint64_t)a->ldo, 32, 32, swz);
     if (rc) return rc;
-    rc = make_tmap_box(&to2, a->out2, (uint64_t)a->N, (uint64_t)a->M, (uint64_t)a->ldo, 32, 32, swz);
-    if (rc) return rc;
+    if (a->epilogue == TAE_EPI_BF16_GELU) {
+      rc = make_tmap_box(&to2, a->out2, (uint64_t)a->N, (uint64_t)a->M, (uint64_t)a->ldo, 32, 32, swz);
+      if (rc) return rc;
+    }
   }
 #endif
   if (use2) {

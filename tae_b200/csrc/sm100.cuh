@@ -304,6 +304,7 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tmap, const void
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read_le1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // Instruction descriptor for kind::f16: c=F32 (bit 4), a=b=BF16 (bits 7,10), majors (bits 15,16; 1 = MN-major),

@@ -43,6 +43,7 @@ def main():
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--attn-only", action="store_true")
     ap.add_argument("--gemm-only", action="store_true")
+    ap.add_argument("--only", default=None, help="with --gemm-only: just the layers whose name starts with this (qkv, proj, fc1, fc2)")
     args = ap.parse_args()
     hbm, tf, how = peaks()
     dev = "cuda"
@@ -57,6 +58,8 @@ def main():
     D = 1024
     x = rnd(M, D)
     shapes = [("qkv  fwd", D, 3 * D), ("proj fwd", D, D), ("fc1  fwd", D, 4 * D), ("fc2  fwd", 4 * D, D)]
+    if args.only:
+        shapes = [t for t in shapes if t[0].startswith(args.only)]
     for name, K, N in ([] if args.attn_only else shapes):
         A, W = rnd(M, K), rnd(N, K)
         bias = torch.randn(N, device=dev)
