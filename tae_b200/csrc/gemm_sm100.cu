@@ -46,6 +46,12 @@
 #ifndef TAE_GELU_EW
 #define TAE_GELU_EW 8
 #endif
+// TAE_DGELU_TMA_EPI (default 0, experimental): row-layout GELU' epilogue — the gelu'(h) tile arrives by TMA load into
+//   the staging box, the product overwrites it in place and leaves by TMA store, the bias column sums are read back
+//   from the staged box; 8 epilogue warps.
+#ifndef TAE_DGELU_TMA_EPI
+#define TAE_DGELU_TMA_EPI 0
+#endif
 #ifndef TAE_DIAG_GELU_ONE_OUT
 #define TAE_DIAG_GELU_ONE_OUT 0
 #endif
@@ -142,6 +148,18 @@ __device__ __forceinline__ uint32_t stg64_off(int row, int chunk) {
 }
 __device__ __forceinline__ void st_shared_u16(uint32_t addr, unsigned short v) {
   asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_shared_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+// TMA load into this CTA's shared memory (addresses given as shared-space integers), completing on a local mbarrier
+__device__ __forceinline__ void tma_load_2d_sa(uint32_t smem_dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_dst),
+      "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
 }
 __device__ __forceinline__ void tma_store_2d_sa(const CUtensorMap* tmap, uint32_t smem_addr, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tmap), "r"(smem_addr),
@@ -554,6 +572,7 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
   constexpr bool kGeluTma = TAE_GELU_TMA_EPI && EPI == TAE_EPI_BF16_GELU && EW == TAE_GELU_EW;
   constexpr bool kPlainTma = TAE_BF16_TMA_EPI && EPI == TAE_EPI_BF16 && EW == 8;
   constexpr bool kRowTma = kGeluTma || kPlainTma;
+  constexpr bool kDgeluTma = TAE_DGELU_TMA_EPI && EPI == TAE_EPI_BF16_DGELU && EW == 8;
   constexpr int NUM_EPI_WARPS2 = EW;
   constexpr int COLS_PER_WARP = Cfg2<EW>::kColsPerWarp;
   extern __shared__ uint8_t smem_raw[];
@@ -572,6 +591,10 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
   constexpr int SCHED_RING = 16;  // > the producer's maximum lead over the epilogue (6 smem stages + 2 accumulators)
   uint64_t* sched_full = bars + 2 * STAGES2 + 2 * NUM_ACC + 1;              // [SCHED_RING]
   volatile int* sched_ring = reinterpret_cast<volatile int*>(sched_full + SCHED_RING);  // [SCHED_RING]
+  // row-layout GELU' epilogue: one "aux tile has landed" barrier per staging box, two boxes per epilogue warp
+  uint64_t* aux_bar = sched_full + SCHED_RING + SCHED_RING * sizeof(int) / sizeof(uint64_t);    // [2 * EW]
+  static_assert((2 * STAGES2 + 2 * NUM_ACC + 1 + SCHED_RING + SCHED_RING / 2 + (kDgeluTma ? 2 * EW : 0)) * 8 <= SMEM_BARRIER_BYTES,
+                "barrier region overflow");
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -600,6 +623,9 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       mbar_init(&tmem_empty_bar[a], 2 * NUM_EPI_WARPS2);
     }
     for (int r = 0; r < SCHED_RING; ++r) mbar_init(&sched_full[r], 1);
+    if constexpr (kDgeluTma) {
+      for (int r = 0; r < 2 * EW; ++r) mbar_init(&aux_bar[r], 1);
+    }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc_2sm(tmem_slot, TMEM_COLS);
@@ -716,13 +742,109 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     const uint32_t stg = smem_u32(smem + STAGES2 * STAGE2_BYTES + SMEM_BARRIER_BYTES + ew * STG_BYTES_PER_WARP);
     int acc = 0;
     uint32_t acc_phase = 0;
+    uint32_t aux_phase = 0;  // kDgeluTma: parity of the two aux-box barriers (bit b = box b)
     for (int i = 0;; ++i) {
       const int w = work_at(i);
       if (w >= total_work) break;
       const WorkItem it = decode_work(p, w);
+      const int row_base = it.mt * (2 * BLOCK_M) + (int)rank * BLOCK_M + q * 32;
+      if constexpr (kDgeluTma) {
+        // the first aux (gelu'(h)) box of the tile is requested before the wait for the accumulator
+        const int colw = it.nt * BLOCK_N + cg * COLS_PER_WARP;
+        if (colw < p.N && row_base < p.M && elect_one()) {
+          tma_store_wait_read();  // this warp's earlier TMA stores have finished reading both boxes
+          mbar_expect_tx(&aux_bar[ew * 2], 2048u);
+          tma_load_2d_sa(stg, &tmap_o2, &aux_bar[ew * 2], colw, row_base);
+        }
+      }
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tcgen05_fence_after();
-      const int row_base = it.mt * (2 * BLOCK_M) + (int)rank * BLOCK_M + q * 32;
+      if constexpr (kDgeluTma) {
+        // Row-layout GELU' epilogue: out = bf16(bf16(acc) * gelu'(h)).  Step c works in staging box c & 1: the aux
+        // tile was TMA-loaded into it one step earlier, every thread multiplies its own row in place, the box leaves by
+        // TMA store, and the per-32-row column sums of the rounded products (the fc1 bias gradient) are read back from
+        // the staged box: lane -> (column pair, odd/even rows), one shuffle to fold the two row halves.
+        constexpr int NSTEP = COLS_PER_WARP / EPI_COLS;
+        const int colw = it.nt * BLOCK_N + cg * COLS_PER_WARP;
+        const bool active = colw < p.N && row_base < p.M;  // warp-uniform
+        bool released = false;
+#pragma unroll 1
+        for (int c = 0; c < NSTEP; ++c) {
+          const int col0 = colw + c * EPI_COLS;
+          if (!active || col0 >= p.N) break;
+          const bool last = (c == NSTEP - 1) || (col0 + EPI_COLS >= p.N);
+          const int b = c & 1;
+          const uint32_t box = stg + (uint32_t)b * 2048u;
+          const uint32_t taddr =
+              tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + cg * COLS_PER_WARP + c * EPI_COLS);
+          uint32_t raw[32];
+          tmem_ld_32x32b_x32(taddr, raw);
+          if (!last && elect_one()) {  // next step's aux tile into the other box (its last store has been read)
+            tma_store_wait_read();
+            mbar_expect_tx(&aux_bar[ew * 2 + (b ^ 1)], 2048u);
+            tma_load_2d_sa(stg + (uint32_t)(b ^ 1) * 2048u, &tmap_o2, &aux_bar[ew * 2 + (b ^ 1)], col0 + EPI_COLS, row_base);
+          }
+          tmem_ld_wait();
+          if (last) tcgen05_fence_before();
+          __syncwarp();
+          if (last) {
+            if (lane == 0) mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
+            released = true;
+          }
+          mbar_wait(&aux_bar[ew * 2 + b], (aux_phase >> b) & 1u);
+          aux_phase ^= 1u << b;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint4 m = ld_shared_v4(box + stg64_off(lane, k));
+            const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+            uint32_t ow[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int e = 8 * k + 2 * j;
+              // bf16(acc) first: the dgrad GEMM's own output rounding in the reference
+              const float2 r = round_bf16x2(__uint_as_float(raw[e]), __uint_as_float(raw[e + 1]));
+              float o0, o1;
+              f2_unpack(f2_mul(f2_pack(r.x, r.y), f2_pack(__uint_as_float(mw[j] << 16), __uint_as_float(mw[j] & 0xffff0000u))),
+                        o0, o1);
+              ow[j] = pack_bf16x2(o0, o1);
+            }
+            st_shared_v4(box + stg64_off(lane, k), ow[0], ow[1], ow[2], ow[3]);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (elect_one()) {
+            tma_store_2d_sa(&tmap_o, box, col0, row_base);
+            tma_store_commit();
+          }
+          if (p.colsum_part != nullptr) {
+            const int jp = lane & 15, rh = lane >> 4;  // columns 2 jp, 2 jp + 1; rows rh, rh + 2, ...
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+            for (int rr = 0; rr < 16; ++rr) {
+              const int r = 2 * rr + rh;
+              const uint32_t wv = ld_shared_u32(box + stg64_off(r, jp >> 2) + (uint32_t)(jp & 3) * 4u);
+              s0 += __uint_as_float(wv << 16);
+              s1 += __uint_as_float(wv & 0xffff0000u);
+            }
+            s0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+            const int col = col0 + 2 * jp;
+            if (lane < 16 && col < p.N)
+              *reinterpret_cast<float2*>(p.colsum_part + (size_t)(row_base >> 5) * p.N + col) = make_float2(s0, s1);
+          }
+          __syncwarp();  // every lane is done with the box before a later TMA load may overwrite it
+        }
+        if (!released) {
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
+        }
+        if (++acc == NUM_ACC) {
+          acc = 0;
+          acc_phase ^= 1u;
+        }
+        continue;
+      }
       if constexpr (kRowTma) {
         // Row-layout epilogue: thread = accumulator row, 32 consecutive columns per step.  gelu(h) and gelu'(h) are packed
         // to bf16 straight from the tcgen05.ld registers into two [32 rows x 32 cols] staging boxes (64 B per row,
@@ -848,7 +970,7 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         acc_phase ^= 1u;
       }
     }
-    if constexpr (kRowTma) {
+    if constexpr (kRowTma || kDgeluTma) {
       if (elect_one()) tma_store_wait_all();  // shared memory must outlive the last TMA store's reads
     }
   }
@@ -901,7 +1023,8 @@ static int launch_2sm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtens
                       const Params& p, int clusters, cudaStream_t stream) {
   // epilogue-heavy: GELU always; residual / GELU' epilogues when the main loop per tile is short (K <= 2048)
   const bool heavy = (EPI == TAE_EPI_BF16_GELU && TAE_GELU_EW == 16) ||
-                     ((EPI == TAE_EPI_F32_RESID || EPI == TAE_EPI_BF16_DGELU || EPI == TAE_EPI_BF16_ROWDOT) && p.K <= 2048);
+                     ((EPI == TAE_EPI_F32_RESID || (EPI == TAE_EPI_BF16_DGELU && !TAE_DGELU_TMA_EPI) ||
+                       EPI == TAE_EPI_BF16_ROWDOT) && p.K <= 2048);
   if (heavy) return launch_2sm_cfg<EPI, 16>(ta, tb, to, to2, p, clusters, stream);
   return launch_2sm_cfg<EPI, 8>(ta, tb, to, to2, p, clusters, stream);
 }
@@ -1026,13 +1149,17 @@ extern "C" int tae_gemm(const tae_gemm_args* a, void* stream_) {
 
   const int total = p.m_tiles * p.n_tiles * p.splits;
   CUtensorMap to{}, to2{};  // output maps: only the TMA-store GELU epilogue reads them
-#if TAE_GELU_TMA_EPI || TAE_BF16_TMA_EPI
-  if (use2 && ((TAE_GELU_TMA_EPI && a->epilogue == TAE_EPI_BF16_GELU) || (TAE_BF16_TMA_EPI && a->epilogue == TAE_EPI_BF16))) {
+#if TAE_GELU_TMA_EPI || TAE_BF16_TMA_EPI || TAE_DGELU_TMA_EPI
+  if (use2 && ((TAE_GELU_TMA_EPI && a->epilogue == TAE_EPI_BF16_GELU) || (TAE_BF16_TMA_EPI && a->epilogue == TAE_EPI_BF16) ||
+               (TAE_DGELU_TMA_EPI && a->epilogue == TAE_EPI_BF16_DGELU))) {
     const CUtensorMapSwizzle swz = TAE_GELU_TMA_SWZ64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE;
     rc = make_tmap_box(&to, a->out, (uint64_t)a->N, (uint64_t)a->M, (uint64_t)a->ldo, 32, 32, swz);
     if (rc) return rc;
     if (a->epilogue == TAE_EPI_BF16_GELU) {
       rc = make_tmap_box(&to2, a->out2, (uint64_t)a->N, (uint64_t)a->M, (uint64_t)a->ldo, 32, 32, swz);
+      if (rc) return rc;
+    } else if (a->epilogue == TAE_EPI_BF16_DGELU) {  // the second map carries the aux (gelu'(h)) operand
+      rc = make_tmap_box(&to2, a->aux, (uint64_t)a->N, (uint64_t)a->M, (uint64_t)a->ldaux, 32, 32, swz);
       if (rc) return rc;
     }
   }

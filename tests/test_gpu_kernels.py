@@ -150,6 +150,31 @@ def test_gemm_dgelu_epilogue():
     assert rel_err(ops.colsum_f32(part2), out2.float().sum(0)) < 1e-5
 
 
+@pytest.mark.parametrize("M,N,K,with_partials", [(1000, 264, 72, True), (2048, 4096, 1024, True), (300, 1032, 64, True),
+                                                  (520, 768, 256, False)])
+def test_gemm_dgelu_epilogue_ragged(M, N, K, with_partials):
+    """GELU' epilogue at ragged edges: N % 32 != 0, M % 32 != 0, warps whose rows lie outside the matrix, strided aux and
+    out (views into wider buffers), with and without the column-sum by-product."""
+    ops = _ops()
+    from tae_b200._lib import EPI_BF16_DGELU
+
+    dy, W = randn(M, K, seed=60), randn(K, N, seed=61, scale=0.1)
+    gp_big = randn(M, N + 40, seed=62, scale=0.5)
+    gp = gp_big[:, :N]
+    out_big = torch.full((M + 4, N + 24), 7.0, dtype=torch.bfloat16, device="cuda")
+    nparts = (M + 31) // 32
+    part = torch.full((nparts, N), 7.0, device="cuda") if with_partials else None
+    out = ops.gemm(dy, W, b_mn=True, epilogue=EPI_BF16_DGELU, aux=gp, out=out_big[:M, :N], colsum_partials=part)
+    da = (dy.float() @ W.float()).to(torch.bfloat16).float()
+    ref = da * gp.float()
+    assert max_err_scaled(out.float(), ref) < 1e-2 and rel_err(out.float(), ref) < 5e-3
+    assert bool((out_big[M:] == 7).all()) and bool((out_big[:, N:] == 7).all())
+    if with_partials:
+        pad = torch.zeros(nparts * 32, N, device="cuda")
+        pad[:M] = out.float()
+        assert rel_err(part, pad.view(nparts, 32, N).sum(1)) < 1e-5
+
+
 def test_gemm_rejects_bad_shapes():
     ops = _ops()
     from tae_b200._lib import TaeError
