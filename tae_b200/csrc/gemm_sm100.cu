@@ -53,6 +53,12 @@
 #ifndef TAE_DGELU_TMA_EPI
 #define TAE_DGELU_TMA_EPI 1
 #endif
+// TAE_ROWDOT_TMA_EPI (default 0, not yet measured on a GPU): the row-dot epilogue on the same path — aux tile by TMA
+//   load, bf16(acc + bias) written over it in place, TMA store; the per-head dot product is thread-local in the row
+//   layout (no shuffles).
+#ifndef TAE_ROWDOT_TMA_EPI
+#define TAE_ROWDOT_TMA_EPI 0
+#endif
 #ifndef TAE_DIAG_GELU_ONE_OUT
 #define TAE_DIAG_GELU_ONE_OUT 0
 #endif
@@ -559,7 +565,7 @@ struct Cfg2 {
   static constexpr int kThreads = 128 + EW * 32;
   static constexpr int kStagingBytes = EW * 32 * 128;
   static constexpr int kBiasBytes =  // bf16[32] per epilogue warp (row-layout epilogues)
-      ((TAE_GELU_TMA_EPI && EW == TAE_GELU_EW) || (TAE_BF16_TMA_EPI && EW == 8)) ? EW * 64 : 0;
+      ((TAE_GELU_TMA_EPI && EW == TAE_GELU_EW) || ((TAE_BF16_TMA_EPI || TAE_ROWDOT_TMA_EPI) && EW == 8)) ? EW * 64 : 0;
   static constexpr int kSmemBytes = kStages * STAGE2_BYTES + SMEM_BARRIER_BYTES + kStagingBytes + kBiasBytes + 1024;
   static constexpr int kColsPerWarp = 256 / (EW / 4);
 };
@@ -574,6 +580,8 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
   constexpr bool kPlainTma = TAE_BF16_TMA_EPI && EPI == TAE_EPI_BF16 && EW == 8;
   constexpr bool kRowTma = kGeluTma || kPlainTma;
   constexpr bool kDgeluTma = TAE_DGELU_TMA_EPI && EPI == TAE_EPI_BF16_DGELU && EW == 8;
+  constexpr bool kRowdotTma = TAE_ROWDOT_TMA_EPI && EPI == TAE_EPI_BF16_ROWDOT && EW == 8;
+  constexpr bool kAuxTma = kDgeluTma || kRowdotTma;  // epilogues whose aux operand arrives by TMA load
   constexpr int NUM_EPI_WARPS2 = EW;
   constexpr int COLS_PER_WARP = Cfg2<EW>::kColsPerWarp;
   extern __shared__ uint8_t smem_raw[];
@@ -594,7 +602,7 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
   volatile int* sched_ring = reinterpret_cast<volatile int*>(sched_full + SCHED_RING);  // [SCHED_RING]
   // row-layout GELU' epilogue: one "aux tile has landed" barrier per staging box, two boxes per epilogue warp
   uint64_t* aux_bar = sched_full + SCHED_RING + SCHED_RING * sizeof(int) / sizeof(uint64_t);    // [2 * EW]
-  static_assert((2 * STAGES2 + 2 * NUM_ACC + 1 + SCHED_RING + SCHED_RING / 2 + (kDgeluTma ? 2 * EW : 0)) * 8 <= SMEM_BARRIER_BYTES,
+  static_assert((2 * STAGES2 + 2 * NUM_ACC + 1 + SCHED_RING + SCHED_RING / 2 + (kAuxTma ? 2 * EW : 0)) * 8 <= SMEM_BARRIER_BYTES,
                 "barrier region overflow");
 
   const int warp = threadIdx.x >> 5;
@@ -624,7 +632,7 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       mbar_init(&tmem_empty_bar[a], 2 * NUM_EPI_WARPS2);
     }
     for (int r = 0; r < SCHED_RING; ++r) mbar_init(&sched_full[r], 1);
-    if constexpr (kDgeluTma) {
+    if constexpr (kAuxTma) {
       for (int r = 0; r < 2 * EW; ++r) mbar_init(&aux_bar[r], 1);
     }
     fence_barrier_init();
@@ -743,14 +751,14 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     const uint32_t stg = smem_u32(smem + STAGES2 * STAGE2_BYTES + SMEM_BARRIER_BYTES + ew * STG_BYTES_PER_WARP);
     int acc = 0;
     uint32_t acc_phase = 0;
-    uint32_t aux_phase = 0;  // kDgeluTma: parity of the two aux-box barriers (bit b = box b)
+    uint32_t aux_phase = 0;  // kAuxTma: parity of the two aux-box barriers (bit b = box b)
     for (int i = 0;; ++i) {
       const int w = work_at(i);
       if (w >= total_work) break;
       const WorkItem it = decode_work(p, w);
       const int row_base = it.mt * (2 * BLOCK_M) + (int)rank * BLOCK_M + q * 32;
-      if constexpr (kDgeluTma) {
-        // the first aux (gelu'(h)) box of the tile is requested before the wait for the accumulator
+      if constexpr (kAuxTma) {
+        // the first aux box of the tile (gelu'(h), or the row-dot operand) is requested before the wait for the accumulator
         const int colw = it.nt * BLOCK_N + cg * COLS_PER_WARP;
         if (colw < p.N && row_base < p.M && elect_one()) {
           tma_store_wait_read();  // this warp's earlier TMA stores have finished reading both boxes
@@ -760,7 +768,7 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       }
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tcgen05_fence_after();
-      if constexpr (kDgeluTma) {
+      if constexpr (kAuxTma) {
         // Row-layout GELU' epilogue: out = bf16(bf16(acc) * gelu'(h)).  Step c works in staging box c & 1: the aux
         // tile was TMA-loaded into it one step earlier, every thread multiplies its own row in place, the box leaves by
         // TMA store, and the per-32-row column sums of the rounded products (the fc1 bias gradient) are read back from
@@ -769,6 +777,13 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         const int colw = it.nt * BLOCK_N + cg * COLS_PER_WARP;
         const bool active = colw < p.N && row_base < p.M;  // warp-uniform
         bool released = false;
+        // Row-dot variant: out = bf16(acc + bias) written over the aux tile, and dot = sum over the 64 columns of a head
+        // of out * aux stays in this thread (it owns the row); written after the head's second step.
+#if TAE_ROWDOT_TMA_EPI
+        [[maybe_unused]] const uint32_t bias_sa =
+            smem_u32(smem + STAGES2 * STAGE2_BYTES + SMEM_BARRIER_BYTES + Cfg2<EW>::kStagingBytes) + (uint32_t)ew * 64u;
+        [[maybe_unused]] float dot = 0.f;
+#endif
 #pragma unroll 1
         for (int c = 0; c < NSTEP; ++c) {
           const int col0 = colw + c * EPI_COLS;
@@ -778,8 +793,17 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
           const uint32_t box = stg + (uint32_t)b * 2048u;
           const uint32_t taddr =
               tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + cg * COLS_PER_WARP + c * EPI_COLS);
+#if TAE_ROWDOT_TMA_EPI
+          [[maybe_unused]] float bv = 0.f;
+          if constexpr (kRowdotTma) {
+            if (p.bias != nullptr && col0 + lane < p.N) bv = __ldg(p.bias + col0 + lane);
+          }
+#endif
           uint32_t raw[32];
           tmem_ld_32x32b_x32(taddr, raw);
+#if TAE_ROWDOT_TMA_EPI
+          if constexpr (kRowdotTma) st_shared_u16(bias_sa + (uint32_t)lane * 2u, __bfloat16_as_ushort(__float2bfloat16_rn(bv)));
+#endif
           if (!last && elect_one()) {  // next step's aux tile into the other box (its last store has been read)
             tma_store_wait_read();
             mbar_expect_tx(&aux_bar[ew * 2 + (b ^ 1)], 2048u);
@@ -794,6 +818,13 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
           }
           mbar_wait(&aux_bar[ew * 2 + b], (aux_phase >> b) & 1u);
           aux_phase ^= 1u << b;
+#if TAE_ROWDOT_TMA_EPI
+          [[maybe_unused]] uint4 bq[4];
+          if constexpr (kRowdotTma) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) bq[k] = ld_shared_v4(bias_sa + (uint32_t)k * 16u);  // after the __syncwarp above
+          }
+#endif
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const uint4 m = ld_shared_v4(box + stg64_off(lane, k));
@@ -802,6 +833,20 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const int e = 8 * k + 2 * j;
+#if TAE_ROWDOT_TMA_EPI
+              if constexpr (kRowdotTma) {
+                const uint32_t bw = (&bq[k].x)[j];
+                float s0, s1, d0, d1;
+                f2_unpack(f2_add(f2_pack(__uint_as_float(raw[e]), __uint_as_float(raw[e + 1])),
+                                 f2_pack(__uint_as_float(bw << 16), __uint_as_float(bw & 0xffff0000u))), s0, s1);
+                ow[j] = pack_bf16x2(s0, s1);
+                // dot product of the ROUNDED outputs with aux (the attention kernel sees those values)
+                f2_unpack(f2_mul(f2_pack(__uint_as_float(ow[j] << 16), __uint_as_float(ow[j] & 0xffff0000u)),
+                                 f2_pack(__uint_as_float(mw[j] << 16), __uint_as_float(mw[j] & 0xffff0000u))), d0, d1);
+                dot += d0 + d1;
+                continue;
+              }
+#endif
               // bf16(acc) first: the dgrad GEMM's own output rounding in the reference
               const float2 r = round_bf16x2(__uint_as_float(raw[e]), __uint_as_float(raw[e + 1]));
               float o0, o1;
@@ -811,6 +856,18 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
             }
             st_shared_v4(box + stg64_off(lane, k), ow[0], ow[1], ow[2], ow[3]);
           }
+#if TAE_ROWDOT_TMA_EPI
+          if constexpr (kRowdotTma) {
+            if (c & 1) {  // second half of a 64-column head: rowdot[image, head, token] of this thread's row
+              const int grow = row_base + lane;
+              if (grow < p.M) {
+                const int img = grow / p.rd_tokens, tok = grow - img * p.rd_tokens;
+                p.rowdot[((size_t)img * (p.N >> 6) + (col0 >> 6)) * p.rd_tokens + tok] = dot;
+              }
+              dot = 0.f;
+            }
+          }
+#endif
           fence_proxy_async_smem();
           __syncwarp();
           if (elect_one()) {
@@ -971,7 +1028,7 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         acc_phase ^= 1u;
       }
     }
-    if constexpr (kRowTma || kDgeluTma) {
+    if constexpr (kRowTma || kAuxTma) {
       if (elect_one()) tma_store_wait_all();  // shared memory must outlive the last TMA store's reads
     }
   }
@@ -1025,7 +1082,7 @@ static int launch_2sm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtens
   // epilogue-heavy: GELU always; residual / GELU' epilogues when the main loop per tile is short (K <= 2048)
   const bool heavy = (EPI == TAE_EPI_BF16_GELU && TAE_GELU_EW == 16) ||
                      ((EPI == TAE_EPI_F32_RESID || (EPI == TAE_EPI_BF16_DGELU && !TAE_DGELU_TMA_EPI) ||
-                       EPI == TAE_EPI_BF16_ROWDOT) && p.K <= 2048);
+                       (EPI == TAE_EPI_BF16_ROWDOT && !TAE_ROWDOT_TMA_EPI)) && p.K <= 2048);
   if (heavy) return launch_2sm_cfg<EPI, 16>(ta, tb, to, to2, p, clusters, stream);
   return launch_2sm_cfg<EPI, 8>(ta, tb, to, to2, p, clusters, stream);
 }
@@ -1150,16 +1207,17 @@ extern "C" int tae_gemm(const tae_gemm_args* a, void* stream_) {
 
   const int total = p.m_tiles * p.n_tiles * p.splits;
   CUtensorMap to{}, to2{};  // output maps: only the TMA-store GELU epilogue reads them
-#if TAE_GELU_TMA_EPI || TAE_BF16_TMA_EPI || TAE_DGELU_TMA_EPI
+#if TAE_GELU_TMA_EPI || TAE_BF16_TMA_EPI || TAE_DGELU_TMA_EPI || TAE_ROWDOT_TMA_EPI
   if (use2 && ((TAE_GELU_TMA_EPI && a->epilogue == TAE_EPI_BF16_GELU) || (TAE_BF16_TMA_EPI && a->epilogue == TAE_EPI_BF16) ||
-               (TAE_DGELU_TMA_EPI && a->epilogue == TAE_EPI_BF16_DGELU))) {
+               (TAE_DGELU_TMA_EPI && a->epilogue == TAE_EPI_BF16_DGELU) ||
+               (TAE_ROWDOT_TMA_EPI && a->epilogue == TAE_EPI_BF16_ROWDOT))) {
     const CUtensorMapSwizzle swz = TAE_GELU_TMA_SWZ64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE;
     rc = make_tmap_box(&to, a->out, (uint64_t)a->N, (uint64_t)a->M, (uint64_t)a->ldo, 32, 32, swz);
     if (rc) return rc;
     if (a->epilogue == TAE_EPI_BF16_GELU) {
       rc = make_tmap_box(&to2, a->out2, (uint64_t)a->N, (uint64_t)a->M, (uint64_t)a->ldo, 32, 32, swz);
       if (rc) return rc;
-    } else if (a->epilogue == TAE_EPI_BF16_DGELU) {  // the second map carries the aux (gelu'(h)) operand
+    } else if (a->epilogue == TAE_EPI_BF16_DGELU || a->epilogue == TAE_EPI_BF16_ROWDOT) {  // the second map carries aux
       rc = make_tmap_box(&to2, a->aux, (uint64_t)a->N, (uint64_t)a->M, (uint64_t)a->ldaux, 32, 32, swz);
       if (rc) return rc;
     }
