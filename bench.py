@@ -66,7 +66,7 @@ class ClockSampler:
     """nvidia-smi clocks/throttle reasons sampled every 200 ms during the timed region."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.limit")
 
     def __init__(self, gpu_index: int):
         self.idx, self.proc, self.lines = gpu_index, None, []
@@ -93,7 +93,7 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], None, set()
+        sm, mx, reasons, watts, limit = [], None, set(), [], None
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.lines:
             parts = [x.strip() for x in ln.split(",")]
@@ -107,8 +107,15 @@ class ClockSampler:
             for n, v in zip(names, parts[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
+            try:  # board power under load against its limit: the step runs power-capped
+                watts.append(float(parts[2]))
+                if len(parts) > 7:
+                    limit = float(parts[7])
+            except ValueError:
+                pass
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "samples": len(sm),
-                "reasons": sorted(reasons)}
+                "reasons": sorted(reasons), "power_w": statistics.median(watts) if watts else None,
+                "power_limit_w": limit}
 
 
 # ----------------------------------------------------------------------------------------------------
