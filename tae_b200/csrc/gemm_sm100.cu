@@ -59,6 +59,13 @@
 #ifndef TAE_ROWDOT_TMA_EPI
 #define TAE_ROWDOT_TMA_EPI 0
 #endif
+// TAE_RESID_TMA_EPI (default 0, not yet measured on a GPU): the fp32 residual epilogue on the same path in 16-column
+//   steps — the fp32 residual tile [32 x 16] arrives by TMA load, out = resid + bf16(acc + bias) replaces it in place and
+//   leaves by TMA store; 8 epilogue warps, 6 stages.  The pos-embed broadcast (resid_rows < M) keeps the generic
+//   epilogue.
+#ifndef TAE_RESID_TMA_EPI
+#define TAE_RESID_TMA_EPI 0
+#endif
 #ifndef TAE_DIAG_GELU_ONE_OUT
 #define TAE_DIAG_GELU_ONE_OUT 0
 #endif
@@ -565,7 +572,7 @@ struct Cfg2 {
   static constexpr int kThreads = 128 + EW * 32;
   static constexpr int kStagingBytes = EW * 32 * 128;
   static constexpr int kBiasBytes =  // bf16[32] per epilogue warp (row-layout epilogues)
-      ((TAE_GELU_TMA_EPI && EW == TAE_GELU_EW) || ((TAE_BF16_TMA_EPI || TAE_ROWDOT_TMA_EPI) && EW == 8)) ? EW * 64 : 0;
+      ((TAE_GELU_TMA_EPI && EW == TAE_GELU_EW) || ((TAE_BF16_TMA_EPI || TAE_ROWDOT_TMA_EPI || TAE_RESID_TMA_EPI) && EW == 8)) ? EW * 64 : 0;
   static constexpr int kSmemBytes = kStages * STAGE2_BYTES + SMEM_BARRIER_BYTES + kStagingBytes + kBiasBytes + 1024;
   static constexpr int kColsPerWarp = 256 / (EW / 4);
 };
@@ -581,7 +588,9 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
   constexpr bool kRowTma = kGeluTma || kPlainTma;
   constexpr bool kDgeluTma = TAE_DGELU_TMA_EPI && EPI == TAE_EPI_BF16_DGELU && EW == 8;
   constexpr bool kRowdotTma = TAE_ROWDOT_TMA_EPI && EPI == TAE_EPI_BF16_ROWDOT && EW == 8;
-  constexpr bool kAuxTma = kDgeluTma || kRowdotTma;  // epilogues whose aux operand arrives by TMA load
+  constexpr bool kResidTma = TAE_RESID_TMA_EPI && EPI == TAE_EPI_F32_RESID && EW == 8;
+  constexpr bool kAuxTma = kDgeluTma || kRowdotTma;  // epilogues whose bf16 aux operand arrives by TMA load
+  constexpr bool kInTma = kAuxTma || kResidTma;       // ... or any epilogue input tile
   constexpr int NUM_EPI_WARPS2 = EW;
   constexpr int COLS_PER_WARP = Cfg2<EW>::kColsPerWarp;
   extern __shared__ uint8_t smem_raw[];
@@ -602,7 +611,7 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
   volatile int* sched_ring = reinterpret_cast<volatile int*>(sched_full + SCHED_RING);  // [SCHED_RING]
   // row-layout GELU' epilogue: one "aux tile has landed" barrier per staging box, two boxes per epilogue warp
   uint64_t* aux_bar = sched_full + SCHED_RING + SCHED_RING * sizeof(int) / sizeof(uint64_t);    // [2 * EW]
-  static_assert((2 * STAGES2 + 2 * NUM_ACC + 1 + SCHED_RING + SCHED_RING / 2 + (kAuxTma ? 2 * EW : 0)) * 8 <= SMEM_BARRIER_BYTES,
+  static_assert((2 * STAGES2 + 2 * NUM_ACC + 1 + SCHED_RING + SCHED_RING / 2 + (kInTma ? 2 * EW : 0)) * 8 <= SMEM_BARRIER_BYTES,
                 "barrier region overflow");
 
   const int warp = threadIdx.x >> 5;
@@ -632,7 +641,7 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       mbar_init(&tmem_empty_bar[a], 2 * NUM_EPI_WARPS2);
     }
     for (int r = 0; r < SCHED_RING; ++r) mbar_init(&sched_full[r], 1);
-    if constexpr (kAuxTma) {
+    if constexpr (kInTma) {
       for (int r = 0; r < 2 * EW; ++r) mbar_init(&aux_bar[r], 1);
     }
     fence_barrier_init();
@@ -757,8 +766,9 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       if (w >= total_work) break;
       const WorkItem it = decode_work(p, w);
       const int row_base = it.mt * (2 * BLOCK_M) + (int)rank * BLOCK_M + q * 32;
-      if constexpr (kAuxTma) {
-        // the first aux box of the tile (gelu'(h), or the row-dot operand) is requested before the wait for the accumulator
+      if constexpr (kInTma) {
+        // the first input box of the tile (gelu'(h), the row-dot operand, or the fp32 residual: 2 KB each) is requested
+        // before the wait for the accumulator
         const int colw = it.nt * BLOCK_N + cg * COLS_PER_WARP;
         if (colw < p.N && row_base < p.M && elect_one()) {
           tma_store_wait_read();  // this warp's earlier TMA stores have finished reading both boxes
@@ -768,6 +778,82 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       }
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tcgen05_fence_after();
+#if TAE_RESID_TMA_EPI
+      if constexpr (kResidTma) {
+        // Row-layout residual epilogue in 16-column steps: box c & 1 holds the fp32 residual tile [32 rows x 16 cols]
+        // (64-byte rows, TMA-loaded one step ahead); every thread replaces its own row by resid + bf16(acc + bias) and
+        // the box leaves by TMA store.  resid may alias out: a tile is always loaded before it is stored.
+        constexpr int SC = 16;
+        constexpr int NSTEP = COLS_PER_WARP / SC;
+        const int colw = it.nt * BLOCK_N + cg * COLS_PER_WARP;
+        const bool active = colw < p.N && row_base < p.M;  // warp-uniform
+        const uint32_t bias_sa =
+            smem_u32(smem + STAGES2 * STAGE2_BYTES + SMEM_BARRIER_BYTES + Cfg2<EW>::kStagingBytes) + (uint32_t)ew * 64u;
+        bool released = false;
+#pragma unroll 1
+        for (int c = 0; c < NSTEP; ++c) {
+          const int col0 = colw + c * SC;
+          if (!active || col0 >= p.N) break;
+          const bool last = (c == NSTEP - 1) || (col0 + SC >= p.N);
+          const int b = c & 1;
+          const uint32_t box = stg + (uint32_t)b * 2048u;
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + cg * COLS_PER_WARP + c * SC);
+          float bv = 0.f;
+          if (p.bias != nullptr && col0 + (lane & 15) < p.N) bv = __ldg(p.bias + col0 + (lane & 15));
+          uint32_t raw[16];
+          tmem_ld_32x32b_x16(taddr, raw);
+          if (lane < 16) st_shared_u16(bias_sa + (uint32_t)lane * 2u, __bfloat16_as_ushort(__float2bfloat16_rn(bv)));
+          if (!last && elect_one()) {  // next step's residual tile into the other box (its last store has been read)
+            tma_store_wait_read();
+            mbar_expect_tx(&aux_bar[ew * 2 + (b ^ 1)], 2048u);
+            tma_load_2d_sa(stg + (uint32_t)(b ^ 1) * 2048u, &tmap_o2, &aux_bar[ew * 2 + (b ^ 1)], col0 + SC, row_base);
+          }
+          tmem_ld_wait();
+          if (last) tcgen05_fence_before();
+          __syncwarp();
+          if (last) {
+            if (lane == 0) mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
+            released = true;
+          }
+          mbar_wait(&aux_bar[ew * 2 + b], (aux_phase >> b) & 1u);
+          aux_phase ^= 1u << b;
+          uint4 bq[2];
+          bq[0] = ld_shared_v4(bias_sa);
+          bq[1] = ld_shared_v4(bias_sa + 16u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {  // 4 fp32 columns = one 16-byte chunk of the row
+            const uint4 rv = ld_shared_v4(box + stg64_off(lane, k));
+            const uint32_t bw0 = (&bq[k >> 1].x)[(2 * k) & 3], bw1 = (&bq[k >> 1].x)[(2 * k + 1) & 3];
+            float s0, s1, s2, s3, o0, o1, o2, o3;
+            f2_unpack(f2_add(f2_pack(__uint_as_float(raw[4 * k]), __uint_as_float(raw[4 * k + 1])),
+                             f2_pack(__uint_as_float(bw0 << 16), __uint_as_float(bw0 & 0xffff0000u))), s0, s1);
+            f2_unpack(f2_add(f2_pack(__uint_as_float(raw[4 * k + 2]), __uint_as_float(raw[4 * k + 3])),
+                             f2_pack(__uint_as_float(bw1 << 16), __uint_as_float(bw1 & 0xffff0000u))), s2, s3);
+            const float2 r01 = round_bf16x2(s0, s1), r23 = round_bf16x2(s2, s3);  // the Linear's bf16 output
+            f2_unpack(f2_add(f2_pack(__uint_as_float(rv.x), __uint_as_float(rv.y)), f2_pack(r01.x, r01.y)), o0, o1);
+            f2_unpack(f2_add(f2_pack(__uint_as_float(rv.z), __uint_as_float(rv.w)), f2_pack(r23.x, r23.y)), o2, o3);
+            st_shared_v4(box + stg64_off(lane, k), __float_as_uint(o0), __float_as_uint(o1), __float_as_uint(o2),
+                         __float_as_uint(o3));
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (elect_one()) {
+            tma_store_2d_sa(&tmap_o, box, col0, row_base);
+            tma_store_commit();
+          }
+        }
+        if (!released) {
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
+        }
+        if (++acc == NUM_ACC) {
+          acc = 0;
+          acc_phase ^= 1u;
+        }
+        continue;
+      }
+#endif
       if constexpr (kAuxTma) {
         // Row-layout GELU' epilogue: out = bf16(bf16(acc) * gelu'(h)).  Step c works in staging box c & 1: the aux
         // tile was TMA-loaded into it one step earlier, every thread multiplies its own row in place, the box leaves by
@@ -1028,7 +1114,7 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         acc_phase ^= 1u;
       }
     }
-    if constexpr (kRowTma || kAuxTma) {
+    if constexpr (kRowTma || kInTma) {
       if (elect_one()) tma_store_wait_all();  // shared memory must outlive the last TMA store's reads
     }
   }
@@ -1080,6 +1166,12 @@ template <int EPI>
 static int launch_2sm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& to2,
                       const Params& p, int clusters, cudaStream_t stream) {
   // epilogue-heavy: GELU always; residual / GELU' epilogues when the main loop per tile is short (K <= 2048)
+  // (with TAE_RESID_TMA_EPI the 8-warp residual kernel IS the row-layout one: the pos-embed broadcast, which it does not
+  // handle, goes to the 16-warp generic kernel whatever its K)
+  const bool resid_wrap = EPI == TAE_EPI_F32_RESID && p.resid_rows < p.M;
+  if (TAE_RESID_TMA_EPI && EPI == TAE_EPI_F32_RESID)
+    return resid_wrap ? launch_2sm_cfg<EPI, 16>(ta, tb, to, to2, p, clusters, stream)
+                      : launch_2sm_cfg<EPI, 8>(ta, tb, to, to2, p, clusters, stream);
   const bool heavy = (EPI == TAE_EPI_BF16_GELU && TAE_GELU_EW == 16) ||
                      ((EPI == TAE_EPI_F32_RESID || (EPI == TAE_EPI_BF16_DGELU && !TAE_DGELU_TMA_EPI) ||
                        (EPI == TAE_EPI_BF16_ROWDOT && !TAE_ROWDOT_TMA_EPI)) && p.K <= 2048);
@@ -1207,6 +1299,15 @@ extern "C" int tae_gemm(const tae_gemm_args* a, void* stream_) {
 
   const int total = p.m_tiles * p.n_tiles * p.splits;
   CUtensorMap to{}, to2{};  // output maps: only the TMA-store GELU epilogue reads them
+#if TAE_RESID_TMA_EPI
+  if (use2 && a->epilogue == TAE_EPI_F32_RESID && p.resid_rows >= a->M) {
+    const CUtensorMapSwizzle swz = TAE_GELU_TMA_SWZ64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE;
+    rc = make_tmap_box(&to, a->out, (uint64_t)a->N, (uint64_t)a->M, (uint64_t)a->ldo, 16, 32, swz, true);
+    if (rc) return rc;
+    rc = make_tmap_box(&to2, a->resid, (uint64_t)a->N, (uint64_t)a->M, (uint64_t)a->ldr, 16, 32, swz, true);
+    if (rc) return rc;
+  }
+#endif
 #if TAE_GELU_TMA_EPI || TAE_BF16_TMA_EPI || TAE_DGELU_TMA_EPI || TAE_ROWDOT_TMA_EPI
   if (use2 && ((TAE_GELU_TMA_EPI && a->epilogue == TAE_EPI_BF16_GELU) || (TAE_BF16_TMA_EPI && a->epilogue == TAE_EPI_BF16) ||
                (TAE_DGELU_TMA_EPI && a->epilogue == TAE_EPI_BF16_DGELU) ||

@@ -100,6 +100,15 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // Same wait, but the destination registers of an earlier (software-pipelined) tcgen05.ld are passed through as
 // read-write operands, so the compiler cannot move or copy them before the asynchronous load has landed.
@@ -332,21 +341,22 @@ inline EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// 2-D bf16 tensor map over a row-major matrix [outer, inner] with an explicit box [box_outer, box_inner] and swizzle
-// mode (box_inner * 2 bytes must equal the swizzle span, or be a multiple of 16 bytes without swizzle)
+// 2-D tensor map (bf16, or fp32 when `f32`) over a row-major matrix [outer, inner] with an explicit box
+// [box_outer, box_inner] and swizzle mode (box_inner * element size must equal the swizzle span, or be a multiple of
+// 16 bytes without swizzle)
 inline int make_tmap_box(CUtensorMap* tm, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld_elems,
-                         uint32_t box_inner, uint32_t box_outer, CUtensorMapSwizzle swizzle) {
+                         uint32_t box_inner, uint32_t box_outer, CUtensorMapSwizzle swizzle, bool f32 = false) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled entry point not available");
     return TAE_ERR_CUDA;
   }
   cuuint64_t gdim[2] = {inner, outer};
-  cuuint64_t gstride[1] = {ld_elems * 2};
+  cuuint64_t gstride[1] = {ld_elems * (f32 ? 4u : 2u)};
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+  CUresult r = enc(tm, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr),
+                   gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult %d (inner=%llu outer=%llu ld=%llu box=%ux%u ptr=%p)", (int)r,

@@ -4,6 +4,7 @@ Tolerances: bf16 outputs are compared within a few bf16 ulps of the result magni
 north-star gate for bf16); fp32 outputs of fp32 inputs within 1e-4 relative; integer index maps bit-exact.
 """
 import math
+import os
 
 import numpy as np
 import pytest
@@ -108,6 +109,55 @@ def test_gemm_epilogue_residual_and_posembed():
     out2 = ops.gemm(A, B, epilogue=EPI_F32_RESID, bias=bias, resid=pos, resid_rows=64)
     ref2 = y + pos.repeat(M // 64, 1)
     assert max_err_scaled(out2, ref2) < 1e-2
+
+
+# Written together with the row-layout variants of the residual / row-dot epilogues (TAE_RESID_TMA_EPI,
+# TAE_ROWDOT_TMA_EPI: off by default, no GPU time was left to run them): these cases run when a variant library is under
+# test (tools/gpu_ab.sh sets TAE_B200_LIB) or when asked for, and join the default suite once they have been seen green.
+_variant_cases = pytest.mark.skipif(not (os.environ.get("TAE_B200_LIB") or os.environ.get("TAE_TEST_VARIANT_CASES")),
+                                    reason="edge cases for variant epilogue builds (set TAE_TEST_VARIANT_CASES=1 to run)")
+
+
+@_variant_cases
+@pytest.mark.parametrize("M,N,K", [(1000, 264, 72), (300, 1032, 64), (2048, 1024, 1024), (4096, 1024, 4096)])
+@pytest.mark.parametrize("inplace", [False, True])
+def test_gemm_epilogue_residual_ragged(M, N, K, inplace):
+    """fp32 residual epilogue at ragged edges (N % 16 != 0, M % 32 != 0), strided resid / out views and out aliasing resid."""
+    ops = _ops()
+    from tae_b200._lib import EPI_F32_RESID
+
+    A, B = randn(M, K, seed=70), randn(N, K, seed=71, scale=0.2)
+    bias = randn(N, dtype=torch.float32, seed=72)
+    big = torch.full((M + 3, N + 20), 7.0, dtype=torch.float32, device="cuda")
+    resid_big = randn(M, N + 12, dtype=torch.float32, seed=73)
+    y = (A.float() @ B.float().t() + bias.to(torch.bfloat16).float()).to(torch.bfloat16).float()
+    if inplace:
+        big[:M, :N] = resid_big[:, :N]
+        want = big[:M, :N] + y
+        ops.gemm(A, B, epilogue=EPI_F32_RESID, bias=bias, resid=big[:M, :N], out=big[:M, :N])
+    else:
+        want = resid_big[:, :N] + y
+        ops.gemm(A, B, epilogue=EPI_F32_RESID, bias=bias, resid=resid_big[:, :N], out=big[:M, :N])
+    assert max_err_scaled(big[:M, :N] - want + y, y) < 1e-2 and rel_err(big[:M, :N], want) < 2e-3
+    assert bool((big[M:] == 7).all()) and bool((big[:, N:] == 7).all())
+
+
+@_variant_cases
+@pytest.mark.parametrize("M,N,K,tokens,with_bias", [(4096, 1024, 1024, 256, False), (1000, 192, 72, 100, True),
+                                                     (300, 64, 264, 4, True), (2560, 2560, 128, 16, False)])
+def test_gemm_rowdot_epilogue_ragged(M, N, K, tokens, with_bias):
+    ops = _ops()
+    A, W = randn(M, K, seed=74, scale=0.5), randn(K, N, seed=75, scale=0.5)
+    aux_big = randn(M, N + 8, seed=76)
+    aux = aux_big[:, :N]
+    bias = randn(N, dtype=torch.float32, seed=77) if with_bias else None
+    out_big = torch.full((M + 2, N + 16), 7.0, dtype=torch.bfloat16, device="cuda")
+    out, rd = ops.gemm(A, W, b_mn=True, epilogue=5, aux=aux, rowdot_tokens=tokens, bias=bias, out=out_big[:M, :N])
+    ref = A.float() @ W.float() + (bias.to(torch.bfloat16).float() if with_bias else 0)
+    assert max_err_scaled(out.float(), ref) < 1e-2
+    want = (out.float() * aux.float()).view(M // tokens, tokens, N // 64, 64).sum(-1).permute(0, 2, 1).contiguous()
+    assert rd.shape == (M // tokens, N // 64, tokens) and rel_err(rd, want) < 1e-5
+    assert bool((out_big[M:] == 7).all()) and bool((out_big[:, N:] == 7).all())
 
 
 @pytest.mark.parametrize("splits", [1, 3, 0])
