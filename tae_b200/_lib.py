@@ -108,21 +108,17 @@ def load(build_if_missing: bool = True) -> C.CDLL:
         return _lib
     override = os.environ.get("TAE_B200_LIB")  # developer A/B builds (tae_b200.build --variant); never a fallback
     if override:
-        lib = C.CDLL(os.fspath(Path(override).resolve(strict=True)))
-        for name, (res, args) in PROTOTYPES.items():
-            fn = getattr(lib, name)
-            fn.restype = res
-            fn.argtypes = args
-        _lib = lib
-        return lib
-    if build_if_missing:
-        # no-op when the in-tree library matches the sources' fingerprint; rebuilds (nvcc) when csrc/ changed
-        from . import build as _build
+        path = Path(override).resolve(strict=True)
+    else:
+        if build_if_missing:
+            # no-op when the in-tree library matches the sources' fingerprint; rebuilds (nvcc) when csrc/ changed
+            from . import build as _build
 
-        _build.build()
-    if not LIB_PATH.exists():
-        raise TaeError(f"{LIB_PATH} is missing: build it with `python -m tae_b200.build` (no CPU fallback exists)")
-    lib = C.CDLL(os.fspath(LIB_PATH))
+            _build.build()
+        if not LIB_PATH.exists():
+            raise TaeError(f"{LIB_PATH} is missing: build it with `python -m tae_b200.build` (no CPU fallback exists)")
+        path = LIB_PATH
+    lib = C.CDLL(os.fspath(path))
     for name, (res, args) in PROTOTYPES.items():
         fn = getattr(lib, name)
         fn.restype = res
