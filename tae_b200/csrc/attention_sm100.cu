@@ -403,6 +403,269 @@ attn_fwd_tc_persist(const __grid_constant__ CUtensorMap tm_qkv,  // box 256 rows
 }
 
 // =============================================================================================
+// Forward, RING variant (TAE_ATTN_FWD=ring; written at the end of round 1, NOT yet run on a GPU — the persistent kernel
+// above stays the default until this one has been seen parity-green and measured).
+//
+// Why: in the persistent kernel a query tile's chain S -> max -> exp -> PV -> drain O is strictly serial per item,
+// because S_t(i+1) overwrites the TMEM columns that hold P_t(i) and O_t(i); only the two tiles overlap each other, and an
+// item costs ~11.5k cycles against a MUFU floor of 4.1k.  Here the scores are produced in HALF tiles (128 queries x
+// 128 keys = 128 TMEM columns) that rotate through a ring of three buffers, and the two O accumulators have their own
+// columns, so the tensor core always works one half tile ahead of each softmax group:
+//   TMEM  [0,384): ring of 3 score buffers (S half tile, then P over it: thread half h keeps its 64 keys' P in columns
+//                  +64h .. +64h+31)          [384,512): O_0, O_1 (64 columns each)
+//   jobs of item i, in order: (tile 0, keys 0-127), (tile 1, keys 0-127), (tile 0, keys 128-255), (tile 1, keys 128-255);
+//   job g uses ring buffer g % 3.  MMA thread, iteration g: S(g+2) as soon as PV(g-1) has released its buffer, then
+//   PV(g) as soon as the group has written P(g).
+//   Softmax across the two key halves without rescaling O: the second half keeps the FIRST half's row maximum as its
+//   reference (softmax is shift-invariant; bf16 P and fp32 l, O only need the exponent range), unless the second half's
+//   maximum exceeds it by more than 2^32 — only then O and l are rescaled (warp-uniform slow path).
+//   A group's order of work per item: second half of item i, FIRST half of item i+1, then the epilogue of item i — the
+//   PV of item i's second half finishes behind the next softmax instead of in front of an idle group.
+// =============================================================================================
+constexpr int R_OFF_RED = 2 * G_BUF;         // [2 tiles][ max lo | max hi | sum ][2 halves][128] fp32 = 6 KB (8 KB reserved)
+constexpr int R_OFF_BAR = R_OFF_RED + 8192;
+constexpr int R_SMEM = R_OFF_BAR + 256 + 1024;
+constexpr int R_THREADS = 640;
+constexpr float R_TAU = 32.0f;               // log2 of the largest P the lazy reference may produce
+
+__global__ void __launch_bounds__(R_THREADS, 1)
+attn_fwd_tc_ring(const __grid_constant__ CUtensorMap tm_qkv,  // box 256 rows x 64 cols over qkv [B*N, 3D]
+                 const __grid_constant__ CUtensorMap tm_o,    // box 128 rows x 64 cols over out [B*N, D]
+                 float* __restrict__ lse, int H, int num_items, float scale, float sl2) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + R_OFF_BAR);
+  uint64_t* bar_kq = bars;           // [2 buffers] K and Q landed                      (TMA, every other item)
+  uint64_t* bar_v = bars + 2;        // [2 buffers] V landed
+  uint64_t* bar_buffree = bars + 4;  // [2 buffers] both tiles' output stores have read the buffer (2 arrivals)
+  uint64_t* bar_s = bars + 6;        // [3 ring]    S half tile in TMEM                 (commit, every 3rd job)
+  uint64_t* bar_p = bars + 9;        // [3 ring]    P written over it                   (256 arrivals)
+  uint64_t* bar_pv = bars + 12;      // [3 ring]    PV of that job done: buffer free, O updated (commit)
+  uint64_t* bar_ofree = bars + 15;   // [2 tiles]   O_t read out of TMEM                (256 arrivals, every item)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int D = H * HD;
+  const int my_items = (num_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_qkv);
+    tma_prefetch_desc(&tm_o);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar_kq[i], 1);
+      mbar_init(&bar_v[i], 1);
+      mbar_init(&bar_buffree[i], 2);
+      mbar_init(&bar_ofree[i], 256);
+    }
+    for (int i = 0; i < 3; ++i) {
+      mbar_init(&bar_s[i], 1);
+      mbar_init(&bar_p[i], 256);
+      mbar_init(&bar_pv[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 1) {
+    if (elect_one()) {
+      // ---------------- TMA producer: K, Q, V of item i into operand buffer i & 1 ----------------
+#pragma unroll 1
+      for (int it = 0; it < my_items; ++it) {
+        const int item = (int)blockIdx.x + it * (int)gridDim.x;
+        const int b = item / H, h = item - b * H;
+        const int s = it & 1;
+        if (it >= 2) mbar_wait(&bar_buffree[s], (uint32_t)(((it >> 1) - 1) & 1));
+        uint8_t* buf = smem + s * G_BUF;
+        mbar_expect_tx(&bar_kq[s], 65536);
+        tma_load_2d(buf + 32768, &tm_qkv, &bar_kq[s], D + h * HD, b * N);
+        tma_load_2d(buf, &tm_qkv, &bar_kq[s], h * HD, b * N);
+        mbar_expect_tx(&bar_v[s], 32768);
+        tma_load_2d(buf + 65536, &tm_qkv, &bar_v[s], 2 * D + h * HD, b * N);
+      }
+    }
+  } else if (warp == 0) {
+    if (elect_one()) {
+      // ---------------- MMA issuer ----------------
+      const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+      const uint32_t idesc_pv = make_idesc_bf16(128, 64, 0, 1);
+      const int G = 4 * my_items;
+      auto issue_s = [&](int g) {
+        const int it = g >> 2, j = g & 3, t = j & 1, hi = j >> 1, s = it & 1, rb = g % 3;
+        const uint32_t base = smem_u32(smem + s * G_BUF);
+        mbar_wait(&bar_kq[s], (uint32_t)((it >> 1) & 1));
+        if (g >= 3) mbar_wait(&bar_pv[rb], (uint32_t)(((g - 3) / 3) & 1));  // PV(g-3) has consumed the P in this buffer
+        tcgen05_fence_after();
+        const uint32_t q_lo = desc_lo(base + t * 16384), k_lo = desc_lo(base + 32768 + hi * 16384);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16_lo(tmem + rb * 128, q_lo + k * 2, k_lo + k * 2, idesc_s, k > 0);
+        umma_commit(&bar_s[rb]);
+      };
+      auto issue_pv = [&](int g) {
+        const int it = g >> 2, j = g & 3, t = j & 1, hi = j >> 1, s = it & 1, rb = g % 3;
+        const uint32_t sV = smem_u32(smem + s * G_BUF + 65536);
+        mbar_wait(&bar_v[s], (uint32_t)((it >> 1) & 1));
+        if (!hi && it >= 1) mbar_wait(&bar_ofree[t], (uint32_t)((it - 1) & 1));  // the previous item's O_t has been read
+        mbar_wait(&bar_p[rb], (uint32_t)((g / 3) & 1));
+        tcgen05_fence_after();
+        const uint32_t o_t = tmem + 384 + t * 64, p_t = tmem + rb * 128;
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj)  // 16 keys = 8 TMEM columns of P per instruction
+          umma_f16_ts(o_t, p_t + (jj >> 2) * 64 + (jj & 3) * 8, make_smem_desc(sV + (hi * 8 + jj) * 2048, 8192, 1024), idesc_pv,
+                      (hi || jj > 0) ? 1u : 0u);
+        umma_commit(&bar_pv[rb]);
+      };
+      if (G > 0) issue_s(0);
+      if (G > 1) issue_s(1);
+#pragma unroll 1
+      for (int g = 0; g < G; ++g) {
+        if (g + 2 < G) issue_s(g + 2);
+        issue_pv(g);
+      }
+    }
+  } else if (warp >= 4) {
+    // ---------------- softmax + epilogue groups ----------------
+    const int t = (warp - 4) >> 3;               // query tile of this group
+    const int wg = (warp - 4) & 7;               // warp inside the group
+    const int q = warp & 3;                      // TMEM lane quarter (== warp % 4)
+    const int half = wg >> 2;                    // which 64 keys of a 128-key half tile
+    const int r = q * 32 + lane;                 // query row inside the tile == TMEM lane
+    const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
+    float* red = reinterpret_cast<float*>(smem + R_OFF_RED) + t * 768;  // [max lo | max hi | sum][2 halves][128]
+    const bool storer = (wg == 0);
+    float m_ref = 0.f, l = 0.f;
+
+    // one half-tile job: scores of ring buffer g % 3 -> P (bf16, over the scores); updates m_ref / l
+    auto softmax_job = [&](int g, int hi) {
+      const int rb = g % 3;
+      const uint32_t tS = tlane + (uint32_t)(rb * 128 + half * 64);
+      mbar_wait(&bar_s[rb], (uint32_t)((g / 3) & 1));
+      tcgen05_fence_after();
+      uint32_t buf[2][32];
+      tmem_ld_32x32b_x32(tS, buf[0]);
+      tmem_ld_32x32b_x32(tS + 32, buf[1]);
+      tmem_ld_wait_regs(buf[0]);
+      tmem_ld_wait_regs(buf[1]);
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(buf[0][i]));
+        mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(buf[1][i]));
+      }
+      float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+      float* s_max = red + hi * 256;
+      s_max[half * 128 + r] = mx;
+      tmem_ld_32x32b_x32(tS, buf[0]);  // first chunk of the exp pass in flight across the barrier
+      named_bar_sync(1 + t, 256);
+      mx = fmaxf(mx, s_max[(half ^ 1) * 128 + r]);  // row maximum over the 128 keys of this half tile
+      if (!hi) {
+        m_ref = mx;
+        l = 0.f;
+      } else {
+        // lazy reference: keep the first half's maximum unless this half's exceeds it by more than 2^R_TAU
+        const bool need = (mx - m_ref) * sl2 > R_TAU;
+        if (__any_sync(0xffffffffu, need)) {
+          const float m_new = need ? mx : m_ref;
+          const float f = ex2_approx((m_ref - m_new) * sl2);
+          l *= f;
+          m_ref = m_new;
+          // O_t holds the first half's product: job g - 2 of this tile
+          mbar_wait(&bar_pv[(g - 2) % 3], (uint32_t)(((g - 2) / 3) & 1));
+          tcgen05_fence_after();
+          tmem_ld_wait_regs(buf[0]);  // (the chunk already in flight)
+          uint32_t o[32];
+          const uint32_t tO = tlane + (uint32_t)(384 + t * 64 + half * 32);
+          tmem_ld_32x32b_x32(tO, o);
+          tmem_ld_wait_regs(o);
+          uint32_t o_lo[16], o_hi[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            o_lo[i] = __float_as_uint(__uint_as_float(o[i]) * f);
+            o_hi[i] = __float_as_uint(__uint_as_float(o[16 + i]) * f);
+          }
+          tmem_st_32x32b_x16(tO, o_lo);
+          tmem_st_32x32b_x16(tO + 16, o_hi);
+          tmem_st_wait();
+        }
+      }
+      const float m2 = m_ref * sl2;
+      float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        tmem_ld_wait_regs(buf[c]);
+        if (c == 0) tmem_ld_32x32b_x32(tS + 32, buf[1]);
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float p0 = ex2_approx(fmaf(__uint_as_float(buf[c][2 * i]), sl2, -m2));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(buf[c][2 * i + 1]), sl2, -m2));
+          l0 += p0;
+          l1 += p1;
+          pk[i] = pack_bf16x2(p0, p1);
+        }
+        tmem_st_32x32b_x16(tS + c * 16, pk);  // P chunk c over score columns this thread has already consumed
+      }
+      l += l0 + l1;
+      tmem_st_wait();
+      tcgen05_fence_before();
+      mbar_arrive(&bar_p[rb]);
+    };
+
+    if (my_items > 0) softmax_job(t, 0);
+#pragma unroll 1
+    for (int it = 0; it < my_items; ++it) {
+      const int item = (int)blockIdx.x + it * (int)gridDim.x;
+      const int b = item / H, h = item - b * H;
+      const int s = it & 1;
+      const int g_hi = 4 * it + 2 + t;
+      softmax_job(g_hi, 1);
+      const float m_fin = m_ref, l_part = l;
+      if (it + 1 < my_items) softmax_job(4 * (it + 1) + t, 0);  // overwrites m_ref / l with the next item's
+      // ---- epilogue of item `it`: each thread normalises 32 of the row's 64 output columns ----
+      float* s_sum = red + 512;
+      s_sum[half * 128 + r] = l_part;
+      named_bar_sync(1 + t, 256);
+      const float l_tot = l_part + s_sum[(half ^ 1) * 128 + r];
+      mbar_wait(&bar_pv[g_hi % 3], (uint32_t)((g_hi / 3) & 1));  // O_t complete
+      tcgen05_fence_after();
+      if (half == 0) lse[((size_t)b * H + h) * N + t * 128 + r] = m_fin * scale + __logf(l_tot);
+      const float inv = 1.0f / l_tot;
+      const uint32_t stage = smem_u32(smem + s * G_BUF + t * 16384);  // the item's dead Q tile
+      {
+        uint32_t raw[32];
+        tmem_ld_32x32b_x32(tlane + (uint32_t)(384 + t * 64 + half * 32), raw);
+        tmem_ld_wait_regs(raw);
+        tcgen05_fence_before();
+        mbar_arrive(&bar_ofree[t]);  // O_t may take the next item's first PV
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint32_t o[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            o[j] = pack_bf16x2(__uint_as_float(raw[i * 8 + 2 * j]) * inv, __uint_as_float(raw[i * 8 + 2 * j + 1]) * inv);
+          st_shared_v4(stage + sw128(r, half * 4 + i), o[0], o[1], o[2], o[3]);
+        }
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(1 + t, 256);  // staging complete; also: every thread has read s_sum before the next item rewrites it
+      if (storer && elect_one()) {
+        tma_store_2d(&tm_o, smem + s * G_BUF + t * 16384, h * HD, b * N + t * 128);
+        tma_store_commit();
+        tma_store_wait_read();
+        mbar_arrive(&bar_buffree[s]);  // (with the other tile's arrival) the producer may refill this buffer
+      }
+    }
+    if (storer && elect_one()) tma_store_wait_all();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// =============================================================================================
 // Backward
 // =============================================================================================
 constexpr int B_OFF_Q = 0;
@@ -1339,9 +1602,27 @@ int attention_fwd_tcgen05(const bf16* qkv, bf16* out, float* lse, int B, int H, 
   static int variant = -1;
   if (variant < 0) {
     const char* e = getenv("TAE_ATTN_FWD");
-    variant = (e != nullptr && e[0] == 'v') ? 0 : 1;
+    variant = (e != nullptr && e[0] == 'v') ? 0 : (e != nullptr && e[0] == 'r') ? 2 : 1;  // v1 | ring | (default) persistent
   }
   int rc;
+  if (variant == 2) {
+    static cudaError_t err3 = cudaSuccess;
+    static std::once_flag once3;
+    rc = set_smem_once(attn_fwd_tc_ring, R_SMEM, &err3, &once3);
+    if (rc) return rc;
+    CUtensorMap tkv, to;
+    rc = sm100::make_tmap(&tkv, qkv, (uint64_t)3 * D, (uint64_t)B * N, (uint64_t)3 * D, 256);
+    if (rc) return rc;
+    rc = sm100::make_tmap(&to, out, (uint64_t)D, (uint64_t)B * N, (uint64_t)D, 128);
+    if (rc) return rc;
+    const int sms = num_sms();
+    if (sms <= 0) return TAE_ERR_CUDA;
+    const int items = B * H;
+    attn_fwd_tc_ring<<<items < sms ? items : sms, R_THREADS, R_SMEM, stream>>>(tkv, to, lse, H, items, scale,
+                                                                               scale * 1.44269504088896340736f);
+    TAE_CHECK_LAUNCH();
+    return TAE_OK;
+  }
   if (variant == 1) {
     static cudaError_t err2 = cudaSuccess;
     static std::once_flag once2;

@@ -113,8 +113,10 @@ def test_gemm_epilogue_residual_and_posembed():
 
 # Written together with the row-layout variants of the residual / row-dot epilogues (TAE_RESID_TMA_EPI,
 # TAE_ROWDOT_TMA_EPI: off by default, no GPU time was left to run them): these cases run when a variant library is under
-# test (tools/gpu_ab.sh sets TAE_B200_LIB) or when asked for, and join the default suite once they have been seen green.
-_variant_cases = pytest.mark.skipif(not (os.environ.get("TAE_B200_LIB") or os.environ.get("TAE_TEST_VARIANT_CASES")),
+# test (tools/gpu_ab.sh sets TAE_B200_LIB; TAE_ATTN_FWD=ring selects the ring attention forward) or when asked for, and
+# join the default suite once they have been seen green.
+_variant_cases = pytest.mark.skipif(not (os.environ.get("TAE_B200_LIB") or os.environ.get("TAE_TEST_VARIANT_CASES") or
+                                         os.environ.get("TAE_ATTN_FWD")),
                                     reason="edge cases for variant epilogue builds (set TAE_TEST_VARIANT_CASES=1 to run)")
 
 
@@ -608,3 +610,23 @@ def test_dynamic_scheduling_matches_static():
             ops.set_dynamic_scheduling(False)
     ref = (A.float() @ W.float().t() + bias.to(torch.bfloat16).float())
     assert max_err_scaled(static[0].float(), ref) < 1e-2
+
+
+@_variant_cases
+@pytest.mark.parametrize("B,H,kscale_hi", [(3, 2, 1.0), (2, 3, 12.0), (5, 1, 0.05)])
+def test_attention_fwd_two_key_halves(B, H, kscale_hi):
+    """Forward attention at N = 256 when the two 128-key halves of a row have very different score ranges.  Written for
+    the ring kernel (TAE_ATTN_FWD=ring: it carries the first half's row maximum into the second half and rescales the
+    accumulator only when the second half's maximum exceeds it by 2^32); any forward kernel has to pass it.
+    kscale_hi = 12: most rows take the rescale path; 0.05: the second half is negligible; 1: the common case."""
+    ops = _ops()
+    N, hd = 256, 64
+    D = H * hd
+    qkv = randn(B * N, 3 * D, seed=90)
+    k = qkv.view(B, N, 3, H, hd)[:, 128:, 1]
+    k.mul_(kscale_hi)  # keys 128..255 of every image and head
+    out, lse = ops.attention_fwd(qkv, B, N, H, hd)
+    oref, lref, _ = _attn_ref(qkv, B, N, H, hd)
+    assert torch.isfinite(out.float()).all() and torch.isfinite(lse).all()
+    assert max_err_scaled(out.float(), oref) < 1.5e-2 and rel_err(out.float(), oref) < 8e-3
+    assert float((lse - lref).abs().max()) < 2e-3 * max(1.0, kscale_hi)

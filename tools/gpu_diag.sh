@@ -10,3 +10,5 @@ for v in default "$@"; do
   timeout 200 python tools/gpu_probe.py --gemm-only --only fc1 > gpurun_out/probe_$v.log 2>&1
   echo "$v: $(grep -h 'fc1  fwd' gpurun_out/probe_$v.log)"
 done
+# ring attention forward (TAE_ATTN_FWD=ring): parity, then timing against the default persistent kernel
+#   TAE_ATTN_FWD=ring python -m pytest tests -m gpu -q -k attention ; TAE_ATTN_FWD=ring python tools/gpu_probe.py --attn-only
