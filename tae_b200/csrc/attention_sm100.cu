@@ -428,6 +428,33 @@ constexpr int R_SMEM = R_OFF_BAR + 256 + 1024;
 constexpr int R_THREADS = 640;
 constexpr float R_TAU = 32.0f;               // log2 of the largest P the lazy reference may produce
 
+// TAE_ATTN_EXP2_POLY = E (0..4, default 0): E of every 4 score pairs of the ring kernel take 2^x from the FMA pipes instead
+// of MUFU.EX2 (the forward is MUFU-bound once the chains overlap: 65536 exponentials per item = 4.1k cycles per SM).
+// x = s*sl2 - m2 <= 0 is split by the round-to-nearest magic constant: t = fma(s, sl2, MAGIC - m2) carries n = rint(x)
+// in its low mantissa bits, f = x - n in [-0.5, 0.5] comes from a second fma, 2^f from a degree-3 polynomial (max
+// relative error 7.5e-5 = 2^-13.7, fitted for relative error; P is rounded to bf16 = 2^-9 afterwards), and n is added
+// into the exponent field with one integer shift-add.  Everything but the clamp and the shift-add runs on packed pairs.
+#ifndef TAE_ATTN_EXP2_POLY
+#define TAE_ATTN_EXP2_POLY 0
+#endif
+__device__ __forceinline__ void exp2_poly_pair(float s0, float s1, float sl2, float kmagic, float& p0, float& p1) {
+  constexpr float kMagic = 12582912.0f;  // 1.5 * 2^23
+  const f32x2 s = f2_pack(s0, s1), a = f2_bcast(sl2), k = f2_bcast(kmagic);  // kmagic = kMagic - m2
+  float t0, t1;
+  f2_unpack(f2_fma(s, a, k), t0, t1);
+  t0 = fmaxf(t0, kMagic - 126.0f);  // x < -126 would run the exponent field below zero
+  t1 = fmaxf(t1, kMagic - 126.0f);
+  const f32x2 t = f2_pack(t0, t1);
+  const f32x2 f = f2_fma(s, a, f2_fma(t, f2_bcast(-1.0f), k));  // x - n = s*sl2 + (kmagic - t)
+  f32x2 p = f2_fma(f, f2_bcast(0.0551716685f), f2_bcast(0.2426111251f));
+  p = f2_fma(p, f, f2_bcast(0.6932609677f));
+  p = f2_fma(p, f, f2_bcast(0.9999280572f));
+  float q0, q1;
+  f2_unpack(p, q0, q1);
+  p0 = __uint_as_float(__float_as_uint(q0) + (__float_as_uint(t0) << 23));
+  p1 = __uint_as_float(__float_as_uint(q1) + (__float_as_uint(t1) << 23));
+}
+
 __global__ void __launch_bounds__(R_THREADS, 1)
 attn_fwd_tc_ring(const __grid_constant__ CUtensorMap tm_qkv,  // box 256 rows x 64 cols over qkv [B*N, 3D]
                  const __grid_constant__ CUtensorMap tm_o,    // box 128 rows x 64 cols over out [B*N, D]
@@ -535,9 +562,11 @@ attn_fwd_tc_ring(const __grid_constant__ CUtensorMap tm_qkv,  // box 256 rows x 
     const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
     float* red = reinterpret_cast<float*>(smem + R_OFF_RED) + t * 768;  // [max lo | max hi | sum][2 halves][128]
     const bool storer = (wg == 0);
-    float m_ref = 0.f, l = 0.f;
+    // m2: the row's softmax reference in the exp2 domain, an INTEGER (rint of max * scale * log2 e) — any reference
+    // gives the same softmax, an integer one keeps MAGIC - m2 exact for the polynomial path and makes rescales powers of 2
+    float m2 = 0.f, l = 0.f;
 
-    // one half-tile job: scores of ring buffer g % 3 -> P (bf16, over the scores); updates m_ref / l
+    // one half-tile job: scores of ring buffer g % 3 -> P (bf16, over the scores); updates m2 / l
     auto softmax_job = [&](int g, int hi) {
       const int rb = g % 3;
       const uint32_t tS = tlane + (uint32_t)(rb * 128 + half * 64);
@@ -561,16 +590,16 @@ attn_fwd_tc_ring(const __grid_constant__ CUtensorMap tm_qkv,  // box 256 rows x 
       named_bar_sync(1 + t, 256);
       mx = fmaxf(mx, s_max[(half ^ 1) * 128 + r]);  // row maximum over the 128 keys of this half tile
       if (!hi) {
-        m_ref = mx;
+        m2 = rintf(mx * sl2);
         l = 0.f;
       } else {
         // lazy reference: keep the first half's maximum unless this half's exceeds it by more than 2^R_TAU
-        const bool need = (mx - m_ref) * sl2 > R_TAU;
+        const bool need = fmaf(mx, sl2, -m2) > R_TAU;
         if (__any_sync(0xffffffffu, need)) {
-          const float m_new = need ? mx : m_ref;
-          const float f = ex2_approx((m_ref - m_new) * sl2);
+          const float m_new = need ? rintf(mx * sl2) : m2;
+          const float f = ex2_approx(m2 - m_new);
           l *= f;
-          m_ref = m_new;
+          m2 = m_new;
           // O_t holds the first half's product: job g - 2 of this tile
           mbar_wait(&bar_pv[(g - 2) % 3], (uint32_t)(((g - 2) / 3) & 1));
           tcgen05_fence_after();
@@ -590,7 +619,6 @@ attn_fwd_tc_ring(const __grid_constant__ CUtensorMap tm_qkv,  // box 256 rows x 
           tmem_st_wait();
         }
       }
-      const float m2 = m_ref * sl2;
       float l0 = 0.f, l1 = 0.f;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
@@ -599,8 +627,13 @@ attn_fwd_tc_ring(const __grid_constant__ CUtensorMap tm_qkv,  // box 256 rows x 
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const float p0 = ex2_approx(fmaf(__uint_as_float(buf[c][2 * i]), sl2, -m2));
-          const float p1 = ex2_approx(fmaf(__uint_as_float(buf[c][2 * i + 1]), sl2, -m2));
+          float p0, p1;
+          if ((i & 3) < TAE_ATTN_EXP2_POLY) {
+            exp2_poly_pair(__uint_as_float(buf[c][2 * i]), __uint_as_float(buf[c][2 * i + 1]), sl2, 12582912.0f - m2, p0, p1);
+          } else {
+            p0 = ex2_approx(fmaf(__uint_as_float(buf[c][2 * i]), sl2, -m2));
+            p1 = ex2_approx(fmaf(__uint_as_float(buf[c][2 * i + 1]), sl2, -m2));
+          }
           l0 += p0;
           l1 += p1;
           pk[i] = pack_bf16x2(p0, p1);
@@ -621,8 +654,8 @@ attn_fwd_tc_ring(const __grid_constant__ CUtensorMap tm_qkv,  // box 256 rows x 
       const int s = it & 1;
       const int g_hi = 4 * it + 2 + t;
       softmax_job(g_hi, 1);
-      const float m_fin = m_ref, l_part = l;
-      if (it + 1 < my_items) softmax_job(4 * (it + 1) + t, 0);  // overwrites m_ref / l with the next item's
+      const float m2_fin = m2, l_part = l;
+      if (it + 1 < my_items) softmax_job(4 * (it + 1) + t, 0);  // overwrites m2 / l with the next item's
       // ---- epilogue of item `it`: each thread normalises 32 of the row's 64 output columns ----
       float* s_sum = red + 512;
       s_sum[half * 128 + r] = l_part;
@@ -630,7 +663,7 @@ attn_fwd_tc_ring(const __grid_constant__ CUtensorMap tm_qkv,  // box 256 rows x 
       const float l_tot = l_part + s_sum[(half ^ 1) * 128 + r];
       mbar_wait(&bar_pv[g_hi % 3], (uint32_t)((g_hi / 3) & 1));  // O_t complete
       tcgen05_fence_after();
-      if (half == 0) lse[((size_t)b * H + h) * N + t * 128 + r] = m_fin * scale + __logf(l_tot);
+      if (half == 0) lse[((size_t)b * H + h) * N + t * 128 + r] = fmaf(m2_fin, 0.69314718055994530942f, __logf(l_tot));
       const float inv = 1.0f / l_tot;
       const uint32_t stage = smem_u32(smem + s * G_BUF + t * 16384);  // the item's dead Q tile
       {
