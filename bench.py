@@ -1,22 +1,33 @@
 #!/usr/bin/env python
-"""Benchmark of the TAE hot path on B200: training images/sec at px256 / patch16 (BASELINE.json `metric`).
+"""Benchmark of the TAE hot path on B200 (BASELINE.json `metric`: train images/sec at px256 patch16; encode img/s).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--model tae_patch16_vocab256_px256] [--batch 256]
-    python bench.py --impl reference ...      # the reference algorithm on the host CPU cores (oracle port)
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config 2|3|4|5 | --model NAME] [--batch 256]
+    python bench.py --impl reference ...       # the reference's own tae.py on the host CPU cores (oracle/_ref, else the port)
+    python bench.py --impl gpu_reference --ref-mode bf16_eager|bf16_compile|fp16_scaler   # reference on the same B200
 
 N > 1 is launched by torchrun (one rank per GPU, NCCL); rank 0 prints ONE JSON line.
 
-Workload (BASELINE.json configs[1]): tae_patch16_vocab256_px256, bf16 compute, batch 256 per GPU, one full
+Default workload = BASELINE.json configs[1]: tae_patch16_vocab256_px256, bf16 compute, batch 256 per GPU, one full
 training step = forward + loss + backward (+ bucketed gradient all-reduce) + fused AdamW + zero_grad, on synthetic
-256x256x3 inputs and reference-style random-init weights.  `value` times K steps with the inputs resident in HBM;
-`e2e` times the same steps fed from pinned host memory through the public API (H2D copy of every batch and a D2H
-read of every step's loss inside the timed region).
+256x256x3 inputs and reference-style random-init weights.  `value` times K steps with the inputs resident in HBM; `e2e`
+times the same steps fed from pinned host memory through the public API (H2D copy of every batch and a D2H read of every
+step's loss inside the timed region).  The same line also carries
+  * `roofline` / `roofline_detail`: per-launch CUDA-event timing of every kernel family (instrumented steps after the
+    timed regions) against MEASURED_PEAKS.json;
+  * `secondary`: BASELINE configs 3 (patch32_v1024 training) and 4 (patch128_v16384 training), `encode`: config 5;
+  * `gpu_reference`: the UNMODIFIED reference (oracle/_ref/tae.py) on the same GPU — bf16 autocast eager, bf16 +
+    torch.compile (train.py --compile) and fp16 + GradScaler as shipped — each in its own subprocess, never inside this
+    arm's timed regions;
+  * `cpu_baseline`: the reference on the host cores (bounded sample);
+  * `ddp_check` (N > 1): max |delta| of the parameter checksum across ranks after the timed regions (0 = replicas equal).
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
+import re
 import statistics
 import subprocess
 import sys
@@ -26,22 +37,49 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# BASELINE.json `configs` (1-based as in SURVEY.md §8d): model and mode
+CONFIGS = {2: ("tae_patch16_vocab256_px256", "train"), 3: ("tae_patch32_vocab1024_px256", "train"),
+           4: ("tae_patch128_vocab16384_px256", "train"), 5: ("tae_patch64_vocab4096_px256", "encode")}
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--model", default="tae_patch16_vocab256_px256")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "gpu_reference"])
+    ap.add_argument("--config", type=int, default=None, choices=sorted(CONFIGS), help="BASELINE.json config number")
+    ap.add_argument("--model", default=None)
     ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
-    ap.add_argument("--mode", default="train", choices=["train", "encode"])
+    ap.add_argument("--mode", default=None, choices=["train", "encode"])
+    ap.add_argument("--graph", action="store_true", help="replay the step as one CUDA graph (single GPU)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
-    ap.add_argument("--no-encode", action="store_true", help="skip the secondary encode.py-path measurement")
-    ap.add_argument("--encode-model", default="tae_patch64_vocab4096_px256")
+    ap.add_argument("--no-encode", action="store_true", help="skip the encode.py-path measurement (config 5)")
+    ap.add_argument("--no-secondary", action="store_true", help="skip BASELINE configs 3 and 4")
+    ap.add_argument("--no-gpu-reference", action="store_true", help="skip the reference-on-the-same-GPU legs")
+    ap.add_argument("--ref-mode", default="bf16_eager", choices=["bf16_eager", "bf16_compile", "fp16_scaler"])
+    ap.add_argument("--ref-modes", default="bf16_eager,fp16_scaler,bf16_compile")
     ap.add_argument("--cpu-batch", type=int, default=2)
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.config is not None:
+        m, mode = CONFIGS[a.config]
+        a.model = a.model or m
+        a.mode = a.mode or mode
+    a.model = a.model or CONFIGS[2][0]
+    a.mode = a.mode or "train"
+    return a
+
+
+def patch_of(model_name: str) -> int:
+    m = re.search(r"patch(\d+)", model_name)
+    return int(m.group(1)) if m else 0
+
+
+def metric_name(model_name: str, mode: str = "train") -> str:
+    return (f"train images/sec at px256 patch{patch_of(model_name)}" if mode == "train"
+            else f"encode images/sec at px256 patch{patch_of(model_name)}")
 
 
 def measured_peaks():
@@ -54,12 +92,26 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
-def train_flops_per_image(cfg) -> float:
-    """F_train = 3 F_fwd - 2*196608*D."""
-    N, D, L, V = cfg.num_patches, cfg.embed_dim, cfg.depth, cfg.vocab_size
-    pix = 3 * cfg.img_size * cfg.img_size
+def model_dims(model):
+    """(N tokens, D width, L blocks per side, V latent width, image side) read off the model object itself."""
+    return (model.patch_embed.num_patches, model.pos_embed.shape[-1], len(model.blocks), model.dict_proj.weight.shape[0],
+            model.patch_embed.img_size[0])
+
+
+def train_flops_per_image(N, D, L, V, S) -> float:
+    """F_train = 3 F_fwd - 2*196608*D (attention backward counted as 2x forward)."""
+    pix = 3 * S * S
     f_fwd = 2 * pix * D + 2 * L * (24 * N * D * D + 4 * N * N * D) + 4 * N * D * V + 2 * pix * D
     return 3.0 * f_fwd - 2.0 * pix * D
+
+
+def gemm_sources_fingerprint() -> str:
+    """Hash of the sources the GEMM kernel is compiled from: ncu traffic evidence is only quoted for the same kernel."""
+    h = hashlib.sha256()
+    for name in ("gemm_sm100.cu", "sm100.cuh", "common.cuh"):
+        with open(os.path.join(ROOT, "tae_b200", "csrc", name), "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()[:16]
 
 
 class ClockSampler:
@@ -119,54 +171,94 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------------
-# CPU arm: the reference algorithm (oracle port) on the host cores
+# The reference itself (oracle/_ref = byte-identical copies of /root/reference/tae.py + util/misc.py, staged by
+# oracle/make_ref.sh; git-ignored, travels to the GPU box).  Checker / baseline only.
 # ----------------------------------------------------------------------------------------------------
-def cpu_reference_step_time(model_name: str, batch: int, steps: int, warmup: int):
-    """Times the reference's training step (train.py:122-150 restated: forward+loss, backward, AdamW, zero_grad) with
-    the oracle port on all host threads.  Returns (images_per_sec, cores, seconds_per_step)."""
-    import torch
+def load_reference_modules():
+    """(tae module, util.misc module) of the unmodified reference, or None when oracle/_ref is absent."""
+    if not os.path.exists(os.path.join(REF_DIR, "tae.py")):
+        return None
+    import importlib.util
 
-    from oracle import tae_oracle as O
+    def load(name, path):
+        spec = importlib.util.spec_from_file_location(name, path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return mod
+
+    # loaded under private names: `import tae` must not shadow / be shadowed by anything else on sys.path
+    return load("_ref_tae", os.path.join(REF_DIR, "tae.py")), load("_ref_misc", os.path.join(REF_DIR, "util", "misc.py"))
+
+
+def cpu_reference_step_time(model_name: str, batch: int, steps: int, warmup: int):
+    """Times the reference's training step (train.py:122-150 restated: forward+loss, backward, AdamW, zero_grad) on all
+    host threads, fp32 (CUDA autocast self-disables without CUDA).  Uses the unmodified reference from oracle/_ref when
+    staged (kind "reference"), else the oracle port (kind "port").  Returns (images/s, cores, s/step, kind)."""
+    import torch
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    cfg = O.zoo_config(model_name)
-    sd = O.init_state_dict(cfg, seed=0)
-    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
-    no_decay, decay = O.add_weight_decay_names([(k, tuple(v.shape)) for k, v in sd.items()], 0.05)
-    opt = torch.optim.AdamW([{"params": [params[k] for k in no_decay], "weight_decay": 0.0},
-                             {"params": [params[k] for k in decay], "weight_decay": 0.05}], lr=1e-4, betas=(0.9, 0.95))
-    x = torch.randn(batch, 3, cfg.img_size, cfg.img_size, generator=torch.Generator().manual_seed(1234))
+    ref = load_reference_modules()
+    torch.manual_seed(0)
+    if ref is not None:
+        ref_tae, ref_misc = ref
+        model = ref_tae.__dict__[model_name]()
+        model.train()
+        opt = torch.optim.AdamW(ref_misc.add_weight_decay(model, 0.05, bias_wd=False), lr=1e-4, betas=(0.9, 0.95))
+        S = model.patch_embed.img_size[0]
+
+        def step(x):
+            loss, _ = model(x)
+            loss.backward()
+            opt.step()
+            opt.zero_grad()
+        kind = "reference"
+    else:
+        from oracle import tae_oracle as O
+
+        cfg = O.zoo_config(model_name)
+        sd = O.init_state_dict(cfg, seed=0)
+        params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+        no_decay, decay = O.add_weight_decay_names([(k, tuple(v.shape)) for k, v in sd.items()], 0.05)
+        opt = torch.optim.AdamW([{"params": [params[k] for k in no_decay], "weight_decay": 0.0},
+                                 {"params": [params[k] for k in decay], "weight_decay": 0.05}], lr=1e-4, betas=(0.9, 0.95))
+        S = cfg.img_size
+
+        def step(x):
+            loss, _, _ = O.forward(params, x, cfg, "fp32")
+            loss.backward()
+            opt.step()
+            opt.zero_grad(set_to_none=True)
+        kind = "port"
+    x = torch.randn(batch, 3, S, S, generator=torch.Generator().manual_seed(1234))
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        loss, _, _ = O.forward(params, x, cfg, "fp32")
-        loss.backward()
-        opt.step()
-        opt.zero_grad(set_to_none=True)
+        step(x)
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
     sec = sum(times) / len(times)
-    return batch / sec, cores, sec
+    return batch / sec, cores, sec, kind
 
 
 def run_reference(args):
+    """CPU arm of the driver's ratio: the reference's own implementation on the host cores, bounded sample."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps, warmup = max(1, args.steps), max(0, args.warmup)
-    # bounded: each step is `cpu_batch` images of the same workload; cap the number of CPU steps to stay in minutes
-    steps_run, warm_run = min(steps, 12), min(warmup, 2)  # ~10-15 s of CPU work at ~0.9 s per 2-image step
-    ips, cores, sec = cpu_reference_step_time(args.model, args.cpu_batch, steps_run, warm_run)
+    # bounded: each step is `cpu_batch` images of the same workload; at most 12 timed CPU steps (~1 s each on 2 images)
+    steps_run, warm_run = max(1, min(args.steps, 12)), max(0, min(args.warmup, 2))
+    ips, cores, sec, kind = cpu_reference_step_time(args.model, args.cpu_batch, steps_run, warm_run)
+    what = "unmodified reference tae.py (oracle/_ref)" if kind == "reference" else "oracle port of tae.py"
     line = {
-        "impl": "reference", "metric": "train images/sec at px256 patch16", "value": ips, "unit": "images/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
+        "impl": "reference", "metric": metric_name(args.model), "value": ips, "unit": "images/s",
+        "n_gpus": args.gpus, "steps": steps_run, "warmup": warm_run, "ms_per_step": sec * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.model} training step (fwd+loss+bwd+AdamW), px256", "batch_per_step": args.cpu_batch,
-                   "note": f"bounded sample: {steps_run} timed CPU steps of {args.cpu_batch} images (requested "
-                           f"steps={steps}); reference algorithm = oracle port of tae.py on host cores"},
-        "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
+                   "note": f"bounded sample: {steps_run} timed + {warm_run} warm-up CPU steps of {args.cpu_batch} images "
+                           f"(requested steps={args.steps}, warmup={args.warmup}); {what} on the host cores"},
+        "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": kind,
                          "sample": f"{steps_run} steps x {args.cpu_batch} images, fp32, torch CPU, {cores} threads"},
         "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -174,16 +266,251 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def run_gpu_reference(args):
+    """The UNMODIFIED reference model on cuda:0 (same GPU, same batch, same synthetic inputs, same optimizer settings):
+    the training loop of train.py:122-150 restated around a resident tensor.  Modes: bf16_eager / bf16_compile
+    (torch.autocast(dtype=bfloat16), plain backward; `--compile` as train.py:99-100) and fp16_scaler (exactly as
+    shipped: torch.cuda.amp.autocast() + NativeScalerWithGradNormCount = GradScaler, util/misc.py:245-271).  The
+    per-step loss.item() + synchronize of the reference loop are NOT timed (favourable to the reference).  Prints one
+    JSON line; runs in its own process so that none of it shares a timed region or an allocator with the B200 arm."""
+    import torch
+
+    mode, B = args.ref_mode, args.batch
+    out = {"impl": "gpu_reference", "mode": mode, "model": args.model}
+    ref = load_reference_modules()
+    if ref is None:
+        out["unavailable"] = "oracle/_ref not staged (run oracle/make_ref.sh where /root/reference exists)"
+        print(json.dumps(out), flush=True)
+        return
+    ref_tae, ref_misc = ref
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    def attempt(B):
+        torch.manual_seed(0)
+        model = ref_tae.__dict__[args.model]().to(dev)
+        model.train()
+        net = torch.compile(model) if mode == "bf16_compile" else model
+        opt = torch.optim.AdamW(ref_misc.add_weight_decay(model, 0.05, bias_wd=False), lr=1e-4, betas=(0.9, 0.95), fused=True)
+        scaler = ref_misc.NativeScalerWithGradNormCount() if mode == "fp16_scaler" else None
+        S = model.patch_embed.img_size[0]
+        gen = torch.Generator().manual_seed(1234)
+        xs = [torch.randn(B, 3, S, S, generator=gen).to(dev) for _ in range(2)]
+
+        def step(i):
+            ref_misc.adjust_learning_rate(opt, 1e-4, 1e-5, i, 450_000)
+            if scaler is not None:
+                with torch.cuda.amp.autocast():
+                    loss, _ = net(xs[i % 2])
+                scaler(loss, opt, parameters=model.parameters(), update_grad=True)
+            else:
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    loss, _ = net(xs[i % 2])
+                loss.backward()
+                opt.step()
+            opt.zero_grad()
+            return loss
+
+        t0 = time.perf_counter()
+        for i in range(max(3, args.warmup)):
+            loss = step(i)
+        torch.cuda.synchronize()
+        warm_s = time.perf_counter() - t0
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            loss = step(i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        return {"value": B / (ms / 1e3), "unit": "images/s", "ms_per_step": ms, "batch": B, "steps": args.steps,
+                "warmup_s": warm_s, "final_loss": float(loss), "torch": torch.__version__,
+                "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}
+
+    import gc
+
+    while B >= 16:
+        oom = False
+        try:
+            out.update(attempt(B))
+        except torch.OutOfMemoryError:
+            oom = True
+        except Exception as e:  # e.g. torch.compile not functional on the box
+            out["unavailable"] = f"{type(e).__name__}: {str(e)[:300]}"
+        if not oom:
+            break
+        gc.collect()
+        torch.cuda.empty_cache()
+        B //= 2
+        out["note"] = f"out of memory at the benchmark batch; re-run at batch {B}"
+    print(json.dumps(out), flush=True)
+
+
+def gpu_reference_legs(args, modes, steps=8, timeout_s=420):
+    """Runs `--impl gpu_reference` once per mode in a subprocess (after this process has released its GPU memory)."""
+    res = {}
+    for mode in modes:
+        cmd = [sys.executable, os.path.abspath(__file__), "--impl", "gpu_reference", "--ref-mode", mode, "--model", args.model,
+               "--batch", str(args.batch), "--steps", str(steps), "--warmup", "3"]
+        env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT")}
+        t0 = time.perf_counter()
+        try:
+            p = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout_s, env=env)
+            line = next((l for l in reversed(p.stdout.splitlines()) if l.startswith("{")), None)
+            res[mode] = json.loads(line) if line else {"unavailable": f"rc {p.returncode}: {p.stderr[-300:]}"}
+        except subprocess.TimeoutExpired:
+            res[mode] = {"unavailable": f"timed out after {timeout_s} s"}
+        res[mode]["wall_s"] = time.perf_counter() - t0
+        for k in ("impl", "mode", "model"):
+            res[mode].pop(k, None)
+    return res
+
+
 # ----------------------------------------------------------------------------------------------------
 # B200 arm
 # ----------------------------------------------------------------------------------------------------
+class Dist:
+    """Rank plumbing shared by the measurement helpers."""
+
+    def __init__(self, torch, dist, dev, world, rank):
+        self.torch, self.dist, self.dev, self.world, self.rank = torch, dist, dev, world, rank
+
+    def sync_all(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+            self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, ms: float) -> float:
+        t = self.torch.tensor([ms], device=self.dev, dtype=self.torch.float64)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t)
+
+
+def bench_train(D: Dist, model_name, B, steps, warmup, *, want_roofline, want_clocks, use_graph=False):
+    """One training workload: resident-input region, end-to-end region, resident region repeated, optional per-kernel
+    roofline pass, data-parallel consistency check.  Returns a dict (every rank runs it; rank 0's is reported)."""
+    torch, dist = D.torch, D.dist
+    from tae_b200 import engine, misc, ops
+    from tae_b200.ddp import DistributedDataParallel
+
+    world, rank, dev = D.world, D.rank, D.dev
+    torch.manual_seed(0)
+    model = engine.build_model(model_name, dev)
+    model.train()
+    N, Dm, L, V, S = model_dims(model)
+    optimizer = engine.build_optimizer(model, max_lr=1e-4, weight_decay=0.05)
+    scaler = misc.NativeScalerWithGradNormCount(compute_norm=False)
+    net = DistributedDataParallel(model, optimizer=optimizer) if world > 1 else model
+
+    gen = torch.Generator(device="cpu").manual_seed(1234 + rank)
+    n_host = 2
+    host = [torch.randn(B, 3, S, S, generator=gen).pin_memory() for _ in range(n_host)]
+    resident = [h.to(dev) for h in host]
+    graphed = None
+    if use_graph and world == 1:
+        graphed = engine.GraphedTrainStep(model, optimizer, resident[0], warmup_steps=min(2, warmup))
+
+    def step_on(x, i):
+        if graphed is not None:
+            return graphed(x, i)
+        return engine.train_step(net, optimizer, scaler, x, i)
+
+    for i in range(max(warmup, 3 if graphed is not None else 0)):
+        step_on(resident[i % n_host], i)
+    D.sync_all()
+
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed_resident():
+        e0.record()
+        for i in range(steps):
+            loss = step_on(resident[i % n_host], i)
+        e1.record()
+        D.sync_all()
+        return D.max_over_ranks(e0.elapsed_time(e1)), loss
+
+    # ---- timed region 1: inputs resident in HBM (the line's `value`) ----
+    sampler = ClockSampler(dev.index) if (want_clocks and rank == 0) else None
+    if sampler:
+        sampler.start()
+    l0 = ops.launch_count()
+    ms_total, loss = timed_resident()
+    launches = ops.launch_count() - l0
+    if graphed is not None:
+        launches = graphed.launches_per_step * steps  # replayed from the captured graph: counted at capture time
+    clocks = sampler.stop() if sampler else None
+    final_loss = float(loss)
+
+    # ---- timed region 2: end to end through the public API, host buffers ----
+    feeder = engine.HostBatchFeeder(host, dev)
+    loss_host = torch.zeros(steps, dtype=torch.float32).pin_memory()
+    D.sync_all()
+    e0.record()
+    for i in range(steps):
+        x = feeder.next()
+        loss = step_on(x, i)
+        feeder.release()
+        loss_host[i:i + 1].copy_(loss.reshape(1), non_blocking=True)  # D2H read of the step's result
+    e1.record()
+    D.sync_all()
+    ms_e2e = D.max_over_ranks(e0.elapsed_time(e1))
+    assert all(map(lambda v: v == v, loss_host.tolist())), "non-finite loss in e2e region"
+
+    # ---- region 1 again: the two regions run back to back under a power cap, so their order biases them; the repeat
+    # brackets the end-to-end region (VERDICT r1 'weak' 12) ----
+    ms_repeat, _ = timed_resident()
+
+    # ---- data-parallel consistency: parameter checksums must agree across ranks (train.py:102 keeps replicas equal) ----
+    ddp_check = None
+    if world > 1:
+        sums = torch.stack([torch.stack([ar.p.double().sum(), ar.p.view(torch.int32).sum(dtype=torch.int64).double()])
+                            for ar in optimizer.arenas])
+        hi, lo = sums.clone(), sums.clone()
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        ddp_check = {"max_abs_delta": float((hi - lo)[:, 0].abs().max()), "bit_identical": bool(((hi - lo)[:, 1] == 0).all())}
+
+    roof = detail = None
+    if want_roofline:
+        # every rank runs the instrumented steps (they contain collectives); only rank 0 reports
+        roof, detail = kernel_rooflines(torch, ops, lambda i: engine.train_step(net, optimizer, scaler, resident[i % n_host], i),
+                                        measured_peaks())
+    if world > 1:
+        dist.barrier()
+    fpi = train_flops_per_image(N, Dm, L, V, S)
+    ips = world * B * steps / (ms_total / 1e3)
+    peaks = measured_peaks()
+    res = {
+        "metric": metric_name(model_name), "model": model_name, "value": ips, "unit": "images/s",
+        "ms_per_step": ms_total / steps, "steps": steps, "warmup": warmup, "batch_per_gpu": B, "tokens_per_image": N,
+        "final_loss": final_loss,
+        "value_repeat": world * B * steps / (ms_repeat / 1e3),
+        "e2e": {"value": world * B * steps / (ms_e2e / 1e3), "unit": "images/s", "h2d_bytes_per_step": feeder.bytes_per_batch,
+                "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / steps},
+        "model_tflops_per_gpu": fpi * ips / world / 1e12,
+        "frac_of_bf16_peak_sustained": fpi * ips / world / 1e12 / peaks["bf16_tflops_sustained"],
+        "gpu_launches": int(launches), "clocks": clocks, "graph": graphed is not None,
+    }
+    if ddp_check is not None:
+        res["ddp_check"] = ddp_check["max_abs_delta"]
+        res["ddp_check_detail"] = ddp_check
+    if roof is not None:
+        res["roofline"], res["roofline_detail"] = roof, detail
+    # release everything this workload held before the next one is built
+    del feeder, graphed, net, optimizer, model, resident, host
+    import gc
+
+    gc.collect()
+    torch.cuda.empty_cache()
+    return res
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
 
-    from oracle import tae_oracle as O  # config table + FLOP model only; never on the timed path
-    from tae_b200 import _lib, engine, misc, ops
-    from tae_b200.ddp import DistributedDataParallel
+    from tae_b200 import _lib, engine
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -197,127 +524,87 @@ def run_b200(args):
         # short collective timeout: a rank mismatch must abort in minutes, not hang the box
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=240))
     _lib.require_device()
-    cfg = O.zoo_config(args.model)
+    D = Dist(torch, dist, dev, world, rank)
     B = args.batch
 
-    torch.manual_seed(0)
-    model = engine.build_model(args.model, dev)
-    model.train()
-    optimizer = engine.build_optimizer(model, max_lr=1e-4, weight_decay=0.05)
-    scaler = misc.NativeScalerWithGradNormCount(compute_norm=False)
-    net = DistributedDataParallel(model, optimizer=optimizer) if world > 1 else model
-
-    gen = torch.Generator(device="cpu").manual_seed(1234 + rank)
-    n_host = 2
-    host = [torch.randn(B, 3, cfg.img_size, cfg.img_size, generator=gen).pin_memory() for _ in range(n_host)]
-    resident = [h.to(dev) for h in host]
-
-    def sync_all():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    def step_resident(i):
-        return engine.train_step(net, optimizer, scaler, resident[i % n_host], i)
-
-    for i in range(args.warmup):
-        step_resident(i)
-    sync_all()
-
-    # ---- timed region 1: inputs resident in HBM ----
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    l0 = ops.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args.steps):
-        loss = step_resident(i)
-    e1.record()
-    sync_all()
-    launches = ops.launch_count() - l0
-    clocks = sampler.stop() if rank == 0 else None
-    ms = e0.elapsed_time(e1)
-    t = torch.tensor([ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t)
-    final_loss = float(loss)
-
-    # ---- timed region 2: end to end through the public API, host buffers ----
-    feeder = engine.HostBatchFeeder(host, dev)
-    loss_host = torch.zeros(args.steps, dtype=torch.float32).pin_memory()
-    sync_all()
-    e0.record()
-    for i in range(args.steps):
-        x = feeder.next()
-        loss = engine.train_step(net, optimizer, scaler, x, i)
-        feeder.release()
-        loss_host[i:i + 1].copy_(loss.reshape(1), non_blocking=True)  # D2H read of the step's result
-    e1.record()
-    sync_all()
-    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_e2e = float(t)
-    assert all(map(lambda v: v == v, loss_host.tolist())), "non-finite loss in e2e region"
-
-    # ---- roofline of the dominant kernel (the tcgen05 GEMM), instrumented pass after the timed regions ----
-    roof, detail = None, None
-    if not args.no_roofline:
-        # every rank runs the instrumented steps (they contain collectives); only rank 0 reports
-        roof, detail = gemm_roofline(torch, ops, lambda i: step_resident(i), measured_peaks())
-    if world > 1:
-        dist.barrier()
-
-    enc = None
-    if not args.no_encode:
-        optimizer.zero_grad()
-        torch.cuda.empty_cache()
-        enc = encode_throughput(torch, dist, engine, args.encode_model, B, dev, world)
-
-    ips = world * B * args.steps / (ms_total / 1e3)
-    ips_e2e = world * B * args.steps / (ms_e2e / 1e3)
-    if rank != 0:
+    if args.mode == "encode":  # config 5 as the headline of this invocation
+        enc = encode_throughput(torch, dist, engine, args.model, B, dev, world, iters=args.steps, warmup=args.warmup)
+        if rank == 0:
+            print(json.dumps({
+                "metric": metric_name(args.model, "encode"), "value": enc["value"], "unit": "images/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": enc["ms_per_step"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": f"{args.model} forward_encoder under no_grad (encode.py:80-88), batch-sharded, no "
+                                       "communication", "batch_per_gpu": B, "parallelism": f"dp{world}",
+                           "l2": "201 MB input batch per step >> 126 MB L2"},
+                "e2e": {"value": enc["e2e"], "unit": "images/s", "h2d_bytes_per_step": enc["h2d_bytes_per_step"],
+                        "d2h_bytes_per_step": enc["d2h_bytes_per_step"]},
+                "gpu_launches": enc["gpu_launches"]}), flush=True)
         if world > 1:
             dist.destroy_process_group()
         return
-    peaks = measured_peaks()
-    fpi = train_flops_per_image(cfg)
+
+    main = bench_train(D, args.model, B, args.steps, args.warmup, want_roofline=not args.no_roofline, want_clocks=True,
+                       use_graph=args.graph)
+    secondary = {}
+    if not args.no_secondary:
+        # BASELINE configs 3 and 4 next to the headline (fewer steps; same regions, no roofline pass)
+        for cfg_no in (3, 4):
+            name = CONFIGS[cfg_no][0]
+            if name == args.model:
+                continue
+            r = bench_train(D, name, B, max(3, min(args.steps, 6)), 3, want_roofline=False, want_clocks=False)
+            secondary[f"config{cfg_no}_{name}"] = {k: r[k] for k in ("metric", "value", "unit", "ms_per_step", "steps", "batch_per_gpu",
+                                                                      "e2e", "model_tflops_per_gpu", "frac_of_bf16_peak_sustained",
+                                                                      "gpu_launches", "final_loss", "ddp_check") if k in r}
+    enc = None
+    if not args.no_encode:
+        enc = encode_throughput(torch, dist, engine, CONFIGS[5][0], B, dev, world)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    torch.cuda.empty_cache()
     line = {
-        "metric": "train images/sec at px256 patch16", "value": ips, "unit": "images/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+        "metric": main["metric"], "value": main["value"], "unit": "images/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": main["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": f"{args.model} bf16 training step (fwd+loss+bwd+allreduce+AdamW), px256",
-                   "batch_per_gpu": B, "global_batch": B * world, "tokens_per_image": cfg.num_patches,
+                   "batch_per_gpu": B, "global_batch": B * world, "tokens_per_image": main["tokens_per_image"],
                    "parallelism": f"dp{world}", "l2": "per-step working set (201 MB batch, ~70 GB activations) >> 126 MB L2",
-                   "final_loss": final_loss},
-        "model_tflops_per_gpu": fpi * ips / world / 1e12,
-        "frac_of_bf16_peak_sustained": fpi * ips / world / 1e12 / peaks["bf16_tflops_sustained"],
-        "clocks": clocks,
-        "e2e": {"value": ips_e2e, "unit": "images/s", "h2d_bytes_per_step": feeder.bytes_per_batch,
-                "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": int(launches),
+                   "final_loss": main["final_loss"], "cuda_graph": main["graph"]},
+        "model_tflops_per_gpu": main["model_tflops_per_gpu"],
+        "frac_of_bf16_peak_sustained": main["frac_of_bf16_peak_sustained"],
+        "clocks": main["clocks"], "e2e": main["e2e"], "value_repeat": main["value_repeat"],
+        "gpu_launches": main["gpu_launches"],
     }
-    if roof is not None:
-        line["roofline"] = roof
-        line["roofline_detail"] = detail
+    for k in ("ddp_check", "ddp_check_detail", "roofline", "roofline_detail"):
+        if k in main:
+            line[k] = main[k]
+    if secondary:
+        line["secondary"] = secondary
     if enc is not None:
         line["encode"] = enc
-    if not args.no_cpu_baseline and world == 1:
-        cips, cores, csec = cpu_reference_step_time(args.model, args.cpu_batch, 10, 1)  # ~10 s of CPU work
-        line["cpu_baseline"] = {"value": cips, "unit": "images/s", "cores": cores, "kind": "port",
-                                "sample": f"10 timed steps x {args.cpu_batch} images of the same training step, fp32, oracle port, "
-                                          f"{cores} threads ({csec:.1f} s/step)"}
+    if world == 1:
+        if not args.no_gpu_reference:
+            line["gpu_reference"] = gpu_reference_legs(args, [m for m in args.ref_modes.split(",") if m])
+            best = max((v.get("value", 0.0) for v in line["gpu_reference"].values()), default=0.0)
+            if best > 0:
+                line["gpu_reference"]["speedup_over_best"] = main["value"] / best
+        if not args.no_cpu_baseline:
+            cips, cores, csec, kind = cpu_reference_step_time(args.model, args.cpu_batch, 10, 1)  # ~10 s of CPU work
+            line["cpu_baseline"] = {"value": cips, "unit": "images/s", "cores": cores, "kind": kind,
+                                    "sample": f"10 timed steps x {args.cpu_batch} images of the same training step, fp32, "
+                                              f"{'unmodified reference tae.py' if kind == 'reference' else 'oracle port'}, "
+                                              f"{cores} threads ({csec:.1f} s/step)"}
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
 
 
 def encode_throughput(torch, dist, engine, model_name, B, dev, world, iters=10, warmup=3):
     """BASELINE.json configs[4]: the encode.py path (forward_encoder under no_grad, encode.py:80-88), batch-sharded over
-    the ranks with no communication.  Returns (images/s resident, images/s end-to-end with H2D + latent D2H)."""
+    the ranks with no communication.  Returns images/s resident and end-to-end (H2D of every batch + latent D2H)."""
+    from tae_b200 import ops
     from tae_b200 import tae as T
 
     torch.manual_seed(0)
@@ -326,7 +613,7 @@ def encode_throughput(torch, dist, engine, model_name, B, dev, world, iters=10, 
     model.eval()
     host = [torch.randn(B, 3, 256, 256).pin_memory() for _ in range(2)]
     res = [h.to(dev) for h in host]
-    for i in range(warmup):
+    for i in range(max(3, warmup)):
         z = engine.encode_batch(model, res[i % 2])
     lat_host = torch.empty(z.shape, dtype=z.dtype).pin_memory()
 
@@ -343,9 +630,11 @@ def encode_throughput(torch, dist, engine, model_name, B, dev, world, iters=10, 
         t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return world * B * iters / (float(t) / 1e3)
+        return float(t)
 
-    ips = timed(lambda i: engine.encode_batch(model, res[i % 2]))
+    n0 = ops.launch_count()
+    ms = timed(lambda i: engine.encode_batch(model, res[i % 2]))
+    launches = ops.launch_count() - n0
     feeder = engine.HostBatchFeeder(host, dev)
 
     def e2e_step(i):
@@ -354,14 +643,16 @@ def encode_throughput(torch, dist, engine, model_name, B, dev, world, iters=10, 
         feeder.release()
         lat_host.copy_(z, non_blocking=True)  # encode.py:87 `latents.cpu()`
 
-    ips_e2e = timed(e2e_step)
+    ms_e2e = timed(e2e_step)
     del model
     torch.cuda.empty_cache()
-    return {"metric": "encode images/sec", "model": model_name, "batch_per_gpu": B, "value": ips, "e2e": ips_e2e,
-            "unit": "images/s", "h2d_bytes_per_step": host[0].numel() * 4, "d2h_bytes_per_step": lat_host.numel() * 2}
+    return {"metric": metric_name(model_name, "encode"), "model": model_name, "batch_per_gpu": B,
+            "value": world * B * iters / (ms / 1e3), "e2e": world * B * iters / (ms_e2e / 1e3), "unit": "images/s",
+            "ms_per_step": ms / iters, "h2d_bytes_per_step": host[0].numel() * 4, "d2h_bytes_per_step": lat_host.numel() * 2,
+            "gpu_launches": int(launches)}
 
 
-def gemm_roofline(torch, ops, step_fn, peaks):
+def kernel_rooflines(torch, ops, step_fn, peaks):
     """Per-launch CUDA-event timing of every kernel family during 2 instrumented training steps (after the timed
     regions).  Returns (roofline of the dominant kernel = the tcgen05 GEMM, per-family detail)."""
     records = []
@@ -413,9 +704,10 @@ def gemm_roofline(torch, ops, step_fn, peaks):
         # loss: pred bf16 + imgs fp32 (+ dpred bf16)
         "mse_loss": wrap("mse_loss", lambda pred, imgs, p, **k: (8.0 if k.get("want_grad") else 6.0) * pred.numel(), "hbm"),
         "im2col": wrap("im2col", lambda imgs, p: 6.0 * imgs.numel(), "hbm"),
-        # attention: 4 N^2 hd flops per (image, head) forward; backward counted algorithmically as 2.5x (5 GEMMs vs 2)
+        # attention: 4 N^2 hd flops per (image, head) forward; backward counted algorithmically as 2x forward
+        # (recomputation of the scores is not credited)
         "attention_fwd": wrap("attention_fwd", lambda qkv, B, N, H, hd: 4.0 * B * H * N * N * hd, "tensor"),
-        "attention_bwd": wrap("attention_bwd", lambda qkv, o, do, lse, B, N, H, hd, **k: 10.0 * B * H * N * N * hd, "tensor"),
+        "attention_bwd": wrap("attention_bwd", lambda qkv, o, do, lse, B, N, H, hd, **k: 8.0 * B * H * N * N * hd, "tensor"),
     }
     ops.gemm = timed_gemm
     try:
@@ -440,14 +732,23 @@ def gemm_roofline(torch, ops, step_fn, peaks):
         tot_by += by
     achieved = tot_fl / (tot_ms * 1e-3) / 1e12
     peak = peaks["bf16_tflops_sustained"]
+    # ncu evidence (dram__bytes_read.sum + dram__bytes_write.sum per launch) is quoted only when it was captured from
+    # the very GEMM sources this library was built from
     traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    if os.path.exists(tpath):  # committed ncu evidence (dram__bytes_read.sum + dram__bytes_write.sum per launch)
+    fp = gemm_sources_fingerprint()
+    for tname in ("r2_traffic.json", "r1_traffic.json"):
+        tpath = os.path.join(ROOT, "profiles", tname)
+        if not os.path.exists(tpath):
+            continue
         with open(tpath) as f:
             tj = json.load(f)
         k = tj["kernels"].get("gemm_bf16_tcgen05")
-        if k:
-            traffic, traffic_src = k["dram_bytes_per_launch"], "profiles/r1_traffic.json: " + tj["source"]
+        if k and tj.get("gemm_sources_fingerprint") == fp:
+            traffic, traffic_src = k["dram_bytes_per_launch"], f"profiles/{tname}: " + tj["source"]
+        else:
+            traffic_src = (f"profiles/{tname} was captured from other GEMM sources (fingerprint "
+                           f"{tj.get('gemm_sources_fingerprint')} != {fp}); not quoted")
+        break
     roof = {"bound": "tensor", "kernel": "gemm_bf16_tcgen05 (all epilogue instantiations)", "achieved": achieved,
             "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
             "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a long step)",
@@ -477,6 +778,8 @@ def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "gpu_reference":
+        run_gpu_reference(args)
     else:
         run_b200(args)
 

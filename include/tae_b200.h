@@ -38,6 +38,7 @@ typedef uint16_t tae_bf16;
 
 /* ---- library / device ------------------------------------------------------------------- */
 int tae_version(void);                       /* ABI version, currently 1 */
+const char* tae_build_fingerprint(void);     /* sha256 of the sources the library was built from ("unknown" if unset) */
 const char* tae_last_error_string(void);     /* thread-local, never NULL */
 int tae_device_check(void);                  /* 0 iff current device is sm_100 (B200) */
 int tae_num_sms(void);                       /* SM count of the current device (148 on B200), <0 on error */
@@ -213,6 +214,16 @@ int tae_token_mean_bwd_f32(const float* dy, float* dx, int32_t B, int32_t N, int
 int tae_adamw_step(float* p, const float* g, float* m, float* v, tae_bf16* p_bf16, size_t n,
                    float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step,
                    float grad_scale, float* grad_sq_sum, const int32_t* found_inf, void* stream);
+/* The same step with its scalars in DEVICE memory, so that a CUDA graph of the whole training step (train.py:122-150)
+ * can be replayed with a new learning rate (util/misc.py:400-412 writes it every iteration) and step count:
+ * tae_adamw_hyper is a HOST function that fills `out[TAE_ADAMW_HYPER_FLOATS]` with the derived scalars (the very ones
+ * tae_adamw_step computes internally — both paths are bit-identical); the caller copies them to the device and passes
+ * that pointer as `hyper_dev`. */
+#define TAE_ADAMW_HYPER_FLOATS 9
+int tae_adamw_hyper(float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step,
+                    float grad_scale, float* out);
+int tae_adamw_step_dev(float* p, const float* g, float* m, float* v, tae_bf16* p_bf16, size_t n,
+                       const float* hyper_dev, float* grad_sq_sum, const int32_t* found_inf, void* stream);
 /* dst = bf16(src), n elements */
 int tae_cast_f32_to_bf16(const float* src, tae_bf16* dst, size_t n, void* stream);
 /* non-finite check + sum of squares over a fp32 arena: found_inf[0] |= any(!isfinite), sq_sum[0] += sum g^2 */

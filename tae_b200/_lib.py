@@ -56,6 +56,7 @@ _vp, _i32, _f32, _sz = C.c_void_p, C.c_int32, C.c_float, C.c_size_t
 # name -> (restype, argtypes); every symbol include/tae_b200.h declares
 PROTOTYPES = {
     "tae_version": (C.c_int, []),
+    "tae_build_fingerprint": (C.c_char_p, []),
     "tae_last_error_string": (C.c_char_p, []),
     "tae_device_check": (C.c_int, []),
     "tae_num_sms": (C.c_int, []),
@@ -78,6 +79,8 @@ PROTOTYPES = {
     "tae_colsum_f32": (C.c_int, [_vp, _i32, _i32, _vp, _i32, _vp]),
     "tae_batch_sum_f32": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _i32, _vp]),
     "tae_adamw_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _sz, _f32, _f32, _f32, _f32, _f32, _i32, _f32, _vp, _vp, _vp]),
+    "tae_adamw_hyper": (C.c_int, [_f32, _f32, _f32, _f32, _f32, _i32, _f32, C.POINTER(C.c_float)]),
+    "tae_adamw_step_dev": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp, _vp, _vp]),
     "tae_cast_f32_to_bf16": (C.c_int, [_vp, _vp, _sz, _vp]),
     "tae_grad_stats": (C.c_int, [_vp, _sz, _vp, _vp, _vp]),
     "tae_patchify_c": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
@@ -120,9 +123,19 @@ def load(build_if_missing: bool = True) -> C.CDLL:
         path = LIB_PATH
     lib = C.CDLL(os.fspath(path))
     for name, (res, args) in PROTOTYPES.items():
-        fn = getattr(lib, name)
+        fn = getattr(lib, name, None)
+        if fn is None:
+            raise TaeError(f"{path} does not export {name}: it was built from other sources — rebuild it "
+                           "(`python -m tae_b200.build --force`, variants: tools/build_variants.sh)")
         fn.restype = res
         fn.argtypes = args
+    # a library built from other sources may disagree about struct layouts and prototypes: refuse it
+    from . import build as _build
+
+    built_from, have = lib.tae_build_fingerprint().decode(), _build.fingerprint()
+    if built_from != have and os.environ.get("TAE_ALLOW_STALE_LIB") != "1":
+        raise TaeError(f"{path} was built from sources with fingerprint {built_from[:12]}, the checkout has {have[:12]}: "
+                       "rebuild it (`python -m tae_b200.build --force`), or set TAE_ALLOW_STALE_LIB=1 to load it anyway")
     _lib = lib
     return lib
 

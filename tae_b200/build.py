@@ -46,14 +46,20 @@ def _fingerprint() -> str:
     return h.hexdigest()
 
 
+def fingerprint() -> str:
+    return _fingerprint()
+
+
 def build(force: bool = False, verbose: bool = False) -> Path:
     stamp = BUILD_DIR / "fingerprint.txt"
     fp = _fingerprint()
     if not force and LIB_PATH.exists() and stamp.exists() and stamp.read_text() == fp:
         return LIB_PATH
     if not Path(NVCC).exists():
+        # no toolchain: a prebuilt library is only usable if it was built from these very sources — the loader
+        # (tae_b200._lib.load) compares the fingerprint embedded in the .so and raises on a mismatch
         if LIB_PATH.exists():
-            return LIB_PATH  # GPU box without a toolchain change: use the prebuilt library
+            return LIB_PATH
         raise RuntimeError(f"nvcc not found at {NVCC} and {LIB_PATH} is missing")
     BUILD_DIR.mkdir(parents=True, exist_ok=True)
     # One builder at a time (torchrun starts one process per GPU, all of which import the package): the others block
@@ -72,7 +78,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 def _build_locked(fp: str, stamp: Path, verbose: bool) -> Path:
     def compile_one(src: Path) -> Path:
         obj = BUILD_DIR / (src.stem + ".o")
-        cmd = [NVCC, *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
+        cmd = [NVCC, *NVCC_FLAGS, f'-DTAE_SRC_FINGERPRINT="{fp}"', "-c", str(src), "-o", str(obj)]
         if verbose:
             cmd.insert(1, "-Xptxas")
             cmd.insert(2, "-v")
@@ -102,10 +108,11 @@ def build_variant(name: str, defines: list[str], verbose: bool = False) -> Path:
     out_dir = BUILD_DIR / name
     out_dir.mkdir(parents=True, exist_ok=True)
     lib = PKG_DIR / f"libtae_b200.{name}.so"
+    fp = _fingerprint()
 
     def compile_one(src: Path) -> Path:
         obj = out_dir / (src.stem + ".o")
-        cmd = [NVCC, *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-c", str(src), "-o", str(obj)]
+        cmd = [NVCC, *NVCC_FLAGS, f'-DTAE_SRC_FINGERPRINT="{fp}"', *[f"-D{d}" for d in defines], "-c", str(src), "-o", str(obj)]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src.name}:\n{res.stdout}\n{res.stderr}")

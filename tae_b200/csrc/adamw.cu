@@ -5,6 +5,7 @@
 // p, g, m, v, writes p, m, v and the bf16 shadow copy the GEMMs consume, optionally accumulating sum(g^2)
 // and honouring a device-side found_inf flag (GradScaler.step skip semantics).
 #include <math.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -29,10 +30,14 @@ __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, 
   p -= a.step_size * (m / denom);
 }
 
+// `dev_args` != nullptr: the step's scalars live in device memory (9 floats written by tae_adamw_hyper + a copy), so a
+// captured CUDA graph of the training step can be replayed with a new lr / step count without re-capturing.
 __global__ void __launch_bounds__(256)
 adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-             bf16* __restrict__ pb, size_t n, AdamArgs a, float* grad_sq_sum, const int* __restrict__ found_inf) {
+             bf16* __restrict__ pb, size_t n, AdamArgs a, const AdamArgs* __restrict__ dev_args, float* grad_sq_sum,
+             const int* __restrict__ found_inf) {
   if (found_inf != nullptr && *found_inf != 0) return;
+  if (dev_args != nullptr) a = *dev_args;
   const size_t n4 = n / 4;
   float sq = 0.f;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
@@ -144,18 +149,14 @@ static int flat_grid(size_t nvec) {
 }  // namespace opt
 }  // namespace tae
 
-extern "C" int tae_adamw_step(float* p, const float* g, float* m, float* v, tae_bf16* p_bf16, size_t n, float lr,
-                              float beta1, float beta2, float eps, float weight_decay, int32_t step, float grad_scale,
-                              float* grad_sq_sum, const int32_t* found_inf, void* stream_) {
+static_assert(sizeof(tae::opt::AdamArgs) == TAE_ADAMW_HYPER_FLOATS * sizeof(float), "tae_adamw_hyper layout");
+
+extern "C" int tae_adamw_hyper(float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step,
+                               float grad_scale, float* out) {
   using namespace tae;
   using namespace tae::opt;
-  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  if (n == 0) return TAE_OK;
-  TAE_CHECK_SHAPE(p && g && m && v, "tae_adamw_step: NULL arena");
-  TAE_CHECK_SHAPE(step >= 1, "tae_adamw_step: step must be >= 1 (got %d)", step);
-  TAE_CHECK_SHAPE(((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
-                    reinterpret_cast<uintptr_t>(v)) & 15) == 0 && (reinterpret_cast<uintptr_t>(p_bf16) & 7) == 0,
-                  "tae_adamw_step: arenas must be 16-byte aligned");
+  TAE_CHECK_SHAPE(out != nullptr, "tae_adamw_hyper: NULL output");
+  TAE_CHECK_SHAPE(step >= 1, "tae_adamw_hyper: step must be >= 1 (got %d)", step);
   AdamArgs a;
   const double bc1 = 1.0 - pow((double)beta1, (double)step);
   const double bc2 = 1.0 - pow((double)beta2, (double)step);
@@ -168,10 +169,45 @@ extern "C" int tae_adamw_step(float* p, const float* g, float* m, float* v, tae_
   a.inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
   a.eps = eps;
   a.grad_scale = grad_scale;
+  memcpy(out, &a, sizeof(a));
+  return TAE_OK;
+}
+
+static int adamw_launch(float* p, const float* g, float* m, float* v, tae_bf16* p_bf16, size_t n,
+                        const tae::opt::AdamArgs& a, const float* dev_hyper, float* grad_sq_sum,
+                        const int32_t* found_inf, void* stream_) {
+  using namespace tae;
+  using namespace tae::opt;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  TAE_CHECK_SHAPE(p && g && m && v, "tae_adamw_step: NULL arena");
+  TAE_CHECK_SHAPE(((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                    reinterpret_cast<uintptr_t>(v)) & 15) == 0 && (reinterpret_cast<uintptr_t>(p_bf16) & 7) == 0 &&
+                      (reinterpret_cast<uintptr_t>(dev_hyper) & 3) == 0,
+                  "tae_adamw_step: arenas must be 16-byte aligned");
   adamw_kernel<<<flat_grid(n / 4 + 1), 256, 0, stream>>>(p, g, m, v, reinterpret_cast<bf16*>(p_bf16), n, a,
-                                                          grad_sq_sum, reinterpret_cast<const int*>(found_inf));
+                                                          reinterpret_cast<const AdamArgs*>(dev_hyper), grad_sq_sum,
+                                                          reinterpret_cast<const int*>(found_inf));
   TAE_CHECK_LAUNCH();
   return TAE_OK;
+}
+
+extern "C" int tae_adamw_step(float* p, const float* g, float* m, float* v, tae_bf16* p_bf16, size_t n, float lr,
+                              float beta1, float beta2, float eps, float weight_decay, int32_t step, float grad_scale,
+                              float* grad_sq_sum, const int32_t* found_inf, void* stream_) {
+  if (n == 0) return TAE_OK;
+  tae::opt::AdamArgs a;
+  const int rc = tae_adamw_hyper(lr, beta1, beta2, eps, weight_decay, step, grad_scale, reinterpret_cast<float*>(&a));
+  if (rc != TAE_OK) return rc;
+  return adamw_launch(p, g, m, v, p_bf16, n, a, nullptr, grad_sq_sum, found_inf, stream_);
+}
+
+extern "C" int tae_adamw_step_dev(float* p, const float* g, float* m, float* v, tae_bf16* p_bf16, size_t n,
+                                  const float* hyper_dev, float* grad_sq_sum, const int32_t* found_inf, void* stream_) {
+  using namespace tae;
+  if (n == 0) return TAE_OK;
+  TAE_CHECK_SHAPE(hyper_dev != nullptr, "tae_adamw_step_dev: NULL hyper-parameter block");
+  tae::opt::AdamArgs a = {};
+  return adamw_launch(p, g, m, v, p_bf16, n, a, hyper_dev, grad_sq_sum, found_inf, stream_);
 }
 
 extern "C" int tae_cast_f32_to_bf16(const float* src, tae_bf16* dst, size_t n, void* stream_) {

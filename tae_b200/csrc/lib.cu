@@ -83,6 +83,13 @@ int* sched_counter_slot() {
 
 extern "C" int tae_version(void) { return 1; }
 
+// Hash of the sources this library was compiled from (tae_b200/build.py passes it): the loader refuses a library whose
+// sources differ from the checkout's, because a changed `tae_gemm_args` layout would silently corrupt arguments.
+#ifndef TAE_SRC_FINGERPRINT
+#define TAE_SRC_FINGERPRINT "unknown"
+#endif
+extern "C" const char* tae_build_fingerprint(void) { return TAE_SRC_FINGERPRINT; }
+
 extern "C" const char* tae_last_error_string(void) { return tae::tl_error; }
 
 extern "C" int tae_num_sms(void) {

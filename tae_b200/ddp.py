@@ -27,10 +27,15 @@ from torch.autograd import Variable
 
 
 class _Bucket:
-    __slots__ = ("flat", "params", "pending", "work")
+    __slots__ = ("flat", "params", "pending", "work", "seen")
 
     def __init__(self, flat, params):
-        self.flat, self.params, self.pending, self.work = flat, params, len(params), None
+        self.flat, self.params, self.work, self.seen = flat, params, None, set()
+        self.pending = len(params)
+
+    def rearm(self):
+        self.pending, self.work = len(self.params), None
+        self.seen.clear()
 
 
 def plan_buckets(order, offsets, numel_of, bucket_elems):
@@ -112,10 +117,8 @@ class DistributedDataParallel(nn.Module):
     def forward(self, *args, **kwargs):
         if torch.is_grad_enabled() and self.world_size > 1:
             self._lazy_attach()
-            for b in self._buckets:
-                b.pending = len(b.params)
-                b.work = None
-            self._callback_queued = False
+            if self._launched:
+                raise RuntimeError("tae_b200.DistributedDataParallel: a previous backward left reduced buckets un-finalised")
         elif self._needs_broadcast and self._optimizer is None:
             # inference-only replica: broadcast the plain parameters once
             for p in self.module.parameters():
@@ -141,6 +144,13 @@ class DistributedDataParallel(nn.Module):
             Variable._execution_engine.queue_callback(self._finalize_backward)
             self._callback_queued = True
         b = p._tae_bucket
+        if id(p) in b.seen:
+            # a parameter used twice in one forward reports twice; its bucket must not have left yet
+            if b.work is not None:
+                raise RuntimeError("tae_b200.DistributedDataParallel: a gradient arrived after its bucket had been "
+                                   "all-reduced (parameter shared between modules?) — replicas would diverge")
+            return
+        b.seen.add(id(p))
         b.pending -= 1
         if b.pending == 0:
             self._launch(b)
@@ -169,6 +179,10 @@ class DistributedDataParallel(nn.Module):
             torch.cuda.current_stream().wait_stream(self._comm_stream)
         self._launched.clear()
         self._callback_queued = False
+        # re-arm here, not in forward(): a training forward through the unwrapped module, or several forwards before
+        # one backward, must find the bookkeeping fresh (every backward that produced a gradient ends in this callback)
+        for b in self._buckets:
+            b.rearm()
 
     # -- nn.Module plumbing so that checkpoints hold the unwrapped names --------------------------------
     def state_dict(self, *args, **kwargs):

@@ -3,6 +3,7 @@
   train_step        train.py:122-150   lr schedule -> forward -> backward (+ bucketed all-reduce) -> AdamW -> zero_grad
   evaluate_batch    train.py:203-223 / evaluate.py:84-102   forward under no_grad, loss only
   encode_batch      encode.py:80-88    forward_encoder under no_grad
+  GraphedTrainStep  the same iteration captured once as a CUDA graph and replayed
   HostBatchFeeder   train.py:134 / encode.py:82   pinned-host -> device copies, double-buffered on a copy stream
                     (the synchronous 201 MB H2D per step is the adjacent host overhead)
   shard_for_rank    batch sharding for multi-GPU encode / evaluate (no communication; rank r takes slice r)
@@ -55,6 +56,70 @@ def train_step(model, optimizer, loss_scaler, samples, it: int, *, max_lr=1e-4, 
     if update:
         optimizer.zero_grad()
     return loss.detach()
+
+
+class GraphedTrainStep:
+    """train_step() captured ONCE as a CUDA graph (forward, loss, hand-written backward, fused AdamW, zero_grad) and
+    replayed per iteration: ~1200 kernel launches (patch16) leave the host as one `cudaGraphLaunch`.
+
+    What makes the step capturable: every kernel of the path is launched by the C ABI on the current stream with no
+    allocation, synchronisation or host read-back; activations come from the graph's private memory pool; the optimizer's
+    scalars (lr from adjust_learning_rate, bias corrections) live in device memory (`FusedAdamW.make_capturable`).  The
+    first `warmup_steps` calls run eagerly (they are real training steps), the next one captures.  Single process only:
+    with data parallelism use the eager step (the bucketed all-reduce is driven from autograd callbacks).
+
+        step = GraphedTrainStep(model, optimizer, example_batch, max_lr=1e-4, min_lr=1e-5, switch_it=450_000)
+        for it, samples in enumerate(loader): loss = step(samples, it)      # device tensor, no host sync
+    """
+
+    def __init__(self, model, optimizer, example, *, max_lr=1e-4, min_lr=1e-5, switch_it=450_000, warmup_steps=3):
+        if misc.get_world_size() > 1:
+            raise RuntimeError("GraphedTrainStep is single-process; use train_step under tae_b200.ddp")
+        self.model, self.optimizer = model, optimizer
+        self.sched = (max_lr, min_lr, switch_it)
+        self.warmup_steps = warmup_steps
+        self.static_in = torch.empty_like(example)
+        self.static_loss = None
+        self.graph = None
+        self.calls = 0
+        self.launches_per_step = 0
+        self._scaler = misc.NativeScalerWithGradNormCount(compute_norm=False)
+        optimizer.make_capturable()
+
+    @property
+    def captured(self) -> bool:
+        return self.graph is not None
+
+    def _capture(self):
+        from . import ops
+
+        model, opt = self.model, self.optimizer
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()  # the eager warm-up's cached activations and the graph's pool must not both stay resident
+        n0 = ops.launch_count()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            loss, _ = model(self.static_in)
+            self._scaler(loss, opt, parameters=None, update_grad=True)
+            opt.zero_grad()
+            self.static_loss = loss.detach()
+        self.launches_per_step = ops.launch_count() - n0
+        self.graph = g
+
+    def __call__(self, samples, it: int):
+        misc.adjust_learning_rate(self.optimizer, self.sched[0], self.sched[1], it, self.sched[2])
+        self.calls += 1
+        if self.calls <= self.warmup_steps:
+            loss, _ = self.model(samples)
+            self._scaler(loss, self.optimizer, parameters=None, update_grad=True)
+            self.optimizer.zero_grad()
+            return loss.detach()
+        if self.graph is None:
+            self._capture()
+        self.static_in.copy_(samples, non_blocking=True)
+        self.optimizer.prepare_step()
+        self.graph.replay()
+        return self.static_loss.clone()
 
 
 @torch.no_grad()

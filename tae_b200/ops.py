@@ -364,6 +364,25 @@ def adamw_step(p, g, m, v, p_bf16, *, lr, beta1, beta2, eps, weight_decay, step,
                               _ptr(grad_sq_sum), _ptr(found_inf), _stream()), "tae_adamw_step")
 
 
+ADAMW_HYPER_FLOATS = 9
+
+
+def adamw_hyper(*, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0) -> list:
+    """Host side of the device-scalar AdamW step: the 9 derived floats `tae_adamw_step_dev` reads from device memory."""
+    buf = (C.c_float * ADAMW_HYPER_FLOATS)()
+    check(_L().tae_adamw_hyper(float(lr), float(beta1), float(beta2), float(eps), float(weight_decay), int(step),
+                               float(grad_scale), buf), "tae_adamw_hyper")
+    return list(buf)
+
+
+def adamw_step_dev(p, g, m, v, p_bf16, hyper_dev: torch.Tensor, *, grad_sq_sum=None, found_inf=None):
+    """AdamW step whose scalars come from `hyper_dev` (fp32 [9] on the device): replayable inside a CUDA graph."""
+    _req(hyper_dev, f32, "adamw hyper")
+    assert hyper_dev.numel() == ADAMW_HYPER_FLOATS and hyper_dev.is_contiguous()
+    check(_L().tae_adamw_step_dev(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), _ptr(p_bf16), p.numel(),
+                                  hyper_dev.data_ptr(), _ptr(grad_sq_sum), _ptr(found_inf), _stream()), "tae_adamw_step_dev")
+
+
 def grad_stats(g: torch.Tensor, sq_sum: torch.Tensor | None, found_inf: torch.Tensor | None):
     check(_L().tae_grad_stats(g.data_ptr(), g.numel(), _ptr(sq_sum), _ptr(found_inf), _stream()), "tae_grad_stats")
 

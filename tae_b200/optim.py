@@ -40,15 +40,25 @@ class _Arena:
         self.m = torch.zeros(off, dtype=f32, device=dev)
         self.v = torch.zeros(off, dtype=f32, device=dev)
         self.pb = torch.zeros(off, dtype=torch.bfloat16, device=dev)
+        # host-side bookkeeping that lets step() skip the per-parameter walk in the common case: how many parameters
+        # had their gradient written by the hand-written backward since zero_grad(), and whether autograd's own
+        # AccumulateGrad ran for any of them (a torch-native op used the parameter)
+        self.n_direct = 0
+        self.foreign = False
 
     def view(self, arena, p):
         o = self.offsets[id(p)]
         return arena[o:o + p.numel()].view(p.shape)
 
 
+def _foreign_grad_hook(p):
+    """Runs after autograd's AccumulateGrad touched p.grad: the gradient did not come through tae_b200's backward."""
+    p._tae_arena.foreign = True
+
+
 class FusedAdamW(torch.optim.Optimizer):
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, grad_scale=1.0,
-                 track_grad_norm=False, fused=True):
+                 track_grad_norm=False, fused=True, capturable=False):
         if lr < 0 or eps < 0 or not (0 <= betas[0] < 1) or not (0 <= betas[1] < 1) or weight_decay < 0:
             raise ValueError("invalid AdamW hyper-parameters")
         defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
@@ -58,7 +68,10 @@ class FusedAdamW(torch.optim.Optimizer):
         self._arenas = []
         self._steps = []
         self._grad_sq = None
+        self._hyper = None  # capturable mode: [n_groups, 9] derived scalars in device memory (see make_capturable)
         self._build()
+        if capturable:
+            self.make_capturable()
 
     # ------------------------------------------------------------------------------------------
     def _build(self):
@@ -83,9 +96,12 @@ class FusedAdamW(torch.optim.Optimizer):
                     g = ar.view(ar.g, p)
                     if old_grad is not None:
                         g.copy_(old_grad)
-                    p.grad = g
+                    p.grad = g if old_grad is not None else None
                     p._tae_grad = g
+                    p._tae_arena = ar
                     p._tae_dirty = 1 if old_grad is not None else 0
+                    ar.n_direct += p._tae_dirty
+                    p.register_post_accumulate_grad_hook(_foreign_grad_hook)
                     p._tae_bf16 = ar.view(ar.pb, p)
                     p._tae_bf16_version = p._version
                     p._tae_bf16_ptr = p.data_ptr()
@@ -102,12 +118,47 @@ class FusedAdamW(torch.optim.Optimizer):
 
     # ------------------------------------------------------------------------------------------
     def zero_grad(self, set_to_none: bool = True):
-        """Gradients live in the arena permanently; 'zeroing' just arms beta=0 for the next backward's first write."""
+        """Gradients live in the arena permanently; 'zeroing' arms beta=0 for the next backward's first write and drops
+        `p.grad` (as torch's set_to_none=True does).  The hand-written backward re-points `p.grad` at the arena slice
+        when it writes it; a gradient that arrives through autograd's own AccumulateGrad (a torch-native op using the
+        parameter) therefore lands in a fresh tensor, never on stale arena contents, and is folded in by `_sink` /
+        `step()`."""
         for ar in self.arenas:
             for p in ar.params:
                 p._tae_dirty = 0
-                if p.grad is None or p.grad.data_ptr() != p._tae_grad.data_ptr():
-                    p.grad = p._tae_grad
+                p.grad = None
+            ar.n_direct = 0
+            ar.foreign = False
+
+    # ------------------------------------------------------------------------------------------
+    # CUDA-graph support: scalars in device memory
+    @property
+    def capturable(self) -> bool:
+        return self._hyper is not None
+
+    def make_capturable(self):
+        """From now on step() reads lr / bias corrections / weight decay from a device buffer that `prepare_step()`
+        refreshes, so a captured graph of the step can be replayed while `param_groups[i]["lr"]` keeps changing
+        (util/misc.py:400-412).  Results are bit-identical to the host-scalar path (same derived floats)."""
+        if self._hyper is None:
+            dev = next(a.p.device for a in self._arenas if a is not None)
+            self._hyper = torch.zeros((len(self.param_groups), ops.ADAMW_HYPER_FLOATS), dtype=torch.float32, device=dev)
+        return self
+
+    def prepare_step(self):
+        """Advance the step counters and upload this step's scalars (one small H2D copy from pageable memory, which the
+        driver stages before returning — the host may run ahead).  Called by step() itself outside graph capture, and by
+        the owner of a captured graph before every replay."""
+        rows = []
+        for gi, (group, ar) in enumerate(zip(self.param_groups, self._arenas)):
+            if ar is None:
+                rows.append([0.0] * ops.ADAMW_HYPER_FLOATS)
+                continue
+            self._steps[gi] += 1
+            b1, b2 = group["betas"]
+            rows.append(ops.adamw_hyper(lr=group["lr"], beta1=b1, beta2=b2, eps=group["eps"],
+                                        weight_decay=group["weight_decay"], step=self._steps[gi], grad_scale=self.grad_scale))
+        self._hyper.copy_(torch.tensor(rows, dtype=torch.float32), non_blocking=True)
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -117,24 +168,38 @@ class FusedAdamW(torch.optim.Optimizer):
                 loss = closure()
         if self._grad_sq is not None and self.track_grad_norm:
             self._grad_sq.zero_()
+        if self._hyper is not None and not torch.cuda.is_current_stream_capturing():
+            self.prepare_step()
         for gi, (group, ar) in enumerate(zip(self.param_groups, self._arenas)):
             if ar is None:
                 continue
-            for p in ar.params:
-                if p._tae_dirty == 0:
-                    # parameter received no gradient since zero_grad(): its arena slice is stale -> treat as zero
-                    g = p.grad
-                    if g is not None and g.data_ptr() != p._tae_grad.data_ptr():
-                        p._tae_grad.copy_(g)  # a foreign backward produced a separate .grad tensor
-                    else:
-                        p._tae_grad.zero_()
-                elif p.grad is not None and p.grad.data_ptr() != p._tae_grad.data_ptr():
-                    p._tae_grad.add_(p.grad)
+            if ar.foreign or ar.n_direct != len(ar.params):
+                # slow path (never taken by a plain TAE step): fold in gradients that autograd accumulated itself, and
+                # give parameters without any gradient a ZERO gradient.  torch.optim.AdamW skips such parameters
+                # entirely (no weight decay, no moment decay); one launch over a flat arena cannot, so here they decay
+                # as if their gradient were zero — documented difference, irrelevant for TAE (every parameter is used).
+                for p in ar.params:
+                    g, t = p.grad, p._tae_grad
+                    foreign = g is not None and g.data_ptr() != t.data_ptr()
+                    if p._tae_dirty == 0:
+                        if foreign:
+                            t.copy_(g)
+                        else:
+                            t.zero_()
+                    elif foreign:
+                        t.add_(g)
+                    if foreign:
+                        p.grad = t
+                        p._tae_dirty = 1
+            gsq = self._grad_sq if self.track_grad_norm else None
+            if self._hyper is not None:
+                ops.adamw_step_dev(ar.p, ar.g, ar.m, ar.v, ar.pb, self._hyper[gi], grad_sq_sum=gsq)
+                continue
             self._steps[gi] += 1
             b1, b2 = group["betas"]
             ops.adamw_step(ar.p, ar.g, ar.m, ar.v, ar.pb, lr=group["lr"], beta1=b1, beta2=b2, eps=group["eps"],
                            weight_decay=group["weight_decay"], step=self._steps[gi], grad_scale=self.grad_scale,
-                           grad_sq_sum=self._grad_sq if self.track_grad_norm else None)
+                           grad_sq_sum=gsq)
         return loss
 
     def grad_norm(self) -> torch.Tensor:

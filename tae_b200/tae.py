@@ -62,7 +62,17 @@ def _sink(p):
     if t is None:
         return None, 0
     acc = p._tae_dirty
-    p._tae_dirty = 1
+    g = p.grad
+    if g is not t:
+        if g is not None and g.data_ptr() != t.data_ptr():
+            # autograd's AccumulateGrad got here first (a torch-native op also uses this parameter): keep its gradient
+            with torch.no_grad():
+                (t.add_ if acc else t.copy_)(g)
+            acc = 1
+        p.grad = t
+    if not p._tae_dirty:
+        p._tae_dirty = 1
+        p._tae_arena.n_direct += 1
     return t, acc
 
 

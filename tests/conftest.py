@@ -43,3 +43,16 @@ def oracle_cfg(kw):
 
     return O.TAEConfig(kw["img_size"], kw["patch_size"], kw["embed_dim"], kw["vocab_size"], kw["depth"], kw["num_heads"],
                        kw["decoder_embed_dim"], kw["decoder_depth"], kw["decoder_num_heads"], kw["mlp_ratio"])
+
+
+def report(tag, rows):
+    """Worst tensors per model, printed (pytest -s / -rA) and appended to gpurun_out/grad_parity.txt on the GPU box."""
+    import os
+
+    rows = sorted(rows, key=lambda r: -r[1])[:5]
+    line = tag + ": " + ", ".join(f"{n} {e:.2e}" for n, e in rows)
+    print(line)
+    if os.path.isdir("gpurun_out"):
+        with open("gpurun_out/grad_parity.txt", "a") as f:
+            f.write(line + "\n")
+    return rows[0] if rows else ("", 0.0)

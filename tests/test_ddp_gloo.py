@@ -69,24 +69,35 @@ def _worker(rank, world, port, q):
         assert torch.equal(ref[0], ref[1])
 
         x = torch.ones(1, requires_grad=True)
-        for it in range(2):  # two steps: bucket state must reset
+        for it in range(3):  # several steps, never through ddp.forward(): the end-of-backward callback re-arms
             with torch.enable_grad():
-                ddp._lazy_attach()
-                for b in ddp._buckets:
-                    b.pending, b.work = len(b.params), None
-                ddp._callback_queued = False
                 loss = _WriteGrads.apply(x, params, rank)
                 loss.backward()
+            assert all(b.work is None and b.pending == len(b.params) and not b.seen for b in ddp._buckets)
             mean_scale = sum(r + 1 for r in range(world)) / world
             for i, p in enumerate(reversed(params)):
                 want = mean_scale * (i + 1)
                 assert torch.allclose(p.grad, torch.full_like(p.grad, want)), (rank, i, p.grad.flatten()[:3], want)
         # no_sync: gradients stay local
         with ddp.no_sync():
-            for b in ddp._buckets:
-                b.pending, b.work = len(b.params), None
             _WriteGrads.apply(x, params, rank).backward()
         assert torch.allclose(params[-1].grad, torch.full_like(params[-1].grad, float(rank + 1)))
+        # a parameter that reports twice in one backward: harmless while its bucket has not left, an error afterwards
+        b0 = ddp._buckets[0]
+        first = b0.params[0]
+        ddp._callback_queued = True  # outside a backward pass: finalised by hand below
+        ddp._on_ready(first)
+        ddp._on_ready(first)
+        assert b0.pending == len(b0.params) - 1
+        for p in b0.params[1:]:
+            ddp._on_ready(p)
+        assert b0.work is not None
+        try:
+            ddp._on_ready(first)
+            raise AssertionError("late gradient was not detected")
+        except RuntimeError:
+            pass
+        ddp._finalize_backward()
         dist.barrier()
         dist.destroy_process_group()
         q.put((rank, "ok"))

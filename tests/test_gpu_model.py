@@ -11,7 +11,7 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-from conftest import TINY_CASES, oracle_cfg  # noqa: E402
+from conftest import TINY_CASES, oracle_cfg, report  # noqa: E402
 from oracle import tae_oracle as O  # noqa: E402  (checker only)
 
 BF16_TOL = 2e-2
@@ -72,22 +72,21 @@ def test_forward_backward_matches_golden_and_oracle(case, golden_meta, golden_te
     assert abs(float(loss) - float(lo)) < 5e-3 * float(lo)
     assert rel(pred.float(), po.float()) < BF16_TOL
     assert rel(latent.float(), zo.float()) < BF16_TOL
-    worst = ("", 0.0)
+    vs_oracle, vs_norm, vs_ref = [], [], []
     for n, p in model.named_parameters():
         assert p.grad is not None and p.grad.dtype == torch.float32, n
-        e = rel(p.grad, go[n].float())
-        if e > worst[1]:
-            worst = (n, e)
+        vs_oracle.append((n, rel(p.grad, go[n].float())))
         gn = float(p.grad.norm())
-        assert abs(gn - g["grad_norm"][n]) < 3e-2 * g["grad_norm"][n] + 1e-7, (n, gn, g["grad_norm"][n])
-    assert worst[1] < 3e-2, worst
+        vs_norm.append((n, abs(gn - g["grad_norm"][n]) / (g["grad_norm"][n] + 1e-7)))
+        key = f"bf16.grad.{n}"  # 1-D gradients stored in full by the reference
+        if key in t and float(t[key].norm()) > 1e-6:
+            vs_ref.append((n, rel(p.grad.cpu(), t[key])))
+    worst = [report(f"{case} grad vs oracle", vs_oracle), report(f"{case} grad norm vs reference", vs_norm),
+             report(f"{case} 1-D grad vs reference", vs_ref)]
+    # north star: every gradient within 2e-2 of the reference's bf16 path
+    assert all(w[1] < BF16_TOL for w in worst), worst
     gnorm = float(torch.norm(torch.stack([p.grad.norm() for p in model.parameters()])))
     assert abs(gnorm - g["global_grad_norm"]) < BF16_TOL * g["global_grad_norm"]
-    # 1-D gradients stored in full by the reference
-    for n, p in model.named_parameters():
-        key = f"bf16.grad.{n}"
-        if key in t and float(t[key].norm()) > 1e-6:
-            assert rel(p.grad.cpu(), t[key]) < 4e-2, n
 
 
 @pytest.mark.parametrize("case", TINY_CASES)
@@ -176,15 +175,13 @@ def test_full_size_models_match_oracle(name, batch):
     leaves = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items()}
     lo2, _, _ = O.forward(leaves, x, cfg, "bf16")
     lo2.backward()
-    worst, nbad = ("", 0.0), 0
+    errs = []
     for n, p in model.named_parameters():
         g, go = p.grad, leaves[n].grad
         assert g is not None and go is not None, n
-        e = rel(g, go.float())
-        if e > worst[1]:
-            worst = (n, e)
-        nbad += e > 3e-2
-    assert nbad == 0, (worst, nbad)
+        errs.append((n, rel(g, go.float())))
+    worst = report(f"{name} B={batch} grad vs oracle", errs)
+    assert worst[1] < BF16_TOL, (worst, sum(e >= BF16_TOL for _, e in errs))
     gn = float(torch.norm(torch.stack([p.grad.norm() for p in model.parameters()])))
     gno = float(torch.norm(torch.stack([v.grad.float().norm() for v in leaves.values()])))
     assert abs(gn - gno) < BF16_TOL * gno

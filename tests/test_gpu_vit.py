@@ -1,5 +1,5 @@
 """GPU parity of the downstream ViTs (reference tae.py:274-429) against fixtures generated from the unmodified reference
-(tests/golden/make_golden_vit.py): outputs, loss and every stored gradient; bf16 path within 2e-2, fp32 mode within 1e-4
+(tests/golden/make_golden_vit.py): outputs, loss and every stored gradient; bf16 path within 2e-2 (gradients too), fp32 mode within 1e-4
 (2e-4 on gradients)."""
 import json
 import os
@@ -11,7 +11,7 @@ import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
 
-from conftest import GOLDEN_DIR  # noqa: E402
+from conftest import GOLDEN_DIR, report  # noqa: E402
 
 CASES = ["vitrec_n16_hd32_c37", "vitrec_n256_hd64_c16", "vitseg_n16_p8_c5"]
 
@@ -33,7 +33,7 @@ def loss_of(cls, out, labels):
     return F.cross_entropy(out["out"].float(), labels) + 0.5 * F.cross_entropy(out["aux"].float(), labels)
 
 
-@pytest.mark.parametrize("mode,tol,gtol", [("bf16", 2e-2, 4e-2), ("fp32", 1e-4, 2e-4)])
+@pytest.mark.parametrize("mode,tol,gtol", [("bf16", 2e-2, 2e-2), ("fp32", 1e-4, 2e-4)])
 @pytest.mark.parametrize("case", CASES)
 def test_vit_forward_backward_matches_reference(case, mode, tol, gtol, vit_meta):
     from tae_b200 import tae as T
@@ -54,13 +54,16 @@ def test_vit_forward_backward_matches_reference(case, mode, tol, gtol, vit_meta)
         assert tuple(v.shape) == tuple(t[f"{mode}.{k}"].shape)
         assert rel(v.float().cpu(), t[f"{mode}.{k}"]) < tol, k
     assert abs(float(loss) - g["loss"]) < tol * abs(g["loss"])
+    vs_norm, vs_ref = [], []
     for n, p in model.named_parameters():
         assert p.grad is not None and p.grad.dtype == torch.float32, n
         gn = float(p.grad.norm())
-        assert abs(gn - g["grad_norm"][n]) < gtol * g["grad_norm"][n] + 1e-7, (n, gn, g["grad_norm"][n])
+        vs_norm.append((n, abs(gn - g["grad_norm"][n]) / (g["grad_norm"][n] + 1e-7)))
         key = f"{mode}.grad.{n}"
         if key in t and float(t[key].norm()) > 1e-6:
-            assert rel(p.grad.cpu(), t[key]) < gtol, n
+            vs_ref.append((n, rel(p.grad.cpu(), t[key])))
+    worst = [report(f"{case} {mode} grad norm vs reference", vs_norm), report(f"{case} {mode} grad vs reference", vs_ref)]
+    assert all(w[1] < gtol for w in worst), worst
 
 
 def test_vit_recognition_features_and_headless(vit_meta):
