@@ -4,11 +4,13 @@
 // with the qkv un-bind permute (tae.py:74-75) and the head merge (tae.py:80): the kernels index the packed
 // [B*N, 3*H*hd] qkv buffer directly and write the merged [B*N, H*hd] layout, so neither permute is materialised.
 //
-// Two code paths:
-//   * tensor-core path (hd == 64, N in {64, 256}: the patch32 / patch16 grids): one CTA per (image, head),
-//     one warp per 16 query rows, bf16 mma.sync.m16n8k16 with fp32 accumulation, exp2-domain online softmax with
-//     quad shuffles.  Backward recomputes P from the saved log-sum-exp and runs two register-resident phases
-//     (dK/dV with one warp per 16 keys, then dQ with one warp per 16 queries) — no atomics, deterministic.
+// Code paths:
+//   * N = 256, hd = 64 (patch16): the tcgen05 kernels of attention_sm100.cu;
+//   * N = 64, hd = 64 (patch32): persistent CTAs, one warp per 16 query rows / 16 keys, bf16 mma.sync.m16n8k16 with fp32
+//     accumulation, exp2-domain online softmax with quad shuffles.  Backward recomputes P from the saved log-sum-exp:
+//     dK/dV with one warp per 16 keys, dS^T handed through shared memory, then dQ with one warp per 16 queries — no
+//     atomics, deterministic;
+//   * N <= 16 (patch64 / patch128, hd 32/64/80): one warp per (image, head), mma.sync on a padded 16x16 score tile;
 //   * generic path (any N <= 128, hd <= 128; the 4- and 16-token grids of patch128 / patch64 with hd = 80):
 //     one warp per (image, head), fp32 FMA in shared memory — these problems are a few KB each and are
 //     launch/latency-bound, tensor cores do not pay.
@@ -25,15 +27,6 @@ int attention_bwd_tcgen05(const bf16* qkv, const bf16* out, const bf16* dout, co
 
 namespace attn {
 
-// TAE_ATTN_LEGACY=1 forces the mma.sync kernels for N=256 (A/B testing of the tcgen05 path)
-static bool use_tcgen05() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("TAE_ATTN_LEGACY");
-    v = (e != nullptr && e[0] == '1') ? 0 : 1;
-  }
-  return v == 1;
-}
 
 // =============================================================================================
 // Tensor-core path
@@ -256,17 +249,38 @@ attn_fwd_mma(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* __rest
   }
 }
 
-template <int N>
-__global__ void __launch_bounds__(N * 2, 1)
-attn_bwd_mma(const bf16* __restrict__ qkv, const bf16* __restrict__ out, const bf16* __restrict__ dout,
-             const float* __restrict__ lse, bf16* __restrict__ dqkv, int H, int BH, float scale, float scale_log2) {
-  constexpr int NT = N * 2;
-  constexpr int NBUF = N <= 64 ? 2 : 1;      // N = 64: operands of item i+1 arrive (cp.async) while item i computes
-  constexpr int BUF = 5 * N * LDS;           // elements of one operand buffer: Q | K | V | dO | O
+// A operand (16 rows m0.. x 16 k k0..) from smem stored TRANSPOSED, [k][m] with m contiguous, loaded with .trans:
+// matrices (k 0-7, m 0-7), (k 0-7, m 8-15), (k 8-15, m 0-7), (k 8-15, m 8-15) -> a0..a3
+__device__ __forceinline__ uint32_t addr_at(uint32_t base, int k0, int m0, int lane) {
+  const int row = k0 + (lane & 7) + (lane >> 4) * 8;
+  const int col = m0 + ((lane >> 3) & 1) * 8;
+  return base + (uint32_t)(row * LDS + col) * 2u;
+}
+
+// Backward for the 64-token grid (patch32: N = 64, hd = 64), persistent over (image, head) items with the operands of
+// item i+1 arriving (cp.async) while item i computes.  One warp per 16 keys:
+//   phase 1  S^T = K_j Q^T, dP^T = V_j dO^T for the warp's 16 keys against all 64 queries (4 steps of 16 queries);
+//            P^T = exp2(S^T*c - lse2[q]), dS^T = P^T (dP^T - delta[q]); dV += P^T dO, dK += dS^T Q stay in registers;
+//            the bf16 dS^T block is also written over the warp's own (dead: its V fragments are register-resident)
+//            rows of the V tile, as [key][query];
+//   phase 2  dQ = dS K: one warp per 16 queries, A fragments = that shared dS^T tile read transposed (ldmatrix.trans),
+//            32 MMAs — instead of recomputing S and dP for every (query, key) pair a second time (96 MMAs).
+// HAS_DELTA: delta = rowsum(dO * O) arrives precomputed (the proj dgrad's TAE_EPI_BF16_ROWDOT by-product), so O is
+// neither read from HBM nor staged: 4 operand tiles of 9 KB, 74 KB per CTA double-buffered -> 3 CTAs per SM.  Without it
+// (direct C-ABI use) O is staged as a fifth tile and delta computed from shared memory (92 KB, 2 CTAs per SM).
+// No atomics, deterministic.
+template <bool HAS_DELTA>
+__global__ void __launch_bounds__(128, HAS_DELTA ? 3 : 2)
+attn_bwd_mma64(const bf16* __restrict__ qkv, const bf16* __restrict__ out, const bf16* __restrict__ dout,
+               const float* __restrict__ lse, const float* __restrict__ delta_in, bf16* __restrict__ dqkv, int H, int BH,
+               float scale, float scale_log2) {
+  constexpr int N = 64, NT = 128;
+  constexpr int NMAT = HAS_DELTA ? 4 : 5;    // Q | K | V | dO (| O)
+  constexpr int BUF = NMAT * N * LDS;        // elements of one operand buffer
   extern __shared__ uint4 smem_u4[];
   bf16* sbase = reinterpret_cast<bf16*>(smem_u4);
-  float* sLse = reinterpret_cast<float*>(sbase + NBUF * BUF);  // lse * log2(e)
-  float* sDelta = sLse + N;                                    // rowsum(dO * O)
+  float* sLse = reinterpret_cast<float*>(sbase + 2 * BUF);  // lse * log2(e)
+  float* sDelta = sLse + N;                                  // rowsum(dO * O)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int D = H * HD;
   const size_t ldq = (size_t)3 * D;
@@ -278,183 +292,160 @@ attn_bwd_mma(const bf16* __restrict__ qkv, const bf16* __restrict__ out, const b
     load_rows_async<N, NT>(q + N * LDS, gq + D, ldq, tid);
     load_rows_async<N, NT>(q + 2 * N * LDS, gq + 2 * D, ldq, tid);
     load_rows_async<N, NT>(q + 3 * N * LDS, dout + (size_t)b * N * D + (size_t)h * HD, (size_t)D, tid);
-    load_rows_async<N, NT>(q + 4 * N * LDS, out + (size_t)b * N * D + (size_t)h * HD, (size_t)D, tid);
+    if (!HAS_DELTA) load_rows_async<N, NT>(q + 4 * N * LDS, out + (size_t)b * N * D + (size_t)h * HD, (size_t)D, tid);
   };
   int stage = 0;
-  if (NBUF == 2 && (int)blockIdx.x < BH) {
+  if ((int)blockIdx.x < BH) {
     issue(blockIdx.x, 0);
     cp_async_commit();
   }
 #pragma unroll 1
   for (int item = blockIdx.x; item < BH; item += gridDim.x) {
-  if (NBUF == 2) {
     const int nxt = item + gridDim.x;
     if (nxt < BH) issue(nxt, stage ^ 1);
-    cp_async_commit();
+    cp_async_commit();  // (possibly empty) keeps one group per iteration
+    const int b = item / H, h = item - b * H;
+    // per-row scalars straight from global memory while the operand copies land
+    if (tid < N) {
+      const size_t r = ((size_t)b * H + h) * N + tid;
+      sLse[tid] = lse[r] * 1.44269504088896340736f;
+      if (HAS_DELTA) sDelta[tid] = delta_in[r];
+    }
     cp_async_wait<1>();
-  } else {
-    issue(item, 0);
-    cp_async_commit();
-    cp_async_wait<0>();
-  }
-  __syncthreads();
-  bf16* sQ = sbase + stage * BUF;
-  bf16* sK = sQ + N * LDS;
-  bf16* sV = sK + N * LDS;
-  bf16* sdO = sV + N * LDS;
-  const bf16* sO = sdO + N * LDS;
-  const int b = item / H, h = item - b * H;
-  // delta = rowsum(dO * O) out of shared memory: 8 consecutive lanes own the 8 16-byte chunks of one row
-  for (int c = tid; c < N * 8; c += NT) {
-    const int row = c >> 3, ch = c & 7;
-    const uint4 dv = *reinterpret_cast<const uint4*>(sdO + row * LDS + ch * 8);
-    const uint4 ov = *reinterpret_cast<const uint4*>(sO + row * LDS + ch * 8);
-    const uint32_t dw[4] = {dv.x, dv.y, dv.z, dv.w}, ow[4] = {ov.x, ov.y, ov.z, ov.w};
-    float acc = 0.f;
+    __syncthreads();
+    bf16* sQ = sbase + stage * BUF;
+    bf16* sK = sQ + N * LDS;
+    bf16* sV = sK + N * LDS;
+    bf16* sdO = sV + N * LDS;
+    if (!HAS_DELTA) {
+      // delta = rowsum(dO * O) out of shared memory: 8 consecutive lanes own the 8 16-byte chunks of one row
+      const bf16* sO = sdO + N * LDS;
+      for (int c = tid; c < N * 8; c += NT) {
+        const int row = c >> 3, ch = c & 7;
+        const uint4 dv = *reinterpret_cast<const uint4*>(sdO + row * LDS + ch * 8);
+        const uint4 ov = *reinterpret_cast<const uint4*>(sO + row * LDS + ch * 8);
+        const uint32_t dw[4] = {dv.x, dv.y, dv.z, dv.w}, ow[4] = {ov.x, ov.y, ov.z, ov.w};
+        float acc = 0.f;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 d2 = unpack_bf16x2(dw[j]), o2 = unpack_bf16x2(ow[j]);
-      acc += d2.x * o2.x + d2.y * o2.y;
-    }
-    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-    if (ch == 0) sDelta[row] = acc;
-  }
-  for (int r = tid; r < N; r += NT) sLse[r] = lse[((size_t)b * H + h) * N + r] * 1.44269504088896340736f;
-  __syncthreads();
-
-  const uint32_t bQ = smem_u32(sQ), bK = smem_u32(sK), bV = smem_u32(sV), bdO = smem_u32(sdO);
-  const int g = lane >> 2, t = lane & 3;
-  bf16* gdq = dqkv + (size_t)b * N * ldq + (size_t)h * HD;
-
-  // ---------------- phase 1: this warp owns keys j0..j0+15 -> dK, dV ----------------
-  {
-    const int j0 = warp * 16;
-    uint32_t kf[4][4];
-#pragma unroll
-    for (int ks = 0; ks < 4; ++ks) ldsm_x4(kf[ks], addr_a(bK, j0, ks * 16, lane));
-    float dk[8][4], dv[8][4];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = 0.f;
-      dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f;
-    }
-#pragma unroll 1
-    for (int i0 = 0; i0 < N; i0 += 16) {
-      // S^T[key, query] = K_j Q_i^T ; dP^T[key, query] = V_j dO_i^T
-      float st[2][4], dpt[2][4];
-#pragma unroll
-      for (int nt = 0; nt < 2; ++nt) {
-        st[nt][0] = st[nt][1] = st[nt][2] = st[nt][3] = 0.f;
-        dpt[nt][0] = dpt[nt][1] = dpt[nt][2] = dpt[nt][3] = 0.f;
+        for (int j = 0; j < 4; ++j) {
+          const float2 d2 = unpack_bf16x2(dw[j]), o2 = unpack_bf16x2(ow[j]);
+          acc += d2.x * o2.x + d2.y * o2.y;
+        }
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+        if (ch == 0) sDelta[row] = acc;
       }
+      __syncthreads();
+    }
+
+    const uint32_t bQ = smem_u32(sQ), bK = smem_u32(sK), bV = smem_u32(sV), bdO = smem_u32(sdO);
+    const int g = lane >> 2, t = lane & 3;
+    bf16* gdq = dqkv + (size_t)b * N * ldq + (size_t)h * HD;
+
+    // ---------------- phase 1: this warp owns keys j0..j0+15 -> dK, dV, and the dS^T rows of those keys ----------------
+    {
+      const int j0 = warp * 16;
+      uint32_t kf[4][4], vf[4][4];
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {
-        uint32_t qb[4], vf[4], ob[4];
-        ldsm_x4(qb, addr_b(bQ, i0, ks * 16, lane));
-        mma16816(st[0], kf[ks], qb[0], qb[1]);
-        mma16816(st[1], kf[ks], qb[2], qb[3]);
-        ldsm_x4(vf, addr_a(bV, j0, ks * 16, lane));
-        ldsm_x4(ob, addr_b(bdO, i0, ks * 16, lane));
-        mma16816(dpt[0], vf, ob[0], ob[1]);
-        mma16816(dpt[1], vf, ob[2], ob[3]);
+        ldsm_x4(kf[ks], addr_a(bK, j0, ks * 16, lane));
+        ldsm_x4(vf[ks], addr_a(bV, j0, ks * 16, lane));
       }
-      // P^T = exp2(S^T*scale*log2e - lse2[query]); dS^T = P^T * (dP^T - delta[query])   (queries index columns)
-      uint32_t pa[4], dsa[4];
+      __syncwarp();  // every lane holds its V fragments: rows j0..j0+15 of the V tile are dead from here on
+      float dk[8][4], dv[8][4];
 #pragma unroll
-      for (int nt = 0; nt < 2; ++nt) {
-        const int qc = i0 + nt * 8 + 2 * t;
-        const float l0 = sLse[qc], l1 = sLse[qc + 1];
-        const float d0 = sDelta[qc], d1 = sDelta[qc + 1];
-        const float p0 = exp2f(st[nt][0] * scale_log2 - l0), p1 = exp2f(st[nt][1] * scale_log2 - l1);
-        const float p2 = exp2f(st[nt][2] * scale_log2 - l0), p3 = exp2f(st[nt][3] * scale_log2 - l1);
-        pa[nt * 2 + 0] = pack_bf16x2(p0, p1);
-        pa[nt * 2 + 1] = pack_bf16x2(p2, p3);
-        dsa[nt * 2 + 0] = pack_bf16x2(p0 * (dpt[nt][0] - d0), p1 * (dpt[nt][1] - d1));
-        dsa[nt * 2 + 1] = pack_bf16x2(p2 * (dpt[nt][2] - d0), p3 * (dpt[nt][3] - d1));
+      for (int i = 0; i < 8; ++i) {
+        dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = 0.f;
+        dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f;
       }
-      // dV += P^T dO_i ; dK += dS^T Q_i     (k = 16 queries; B operands [query][hd] loaded transposed)
-#pragma unroll
-      for (int dp = 0; dp < 4; ++dp) {
-        uint32_t ob[4], qb[4];
-        ldsm_x4_t(ob, addr_bt(bdO, i0, dp * 16, lane));
-        mma16816(dv[2 * dp], pa, ob[0], ob[1]);
-        mma16816(dv[2 * dp + 1], pa, ob[2], ob[3]);
-        ldsm_x4_t(qb, addr_bt(bQ, i0, dp * 16, lane));
-        mma16816(dk[2 * dp], dsa, qb[0], qb[1]);
-        mma16816(dk[2 * dp + 1], dsa, qb[2], qb[3]);
-      }
-    }
-    bf16* gdk = gdq + D;
-    bf16* gdv = gdq + 2 * D;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int col = i * 8 + 2 * t;
-      *reinterpret_cast<uint32_t*>(gdk + (size_t)(j0 + g) * ldq + col) = pack_bf16x2(dk[i][0] * scale, dk[i][1] * scale);
-      *reinterpret_cast<uint32_t*>(gdk + (size_t)(j0 + g + 8) * ldq + col) = pack_bf16x2(dk[i][2] * scale, dk[i][3] * scale);
-      *reinterpret_cast<uint32_t*>(gdv + (size_t)(j0 + g) * ldq + col) = pack_bf16x2(dv[i][0], dv[i][1]);
-      *reinterpret_cast<uint32_t*>(gdv + (size_t)(j0 + g + 8) * ldq + col) = pack_bf16x2(dv[i][2], dv[i][3]);
-    }
-  }
-
-  // ---------------- phase 2: this warp owns queries i0..i0+15 -> dQ ----------------
-  {
-    const int i0 = warp * 16;
-    uint32_t qf[4][4], of[4][4];
-#pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {
-      ldsm_x4(qf[ks], addr_a(bQ, i0, ks * 16, lane));
-      ldsm_x4(of[ks], addr_a(bdO, i0, ks * 16, lane));
-    }
-    const float l0 = sLse[i0 + g], l1 = sLse[i0 + g + 8];
-    const float d0 = sDelta[i0 + g], d1 = sDelta[i0 + g + 8];
-    float dq[8][4];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
 #pragma unroll 1
-    for (int j0 = 0; j0 < N; j0 += 16) {
-      float s[2][4], dp_[2][4];
+      for (int i0 = 0; i0 < N; i0 += 16) {
+        // S^T[key, query] = K_j Q_i^T ; dP^T[key, query] = V_j dO_i^T
+        float st[2][4], dpt[2][4];
 #pragma unroll
-      for (int nt = 0; nt < 2; ++nt) {
-        s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
-        dp_[nt][0] = dp_[nt][1] = dp_[nt][2] = dp_[nt][3] = 0.f;
+        for (int nt = 0; nt < 2; ++nt) {
+          st[nt][0] = st[nt][1] = st[nt][2] = st[nt][3] = 0.f;
+          dpt[nt][0] = dpt[nt][1] = dpt[nt][2] = dpt[nt][3] = 0.f;
+        }
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          uint32_t qb[4], ob[4];
+          ldsm_x4(qb, addr_b(bQ, i0, ks * 16, lane));
+          ldsm_x4(ob, addr_b(bdO, i0, ks * 16, lane));
+          mma16816(st[0], kf[ks], qb[0], qb[1]);
+          mma16816(st[1], kf[ks], qb[2], qb[3]);
+          mma16816(dpt[0], vf[ks], ob[0], ob[1]);
+          mma16816(dpt[1], vf[ks], ob[2], ob[3]);
+        }
+        // P^T = exp2(S^T*scale*log2e - lse2[query]); dS^T = P^T * (dP^T - delta[query])   (queries index columns)
+        uint32_t pa[4], dsa[4];
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+          const int qc = i0 + nt * 8 + 2 * t;
+          const float2 l01 = *reinterpret_cast<const float2*>(sLse + qc), d01 = *reinterpret_cast<const float2*>(sDelta + qc);
+          const float p0 = exp2f(fmaf(st[nt][0], scale_log2, -l01.x)), p1 = exp2f(fmaf(st[nt][1], scale_log2, -l01.y));
+          const float p2 = exp2f(fmaf(st[nt][2], scale_log2, -l01.x)), p3 = exp2f(fmaf(st[nt][3], scale_log2, -l01.y));
+          pa[nt * 2 + 0] = pack_bf16x2(p0, p1);
+          pa[nt * 2 + 1] = pack_bf16x2(p2, p3);
+          dsa[nt * 2 + 0] = pack_bf16x2(p0 * (dpt[nt][0] - d01.x), p1 * (dpt[nt][1] - d01.y));
+          dsa[nt * 2 + 1] = pack_bf16x2(p2 * (dpt[nt][2] - d01.x), p3 * (dpt[nt][3] - d01.y));
+          // dS^T block -> this warp's rows of the V tile, [key][query]: rows j0+g / j0+g+8, columns qc, qc+1
+          *reinterpret_cast<uint32_t*>(sV + (j0 + g) * LDS + qc) = dsa[nt * 2 + 0];
+          *reinterpret_cast<uint32_t*>(sV + (j0 + g + 8) * LDS + qc) = dsa[nt * 2 + 1];
+        }
+        // dV += P^T dO_i ; dK += dS^T Q_i     (k = 16 queries; B operands [query][hd] loaded transposed)
+#pragma unroll
+        for (int dp = 0; dp < 4; ++dp) {
+          uint32_t ob[4], qb[4];
+          ldsm_x4_t(ob, addr_bt(bdO, i0, dp * 16, lane));
+          mma16816(dv[2 * dp], pa, ob[0], ob[1]);
+          mma16816(dv[2 * dp + 1], pa, ob[2], ob[3]);
+          ldsm_x4_t(qb, addr_bt(bQ, i0, dp * 16, lane));
+          mma16816(dk[2 * dp], dsa, qb[0], qb[1]);
+          mma16816(dk[2 * dp + 1], dsa, qb[2], qb[3]);
+        }
       }
+      bf16* gdk = gdq + D;
+      bf16* gdv = gdq + 2 * D;
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
-        uint32_t kb[4], vb[4];
-        ldsm_x4(kb, addr_b(bK, j0, ks * 16, lane));
-        mma16816(s[0], qf[ks], kb[0], kb[1]);
-        mma16816(s[1], qf[ks], kb[2], kb[3]);
-        ldsm_x4(vb, addr_b(bV, j0, ks * 16, lane));
-        mma16816(dp_[0], of[ks], vb[0], vb[1]);
-        mma16816(dp_[1], of[ks], vb[2], vb[3]);
-      }
-      uint32_t dsa[4];
-#pragma unroll
-      for (int nt = 0; nt < 2; ++nt) {
-        const float p0 = exp2f(s[nt][0] * scale_log2 - l0), p1 = exp2f(s[nt][1] * scale_log2 - l0);
-        const float p2 = exp2f(s[nt][2] * scale_log2 - l1), p3 = exp2f(s[nt][3] * scale_log2 - l1);
-        dsa[nt * 2 + 0] = pack_bf16x2(p0 * (dp_[nt][0] - d0), p1 * (dp_[nt][1] - d0));
-        dsa[nt * 2 + 1] = pack_bf16x2(p2 * (dp_[nt][2] - d1), p3 * (dp_[nt][3] - d1));
-      }
-#pragma unroll
-      for (int dp = 0; dp < 4; ++dp) {
-        uint32_t kb[4];
-        ldsm_x4_t(kb, addr_bt(bK, j0, dp * 16, lane));
-        mma16816(dq[2 * dp], dsa, kb[0], kb[1]);
-        mma16816(dq[2 * dp + 1], dsa, kb[2], kb[3]);
+      for (int i = 0; i < 8; ++i) {
+        const int col = i * 8 + 2 * t;
+        *reinterpret_cast<uint32_t*>(gdk + (size_t)(j0 + g) * ldq + col) = pack_bf16x2(dk[i][0] * scale, dk[i][1] * scale);
+        *reinterpret_cast<uint32_t*>(gdk + (size_t)(j0 + g + 8) * ldq + col) = pack_bf16x2(dk[i][2] * scale, dk[i][3] * scale);
+        *reinterpret_cast<uint32_t*>(gdv + (size_t)(j0 + g) * ldq + col) = pack_bf16x2(dv[i][0], dv[i][1]);
+        *reinterpret_cast<uint32_t*>(gdv + (size_t)(j0 + g + 8) * ldq + col) = pack_bf16x2(dv[i][2], dv[i][3]);
       }
     }
+    __syncthreads();  // the whole dS^T tile [64 keys][64 queries] is in shared memory
+
+    // ---------------- phase 2: this warp owns queries i0..i0+15 -> dQ = dS K ----------------
+    {
+      const int i0 = warp * 16;
+      float dq[8][4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int col = i * 8 + 2 * t;
-      *reinterpret_cast<uint32_t*>(gdq + (size_t)(i0 + g) * ldq + col) = pack_bf16x2(dq[i][0] * scale, dq[i][1] * scale);
-      *reinterpret_cast<uint32_t*>(gdq + (size_t)(i0 + g + 8) * ldq + col) = pack_bf16x2(dq[i][2] * scale, dq[i][3] * scale);
+      for (int i = 0; i < 8; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {  // 16 keys per step
+        uint32_t dsf[4];
+        ldsm_x4_t(dsf, addr_at(bV, ks * 16, i0, lane));
+#pragma unroll
+        for (int dp = 0; dp < 4; ++dp) {
+          uint32_t kb[4];
+          ldsm_x4_t(kb, addr_bt(bK, ks * 16, dp * 16, lane));
+          mma16816(dq[2 * dp], dsf, kb[0], kb[1]);
+          mma16816(dq[2 * dp + 1], dsf, kb[2], kb[3]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int col = i * 8 + 2 * t;
+        *reinterpret_cast<uint32_t*>(gdq + (size_t)(i0 + g) * ldq + col) = pack_bf16x2(dq[i][0] * scale, dq[i][1] * scale);
+        *reinterpret_cast<uint32_t*>(gdq + (size_t)(i0 + g + 8) * ldq + col) = pack_bf16x2(dq[i][2] * scale, dq[i][3] * scale);
+      }
     }
-  }
-  __syncthreads();  // every warp is done with this buffer (and lse/delta) before the next iteration overwrites them
-  if (NBUF == 2) stage ^= 1;
+    __syncthreads();  // every warp is done with this buffer (and lse/delta) before the next iteration overwrites them
+    stage ^= 1;
   }
 }
 
@@ -931,6 +922,33 @@ static int set_smem(K kernel, int bytes) {
 }  // namespace attn
 }  // namespace tae
 
+namespace tae {
+namespace attn {
+// N = 64, hd = 64: delta != NULL selects the 4-tile kernel (3 CTAs per SM), otherwise O is staged and delta computed
+static int launch_bwd64(const bf16* qkv, const bf16* out, const bf16* dout, const float* lse, const float* delta, bf16* dqkv,
+                        int B, int H, float scale, cudaStream_t stream) {
+  constexpr int N = 64;
+  const float sl2 = scale * 1.44269504088896340736f;
+  const int sms = num_sms() > 0 ? num_sms() : 148;
+  if (delta != nullptr) {
+    const int smem = 2 * 4 * N * LDS * 2 + 2 * N * 4;  // 74 240 B: three CTAs per SM
+    int rc = set_smem(attn_bwd_mma64<true>, smem);
+    if (rc) return rc;
+    const int grid = B * H < sms * 3 ? B * H : sms * 3;
+    attn_bwd_mma64<true><<<grid, 128, smem, stream>>>(qkv, nullptr, dout, lse, delta, dqkv, H, B * H, scale, sl2);
+  } else {
+    const int smem = 2 * 5 * N * LDS * 2 + 2 * N * 4;  // 92 672 B: two CTAs per SM
+    int rc = set_smem(attn_bwd_mma64<false>, smem);
+    if (rc) return rc;
+    const int grid = B * H < sms * 2 ? B * H : sms * 2;
+    attn_bwd_mma64<false><<<grid, 128, smem, stream>>>(qkv, out, dout, lse, nullptr, dqkv, H, B * H, scale, sl2);
+  }
+  TAE_CHECK_LAUNCH();
+  return TAE_OK;
+}
+}  // namespace attn
+}  // namespace tae
+
 extern "C" int tae_attention_fwd(const tae_bf16* qkv_, tae_bf16* out_, float* lse, int32_t B, int32_t N, int32_t H,
                                  int32_t hd, void* stream_) {
   using namespace tae;
@@ -941,22 +959,15 @@ extern "C" int tae_attention_fwd(const tae_bf16* qkv_, tae_bf16* out_, float* ls
   TAE_CHECK_SHAPE(B > 0 && N > 0 && H > 0 && hd > 0, "tae_attention_fwd: non-positive dims");
   TAE_CHECK_SHAPE(hd % 8 == 0 && hd <= 128, "tae_attention_fwd: hd=%d unsupported (need hd %% 8 == 0, hd <= 128)", hd);
   const float scale = 1.0f / sqrtf((float)hd);
-  if (hd == HD && N == 256 && use_tcgen05()) return attention_fwd_tcgen05(qkv, out, lse, B, H, stream);
-  if (hd == HD && (N == 64 || N == 256)) {
+  if (hd == HD && N == 256) return attention_fwd_tcgen05(qkv, out, lse, B, H, stream);
+  if (hd == HD && N == 64) {
     const float sl2 = scale * 1.44269504088896340736f;
-    const int smem = 3 * N * LDS * 2;
-    if (N == 256) {
-      int rc = set_smem(attn_fwd_mma<256>, smem);
-      if (rc) return rc;
-      attn_fwd_mma<256><<<B * H, 512, smem, stream>>>(qkv, out, lse, H, B * H, sl2);
-    } else {
-      const int smem2 = 2 * smem;  // double-buffered operands
-      int rc = set_smem(attn_fwd_mma<64>, smem2);
-      if (rc) return rc;
-      const int sms = num_sms() > 0 ? num_sms() : 148;
-      const int grid = B * H < sms * 3 ? B * H : sms * 3;  // 3 resident CTAs per SM (140 registers, 54 KB each)
-      attn_fwd_mma<64><<<grid, 128, smem2, stream>>>(qkv, out, lse, H, B * H, sl2);
-    }
+    const int smem2 = 2 * 3 * N * LDS * 2;  // double-buffered operands
+    int rc = set_smem(attn_fwd_mma<64>, smem2);
+    if (rc) return rc;
+    const int sms = num_sms() > 0 ? num_sms() : 148;
+    const int grid = B * H < sms * 3 ? B * H : sms * 3;  // 3 resident CTAs per SM (140 registers, 54 KB each)
+    attn_fwd_mma<64><<<grid, 128, smem2, stream>>>(qkv, out, lse, H, B * H, sl2);
     TAE_CHECK_LAUNCH();
     return TAE_OK;
   }
@@ -984,25 +995,8 @@ extern "C" int tae_attention_bwd(const tae_bf16* qkv_, const tae_bf16* out_, con
   TAE_CHECK_SHAPE(B > 0 && N > 0 && H > 0 && hd > 0, "tae_attention_bwd: non-positive dims");
   TAE_CHECK_SHAPE(hd % 8 == 0 && hd <= 128, "tae_attention_bwd: hd=%d unsupported", hd);
   const float scale = 1.0f / sqrtf((float)hd);
-  if (hd == HD && N == 256 && use_tcgen05()) return attention_bwd_tcgen05(qkv, out, dout, lse, nullptr, dqkv, B, H, stream);
-  if (hd == HD && (N == 64 || N == 256)) {
-    const float sl2 = scale * 1.44269504088896340736f;
-    if (N == 256) {
-      const int smem = 5 * N * LDS * 2 + 2 * N * 4;
-      int rc = set_smem(attn_bwd_mma<256>, smem);
-      if (rc) return rc;
-      attn_bwd_mma<256><<<B * H, 512, smem, stream>>>(qkv, out, dout, lse, dqkv, H, B * H, scale, sl2);
-    } else {
-      const int smem = 2 * 5 * N * LDS * 2 + 2 * N * 4;  // double-buffered operands
-      int rc = set_smem(attn_bwd_mma<64>, smem);
-      if (rc) return rc;
-      const int sms = num_sms() > 0 ? num_sms() : 148;
-      const int grid = B * H < sms * 2 ? B * H : sms * 2;  // 2 resident CTAs per SM (93 KB each)
-      attn_bwd_mma<64><<<grid, 128, smem, stream>>>(qkv, out, dout, lse, dqkv, H, B * H, scale, sl2);
-    }
-    TAE_CHECK_LAUNCH();
-    return TAE_OK;
-  }
+  if (hd == HD && N == 256) return attention_bwd_tcgen05(qkv, out, dout, lse, nullptr, dqkv, B, H, stream);
+  if (hd == HD && N == 64) return launch_bwd64(qkv, out, dout, lse, nullptr, dqkv, B, H, scale, stream);
   if (small_ok(N, hd) && !force_simt()) return dispatch_small(true, qkv, dout, dqkv, lse, nullptr, B, N, H, hd, scale, stream);
   int wpc, pw;
   TAE_CHECK_SHAPE(simt_config(N, hd, true, &wpc, &pw) == 0, "tae_attention_bwd: N=%d hd=%d does not fit shared memory", N, hd);
@@ -1020,8 +1014,11 @@ extern "C" int tae_attention_bwd_delta(const tae_bf16* qkv_, const tae_bf16* dou
   using namespace tae;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   TAE_CHECK_SHAPE(qkv_ && dout_ && lse && delta && dqkv_, "tae_attention_bwd_delta: NULL argument");
-  TAE_CHECK_SHAPE(B > 0 && H > 0 && N == 256 && hd == 64,
-                  "tae_attention_bwd_delta: only the tcgen05 path (N=256, hd=64) takes a precomputed delta (got N=%d hd=%d)", N, hd);
+  TAE_CHECK_SHAPE(B > 0 && H > 0 && (N == 256 || N == 64) && hd == 64,
+                  "tae_attention_bwd_delta: only the N=256 / N=64, hd=64 kernels take a precomputed delta (got N=%d hd=%d)", N, hd);
+  if (N == 64)
+    return attn::launch_bwd64(reinterpret_cast<const bf16*>(qkv_), nullptr, reinterpret_cast<const bf16*>(dout_), lse, delta,
+                              reinterpret_cast<bf16*>(dqkv_), B, H, 1.0f / sqrtf((float)hd), reinterpret_cast<cudaStream_t>(stream_));
   return attention_bwd_tcgen05(reinterpret_cast<const bf16*>(qkv_), nullptr, reinterpret_cast<const bf16*>(dout_), lse, delta,
                                reinterpret_cast<bf16*>(dqkv_), B, H, stream);
 }

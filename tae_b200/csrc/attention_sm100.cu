@@ -46,361 +46,7 @@ __device__ __forceinline__ uint32_t sw128(int row, int chunk) { return (uint32_t
 // =============================================================================================
 // Forward
 // =============================================================================================
-constexpr int F_OFF_Q = 0;          // [128 x 64] bf16, 16 KB   (K-major A of MMA1)
-constexpr int F_OFF_K = 16384;      // [256 x 64] bf16, 32 KB   (K-major B of MMA1)
-constexpr int F_OFF_V = 65536;      // [256 x 64] bf16, 32 KB   (MN-major B of MMA2); later the O staging tile
-constexpr int F_OFF_P = 0;          // P [128 x 256] bf16 = 4 k-blocks of 16 KB, overlays Q, K and 16 KB of slack
-constexpr int F_OFF_BAR = 98304;
-constexpr int F_OFF_RED = F_OFF_BAR + 64;   // row max / row sum exchange between the two column halves: 4 x 128 fp32
-constexpr int F_SMEM = F_OFF_RED + 2048 + 1024;
-constexpr int F_THREADS = 288;      // warp 0: TMA + MMA + TMEM alloc; warps 1-8: softmax / epilogue (2 threads per row)
-
-__global__ void __launch_bounds__(F_THREADS, 2)
-attn_fwd_tc(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
-            const __grid_constant__ CUtensorMap tm_o, float* __restrict__ lse, int H, float scale, float sl2) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + F_OFF_BAR);
-  uint64_t* bar_load = bars;
-  uint64_t* bar_s = bars + 1;
-  uint64_t* bar_p = bars + 2;
-  uint64_t* bar_o = bars + 3;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
-  float* s_max = reinterpret_cast<float*>(smem + F_OFF_RED);  // [2][128]
-  float* s_sum = s_max + 256;                                  // [2][128]
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int bh = blockIdx.x >> 1, qt = blockIdx.x & 1;
-  const int b = bh / H, h = bh - b * H;
-  const int D = H * HD;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tm_q);
-    tma_prefetch_desc(&tm_kv);
-    tma_prefetch_desc(&tm_o);
-    mbar_init(bar_load, 1);
-    mbar_init(bar_s, 1);
-    mbar_init(bar_p, 256);
-    mbar_init(bar_o, 1);
-    fence_barrier_init();
-  }
-  if (warp == 0) tmem_alloc(tmem_slot, 256);
-  tcgen05_fence_before();
-  __syncthreads();
-  tcgen05_fence_after();
-  const uint32_t tmem = *tmem_slot;
-  const uint32_t sQ = smem_u32(smem + F_OFF_Q), sK = smem_u32(smem + F_OFF_K), sV = smem_u32(smem + F_OFF_V);
-  const uint32_t sP = smem_u32(smem + F_OFF_P);
-
-  if (warp == 0) {
-    if (elect_one()) {
-      mbar_expect_tx(bar_load, 16384 + 32768 + 32768);
-      tma_load_2d(smem + F_OFF_Q, &tm_q, bar_load, h * HD, b * N + qt * 128);
-      tma_load_2d(smem + F_OFF_K, &tm_kv, bar_load, D + h * HD, b * N);
-      tma_load_2d(smem + F_OFF_V, &tm_kv, bar_load, 2 * D + h * HD, b * N);
-      mbar_wait(bar_load, 0);
-      tcgen05_fence_after();
-      const uint32_t idesc1 = make_idesc_bf16(128, 256, 0, 0);
-      const uint32_t q_lo = desc_lo(sQ), k_lo = desc_lo(sK);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) umma_f16_lo(tmem, q_lo + k * 2, k_lo + k * 2, idesc1, k > 0);
-      umma_commit(bar_s);
-      mbar_wait(bar_p, 0);
-      tcgen05_fence_after();
-      const uint32_t idesc2 = make_idesc_bf16(128, 64, 0, 1);
-      // O = P V with P read from TENSOR MEMORY (bf16 pairs written by the softmax threads over the dead S columns:
-      // keys 0-127 in columns 0-63, keys 128-255 in columns 128-191); the accumulator goes to columns 64-127.
-#pragma unroll
-      for (int j = 0; j < 16; ++j)  // 16 keys = 8 TMEM columns of P per instruction
-        umma_f16_ts(tmem + 64, tmem + (j >> 3) * 128 + (j & 7) * 8, make_smem_desc(sV + j * 2048, 8192, 1024), idesc2, j > 0);
-      umma_commit(bar_o);
-    }
-  } else {
-    const int q = warp & 3;              // TMEM lane quarter of this warp
-    const int half = (warp - 1) >> 2;    // which 128 score columns of the row this thread owns
-    const int r = q * 32 + lane;         // query row inside the tile == TMEM lane
-    const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16);
-    const uint32_t tcol = taddr + half * 128;
-    mbar_wait(bar_s, 0);
-    tcgen05_fence_after();
-    // pass 1: row max over this thread's 128 columns (TMEM loads software-pipelined one chunk ahead)
-    uint32_t buf[2][32];
-    float mx = -INFINITY;
-    tmem_ld_32x32b_x32(tcol, buf[0]);
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      tmem_ld_wait_regs(buf[c & 1]);
-      if (c + 1 < 4) tmem_ld_32x32b_x32(tcol + (c + 1) * 32, buf[(c + 1) & 1]);
-#pragma unroll
-      for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(buf[c & 1][i]));
-    }
-    s_max[half * 128 + r] = mx;
-    tmem_ld_32x32b_x32(tcol, buf[0]);  // first chunk of pass 2 in flight across the barrier
-    named_bar_sync(2, 256);
-    mx = fmaxf(mx, s_max[(half ^ 1) * 128 + r]);
-    const float m2 = mx * sl2;
-    float l = 0.f;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      tmem_ld_wait_regs(buf[c & 1]);
-      if (c + 1 < 4) tmem_ld_32x32b_x32(tcol + (c + 1) * 32, buf[(c + 1) & 1]);
-      uint32_t pk[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const float p0 = ex2_approx(fmaf(__uint_as_float(buf[c & 1][2 * i]), sl2, -m2));
-        const float p1 = ex2_approx(fmaf(__uint_as_float(buf[c & 1][2 * i + 1]), sl2, -m2));
-        l += p0 + p1;
-        pk[i] = pack_bf16x2(p0, p1);
-      }
-      // P chunk c (32 keys = 16 packed cells) over S columns this thread has already consumed
-      tmem_st_32x32b_x16(tcol + c * 16, pk);
-    }
-    s_sum[half * 128 + r] = l;
-    tmem_st_wait();
-    tcgen05_fence_before();
-    mbar_arrive(bar_p);
-    // ---- epilogue: each thread normalises 32 of the row's 64 output columns ----
-    named_bar_sync(2, 256);  // partner's s_sum write is ordered before this read
-    mbar_wait(bar_o, 0);
-    tcgen05_fence_after();
-    l += s_sum[(half ^ 1) * 128 + r];
-    if (half == 0) lse[((size_t)b * H + h) * N + qt * 128 + r] = mx * scale + __logf(l);
-    const float inv = 1.0f / l;
-    {
-      uint32_t raw[32];
-      tmem_ld_32x32b_x32(taddr + 64 + half * 32, raw);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        uint32_t o[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          o[j] = pack_bf16x2(__uint_as_float(raw[i * 8 + 2 * j]) * inv, __uint_as_float(raw[i * 8 + 2 * j + 1]) * inv);
-        st_shared_v4(sV + sw128(r, half * 4 + i), o[0], o[1], o[2], o[3]);
-      }
-    }
-    fence_proxy_async_smem();
-    named_bar_sync(1, 256);
-    if (warp == 1 && lane == 0) {
-      tma_store_2d(&tm_o, smem + F_OFF_V, h * HD, b * N + qt * 128);
-      tma_store_commit();
-      tma_store_wait_all();
-    }
-  }
-  tcgen05_fence_before();
-  __syncthreads();
-  tcgen05_fence_after();
-  if (warp == 0) tmem_dealloc(tmem, 256);
-}
-
-// =============================================================================================
-// Forward, PERSISTENT variant (default): one CTA per SM walks (image, head) items with two items' operands resident
-// (2 x 96 KB) and the two 128-query tiles of an item handled by two independent softmax groups, so loads, the S and PV
-// MMAs, the exp2 work (MUFU) and the output stores of neighbouring tiles / items overlap instead of running as one
-// serial chain per CTA.
-//   warp 0   MMA issue: S_t = Q_t K^T (128x256x64) and O_t = P_t V (P read from TENSOR MEMORY)
-//   warp 1   TMA producer: K, Q, V of item i+1 (+2) into the other operand buffer as soon as it is free
-//   warps 4-11 / 12-19   softmax + epilogue of query tile 0 / 1: two threads per row, P written back over the dead S
-//            columns with tcgen05.st, O normalised and staged over the dead Q tile, TMA store
-//   TMEM: tile t owns columns [256t, 256t+256): S, then P in +0..63 / +128..191 and the O accumulator in +64..127.
-// =============================================================================================
 constexpr int G_BUF = 98304;                 // one item's operands: Q 32 KB | K 32 KB | V 32 KB
-constexpr int G_OFF_RED = 2 * G_BUF;         // [2 tiles][max, sum][2 halves][128] fp32 = 4 KB
-constexpr int G_OFF_BAR = G_OFF_RED + 4096;
-constexpr int G_SMEM = G_OFF_BAR + 256 + 1024;
-constexpr int G_THREADS = 640;
-
-__global__ void __launch_bounds__(G_THREADS, 1)
-attn_fwd_tc_persist(const __grid_constant__ CUtensorMap tm_qkv,  // box 256 rows x 64 cols over qkv [B*N, 3D]
-                    const __grid_constant__ CUtensorMap tm_o,    // box 128 rows x 64 cols over out [B*N, D]
-                    float* __restrict__ lse, int H, int num_items, float scale, float sl2) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G_OFF_BAR);
-  uint64_t* bar_kq = bars;          // [2 buffers] K and Q landed                      (TMA, every other item)
-  uint64_t* bar_v = bars + 2;       // [2 buffers] V landed
-  uint64_t* bar_buffree = bars + 4; // [2 buffers] both tiles' output stores have read the buffer (2 arrivals)
-  uint64_t* bar_s = bars + 6;       // [2 tiles] S_t in TMEM                            (commit, every item)
-  uint64_t* bar_p = bars + 8;       // [2 tiles] P_t written to TMEM                    (256 arrivals)
-  uint64_t* bar_o = bars + 10;      // [2 tiles] O_t accumulated                        (commit)
-  uint64_t* bar_tfree = bars + 12;  // [2 tiles] O_t read out of TMEM: the tile's columns may be overwritten (256)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int D = H * HD;
-  const int my_items = (num_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tm_qkv);
-    tma_prefetch_desc(&tm_o);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&bar_kq[i], 1);
-      mbar_init(&bar_v[i], 1);
-      mbar_init(&bar_buffree[i], 2);
-      mbar_init(&bar_s[i], 1);
-      mbar_init(&bar_p[i], 256);
-      mbar_init(&bar_o[i], 1);
-      mbar_init(&bar_tfree[i], 256);
-    }
-    fence_barrier_init();
-  }
-  if (warp == 0) tmem_alloc(tmem_slot, 512);
-  tcgen05_fence_before();
-  __syncthreads();
-  tcgen05_fence_after();
-  const uint32_t tmem = *tmem_slot;
-
-  if (warp == 1) {
-    if (elect_one()) {
-      // ---------------- TMA producer ----------------
-#pragma unroll 1
-      for (int it = 0; it < my_items; ++it) {
-        const int item = (int)blockIdx.x + it * (int)gridDim.x;
-        const int b = item / H, h = item - b * H;
-        const int s = it & 1;
-        if (it >= 2) mbar_wait(&bar_buffree[s], (uint32_t)(((it >> 1) - 1) & 1));
-        uint8_t* buf = smem + s * G_BUF;
-        mbar_expect_tx(&bar_kq[s], 65536);
-        tma_load_2d(buf + 32768, &tm_qkv, &bar_kq[s], D + h * HD, b * N);
-        tma_load_2d(buf, &tm_qkv, &bar_kq[s], h * HD, b * N);
-        mbar_expect_tx(&bar_v[s], 32768);
-        tma_load_2d(buf + 65536, &tm_qkv, &bar_v[s], 2 * D + h * HD, b * N);
-      }
-    }
-  } else if (warp == 0) {
-    if (elect_one()) {
-      // ---------------- MMA issuer ----------------
-      const uint32_t idesc1 = make_idesc_bf16(128, 256, 0, 0);
-      const uint32_t idesc2 = make_idesc_bf16(128, 64, 0, 1);
-      auto issue_s = [&](int it, int t) {
-        const int s = it & 1;
-        const uint32_t base = smem_u32(smem + s * G_BUF);
-        mbar_wait(&bar_kq[s], (uint32_t)((it >> 1) & 1));
-        if (it >= 1) mbar_wait(&bar_tfree[t], (uint32_t)((it - 1) & 1));
-        tcgen05_fence_after();
-        const uint32_t q_lo = desc_lo(base + t * 16384), k_lo = desc_lo(base + 32768);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) umma_f16_lo(tmem + t * 256, q_lo + k * 2, k_lo + k * 2, idesc1, k > 0);
-        umma_commit(&bar_s[t]);
-      };
-      auto issue_pv = [&](int it, int t) {
-        const int s = it & 1;
-        const uint32_t sV = smem_u32(smem + s * G_BUF + 65536);
-        mbar_wait(&bar_v[s], (uint32_t)((it >> 1) & 1));
-        mbar_wait(&bar_p[t], (uint32_t)(it & 1));
-        tcgen05_fence_after();
-        const uint32_t tt = tmem + t * 256;
-#pragma unroll
-        for (int j = 0; j < 16; ++j)  // 16 keys = 8 TMEM columns of P per instruction
-          umma_f16_ts(tt + 64, tt + (j >> 3) * 128 + (j & 7) * 8, make_smem_desc(sV + j * 2048, 8192, 1024), idesc2, j > 0);
-        umma_commit(&bar_o[t]);
-      };
-      if (my_items > 0) {
-        issue_s(0, 0);
-        issue_s(0, 1);
-      }
-#pragma unroll 1
-      for (int it = 0; it < my_items; ++it) {
-        issue_pv(it, 0);
-        issue_pv(it, 1);
-        if (it + 1 < my_items) {  // each waits until that tile's O has been read out of TMEM
-          issue_s(it + 1, 0);
-          issue_s(it + 1, 1);
-        }
-      }
-    }
-  } else if (warp >= 4) {
-    // ---------------- softmax + epilogue groups ----------------
-    const int t = (warp - 4) >> 3;               // query tile of this group
-    const int wg = (warp - 4) & 7;               // warp inside the group
-    const int q = warp & 3;                      // TMEM lane quarter (== warp % 4)
-    const int half = wg >> 2;                    // which 128 score columns of the row
-    const int r = q * 32 + lane;                 // query row inside the tile == TMEM lane
-    const uint32_t taddr = tmem + t * 256 + ((uint32_t)(q * 32) << 16);
-    const uint32_t tcol = taddr + half * 128;
-    float* s_max = reinterpret_cast<float*>(smem + G_OFF_RED) + t * 512;  // [2 halves][128]
-    float* s_sum = s_max + 256;
-    const bool storer = (wg == 0);
-#pragma unroll 1
-    for (int it = 0; it < my_items; ++it) {
-      const int item = (int)blockIdx.x + it * (int)gridDim.x;
-      const int b = item / H, h = item - b * H;
-      const int s = it & 1;
-      const uint32_t par = (uint32_t)(it & 1);
-      mbar_wait(&bar_s[t], par);
-      tcgen05_fence_after();
-      // pass 1: row max over this thread's 128 columns (TMEM loads software-pipelined one chunk ahead)
-      uint32_t buf[2][32];
-      float mx = -INFINITY;
-      tmem_ld_32x32b_x32(tcol, buf[0]);
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        tmem_ld_wait_regs(buf[c & 1]);
-        if (c + 1 < 4) tmem_ld_32x32b_x32(tcol + (c + 1) * 32, buf[(c + 1) & 1]);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(buf[c & 1][i]));
-      }
-      s_max[half * 128 + r] = mx;
-      tmem_ld_32x32b_x32(tcol, buf[0]);  // first chunk of pass 2 in flight across the barrier
-      named_bar_sync(1 + t, 256);
-      mx = fmaxf(mx, s_max[(half ^ 1) * 128 + r]);
-      const float m2 = mx * sl2;
-      float l = 0.f;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        tmem_ld_wait_regs(buf[c & 1]);
-        if (c + 1 < 4) tmem_ld_32x32b_x32(tcol + (c + 1) * 32, buf[(c + 1) & 1]);
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float p0 = ex2_approx(fmaf(__uint_as_float(buf[c & 1][2 * i]), sl2, -m2));
-          const float p1 = ex2_approx(fmaf(__uint_as_float(buf[c & 1][2 * i + 1]), sl2, -m2));
-          l += p0 + p1;
-          pk[i] = pack_bf16x2(p0, p1);
-        }
-        tmem_st_32x32b_x16(tcol + c * 16, pk);  // P chunk c over S columns this thread has already consumed
-      }
-      s_sum[half * 128 + r] = l;
-      tmem_st_wait();
-      tcgen05_fence_before();
-      mbar_arrive(&bar_p[t]);
-      // ---- epilogue: each thread normalises 32 of the row's 64 output columns ----
-      named_bar_sync(1 + t, 256);  // partner's s_sum write is ordered before this read (and s_max reads are done)
-      mbar_wait(&bar_o[t], par);
-      tcgen05_fence_after();
-      l += s_sum[(half ^ 1) * 128 + r];
-      if (half == 0) lse[((size_t)b * H + h) * N + t * 128 + r] = mx * scale + __logf(l);
-      const float inv = 1.0f / l;
-      const uint32_t stage = smem_u32(smem + s * G_BUF + t * 16384);  // the item's dead Q tile
-      {
-        uint32_t raw[32];
-        tmem_ld_32x32b_x32(taddr + 64 + half * 32, raw);
-        tmem_ld_wait();
-        tcgen05_fence_before();
-        mbar_arrive(&bar_tfree[t]);  // this tile's TMEM columns may take the next item's S
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          uint32_t o[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            o[j] = pack_bf16x2(__uint_as_float(raw[i * 8 + 2 * j]) * inv, __uint_as_float(raw[i * 8 + 2 * j + 1]) * inv);
-          st_shared_v4(stage + sw128(r, half * 4 + i), o[0], o[1], o[2], o[3]);
-        }
-      }
-      fence_proxy_async_smem();
-      named_bar_sync(1 + t, 256);
-      if (storer && elect_one()) {
-        tma_store_2d(&tm_o, smem + s * G_BUF + t * 16384, h * HD, b * N + t * 128);
-        tma_store_commit();
-        tma_store_wait_read();
-        mbar_arrive(&bar_buffree[s]);  // (with the other tile's arrival) the producer may refill this buffer
-      }
-    }
-    if (storer && elect_one()) tma_store_wait_all();
-  }
-  tcgen05_fence_before();
-  __syncthreads();
-  tcgen05_fence_after();
-  if (warp == 0) tmem_dealloc(tmem, 512);
-}
 
 // =============================================================================================
 // Forward, RING variant (TAE_ATTN_FWD=ring; written at the end of round 1, NOT yet run on a GPU — the persistent kernel
@@ -701,497 +347,16 @@ attn_fwd_tc_ring(const __grid_constant__ CUtensorMap tm_qkv,  // box 256 rows x 
 // =============================================================================================
 // Backward
 // =============================================================================================
-constexpr int B_OFF_Q = 0;
-constexpr int B_OFF_K = 32768;
-constexpr int B_OFF_V = 65536;
-constexpr int B_OFF_DO = 98304;
-constexpr int B_OFF_PT = 131072;    // P^T  [128 keys x 128 q] bf16: 2 k-blocks of 16 KB
-constexpr int B_OFF_DST = 163840;   // dS^T [128 keys x 128 q] bf16
-constexpr int B_OFF_LSE = 196608;   // lse * log2(e)  [256] fp32
-constexpr int B_OFF_DELTA = 197632; // rowsum(dO * O) [256] fp32
-constexpr int B_OFF_BAR = 198656;
-constexpr int B_SMEM = B_OFF_BAR + 128 + 1024;
-constexpr int B_THREADS = 384;      // warp 0: TMA + MMA + TMEM alloc; warps 4-11: element-wise + epilogues
-constexpr int TC_S = 0, TC_DP = 128, TC_DV = 256, TC_DK = 320, TC_DQ = 384;  // TMEM column map
-
-__global__ void __launch_bounds__(B_THREADS, 1)
-attn_bwd_tc(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
-            const bf16* __restrict__ out, const bf16* __restrict__ dout, const float* __restrict__ lse,
-            bf16* __restrict__ dqkv, int H, float scale, float sl2) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + B_OFF_BAR);
-  uint64_t* bar_load = bars;
-  uint64_t* bar_s = bars + 1;      // S^T / dP^T of a block are in TMEM          (once per block)
-  uint64_t* bar_p = bars + 2;      // P^T / dS^T tiles written, S/dP TMEM drained  (once per block, 256 arrivals)
-  uint64_t* bar_g = bars + 3;      // dV / dK (and, at the end, dQ) accumulators complete (once per key tile)
-  uint64_t* bar_dfree = bars + 4;  // dV / dK of key tile 0 drained from TMEM      (once, 256 arrivals)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
-  float* sLse = reinterpret_cast<float*>(smem + B_OFF_LSE);
-  float* sDelta = reinterpret_cast<float*>(smem + B_OFF_DELTA);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.x / H, h = blockIdx.x - b * H;
-  const int D = H * HD;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tm_qkv);
-    tma_prefetch_desc(&tm_do);
-    mbar_init(bar_load, 1);
-    mbar_init(bar_s, 1);
-    mbar_init(bar_p, 256);
-    mbar_init(bar_g, 1);
-    mbar_init(bar_dfree, 256);
-    fence_barrier_init();
-  }
-  if (warp == 0) tmem_alloc(tmem_slot, 512);
-  tcgen05_fence_before();
-  __syncthreads();
-  tcgen05_fence_after();
-  const uint32_t tmem = *tmem_slot;
-  const uint32_t sQ = smem_u32(smem + B_OFF_Q), sK = smem_u32(smem + B_OFF_K), sV = smem_u32(smem + B_OFF_V);
-  const uint32_t sdO = smem_u32(smem + B_OFF_DO), sPT = smem_u32(smem + B_OFF_PT), sdST = smem_u32(smem + B_OFF_DST);
-
-  if (warp == 0) {
-    if (elect_one()) {
-      mbar_expect_tx(bar_load, 4 * 32768);
-      tma_load_2d(smem + B_OFF_Q, &tm_qkv, bar_load, h * HD, b * N);
-      tma_load_2d(smem + B_OFF_K, &tm_qkv, bar_load, D + h * HD, b * N);
-      tma_load_2d(smem + B_OFF_V, &tm_qkv, bar_load, 2 * D + h * HD, b * N);
-      tma_load_2d(smem + B_OFF_DO, &tm_do, bar_load, h * HD, b * N);
-      mbar_wait(bar_load, 0);
-      tcgen05_fence_after();
-      const uint32_t id_ss = make_idesc_bf16(128, 128, 0, 0);   // S^T, dP^T
-      const uint32_t id_kn = make_idesc_bf16(128, 64, 0, 1);    // dV, dK : A K-major, B MN-major
-      const uint32_t id_nn = make_idesc_bf16(128, 64, 1, 1);    // dQ     : A MN-major (dS^T re-read), B MN-major
-#pragma unroll 1
-      for (int blk = 0; blk < 4; ++blk) {
-        const int kt = blk >> 1, qt = blk & 1;
-        // S^T = K_kt Q_qt^T ; dP^T = V_kt dO_qt^T       (TMEM S/dP drained: bar_p of the previous block was waited)
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_f16(tmem + TC_S, make_smem_desc(sK + kt * 16384 + k * 32, 0, 1024),
-                   make_smem_desc(sQ + qt * 16384 + k * 32, 0, 1024), id_ss, k > 0);
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_f16(tmem + TC_DP, make_smem_desc(sV + kt * 16384 + k * 32, 0, 1024),
-                   make_smem_desc(sdO + qt * 16384 + k * 32, 0, 1024), id_ss, k > 0);
-        umma_commit(bar_s);
-        mbar_wait(bar_p, blk & 1);
-        tcgen05_fence_after();
-        if (blk == 2) {  // dV/dK accumulators of key tile 0 must have been drained before they are overwritten
-          mbar_wait(bar_dfree, 0);
-          tcgen05_fence_after();
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {  // 16 queries (dV, dK) / 16 keys (dQ) per instruction
-          const uint64_t a_pt = make_smem_desc(sPT + (j >> 2) * 16384 + (j & 3) * 32, 0, 1024);
-          const uint64_t a_dst = make_smem_desc(sdST + (j >> 2) * 16384 + (j & 3) * 32, 0, 1024);
-          const uint64_t b_do = make_smem_desc(sdO + qt * 16384 + j * 2048, 8192, 1024);
-          const uint64_t b_q = make_smem_desc(sQ + qt * 16384 + j * 2048, 8192, 1024);
-          umma_f16(tmem + TC_DV, a_pt, b_do, id_kn, (qt > 0 || j > 0));
-          umma_f16(tmem + TC_DK, a_dst, b_q, id_kn, (qt > 0 || j > 0));
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const uint64_t a_ds = make_smem_desc(sdST + j * 2048, 16384, 1024);  // dS [q x keys], q contiguous
-          const uint64_t b_k = make_smem_desc(sK + kt * 16384 + j * 2048, 8192, 1024);
-          umma_f16(tmem + TC_DQ + qt * 64, a_ds, b_k, id_nn, (kt > 0 || j > 0));
-        }
-        if (qt == 1) umma_commit(bar_g);
-      }
-    }
-  } else if (warp >= 4) {
-    const int te = threadIdx.x - 128;        // 0..255
-    const int q4 = warp & 3;                 // TMEM lane quarter
-    const int half = (warp - 4) >> 2;        // which 64-column half of a 128-column block
-    const int r = q4 * 32 + lane;            // key row inside the key tile == TMEM lane
-    const uint32_t tlane = tmem + ((uint32_t)(q4 * 32) << 16);
-    // ---- prologue: delta = rowsum(dO * O), lse in the exp2 domain ----
-    {
-      const bf16* go = out + (size_t)b * N * D + (size_t)h * HD;
-      const bf16* gdo = dout + (size_t)b * N * D + (size_t)h * HD;
-#pragma unroll
-      for (int pass = 0; pass < 8; ++pass) {
-        const int row = pass * 32 + (te >> 3), ch = te & 7;
-        const uint4 dv = ld_nc_v4(gdo + (size_t)row * D + ch * 8);
-        const uint4 ov = ld_nc_v4(go + (size_t)row * D + ch * 8);
-        const uint32_t dw[4] = {dv.x, dv.y, dv.z, dv.w}, ow[4] = {ov.x, ov.y, ov.z, ov.w};
-        float acc = 0.f;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 d2 = unpack_bf16x2(dw[j]), o2 = unpack_bf16x2(ow[j]);
-          acc += d2.x * o2.x + d2.y * o2.y;
-        }
-        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-        acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-        if (ch == 0) sDelta[row] = acc;
-      }
-      sLse[te] = lse[((size_t)b * H + h) * N + te] * 1.44269504088896340736f;
-      named_bar_sync(1, 256);
-    }
-    bf16* gd = dqkv + (size_t)b * N * 3 * D + (size_t)h * HD;
-    const size_t ldq = (size_t)3 * D;
-
-#pragma unroll 1
-    for (int blk = 0; blk < 4; ++blk) {
-      const int kt = blk >> 1, qt = blk & 1;
-      mbar_wait(bar_s, blk & 1);
-      tcgen05_fence_after();
-#pragma unroll 1
-      for (int sub = 0; sub < 2; ++sub) {
-        const int c0 = half * 64 + sub * 32;  // first query column of this chunk inside the block
-        uint32_t sraw[32], draw[32];
-        tmem_ld_32x32b_x32(tlane + TC_S + c0, sraw);
-        tmem_ld_32x32b_x32(tlane + TC_DP + c0, draw);
-        tmem_ld_wait();
-        const float4* l4 = reinterpret_cast<const float4*>(sLse + qt * 128 + c0);
-        const float4* d4 = reinterpret_cast<const float4*>(sDelta + qt * 128 + c0);
-        uint32_t pk[16], dk[16];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 lv = l4[i], dl = d4[i];
-          const float p0 = ex2_approx(fmaf(__uint_as_float(sraw[4 * i + 0]), sl2, -lv.x));
-          const float p1 = ex2_approx(fmaf(__uint_as_float(sraw[4 * i + 1]), sl2, -lv.y));
-          const float p2 = ex2_approx(fmaf(__uint_as_float(sraw[4 * i + 2]), sl2, -lv.z));
-          const float p3 = ex2_approx(fmaf(__uint_as_float(sraw[4 * i + 3]), sl2, -lv.w));
-          pk[2 * i] = pack_bf16x2(p0, p1);
-          pk[2 * i + 1] = pack_bf16x2(p2, p3);
-          dk[2 * i] = pack_bf16x2(p0 * (__uint_as_float(draw[4 * i + 0]) - dl.x) * scale,
-                                  p1 * (__uint_as_float(draw[4 * i + 1]) - dl.y) * scale);
-          dk[2 * i + 1] = pack_bf16x2(p2 * (__uint_as_float(draw[4 * i + 2]) - dl.z) * scale,
-                                      p3 * (__uint_as_float(draw[4 * i + 3]) - dl.w) * scale);
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const uint32_t off = (uint32_t)half * 16384u + sw128(r, sub * 4 + i);
-          st_shared_v4(sPT + off, pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
-          st_shared_v4(sdST + off, dk[4 * i], dk[4 * i + 1], dk[4 * i + 2], dk[4 * i + 3]);
-        }
-      }
-      fence_proxy_async_smem();
-      tcgen05_fence_before();
-      mbar_arrive(bar_p);
-      if (qt == 1) {
-        // dV_kt (half 0) / dK_kt (half 1): TMEM -> bf16 -> global, one 128-byte row per thread
-        mbar_wait(bar_g, kt & 1);
-        tcgen05_fence_after();
-        const uint32_t tcol = half == 0 ? TC_DV : TC_DK;
-        bf16* dst = gd + (size_t)(kt * 128 + r) * ldq + (half == 0 ? 2 * D : D);
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t raw[32];
-          tmem_ld_32x32b_x32(tlane + tcol + c * 32, raw);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            uint4 o;
-            o.x = pack_bf16x2(__uint_as_float(raw[i * 8 + 0]), __uint_as_float(raw[i * 8 + 1]));
-            o.y = pack_bf16x2(__uint_as_float(raw[i * 8 + 2]), __uint_as_float(raw[i * 8 + 3]));
-            o.z = pack_bf16x2(__uint_as_float(raw[i * 8 + 4]), __uint_as_float(raw[i * 8 + 5]));
-            o.w = pack_bf16x2(__uint_as_float(raw[i * 8 + 6]), __uint_as_float(raw[i * 8 + 7]));
-            *reinterpret_cast<uint4*>(dst + c * 32 + i * 8) = o;
-          }
-        }
-        if (kt == 0) {
-          tcgen05_fence_before();
-          mbar_arrive(bar_dfree);
-        }
-      }
-    }
-    // dQ (bar_g of key tile 1 covers every MMA): half 0 -> queries 0..127, half 1 -> queries 128..255
-    {
-      bf16* dst = gd + (size_t)(half * 128 + r) * ldq;
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t raw[32];
-        tmem_ld_32x32b_x32(tlane + TC_DQ + half * 64 + c * 32, raw);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          uint4 o;
-          o.x = pack_bf16x2(__uint_as_float(raw[i * 8 + 0]), __uint_as_float(raw[i * 8 + 1]));
-          o.y = pack_bf16x2(__uint_as_float(raw[i * 8 + 2]), __uint_as_float(raw[i * 8 + 3]));
-          o.z = pack_bf16x2(__uint_as_float(raw[i * 8 + 4]), __uint_as_float(raw[i * 8 + 5]));
-          o.w = pack_bf16x2(__uint_as_float(raw[i * 8 + 6]), __uint_as_float(raw[i * 8 + 7]));
-          *reinterpret_cast<uint4*>(dst + c * 32 + i * 8) = o;
-        }
-      }
-    }
-  }
-  tcgen05_fence_before();
-  __syncthreads();
-  tcgen05_fence_after();
-  if (warp == 0) tmem_dealloc(tmem, 512);
-}
-
-// =============================================================================================
-// Backward, software-pipelined variant (default).  Same math as attn_bwd_tc, but in [128 keys x 64 queries] blocks with
-// DOUBLE-BUFFERED S^T/dP^T accumulators (TMEM) and P^T/dS^T operand tiles (smem), so that while the element-wise warps
-// work on block b the tensor cores run the gradient MMAs of block b-1 and the score MMAs of block b+1.
-// dQ for a 64-query block is an M=64 UMMA (A = the dS^T tile read MN-major); its accumulator occupies 16 lanes of each
-// TMEM lane quarter, and two query blocks are interleaved in the same 64 columns (lane offsets 0 and 16).
-//   TMEM columns: S^T[2] 0/64, dP^T[2] 128/192, dV 256, dK 320, dQ 384..511 (4 query blocks)
-// =============================================================================================
 constexpr int P_OFF_Q = 0, P_OFF_K = 32768, P_OFF_V = 65536, P_OFF_DO = 98304;
 constexpr int P_OFF_PT = 131072;     // 2 x [128 x 64] bf16 (16 KB each)
 constexpr int P_OFF_DST = 163840;    // 2 x [128 x 64] bf16
-constexpr int P_OFF_LSE = 196608, P_OFF_DELTA = 197632, P_OFF_BAR = 198656;
-constexpr int P_SMEM = P_OFF_BAR + 128 + 1024;
-constexpr int PC_S = 0, PC_DP = 128, PC_DV = 256, PC_DK = 320, PC_DQ = 384;
+constexpr int PC_S = 0, PC_DP = 128, PC_DV = 256, PC_DK = 320, PC_DQ = 384;  // TMEM column map
 
 __device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
   float4 r;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr));
   return r;
 }
-
-__global__ void __launch_bounds__(B_THREADS, 1)
-attn_bwd_tc_pipe(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
-                 const __grid_constant__ CUtensorMap tm_dqkv, const bf16* __restrict__ out,
-                 const bf16* __restrict__ dout, const float* __restrict__ lse, int H, float scale, float sl2,
-                 long long* trace) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P_OFF_BAR);
-  // debug timeline (tools/attn_trace.py): CTA `gridDim.x/2` stamps clock64() at pipeline milestones
-  const bool tr = trace != nullptr && blockIdx.x == gridDim.x / 2;
-#define TRACE_C(i) do { if (tr) trace[(i)] = clock64(); } while (0)
-#define TRACE_E(i) do { if (tr && threadIdx.x == 128) trace[32 + (i)] = clock64(); } while (0)
-  if (tr && threadIdx.x == 0) trace[63] = clock64();
-  uint64_t* bar_load = bars;
-  uint64_t* bar_s = bars + 1;       // [2] S^T/dP^T buffer filled by the tensor cores
-  uint64_t* bar_p = bars + 3;       // [2] P^T/dS^T tile written (and S/dP buffer drained): 256 arrivals
-  uint64_t* bar_pfree = bars + 5;   // [2] gradient MMAs that read the P^T/dS^T tile have retired
-  uint64_t* bar_g = bars + 7;       // dV/dK (and at the end dQ) accumulators complete
-  uint64_t* bar_dfree = bars + 8;   // dV/dK of key tile 0 drained: 256 arrivals
-  uint64_t* bar_load2 = bars + 9;   // V and dO landed (bar_load: K and Q)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
-  float* sLse = reinterpret_cast<float*>(smem + P_OFF_LSE);
-  float* sDelta = reinterpret_cast<float*>(smem + P_OFF_DELTA);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.x / H, h = blockIdx.x - b * H;
-  const int D = H * HD;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tm_qkv);
-    tma_prefetch_desc(&tm_do);
-    tma_prefetch_desc(&tm_dqkv);
-    mbar_init(bar_load, 1);
-    mbar_init(bar_load2, 1);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&bar_s[i], 1);
-      mbar_init(&bar_p[i], 256);
-      mbar_init(&bar_pfree[i], 1);
-    }
-    mbar_init(bar_g, 1);
-    mbar_init(bar_dfree, 256);
-    fence_barrier_init();
-  }
-  if (warp == 0) tmem_alloc(tmem_slot, 512);
-  tcgen05_fence_before();
-  __syncthreads();
-  tcgen05_fence_after();
-  const uint32_t tmem = *tmem_slot;
-  const uint32_t sQ = smem_u32(smem + P_OFF_Q), sK = smem_u32(smem + P_OFF_K), sV = smem_u32(smem + P_OFF_V);
-  const uint32_t sdO = smem_u32(smem + P_OFF_DO), sPT = smem_u32(smem + P_OFF_PT), sdST = smem_u32(smem + P_OFF_DST);
-
-  if (warp == 0) {
-    if (elect_one()) {
-      mbar_expect_tx(bar_load, 2 * 32768);
-      tma_load_2d(smem + P_OFF_K, &tm_qkv, bar_load, D + h * HD, b * N);
-      tma_load_2d(smem + P_OFF_Q, &tm_qkv, bar_load, h * HD, b * N);
-      mbar_expect_tx(bar_load2, 2 * 32768);
-      tma_load_2d(smem + P_OFF_V, &tm_qkv, bar_load2, 2 * D + h * HD, b * N);
-      tma_load_2d(smem + P_OFF_DO, &tm_do, bar_load2, h * HD, b * N);
-      const uint32_t id_s = make_idesc_bf16(128, 64, 0, 0);    // S^T, dP^T: [128 keys x 64 q]
-      const uint32_t id_kn = make_idesc_bf16(128, 64, 0, 1);   // dV, dK
-      const uint32_t id_q = make_idesc_bf16(64, 64, 1, 1);     // dQ: M = 64 queries
-      // descriptor `lo` words (start address >> 4 [| LBO]); byte offsets below are added as (bytes >> 4)
-      const uint32_t q_lo = desc_lo(sQ), k_lo = desc_lo(sK), v_lo = desc_lo(sV), do_lo = desc_lo(sdO);
-      const uint32_t pt_lo = desc_lo(sPT), dst_lo = desc_lo(sdST);
-      const uint32_t qmn_lo = desc_lo(sQ, 8192), kmn_lo = desc_lo(sK, 8192), domn_lo = desc_lo(sdO, 8192);
-      const uint32_t dstmn_lo = desc_lo(sdST, 8192);
-      auto issue_scores = [&](int blk) {
-        const int kt = blk >> 2, j = blk & 3, buf = blk & 1;
-        const uint32_t ka = k_lo + kt * (16384 >> 4), va = v_lo + kt * (16384 >> 4);
-        const uint32_t qb = q_lo + j * (8192 >> 4), ob = do_lo + j * (8192 >> 4);
-        const uint32_t ds = tmem + PC_S + buf * 64, dp = tmem + PC_DP + buf * 64;
-        if (blk == 0) {  // S^T needs K and Q only: start as soon as they have landed
-          mbar_wait(bar_load, 0);
-          tcgen05_fence_after();
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) umma_f16_lo(ds, ka + k * 2, qb + k * 2, id_s, k > 0);
-        if (blk == 0) {
-          mbar_wait(bar_load2, 0);
-          tcgen05_fence_after();
-          TRACE_C(0);
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) umma_f16_lo(dp, va + k * 2, ob + k * 2, id_s, k > 0);
-        umma_commit(&bar_s[buf]);
-      };
-      issue_scores(0);
-      issue_scores(1);
-#pragma unroll 1
-      for (int blk = 0; blk < 8; ++blk) {
-        const int kt = blk >> 2, j = blk & 3, buf = blk & 1;
-        mbar_wait(&bar_p[buf], (blk >> 1) & 1);
-        tcgen05_fence_after();
-        TRACE_C(1 + 2 * blk);
-        if (blk == 4) {  // dV/dK of key tile 0 must be drained before they are overwritten
-          mbar_wait(bar_dfree, 0);
-          tcgen05_fence_after();
-        }
-        const uint32_t a_pt = pt_lo + buf * (16384 >> 4), a_dst = dst_lo + buf * (16384 >> 4);
-        const uint32_t b_do = domn_lo + j * (8192 >> 4), b_q = qmn_lo + j * (8192 >> 4);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {  // 16 queries per instruction
-          umma_f16_lo(tmem + PC_DV, a_pt + k * 2, b_do + k * (2048 >> 4), id_kn, (j > 0 || k > 0));
-          umma_f16_lo(tmem + PC_DK, a_dst + k * 2, b_q + k * (2048 >> 4), id_kn, (j > 0 || k > 0));
-        }
-        const uint32_t dq_addr = tmem + PC_DQ + (j >> 1) * 64 + ((uint32_t)((j & 1) * 16) << 16);
-        const uint32_t a_ds = dstmn_lo + buf * (16384 >> 4), b_k = kmn_lo + kt * (16384 >> 4);
-#pragma unroll
-        for (int k = 0; k < 8; ++k)  // 16 keys per instruction; A = dS^T tile read MN-major (64 queries contiguous)
-          umma_f16_lo(dq_addr, a_ds + k * (2048 >> 4), b_k + k * (2048 >> 4), id_q, (kt > 0 || k > 0));
-        umma_commit(&bar_pfree[buf]);
-        if (j == 3) umma_commit(bar_g);
-        if (blk + 2 < 8) issue_scores(blk + 2);
-        TRACE_C(2 + 2 * blk);
-      }
-    }
-  } else if (warp >= 4) {
-    const int te = threadIdx.x - 128;
-    const int q4 = warp & 3;
-    const int half = (warp - 4) >> 2;   // which 32 query columns of the 64-wide block
-    const int r = q4 * 32 + lane;       // key row inside the key tile == TMEM lane
-    const uint32_t tlane = tmem + ((uint32_t)(q4 * 32) << 16);
-    {
-      const bf16* go = out + (size_t)b * N * D + (size_t)h * HD;
-      const bf16* gdo = dout + (size_t)b * N * D + (size_t)h * HD;
-#pragma unroll
-      for (int pass = 0; pass < 8; ++pass) {
-        const int row = pass * 32 + (te >> 3), ch = te & 7;
-        const uint4 dv = ld_nc_v4(gdo + (size_t)row * D + ch * 8);
-        const uint4 ov = ld_nc_v4(go + (size_t)row * D + ch * 8);
-        const uint32_t dw[4] = {dv.x, dv.y, dv.z, dv.w}, ow[4] = {ov.x, ov.y, ov.z, ov.w};
-        float acc = 0.f;
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-          const float2 d2 = unpack_bf16x2(dw[jj]), o2 = unpack_bf16x2(ow[jj]);
-          acc += d2.x * o2.x + d2.y * o2.y;
-        }
-        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-        acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-        if (ch == 0) sDelta[row] = acc;
-      }
-      sLse[te] = lse[((size_t)b * H + h) * N + te] * 1.44269504088896340736f;
-      named_bar_sync(1, 256);
-    }
-    TRACE_E(0);
-    const uint32_t sLseA = smem_u32(sLse), sDeltaA = smem_u32(sDelta);
-    // TMEM accumulator row (64 fp32 columns at `taddr`) -> bf16 -> row `row` of a 128B-swizzled [rows x 64] staging tile
-    auto stage_row = [&](uint32_t taddr, uint32_t tile, int row) {
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t raw[32];
-        tmem_ld_32x32b_x32(taddr + c * 32, raw);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          st_shared_v4(tile + sw128(row, c * 4 + i),
-                       pack_bf16x2(__uint_as_float(raw[i * 8 + 0]), __uint_as_float(raw[i * 8 + 1])),
-                       pack_bf16x2(__uint_as_float(raw[i * 8 + 2]), __uint_as_float(raw[i * 8 + 3])),
-                       pack_bf16x2(__uint_as_float(raw[i * 8 + 4]), __uint_as_float(raw[i * 8 + 5])),
-                       pack_bf16x2(__uint_as_float(raw[i * 8 + 6]), __uint_as_float(raw[i * 8 + 7])));
-      }
-    };
-
-#pragma unroll 1
-    for (int blk = 0; blk < 8; ++blk) {
-      const int kt = blk >> 2, j = blk & 3, buf = blk & 1;
-      mbar_wait(&bar_s[buf], (blk >> 1) & 1);
-      tcgen05_fence_after();
-      TRACE_E(1 + 3 * blk);
-      uint32_t sraw[32], draw[32];
-      tmem_ld_32x32b_x32(tlane + PC_S + buf * 64 + half * 32, sraw);
-      tmem_ld_32x32b_x32(tlane + PC_DP + buf * 64 + half * 32, draw);
-      tmem_ld_wait();
-      const int qcol = j * 64 + half * 32;
-      uint32_t pk[16], dk[16];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float4 lv = ld_shared_f4(sLseA + (qcol + 4 * i) * 4), dl = ld_shared_f4(sDeltaA + (qcol + 4 * i) * 4);
-        const float p0 = ex2_approx(fmaf(__uint_as_float(sraw[4 * i + 0]), sl2, -lv.x));
-        const float p1 = ex2_approx(fmaf(__uint_as_float(sraw[4 * i + 1]), sl2, -lv.y));
-        const float p2 = ex2_approx(fmaf(__uint_as_float(sraw[4 * i + 2]), sl2, -lv.z));
-        const float p3 = ex2_approx(fmaf(__uint_as_float(sraw[4 * i + 3]), sl2, -lv.w));
-        pk[2 * i] = pack_bf16x2(p0, p1);
-        pk[2 * i + 1] = pack_bf16x2(p2, p3);
-        dk[2 * i] = pack_bf16x2(p0 * (__uint_as_float(draw[4 * i + 0]) - dl.x) * scale,
-                                p1 * (__uint_as_float(draw[4 * i + 1]) - dl.y) * scale);
-        dk[2 * i + 1] = pack_bf16x2(p2 * (__uint_as_float(draw[4 * i + 2]) - dl.z) * scale,
-                                    p3 * (__uint_as_float(draw[4 * i + 3]) - dl.w) * scale);
-      }
-      TRACE_E(2 + 3 * blk);
-      if (blk >= 2) mbar_wait(&bar_pfree[buf], ((blk >> 1) - 1) & 1);  // MMAs of block blk-2 are done with this tile
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const uint32_t off = (uint32_t)buf * 16384u + sw128(r, half * 4 + i);
-        st_shared_v4(sPT + off, pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
-        st_shared_v4(sdST + off, dk[4 * i], dk[4 * i + 1], dk[4 * i + 2], dk[4 * i + 3]);
-      }
-      fence_proxy_async_smem();
-      tcgen05_fence_before();
-      mbar_arrive(&bar_p[buf]);
-      TRACE_E(3 + 3 * blk);
-      if (j == 3) {
-        // dV_kt (half 0) / dK_kt (half 1).  Every MMA that reads V_kt / K_kt has retired (bar_g), so the accumulator is
-        // staged as bf16 over the dead operand tile and leaves with one coalesced TMA store per tile.
-        mbar_wait(bar_g, kt & 1);
-        tcgen05_fence_after();
-        const int off = (half == 0 ? P_OFF_V : P_OFF_K) + kt * 16384;
-        stage_row(tlane + (half == 0 ? PC_DV : PC_DK), smem_u32(smem + off), r);
-        if (kt == 0) {
-          tcgen05_fence_before();
-          mbar_arrive(bar_dfree);
-        }
-        fence_proxy_async_smem();
-        named_bar_sync(2 + half, 128);
-        if ((warp & 3) == 0 && elect_one()) {
-          tma_store_2d(&tm_dqkv, smem + off, (half == 0 ? 2 * D : D) + h * HD, b * N + kt * 128);
-          tma_store_commit();
-        }
-      }
-    }
-    // dQ: M=64 accumulators.  Query block jq lives in columns PC_DQ + (jq>>1)*64 on lanes 16*(jq&1) + {0..15} of every
-    // lane quarter; thread (quarter q4, lane l) therefore owns query  (2*half + (l>>4))*64 + 16*q4 + (l&15).
-    // (the final bar_g wait above covers every MMA, so the Q tile is dead and becomes the staging buffer)
-    {
-      const int qrow = (2 * half + (lane >> 4)) * 64 + 16 * q4 + (lane & 15);
-      stage_row(tlane + PC_DQ + half * 64, sQ, qrow);
-      fence_proxy_async_smem();
-      named_bar_sync(2 + half, 128);  // this half's 128 threads own query rows [half*128, half*128 + 128)
-      if ((warp & 3) == 0 && elect_one()) {
-        tma_store_2d(&tm_dqkv, smem + P_OFF_Q + half * 16384, h * HD, b * N + half * 128);
-        tma_store_commit();
-        tma_store_wait_all();  // smem must stay valid until the bulk stores of this thread have been read
-      }
-    }
-    TRACE_E(28);
-  }
-  tcgen05_fence_before();
-  __syncthreads();
-  tcgen05_fence_after();
-  if (warp == 0) tmem_dealloc(tmem, 512);
-  if (tr && threadIdx.x == 0) trace[62] = clock64();
-#undef TRACE_C
-#undef TRACE_E
-}
-
 
 // =============================================================================================
 // Backward, PERSISTENT variant (default).  One CTA per SM walks a static list of (image, head) items; the block
@@ -1631,61 +796,20 @@ int attention_fwd_tcgen05(const bf16* qkv, bf16* out, float* lse, int B, int H, 
   using namespace attn_tc;
   const int D = H * HD;
   const float scale = 1.0f / sqrtf((float)HD);
-  // TAE_ATTN_FWD=v1 selects the one-shot kernel (A/B testing); default is the persistent kernel
-  static int variant = -1;
-  if (variant < 0) {
-    const char* e = getenv("TAE_ATTN_FWD");
-    variant = (e != nullptr && e[0] == 'v') ? 0 : (e != nullptr && e[0] == 'r') ? 2 : 1;  // v1 | ring | (default) persistent
-  }
-  int rc;
-  if (variant == 2) {
-    static cudaError_t err3 = cudaSuccess;
-    static std::once_flag once3;
-    rc = set_smem_once(attn_fwd_tc_ring, R_SMEM, &err3, &once3);
-    if (rc) return rc;
-    CUtensorMap tkv, to;
-    rc = sm100::make_tmap(&tkv, qkv, (uint64_t)3 * D, (uint64_t)B * N, (uint64_t)3 * D, 256);
-    if (rc) return rc;
-    rc = sm100::make_tmap(&to, out, (uint64_t)D, (uint64_t)B * N, (uint64_t)D, 128);
-    if (rc) return rc;
-    const int sms = num_sms();
-    if (sms <= 0) return TAE_ERR_CUDA;
-    const int items = B * H;
-    attn_fwd_tc_ring<<<items < sms ? items : sms, R_THREADS, R_SMEM, stream>>>(tkv, to, lse, H, items, scale,
-                                                                               scale * 1.44269504088896340736f);
-    TAE_CHECK_LAUNCH();
-    return TAE_OK;
-  }
-  if (variant == 1) {
-    static cudaError_t err2 = cudaSuccess;
-    static std::once_flag once2;
-    rc = set_smem_once(attn_fwd_tc_persist, G_SMEM, &err2, &once2);
-    if (rc) return rc;
-    CUtensorMap tkv, to;
-    rc = sm100::make_tmap(&tkv, qkv, (uint64_t)3 * D, (uint64_t)B * N, (uint64_t)3 * D, 256);
-    if (rc) return rc;
-    rc = sm100::make_tmap(&to, out, (uint64_t)D, (uint64_t)B * N, (uint64_t)D, 128);
-    if (rc) return rc;
-    const int sms = num_sms();
-    if (sms <= 0) return TAE_ERR_CUDA;
-    const int items = B * H;
-    attn_fwd_tc_persist<<<items < sms ? items : sms, G_THREADS, G_SMEM, stream>>>(tkv, to, lse, H, items, scale,
-                                                                                  scale * 1.44269504088896340736f);
-    TAE_CHECK_LAUNCH();
-    return TAE_OK;
-  }
   static cudaError_t err = cudaSuccess;
   static std::once_flag once;
-  rc = set_smem_once(attn_fwd_tc, F_SMEM, &err, &once);
+  int rc = set_smem_once(attn_fwd_tc_ring, R_SMEM, &err, &once);
   if (rc) return rc;
-  CUtensorMap tq, tkv, to;
-  rc = sm100::make_tmap(&tq, qkv, (uint64_t)3 * D, (uint64_t)B * N, (uint64_t)3 * D, 128);
-  if (rc) return rc;
+  CUtensorMap tkv, to;
   rc = sm100::make_tmap(&tkv, qkv, (uint64_t)3 * D, (uint64_t)B * N, (uint64_t)3 * D, 256);
   if (rc) return rc;
   rc = sm100::make_tmap(&to, out, (uint64_t)D, (uint64_t)B * N, (uint64_t)D, 128);
   if (rc) return rc;
-  attn_fwd_tc<<<B * H * 2, F_THREADS, F_SMEM, stream>>>(tq, tkv, to, lse, H, scale, scale * 1.44269504088896340736f);
+  const int sms = num_sms();
+  if (sms <= 0) return TAE_ERR_CUDA;
+  const int items = B * H;
+  attn_fwd_tc_ring<<<items < sms ? items : sms, R_THREADS, R_SMEM, stream>>>(tkv, to, lse, H, items, scale,
+                                                                             scale * 1.44269504088896340736f);
   TAE_CHECK_LAUNCH();
   return TAE_OK;
 }
@@ -1695,56 +819,24 @@ int attention_bwd_tcgen05(const bf16* qkv, const bf16* out, const bf16* dout, co
   using namespace attn_tc;
   static cudaError_t err = cudaSuccess;
   static std::once_flag once;
-  int rc = set_smem_once(attn_bwd_tc, B_SMEM, &err, &once);
+  int rc = set_smem_once(attn_bwd_tc_persist, S_SMEM, &err, &once);
   if (rc) return rc;
   const int D = H * HD;
-  CUtensorMap tqkv, tdo;
-  rc = sm100::make_tmap(&tqkv, qkv, (uint64_t)3 * D, (uint64_t)B * N, (uint64_t)3 * D, 256);
-  if (rc) return rc;
-  rc = sm100::make_tmap(&tdo, dout, (uint64_t)D, (uint64_t)B * N, (uint64_t)D, 256);
-  if (rc) return rc;
   const float scale = 1.0f / sqrtf((float)HD);
-  // TAE_ATTN_BWD = persist (default) | pipe | v1 selects the kernel generation (A/B testing)
-  static int variant = -1;
-  if (variant < 0) {
-    const char* e = getenv("TAE_ATTN_BWD");
-    variant = (e == nullptr) ? 2 : (e[0] == 'v' ? 0 : (e[0] == 'p' && e[1] == 'i' ? 1 : 2));
-  }
-  if (delta != nullptr && variant != 2) {
-    set_error("tae_attention_bwd_delta: a precomputed delta needs the persistent kernel (unset TAE_ATTN_BWD)");
-    return TAE_ERR_UNSUPPORTED;
-  }
   const float sl2 = scale * 1.44269504088896340736f;
-  if (variant == 0) {
-    attn_bwd_tc<<<B * H, B_THREADS, B_SMEM, stream>>>(tqkv, tdo, out, dout, lse, dqkv, H, scale, sl2);
-  } else if (variant == 1) {
-    static cudaError_t err2 = cudaSuccess;
-    static std::once_flag once2;
-    rc = set_smem_once(attn_bwd_tc_pipe, P_SMEM, &err2, &once2);
-    if (rc) return rc;
-    CUtensorMap tdq;
-    rc = sm100::make_tmap(&tdq, dqkv, (uint64_t)3 * D, (uint64_t)B * N, (uint64_t)3 * D, 128);
-    if (rc) return rc;
-    attn_bwd_tc_pipe<<<B * H, B_THREADS, P_SMEM, stream>>>(tqkv, tdo, tdq, out, dout, lse, H, scale, sl2, g_attn_trace);
-  } else {
-    static cudaError_t err3 = cudaSuccess;
-    static std::once_flag once3;
-    rc = set_smem_once(attn_bwd_tc_persist, S_SMEM, &err3, &once3);
-    if (rc) return rc;
-    CUtensorMap tq64, tdo64, tdq;
-    rc = sm100::make_tmap(&tq64, qkv, (uint64_t)3 * D, (uint64_t)B * N, (uint64_t)3 * D, 64);
-    if (rc) return rc;
-    rc = sm100::make_tmap(&tdo64, dout, (uint64_t)D, (uint64_t)B * N, (uint64_t)D, 64);
-    if (rc) return rc;
-    rc = sm100::make_tmap(&tdq, dqkv, (uint64_t)3 * D, (uint64_t)B * N, (uint64_t)3 * D, 128);
-    if (rc) return rc;
-    const int sms = num_sms();
-    if (sms <= 0) return TAE_ERR_CUDA;
-    const int items = B * H;
-    const int grid = items < sms ? items : sms;
-    attn_bwd_tc_persist<<<grid, S_THREADS, S_SMEM, stream>>>(tq64, tdo64, tdq, out, dout, lse, delta, H, items, scale, sl2,
-                                                              g_attn_trace);
-  }
+  CUtensorMap tq64, tdo64, tdq;
+  rc = sm100::make_tmap(&tq64, qkv, (uint64_t)3 * D, (uint64_t)B * N, (uint64_t)3 * D, 64);
+  if (rc) return rc;
+  rc = sm100::make_tmap(&tdo64, dout, (uint64_t)D, (uint64_t)B * N, (uint64_t)D, 64);
+  if (rc) return rc;
+  rc = sm100::make_tmap(&tdq, dqkv, (uint64_t)3 * D, (uint64_t)B * N, (uint64_t)3 * D, 128);
+  if (rc) return rc;
+  const int sms = num_sms();
+  if (sms <= 0) return TAE_ERR_CUDA;
+  const int items = B * H;
+  const int grid = items < sms ? items : sms;
+  attn_bwd_tc_persist<<<grid, S_THREADS, S_SMEM, stream>>>(tq64, tdo64, tdq, out, dout, lse, delta, H, items, scale, sl2,
+                                                            g_attn_trace);
   TAE_CHECK_LAUNCH();
   return TAE_OK;
 }

@@ -31,17 +31,12 @@
 //   the two output streams, not the GELU arithmetic, are what separates this GEMM from the plain one (0.39 ms).
 // TAE_GELU_TMA_SWZ64: 64-byte swizzle of the staging boxes (bank-conflict-free st.shared); 0 = linear boxes.
 // TAE_GELU_EW: epilogue warps for the GELU epilogue, 8 (6 pipeline stages) or 16 (5 stages).
-// TAE_BF16_TMA_EPI (default 0): the same row-layout / TMA-store path for the plain bf16(+bias) epilogue.  Parity-green
-//   but not faster (in-step 1311 vs 1319 TFLOP/s), so the generic epilogue stays.
-// TAE_DIAG_GELU_ONE_OUT: diagnostic only (results are WRONG): drops the gelu(h) store.
+// (The same path for the plain bf16(+bias) epilogue was parity-green but not faster — in-step 1311 vs 1319 TFLOP/s — and was removed.)
 #ifndef TAE_GELU_TMA_EPI
 #define TAE_GELU_TMA_EPI 1
 #endif
 #ifndef TAE_GELU_TMA_SWZ64
 #define TAE_GELU_TMA_SWZ64 1
-#endif
-#ifndef TAE_BF16_TMA_EPI
-#define TAE_BF16_TMA_EPI 0
 #endif
 #ifndef TAE_GELU_EW
 #define TAE_GELU_EW 8
@@ -53,22 +48,11 @@
 #ifndef TAE_DGELU_TMA_EPI
 #define TAE_DGELU_TMA_EPI 1
 #endif
-// TAE_ROWDOT_TMA_EPI (default 0, not yet measured on a GPU): the row-dot epilogue on the same path — aux tile by TMA
+// The row-dot epilogue (proj dgrad emitting the attention backward's delta) runs on the same row-layout path: aux tile by TMA
 //   load, bf16(acc + bias) written over it in place, TMA store; the per-head dot product is thread-local in the row
-//   layout (no shuffles).
-#ifndef TAE_ROWDOT_TMA_EPI
-#define TAE_ROWDOT_TMA_EPI 0
-#endif
-// TAE_RESID_TMA_EPI (default 0, not yet measured on a GPU): the fp32 residual epilogue on the same path in 16-column
-//   steps — the fp32 residual tile [32 x 16] arrives by TMA load, out = resid + bf16(acc + bias) replaces it in place and
-//   leaves by TMA store; 8 epilogue warps, 6 stages.  The pos-embed broadcast (resid_rows < M) keeps the generic
-//   epilogue.
-#ifndef TAE_RESID_TMA_EPI
-#define TAE_RESID_TMA_EPI 0
-#endif
-#ifndef TAE_DIAG_GELU_ONE_OUT
-#define TAE_DIAG_GELU_ONE_OUT 0
-#endif
+//   layout (no shuffles).  Measured in the patch16 step: 987 -> 1100-1120 TFLOP/s for that GEMM family
+//   (profiles/r2_gemm_epilogue_ab.md).  The fp32 residual epilogue was tried on this path as well (16-column fp32 boxes by
+//   TMA load / store): no gain (proj forward 0.150 ms either way — it sits on the HBM roof), so it keeps the generic path.
 
 namespace tae {
 namespace gemm {
@@ -265,9 +249,6 @@ __device__ __forceinline__ void epi_write_rows(const Params& p, uint32_t stg, in
       gelu_and_grad_pair(f2_pack(a0, a1), f2_pack(bias4.x, bias4.y), g01, gp01);
       gelu_and_grad_pair(f2_pack(a2, a3), f2_pack(bias4.z, bias4.w), g23, gp23);
       *reinterpret_cast<uint2*>(optr) = make_uint2(gp01, gp23);
-#if TAE_DIAG_GELU_ONE_OUT
-      if (g01 == 0x12345678u && g23 == 0x9abcdef0u)  // keeps the math alive, never true in practice
-#endif
       *reinterpret_cast<uint2*>(obase2 + it * rstride) = make_uint2(g01, g23);
 #else
       float g[4], gp[4];
@@ -572,7 +553,7 @@ struct Cfg2 {
   static constexpr int kThreads = 128 + EW * 32;
   static constexpr int kStagingBytes = EW * 32 * 128;
   static constexpr int kBiasBytes =  // bf16[32] per epilogue warp (row-layout epilogues)
-      ((TAE_GELU_TMA_EPI && EW == TAE_GELU_EW) || ((TAE_BF16_TMA_EPI || TAE_ROWDOT_TMA_EPI || TAE_RESID_TMA_EPI) && EW == 8)) ? EW * 64 : 0;
+      ((TAE_GELU_TMA_EPI && EW == TAE_GELU_EW) || EW == 8) ? EW * 64 : 0;
   static constexpr int kSmemBytes = kStages * STAGE2_BYTES + SMEM_BARRIER_BYTES + kStagingBytes + kBiasBytes + 1024;
   static constexpr int kColsPerWarp = 256 / (EW / 4);
 };
@@ -584,13 +565,11 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                       const Params p) {
   constexpr int STAGES2 = Cfg2<EW>::kStages;
   constexpr bool kGeluTma = TAE_GELU_TMA_EPI && EPI == TAE_EPI_BF16_GELU && EW == TAE_GELU_EW;
-  constexpr bool kPlainTma = TAE_BF16_TMA_EPI && EPI == TAE_EPI_BF16 && EW == 8;
-  constexpr bool kRowTma = kGeluTma || kPlainTma;
+  constexpr bool kRowTma = kGeluTma;
   constexpr bool kDgeluTma = TAE_DGELU_TMA_EPI && EPI == TAE_EPI_BF16_DGELU && EW == 8;
-  constexpr bool kRowdotTma = TAE_ROWDOT_TMA_EPI && EPI == TAE_EPI_BF16_ROWDOT && EW == 8;
-  constexpr bool kResidTma = TAE_RESID_TMA_EPI && EPI == TAE_EPI_F32_RESID && EW == 8;
+  constexpr bool kRowdotTma = EPI == TAE_EPI_BF16_ROWDOT && EW == 8;
   constexpr bool kAuxTma = kDgeluTma || kRowdotTma;  // epilogues whose bf16 aux operand arrives by TMA load
-  constexpr bool kInTma = kAuxTma || kResidTma;       // ... or any epilogue input tile
+  constexpr bool kInTma = kAuxTma;
   constexpr int NUM_EPI_WARPS2 = EW;
   constexpr int COLS_PER_WARP = Cfg2<EW>::kColsPerWarp;
   extern __shared__ uint8_t smem_raw[];
@@ -778,82 +757,6 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       }
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tcgen05_fence_after();
-#if TAE_RESID_TMA_EPI
-      if constexpr (kResidTma) {
-        // Row-layout residual epilogue in 16-column steps: box c & 1 holds the fp32 residual tile [32 rows x 16 cols]
-        // (64-byte rows, TMA-loaded one step ahead); every thread replaces its own row by resid + bf16(acc + bias) and
-        // the box leaves by TMA store.  resid may alias out: a tile is always loaded before it is stored.
-        constexpr int SC = 16;
-        constexpr int NSTEP = COLS_PER_WARP / SC;
-        const int colw = it.nt * BLOCK_N + cg * COLS_PER_WARP;
-        const bool active = colw < p.N && row_base < p.M;  // warp-uniform
-        const uint32_t bias_sa =
-            smem_u32(smem + STAGES2 * STAGE2_BYTES + SMEM_BARRIER_BYTES + Cfg2<EW>::kStagingBytes) + (uint32_t)ew * 64u;
-        bool released = false;
-#pragma unroll 1
-        for (int c = 0; c < NSTEP; ++c) {
-          const int col0 = colw + c * SC;
-          if (!active || col0 >= p.N) break;
-          const bool last = (c == NSTEP - 1) || (col0 + SC >= p.N);
-          const int b = c & 1;
-          const uint32_t box = stg + (uint32_t)b * 2048u;
-          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + cg * COLS_PER_WARP + c * SC);
-          float bv = 0.f;
-          if (p.bias != nullptr && col0 + (lane & 15) < p.N) bv = __ldg(p.bias + col0 + (lane & 15));
-          uint32_t raw[16];
-          tmem_ld_32x32b_x16(taddr, raw);
-          if (lane < 16) st_shared_u16(bias_sa + (uint32_t)lane * 2u, __bfloat16_as_ushort(__float2bfloat16_rn(bv)));
-          if (!last && elect_one()) {  // next step's residual tile into the other box (its last store has been read)
-            tma_store_wait_read();
-            mbar_expect_tx(&aux_bar[ew * 2 + (b ^ 1)], 2048u);
-            tma_load_2d_sa(stg + (uint32_t)(b ^ 1) * 2048u, &tmap_o2, &aux_bar[ew * 2 + (b ^ 1)], col0 + SC, row_base);
-          }
-          tmem_ld_wait();
-          if (last) tcgen05_fence_before();
-          __syncwarp();
-          if (last) {
-            if (lane == 0) mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
-            released = true;
-          }
-          mbar_wait(&aux_bar[ew * 2 + b], (aux_phase >> b) & 1u);
-          aux_phase ^= 1u << b;
-          uint4 bq[2];
-          bq[0] = ld_shared_v4(bias_sa);
-          bq[1] = ld_shared_v4(bias_sa + 16u);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {  // 4 fp32 columns = one 16-byte chunk of the row
-            const uint4 rv = ld_shared_v4(box + stg64_off(lane, k));
-            const uint32_t bw0 = (&bq[k >> 1].x)[(2 * k) & 3], bw1 = (&bq[k >> 1].x)[(2 * k + 1) & 3];
-            float s0, s1, s2, s3, o0, o1, o2, o3;
-            f2_unpack(f2_add(f2_pack(__uint_as_float(raw[4 * k]), __uint_as_float(raw[4 * k + 1])),
-                             f2_pack(__uint_as_float(bw0 << 16), __uint_as_float(bw0 & 0xffff0000u))), s0, s1);
-            f2_unpack(f2_add(f2_pack(__uint_as_float(raw[4 * k + 2]), __uint_as_float(raw[4 * k + 3])),
-                             f2_pack(__uint_as_float(bw1 << 16), __uint_as_float(bw1 & 0xffff0000u))), s2, s3);
-            const float2 r01 = round_bf16x2(s0, s1), r23 = round_bf16x2(s2, s3);  // the Linear's bf16 output
-            f2_unpack(f2_add(f2_pack(__uint_as_float(rv.x), __uint_as_float(rv.y)), f2_pack(r01.x, r01.y)), o0, o1);
-            f2_unpack(f2_add(f2_pack(__uint_as_float(rv.z), __uint_as_float(rv.w)), f2_pack(r23.x, r23.y)), o2, o3);
-            st_shared_v4(box + stg64_off(lane, k), __float_as_uint(o0), __float_as_uint(o1), __float_as_uint(o2),
-                         __float_as_uint(o3));
-          }
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (elect_one()) {
-            tma_store_2d_sa(&tmap_o, box, col0, row_base);
-            tma_store_commit();
-          }
-        }
-        if (!released) {
-          tcgen05_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
-        }
-        if (++acc == NUM_ACC) {
-          acc = 0;
-          acc_phase ^= 1u;
-        }
-        continue;
-      }
-#endif
       if constexpr (kAuxTma) {
         // Row-layout GELU' epilogue: out = bf16(bf16(acc) * gelu'(h)).  Step c works in staging box c & 1: the aux
         // tile was TMA-loaded into it one step earlier, every thread multiplies its own row in place, the box leaves by
@@ -865,11 +768,9 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         bool released = false;
         // Row-dot variant: out = bf16(acc + bias) written over the aux tile, and dot = sum over the 64 columns of a head
         // of out * aux stays in this thread (it owns the row); written after the head's second step.
-#if TAE_ROWDOT_TMA_EPI
         [[maybe_unused]] const uint32_t bias_sa =
             smem_u32(smem + STAGES2 * STAGE2_BYTES + SMEM_BARRIER_BYTES + Cfg2<EW>::kStagingBytes) + (uint32_t)ew * 64u;
         [[maybe_unused]] float dot = 0.f;
-#endif
 #pragma unroll 1
         for (int c = 0; c < NSTEP; ++c) {
           const int col0 = colw + c * EPI_COLS;
@@ -879,17 +780,13 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
           const uint32_t box = stg + (uint32_t)b * 2048u;
           const uint32_t taddr =
               tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + cg * COLS_PER_WARP + c * EPI_COLS);
-#if TAE_ROWDOT_TMA_EPI
           [[maybe_unused]] float bv = 0.f;
           if constexpr (kRowdotTma) {
             if (p.bias != nullptr && col0 + lane < p.N) bv = __ldg(p.bias + col0 + lane);
           }
-#endif
           uint32_t raw[32];
           tmem_ld_32x32b_x32(taddr, raw);
-#if TAE_ROWDOT_TMA_EPI
           if constexpr (kRowdotTma) st_shared_u16(bias_sa + (uint32_t)lane * 2u, __bfloat16_as_ushort(__float2bfloat16_rn(bv)));
-#endif
           if (!last && elect_one()) {  // next step's aux tile into the other box (its last store has been read)
             tma_store_wait_read();
             mbar_expect_tx(&aux_bar[ew * 2 + (b ^ 1)], 2048u);
@@ -904,13 +801,11 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
           }
           mbar_wait(&aux_bar[ew * 2 + b], (aux_phase >> b) & 1u);
           aux_phase ^= 1u << b;
-#if TAE_ROWDOT_TMA_EPI
           [[maybe_unused]] uint4 bq[4];
           if constexpr (kRowdotTma) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) bq[k] = ld_shared_v4(bias_sa + (uint32_t)k * 16u);  // after the __syncwarp above
           }
-#endif
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const uint4 m = ld_shared_v4(box + stg64_off(lane, k));
@@ -919,7 +814,6 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const int e = 8 * k + 2 * j;
-#if TAE_ROWDOT_TMA_EPI
               if constexpr (kRowdotTma) {
                 const uint32_t bw = (&bq[k].x)[j];
                 float s0, s1, d0, d1;
@@ -932,7 +826,6 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                 dot += d0 + d1;
                 continue;
               }
-#endif
               // bf16(acc) first: the dgrad GEMM's own output rounding in the reference
               const float2 r = round_bf16x2(__uint_as_float(raw[e]), __uint_as_float(raw[e + 1]));
               float o0, o1;
@@ -942,7 +835,6 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
             }
             st_shared_v4(box + stg64_off(lane, k), ow[0], ow[1], ow[2], ow[3]);
           }
-#if TAE_ROWDOT_TMA_EPI
           if constexpr (kRowdotTma) {
             if (c & 1) {  // second half of a 64-column head: rowdot[image, head, token] of this thread's row
               const int grow = row_base + lane;
@@ -953,7 +845,6 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
               dot = 0.f;
             }
           }
-#endif
           fence_proxy_async_smem();
           __syncwarp();
           if (elect_one()) {
@@ -1014,11 +905,8 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
           st_shared_u16(bias_sa + (uint32_t)lane * 2u, __bfloat16_as_ushort(__float2bfloat16_rn(bv)));
           tmem_ld_wait();
           if (last) tcgen05_fence_before();
-          // the staging boxes about to be overwritten are no longer being read: GELU rewrites both boxes every step,
-          // the plain epilogue alternates between its two boxes (one store may stay in flight)
-          if (elect_one()) {
-            if constexpr (kGeluTma) tma_store_wait_read(); else tma_store_wait_read_le1();
-          }
+          // the staging boxes about to be overwritten are no longer being read (GELU rewrites both boxes every step)
+          if (elect_one()) tma_store_wait_read();
           __syncwarp();
           if (last) {
             if (lane == 0) mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
@@ -1027,30 +915,6 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
           uint4 bq[4];
 #pragma unroll
           for (int k = 0; k < 4; ++k) bq[k] = ld_shared_v4(bias_sa + (uint32_t)k * 16u);
-          if constexpr (kPlainTma) {
-            const uint32_t box = stg + (uint32_t)(c & 1) * 2048u;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint32_t bw[4] = {bq[k].x, bq[k].y, bq[k].z, bq[k].w};
-              uint32_t ow[4];
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const int e = 8 * k + 2 * j;
-                float s0, s1;
-                f2_unpack(f2_add(f2_pack(__uint_as_float(raw[e]), __uint_as_float(raw[e + 1])),
-                                 f2_pack(__uint_as_float(bw[j] << 16), __uint_as_float(bw[j] & 0xffff0000u))), s0, s1);
-                ow[j] = pack_bf16x2(s0, s1);
-              }
-              st_shared_v4(box + stg64_off(lane, k), ow[0], ow[1], ow[2], ow[3]);
-            }
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (row_base < p.M && elect_one()) {
-              tma_store_2d_sa(&tmap_o, box, col0, row_base);
-              tma_store_commit();
-            }
-            continue;
-          }
 #pragma unroll
           for (int k = 0; k < 4; ++k) {  // 8 columns = one 16-byte chunk of each output row
             const uint32_t bw[4] = {bq[k].x, bq[k].y, bq[k].z, bq[k].w};
@@ -1067,9 +931,7 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
           fence_proxy_async_smem();
           __syncwarp();
           if (row_base < p.M && elect_one()) {
-#if !TAE_DIAG_GELU_ONE_OUT
             tma_store_2d_sa(&tmap_o2, stg, col0, row_base);
-#endif
             tma_store_2d_sa(&tmap_o, stg + 2048u, col0, row_base);
             tma_store_commit();
           }
@@ -1166,15 +1028,8 @@ template <int EPI>
 static int launch_2sm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& to2,
                       const Params& p, int clusters, cudaStream_t stream) {
   // epilogue-heavy: GELU always; residual / GELU' epilogues when the main loop per tile is short (K <= 2048)
-  // (with TAE_RESID_TMA_EPI the 8-warp residual kernel IS the row-layout one: the pos-embed broadcast, which it does not
-  // handle, goes to the 16-warp generic kernel whatever its K)
-  const bool resid_wrap = EPI == TAE_EPI_F32_RESID && p.resid_rows < p.M;
-  if (TAE_RESID_TMA_EPI && EPI == TAE_EPI_F32_RESID)
-    return resid_wrap ? launch_2sm_cfg<EPI, 16>(ta, tb, to, to2, p, clusters, stream)
-                      : launch_2sm_cfg<EPI, 8>(ta, tb, to, to2, p, clusters, stream);
   const bool heavy = (EPI == TAE_EPI_BF16_GELU && TAE_GELU_EW == 16) ||
-                     ((EPI == TAE_EPI_F32_RESID || (EPI == TAE_EPI_BF16_DGELU && !TAE_DGELU_TMA_EPI) ||
-                       (EPI == TAE_EPI_BF16_ROWDOT && !TAE_ROWDOT_TMA_EPI)) && p.K <= 2048);
+                     ((EPI == TAE_EPI_F32_RESID || (EPI == TAE_EPI_BF16_DGELU && !TAE_DGELU_TMA_EPI)) && p.K <= 2048);
   if (heavy) return launch_2sm_cfg<EPI, 16>(ta, tb, to, to2, p, clusters, stream);
   return launch_2sm_cfg<EPI, 8>(ta, tb, to, to2, p, clusters, stream);
 }
@@ -1298,20 +1153,9 @@ extern "C" int tae_gemm(const tae_gemm_args* a, void* stream_) {
   if (rc) return rc;
 
   const int total = p.m_tiles * p.n_tiles * p.splits;
-  CUtensorMap to{}, to2{};  // output maps: only the TMA-store GELU epilogue reads them
-#if TAE_RESID_TMA_EPI
-  if (use2 && a->epilogue == TAE_EPI_F32_RESID && p.resid_rows >= a->M) {
-    const CUtensorMapSwizzle swz = TAE_GELU_TMA_SWZ64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE;
-    rc = make_tmap_box(&to, a->out, (uint64_t)a->N, (uint64_t)a->M, (uint64_t)a->ldo, 16, 32, swz, true);
-    if (rc) return rc;
-    rc = make_tmap_box(&to2, a->resid, (uint64_t)a->N, (uint64_t)a->M, (uint64_t)a->ldr, 16, 32, swz, true);
-    if (rc) return rc;
-  }
-#endif
-#if TAE_GELU_TMA_EPI || TAE_BF16_TMA_EPI || TAE_DGELU_TMA_EPI || TAE_ROWDOT_TMA_EPI
-  if (use2 && ((TAE_GELU_TMA_EPI && a->epilogue == TAE_EPI_BF16_GELU) || (TAE_BF16_TMA_EPI && a->epilogue == TAE_EPI_BF16) ||
-               (TAE_DGELU_TMA_EPI && a->epilogue == TAE_EPI_BF16_DGELU) ||
-               (TAE_ROWDOT_TMA_EPI && a->epilogue == TAE_EPI_BF16_ROWDOT))) {
+  CUtensorMap to{}, to2{};  // output / aux maps of the row-layout epilogues (GELU, GELU', row-dot)
+  if (use2 && ((TAE_GELU_TMA_EPI && a->epilogue == TAE_EPI_BF16_GELU) ||
+               (TAE_DGELU_TMA_EPI && a->epilogue == TAE_EPI_BF16_DGELU) || a->epilogue == TAE_EPI_BF16_ROWDOT)) {
     const CUtensorMapSwizzle swz = TAE_GELU_TMA_SWZ64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE;
     rc = make_tmap_box(&to, a->out, (uint64_t)a->N, (uint64_t)a->M, (uint64_t)a->ldo, 32, 32, swz);
     if (rc) return rc;
@@ -1323,7 +1167,6 @@ extern "C" int tae_gemm(const tae_gemm_args* a, void* stream_) {
       if (rc) return rc;
     }
   }
-#endif
   if (use2) {
     const int clusters = total < units ? total : units;
     p.sched = total > clusters ? sched_counter_slot() : nullptr;  // one item per cluster needs no scheduler

@@ -431,6 +431,169 @@ ln_bwd_warp_kernel(const bf16* __restrict__ dy, const float* __restrict__ x, con
   }
 }
 
+// Backward, ROW-GROUP variant for the wide residual streams (D = W*512: 2048 for patch32, 2560 for patch64 / patch128).
+// The warp-per-row kernel above would need 16*NV registers of per-column accumulators (NV = 16, 20); the block-per-row
+// kernel synchronises the whole CTA twice per row pair and keeps one CTA per SM (0.59 / 0.33 / 0.21 of the HBM peak at
+// 16384 / 4096 / 1024 rows).  Here W warps share a row (a lane owns 4 column quads, interleaved so that every warp
+// reads 512 contiguous bytes per access), R such groups per CTA walk rows independently, and the only synchronisation is
+// ONE named barrier per row among the group's W warps (the two row sums travel through double-buffered shared-memory
+// slots, together with the next row index when rows are drawn dynamically).  The R groups fold their dgamma / dbeta /
+// colsum accumulators through shared memory at the end: one partial row per CTA, so small-M launches (1024 rows) no
+// longer write and re-read more partial-sum bytes than the finalize pass is worth.
+__device__ __forceinline__ void group_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+template <int W, int R>
+__global__ void __launch_bounds__(32 * W * R, 1)
+ln_bwd_group_kernel(const bf16* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
+                    const float* __restrict__ rstd, const float* __restrict__ gamma, const float* dres_in,
+                    float* dres_out, bf16* __restrict__ dres_out_b, float* __restrict__ partials, int rows, int* sched) {
+  constexpr int NV = 4;
+  constexpr int D = W * 512;
+  __shared__ float s_stat[R][2][W][2];
+  __shared__ int s_next[R][2];
+  __shared__ __align__(16) float s_acc[3 * D];
+  const int lane = threadIdx.x & 31;
+  const int wic = threadIdx.x >> 5;
+  const int rg = wic / W, w = wic - rg * W;
+  const int group = blockIdx.x * R + rg, ngroups = gridDim.x * R;
+  float4 g[NV], acc_dg[NV], acc_db[NV], acc_cs[NV];
+  int col[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    col[i] = ((i * W + w) * 32 + lane) * 4;
+    g[i] = __ldg(reinterpret_cast<const float4*>(gamma + col[i]));
+    acc_dg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    acc_db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    acc_cs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const float invD = 1.0f / (float)D;
+  const bool dynamic = sched != nullptr;
+  int row = group;
+  if (dynamic) {
+    if (w == 0 && lane == 0) s_next[rg][1] = atomicAdd(sched, 1);
+    group_bar_sync(1 + rg, W * 32);
+    row = s_next[rg][1];
+  }
+  int buf = 0;
+#pragma unroll 1
+  while (row < rows) {
+    const size_t base = (size_t)row * D;
+    float4 xh[NV], gy[NV], din[NV];
+    uint2 draw[NV];
+    const float mu = __ldg(mean + row), rs = __ldg(rstd + row);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const size_t off = base + col[i];
+      xh[i] = ld_nc_f4(x + off);
+      draw[i] = ld_nc_v2(dy + off);
+      din[i] = dres_in != nullptr ? *reinterpret_cast<const float4*>(dres_in + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    // the group's leader draws the NEXT row while this row's loads are in flight
+    if (dynamic && w == 0 && lane == 0) s_next[rg][buf] = atomicAdd(sched, 1);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float2 d01 = unpack_bf16x2(draw[i].x), d23 = unpack_bf16x2(draw[i].y);
+      const float4 d = make_float4(d01.x, d01.y, d23.x, d23.y);
+      const float4 h = make_float4((xh[i].x - mu) * rs, (xh[i].y - mu) * rs, (xh[i].z - mu) * rs, (xh[i].w - mu) * rs);
+      xh[i] = h;
+      acc_dg[i].x += d.x * h.x;
+      acc_dg[i].y += d.y * h.y;
+      acc_dg[i].z += d.z * h.z;
+      acc_dg[i].w += d.w * h.w;
+      acc_db[i].x += d.x;
+      acc_db[i].y += d.y;
+      acc_db[i].z += d.z;
+      acc_db[i].w += d.w;
+      const float4 t = make_float4(d.x * g[i].x, d.y * g[i].y, d.z * g[i].z, d.w * g[i].w);
+      gy[i] = t;
+      s1 += (t.x + t.y) + (t.z + t.w);
+      s2 += (t.x * h.x + t.y * h.y) + (t.z * h.z + t.w * h.w);
+    }
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if (lane == 0) {
+      s_stat[rg][buf][w][0] = s1;
+      s_stat[rg][buf][w][1] = s2;
+    }
+    group_bar_sync(1 + rg, W * 32);
+    float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < W; ++k) {  // same order in every warp: all lanes of the row agree bit for bit
+      c1 += s_stat[rg][buf][k][0];
+      c2 += s_stat[rg][buf][k][1];
+    }
+    c1 *= invD;
+    c2 *= invD;
+    const int next_row = dynamic ? s_next[rg][buf] : row + ngroups;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const size_t off = base + col[i];
+      float4 o;
+      o.x = rs * (gy[i].x - c1 - xh[i].x * c2) + din[i].x;
+      o.y = rs * (gy[i].y - c1 - xh[i].y * c2) + din[i].y;
+      o.z = rs * (gy[i].z - c1 - xh[i].z * c2) + din[i].z;
+      o.w = rs * (gy[i].w - c1 - xh[i].w * c2) + din[i].w;
+      *reinterpret_cast<float4*>(dres_out + off) = o;
+      const uint32_t p01 = pack_bf16x2(o.x, o.y), p23 = pack_bf16x2(o.z, o.w);
+      if (dres_out_b != nullptr) *reinterpret_cast<uint2*>(dres_out_b + off) = make_uint2(p01, p23);
+      const float2 r01 = unpack_bf16x2(p01), r23 = unpack_bf16x2(p23);
+      acc_cs[i].x += r01.x;
+      acc_cs[i].y += r01.y;
+      acc_cs[i].z += r23.x;
+      acc_cs[i].w += r23.y;
+    }
+    row = next_row;
+    buf ^= 1;
+  }
+  if (dynamic && w == 0 && lane == 0) {
+    // every group has drawn its last (out-of-range) row before it counts itself done: the last one re-arms the slot
+    if (atomicAdd(sched + 1, 1) == ngroups - 1) {
+      sched[0] = 0;
+      sched[1] = 0;
+      __threadfence();
+    }
+  }
+  // fold the R groups' column accumulators through shared memory: one partial row [3][D] per CTA
+#pragma unroll 1
+  for (int r = 0; r < R; ++r) {
+    if (rg == r) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        float4* a0 = reinterpret_cast<float4*>(s_acc + col[i]);
+        float4* a1 = reinterpret_cast<float4*>(s_acc + D + col[i]);
+        float4* a2 = reinterpret_cast<float4*>(s_acc + 2 * D + col[i]);
+        if (r == 0) {
+          *a0 = acc_dg[i];
+          *a1 = acc_db[i];
+          *a2 = acc_cs[i];
+        } else {
+          float4 v = *a0;
+          *a0 = make_float4(v.x + acc_dg[i].x, v.y + acc_dg[i].y, v.z + acc_dg[i].z, v.w + acc_dg[i].w);
+          v = *a1;
+          *a1 = make_float4(v.x + acc_db[i].x, v.y + acc_db[i].y, v.z + acc_db[i].z, v.w + acc_db[i].w);
+          v = *a2;
+          *a2 = make_float4(v.x + acc_cs[i].x, v.y + acc_cs[i].y, v.z + acc_cs[i].z, v.w + acc_cs[i].w);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  float4* pdst = reinterpret_cast<float4*>(partials + (size_t)blockIdx.x * 3 * D);
+  for (int i = threadIdx.x; i < 3 * D / 4; i += blockDim.x) pdst[i] = reinterpret_cast<const float4*>(s_acc)[i];
+}
+
+static bool bwd_group_ok(int D) { return D == 2048 || D == 2560; }
+static int bwd_group_grid(int rows, int R) {
+  const int sms = num_sms() > 0 ? num_sms() : 148;
+  int grid = (rows + R - 1) / R;
+  if (grid > sms) grid = sms;
+  return grid < 1 ? 1 : grid;
+}
+constexpr int GROUP_R_2048 = 3, GROUP_R_2560 = 2;  // row groups per CTA: 384 / 320 threads, 60 / 51 KB of loads in flight
+
 // warp-per-row backward: which widths, and how many partial rows (= warps) it produces
 static bool bwd_warp_ok(int D) { return D % 128 == 0 && D / 128 <= 8 && (D / 128 == 1 || D / 128 == 2 || D / 128 == 6 || D / 128 == 8); }
 static int bwd_warp_grid(int rows) {
@@ -544,6 +707,7 @@ extern "C" int tae_layernorm_bwd_num_partials(int32_t rows, int32_t D) {
   int vpt, threads;
   if (rows <= 0 || !pick_config(D, &vpt, &threads)) return TAE_ERR_SHAPE;
   if (bwd_warp_ok(D)) return bwd_warp_grid(rows) * 8;
+  if (bwd_group_ok(D)) return bwd_group_grid(rows, D == 2048 ? GROUP_R_2048 : GROUP_R_2560);
   return grid_for(rows, threads, true);
 }
 
@@ -569,6 +733,19 @@ extern "C" int tae_layernorm_bwd(const tae_bf16* dy, const float* x, const float
       case 6: ln_bwd_warp_kernel<6><<<wg, 256, 0, stream>>>(dyy, x, mean, rstd, gamma, dres_in, dres_out, ob, partials, rows, sched); break;
       default: ln_bwd_warp_kernel<8><<<wg, 256, 0, stream>>>(dyy, x, mean, rstd, gamma, dres_in, dres_out, ob, partials, rows, sched); break;
     }
+    TAE_CHECK_LAUNCH();
+    return TAE_OK;
+  }
+  if (bwd_group_ok(D)) {
+    const int R = D == 2048 ? GROUP_R_2048 : GROUP_R_2560;
+    const int gg = bwd_group_grid(rows, R);
+    int* sched = rows > gg * R ? sched_counter_slot() : nullptr;  // more rows than groups: dynamic rows (if enabled)
+    if (D == 2048)
+      ln_bwd_group_kernel<4, GROUP_R_2048><<<gg, 32 * 4 * GROUP_R_2048, 0, stream>>>(dyy, x, mean, rstd, gamma, dres_in, dres_out, ob,
+                                                                                   partials, rows, sched);
+    else
+      ln_bwd_group_kernel<5, GROUP_R_2560><<<gg, 32 * 5 * GROUP_R_2560, 0, stream>>>(dyy, x, mean, rstd, gamma, dres_in, dres_out, ob,
+                                                                                   partials, rows, sched);
     TAE_CHECK_LAUNCH();
     return TAE_OK;
   }

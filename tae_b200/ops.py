@@ -7,7 +7,6 @@ from __future__ import annotations
 
 import ctypes as C
 import math
-import os as _os
 
 import torch
 
@@ -177,7 +176,7 @@ def attention_fwd(qkv: torch.Tensor, B: int, N: int, H: int, hd: int):
 
 def attention_takes_delta(N: int, hd: int) -> bool:
     """True when attention_bwd accepts delta = rowsum(dout * out) precomputed by a TAE_EPI_BF16_ROWDOT GEMM."""
-    return N == 256 and hd == 64 and _os.environ.get("TAE_ATTN_BWD") is None and _os.environ.get("TAE_ATTN_LEGACY") != "1"
+    return N in (256, 64) and hd == 64
 
 
 def attention_bwd(qkv, out, dout, lse, B: int, N: int, H: int, hd: int, delta: torch.Tensor | None = None):

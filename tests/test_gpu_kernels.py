@@ -111,16 +111,6 @@ def test_gemm_epilogue_residual_and_posembed():
     assert max_err_scaled(out2, ref2) < 1e-2
 
 
-# Written together with the row-layout variants of the residual / row-dot epilogues (TAE_RESID_TMA_EPI,
-# TAE_ROWDOT_TMA_EPI: off by default, no GPU time was left to run them): these cases run when a variant library is under
-# test (tools/gpu_ab.sh sets TAE_B200_LIB; TAE_ATTN_FWD=ring selects the ring attention forward) or when asked for, and
-# join the default suite once they have been seen green.
-_variant_cases = pytest.mark.skipif(not (os.environ.get("TAE_B200_LIB") or os.environ.get("TAE_TEST_VARIANT_CASES") or
-                                         os.environ.get("TAE_ATTN_FWD")),
-                                    reason="edge cases for variant epilogue builds (set TAE_TEST_VARIANT_CASES=1 to run)")
-
-
-@_variant_cases
 @pytest.mark.parametrize("M,N,K", [(1000, 264, 72), (300, 1032, 64), (2048, 1024, 1024), (4096, 1024, 4096)])
 @pytest.mark.parametrize("inplace", [False, True])
 def test_gemm_epilogue_residual_ragged(M, N, K, inplace):
@@ -144,7 +134,6 @@ def test_gemm_epilogue_residual_ragged(M, N, K, inplace):
     assert bool((big[M:] == 7).all()) and bool((big[:, N:] == 7).all())
 
 
-@_variant_cases
 @pytest.mark.parametrize("M,N,K,tokens,with_bias", [(4096, 1024, 1024, 256, False), (1000, 192, 72, 100, True),
                                                      (300, 64, 264, 4, True), (2560, 2560, 128, 16, False)])
 def test_gemm_rowdot_epilogue_ragged(M, N, K, tokens, with_bias):
@@ -537,6 +526,35 @@ def test_attention_bwd_with_precomputed_delta():
     assert max_err_scaled(got.float(), ref.float()) < 2e-3
 
 
+@pytest.mark.parametrize("B,H", [(3, 2), (37, 32), (1000, 1)])
+def test_attention_n64_kernels_with_and_without_delta(B, H):
+    """The 64-token grid (patch32): persistent mma.sync kernels, several items per CTA (1184 and 1000 items over 444 / 296
+    CTAs), backward both with O staged (delta computed in the kernel, 2 CTAs per SM) and with the precomputed delta of the
+    row-dot GEMM epilogue (3 CTAs per SM); dS^T goes through shared memory between the two phases."""
+    ops = _ops()
+    N, hd = 64, 64
+    D = H * hd
+    qkv = randn(B * N, 3 * D, seed=50 + H, scale=0.8)
+    dout = randn(B * N, D, seed=51 + H)
+    out, lse = ops.attention_fwd(qkv, B, N, H, hd)
+    oref, lref, dref = _attn_ref(qkv, B, N, H, hd, dout)
+    assert rel_err(out.float(), oref) < 8e-3 and max_err_scaled(out.float(), oref) < 1.5e-2
+    assert float((lse - lref).abs().max()) < 2e-3
+    delta = (dout.float() * out.float()).view(B, N, H, hd).sum(-1).permute(0, 2, 1).contiguous()
+    got = []
+    for kw in ({}, {"delta": delta}):
+        dqkv = ops.attention_bwd(qkv, None if kw else out, dout, lse, B, N, H, hd, **kw)
+        assert rel_err(dqkv.float(), dref) < 1.5e-2 and max_err_scaled(dqkv.float(), dref) < 2e-2
+        for part in range(3):  # q, k, v gradients separately
+            sl = slice(part * D, (part + 1) * D)
+            assert rel_err(dqkv[:, sl].float(), dref[:, sl]) < 2e-2, f"part {part}"
+        per_img = ((dqkv.float() - dref).view(B, -1).norm(dim=1) / dref.view(B, -1).norm(dim=1)).max()
+        assert float(per_img) < 2e-2
+        got.append(dqkv)
+    assert max_err_scaled(got[1].float(), got[0].float()) < 2e-3
+    assert torch.equal(ops.attention_bwd(qkv, None, dout, lse, B, N, H, hd, delta=delta), got[1])  # deterministic
+
+
 @pytest.mark.parametrize("B,H", [(41, 16), (300, 1)])
 def test_attention_persistent_kernels_many_items_per_cta(B, H):
     """The tcgen05 attention kernels are persistent: with more (image, head) items than SMs every CTA walks several
@@ -581,6 +599,13 @@ def test_dynamic_scheduling_matches_static():
     w = randn(1024, dtype=torch.float32, seed=56) * 0.2 + 1
     dy, dres = randn(5000, 1024, seed=57), randn(5000, 1024, dtype=torch.float32, seed=58)
     _, mean, rstd = ops.layernorm_fwd(x, w, torch.zeros_like(w), 1e-6)
+    # the wide-row LayerNorm backward (row groups, D = 2048 / 2560) draws its rows from the same counter slots
+    wide = []
+    for rows_w, Dw in ((3001, 2048), (1500, 2560)):
+        xw = randn(rows_w, Dw, dtype=torch.float32, seed=59) * 2 + 0.5
+        ww = randn(Dw, dtype=torch.float32, seed=60) * 0.2 + 1
+        _, mw, rw = ops.layernorm_fwd(xw, ww, torch.zeros_like(ww), 1e-6)
+        wide.append((randn(rows_w, Dw, seed=61), xw, mw, rw, ww, randn(rows_w, Dw, dtype=torch.float32, seed=62)))
 
     def run():
         plain = ops.gemm(A, W, epilogue=EPI_BF16, bias=bias)
@@ -588,9 +613,11 @@ def test_dynamic_scheduling_matches_static():
         dw = ops.gemm(dY, X, a_mn=True, b_mn=True, epilogue=EPI_F32_ACC, splits=1)
         dw_split = ops.gemm(dY, X, a_mn=True, b_mn=True, epilogue=EPI_F32_ACC, splits=0)
         ln = ops.layernorm_bwd(dy, x, mean, rstd, w, dres)
+        lw = [ops.layernorm_bwd(*a) for a in wide]
         torch.cuda.synchronize()
         # exact: per-element results; approx: sums whose order follows the row -> CTA assignment or the split-K atomics
-        return [plain, gp, g, dw, ln[0], ln[1]], [dw_split, *[t for t in ln[2:] if t is not None]]
+        return ([plain, gp, g, dw, ln[0], ln[1]] + [t for l in lw for t in l[:2]],
+                [dw_split, *[t for t in ln[2:] if t is not None]] + [t for l in lw for t in l[2:] if t is not None])
 
     prev = ops.set_dynamic_scheduling(False)
     try:
@@ -612,12 +639,11 @@ def test_dynamic_scheduling_matches_static():
     assert max_err_scaled(static[0].float(), ref) < 1e-2
 
 
-@_variant_cases
 @pytest.mark.parametrize("B,H,kscale_hi", [(3, 2, 1.0), (2, 3, 12.0), (5, 1, 0.05)])
 def test_attention_fwd_two_key_halves(B, H, kscale_hi):
-    """Forward attention at N = 256 when the two 128-key halves of a row have very different score ranges.  Written for
-    the ring kernel (TAE_ATTN_FWD=ring: it carries the first half's row maximum into the second half and rescales the
-    accumulator only when the second half's maximum exceeds it by 2^32); any forward kernel has to pass it.
+    """Forward attention at N = 256 when the two 128-key halves of a row have very different score ranges: the kernel
+    carries the first half's row maximum into the second half and rescales the accumulator only when the second half's
+    maximum exceeds it by 2^32.
     kscale_hi = 12: most rows take the rescale path; 0.05: the second half is negligible; 1: the common case."""
     ops = _ops()
     N, hd = 256, 64

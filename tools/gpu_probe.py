@@ -43,6 +43,7 @@ def main():
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--attn-only", action="store_true")
     ap.add_argument("--gemm-only", action="store_true")
+    ap.add_argument("--small-grids", action="store_true", help="attention and LayerNorm at the patch32/64/128 shapes only")
     ap.add_argument("--only", default=None, help="with --gemm-only: just the layers whose name starts with this (qkv, proj, fc1, fc2)")
     args = ap.parse_args()
     hbm, tf, how = peaks()
@@ -53,6 +54,37 @@ def main():
 
     def rnd(*s, dtype=bf):
         return (torch.randn(*s, device=dev) * 0.5).to(dtype)
+
+    if args.small_grids:
+        # attention on the short grids (B=256): bytes = qkv read (+ dout) and out / dqkv written
+        for N, H, hd in ((64, 32, 64), (16, 32, 80), (4, 32, 80)):
+            B, D = 256, H * hd
+            qkv, dout = rnd(B * N, 3 * D), rnd(B * N, D)
+            med, _ = timeit(lambda: ops.attention_fwd(qkv, B, N, H, hd))
+            by = B * N * D * 2.0 * 4
+            print(f"attention fwd N={N} H={H} hd={hd}: {med * 1e3:.1f} us  {by / med / 1e6:.0f} GB/s ({by / med / 1e6 / hbm:.2f} of HBM peak)")
+            out, lse = ops.attention_fwd(qkv, B, N, H, hd)
+            med, _ = timeit(lambda: ops.attention_bwd(qkv, out, dout, lse, B, N, H, hd))
+            by = B * N * D * 2.0 * 8
+            print(f"attention bwd N={N} (O staged): {med * 1e3:.1f} us  {by / med / 1e6:.0f} GB/s ({by / med / 1e6 / hbm:.2f})")
+            if ops.attention_takes_delta(N, hd):
+                delta = (dout.float() * out.float()).view(B, N, H, hd).sum(-1).permute(0, 2, 1).contiguous()
+                med, _ = timeit(lambda: ops.attention_bwd(qkv, None, dout, lse, B, N, H, hd, delta=delta))
+                by = B * N * D * 2.0 * 7
+                print(f"attention bwd N={N} (delta given): {med * 1e3:.1f} us  {by / med / 1e6:.0f} GB/s ({by / med / 1e6 / hbm:.2f})")
+        # LayerNorm at the residual-stream shapes of patch32 / patch64 / patch128 (+ patch16 for reference)
+        for rows, D in ((65536, 1024), (16384, 2048), (4096, 2560), (1024, 2560)):
+            xf = torch.randn(rows, D, device=dev)
+            w, b = torch.ones(D, device=dev), torch.zeros(D, device=dev)
+            med, _ = timeit(lambda: ops.layernorm_fwd(xf, w, b, 1e-6))
+            by = rows * D * 6.0
+            print(f"layernorm fwd rows={rows} D={D}: {med * 1e3:.1f} us  {by / med / 1e6:.0f} GB/s ({by / med / 1e6 / hbm:.2f})")
+            y, mean, rstd = ops.layernorm_fwd(xf, w, b, 1e-6)
+            dy, dres = rnd(rows, D), torch.randn(rows, D, device=dev)
+            med, _ = timeit(lambda: ops.layernorm_bwd(dy, xf, mean, rstd, w, dres))
+            by = rows * D * 16.0
+            print(f"layernorm bwd rows={rows} D={D} (+finalize): {med * 1e3:.1f} us  {by / med / 1e6:.0f} GB/s ({by / med / 1e6 / hbm:.2f})")
+        return
 
     # ---- GEMMs of one patch16 block (D=1024) ----
     D = 1024
@@ -102,7 +134,10 @@ def main():
     out, lse = ops.attention_fwd(qkv, B, 256, 16, 64)
     dout = rnd(M, D)
     med, _ = timeit(lambda: ops.attention_bwd(qkv, out, dout, lse, B, 256, 16, 64))
-    print(f"attention bwd: {med:.3f} ms  {2.5 * fl / med / 1e9:.0f} TFLOP/s (algorithmic 2.5x fwd)")
+    print(f"attention bwd: {med:.3f} ms  {2.0 * fl / med / 1e9:.0f} TFLOP/s (algorithmic 2x fwd; 2.5x executed)")
+    delta = (dout.float() * out.float()).view(B, 256, 16, 64).sum(-1).permute(0, 2, 1).contiguous()
+    med, _ = timeit(lambda: ops.attention_bwd(qkv, None, dout, lse, B, 256, 16, 64, delta=delta))
+    print(f"attention bwd (delta given): {med:.3f} ms  {2.0 * fl / med / 1e9:.0f} TFLOP/s")
 
     if args.attn_only:
         return

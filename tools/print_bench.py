@@ -17,3 +17,11 @@ if "encode" in d:
     print("encode", {k: (round(v, 1) if isinstance(v, float) else v) for k, v in d["encode"].items()})
 if "cpu_baseline" in d:
     print("cpu", d["cpu_baseline"])
+for k, v in d.get("secondary", {}).items():
+    print("secondary", k, round(v["value"], 1), "img/s", round(v["ms_per_step"], 2), "ms  e2e", round(v["e2e"]["value"], 1),
+          "frac_sustained", round(v["frac_of_bf16_peak_sustained"], 3))
+for k, v in d.get("gpu_reference", {}).items():
+    print("gpu_reference", k, v if not isinstance(v, dict) else {a: (round(b, 2) if isinstance(b, float) else b) for a, b in v.items()})
+if "ddp_check" in d:
+    print("ddp_check", d["ddp_check"], d.get("ddp_check_detail"))
+print("value_repeat", d.get("value_repeat"))
