@@ -62,6 +62,8 @@ def parse():
     ap.add_argument("--ref-mode", default="bf16_eager", choices=["bf16_eager", "bf16_compile", "fp16_scaler"])
     ap.add_argument("--ref-modes", default="bf16_eager,fp16_scaler,bf16_compile")
     ap.add_argument("--cpu-batch", type=int, default=2)
+    ap.add_argument("--wgrad-overlap-rows", type=int, default=None,
+                    help="A/B: override tae_b200.tae.WGRAD_OVERLAP_MAX_ROWS (0 = weight gradients on the main stream)")
     a = ap.parse_args()
     if a.config is not None:
         m, mode = CONFIGS[a.config]
@@ -524,6 +526,10 @@ def run_b200(args):
         # short collective timeout: a rank mismatch must abort in minutes, not hang the box
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=240))
     _lib.require_device()
+    if args.wgrad_overlap_rows is not None:
+        from tae_b200 import tae as _tae
+
+        _tae.WGRAD_OVERLAP_MAX_ROWS = args.wgrad_overlap_rows
     D = Dist(torch, dist, dev, world, rank)
     B = args.batch
 

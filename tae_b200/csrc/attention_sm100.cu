@@ -2,23 +2,18 @@
 // N = 256, head_dim = 64), forward and backward.  Same contract as attention.cu (tae.py:74-80): packed qkv
 // [B*N, 3*H*64] in, merged [B*N, H*64] out, log-sum-exp saved for backward.
 //
-// Forward: one CTA per (image, head, 128-query tile), two CTAs per SM (96 KB smem, 256 TMEM columns each).
-//   TMA: Q tile, K, V (128B-swizzled boxes straight out of the packed qkv buffer)
-//   MMA1 (tcgen05, 128x256x64):  S = Q K^T into TMEM
-//   softmax: one thread per query row reads its 256 scores from TMEM (no shuffles: the row is thread-private),
-//            two passes (max, then exp2/sum), writes bf16 P into smem in the UMMA K-major operand layout
-//            (over the dead Q/K tiles)
-//   MMA2 (128x64x256):  O = P V  with V consumed MN-major exactly as it sits in the qkv buffer
-//   epilogue: O / l -> bf16 -> swizzled smem -> TMA store; lse = m*scale + ln(l)
+// Forward (attn_fwd_tc_ring): TMA operands, S = Q K^T in 128x128 half tiles through a ring of TMEM buffers, two softmax
+//   groups (exp2 domain, lazy reference across the key halves), P written back to TMEM as the A operand of O = P V
+//   (V consumed MN-major exactly as it sits in the qkv buffer), O / l -> bf16 -> swizzled smem -> TMA store;
+//   lse = m*ln2 + ln(l).
 //
-// Backward: one CTA per (image, head); everything is computed transposed (keys on TMEM lanes) so that every
-// product is a plain UMMA with operands that already exist in shared memory:
+// Backward (attn_bwd_tc_persist): everything is computed transposed (keys on TMEM lanes) so that every product is a plain
+// UMMA with operands that already exist in shared memory:
 //   S^T = K Q^T, dP^T = V dO^T                               (K-major x K-major)
 //   P^T = exp2(S^T*c - lse2[q]),  dS^T = P^T (dP^T - delta[q]) * scale      (thread-per-key-row, written as bf16 A tiles)
 //   dV += P^T dO,  dK += dS^T Q                              (A K-major, B = dO / Q MN-major in place)
 //   dQ += dS K                                               (A = the SAME dS^T tile read MN-major, B = K MN-major)
-// in 128x128 (key tile x query tile) blocks; TMEM holds S^T, dP^T (128 cols each) and the dV, dK, dQ0, dQ1
-// accumulators (64 cols each) = 512 columns.  No atomics, deterministic.
+// in [128 keys x 64 queries] blocks with double-buffered S^T / dP^T accumulators.  No atomics, deterministic.
 #include <stdlib.h>
 
 #include "sm100.cuh"
@@ -44,62 +39,33 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
 __device__ __forceinline__ uint32_t sw128(int row, int chunk) { return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4)); }
 
 // =============================================================================================
-// Forward
-// =============================================================================================
-constexpr int G_BUF = 98304;                 // one item's operands: Q 32 KB | K 32 KB | V 32 KB
-
-// =============================================================================================
-// Forward, RING variant (TAE_ATTN_FWD=ring; written at the end of round 1, NOT yet run on a GPU — the persistent kernel
-// above stays the default until this one has been seen parity-green and measured).
-//
-// Why: in the persistent kernel a query tile's chain S -> max -> exp -> PV -> drain O is strictly serial per item,
-// because S_t(i+1) overwrites the TMEM columns that hold P_t(i) and O_t(i); only the two tiles overlap each other, and an
-// item costs ~11.5k cycles against a MUFU floor of 4.1k.  Here the scores are produced in HALF tiles (128 queries x
-// 128 keys = 128 TMEM columns) that rotate through a ring of three buffers, and the two O accumulators have their own
-// columns, so the tensor core always works one half tile ahead of each softmax group:
+// Forward: persistent, one CTA per SM walks (image, head) items, two items' operands resident (2 x 96 KB, TMA straight out
+// of the packed qkv buffer).
+//   warp 0   MMA issue          warp 1   TMA producer (K, Q, V of item i+1 as soon as its buffer is free)
+//   warps 4-11 / 12-19   softmax + epilogue of query tile 0 / 1: two threads per row
+// The scores are produced in HALF tiles (128 queries x 128 keys = 128 TMEM columns) that rotate through a ring of three
+// buffers, and the two O accumulators have their own columns, so the tensor core always works one half tile ahead of
+// each softmax group (a kernel whose S tile shared its columns with P and O ran the chain S -> max -> exp -> PV -> drain
+// serially per item: 0.172 ms against 0.144 ms for this one at B=256, H=16):
 //   TMEM  [0,384): ring of 3 score buffers (S half tile, then P over it: thread half h keeps its 64 keys' P in columns
 //                  +64h .. +64h+31)          [384,512): O_0, O_1 (64 columns each)
 //   jobs of item i, in order: (tile 0, keys 0-127), (tile 1, keys 0-127), (tile 0, keys 128-255), (tile 1, keys 128-255);
 //   job g uses ring buffer g % 3.  MMA thread, iteration g: S(g+2) as soon as PV(g-1) has released its buffer, then
-//   PV(g) as soon as the group has written P(g).
+//   PV(g) as soon as the group has written P(g) (bf16, read by the MMA as a TMEM A operand).
 //   Softmax across the two key halves without rescaling O: the second half keeps the FIRST half's row maximum as its
 //   reference (softmax is shift-invariant; bf16 P and fp32 l, O only need the exponent range), unless the second half's
 //   maximum exceeds it by more than 2^32 — only then O and l are rescaled (warp-uniform slow path).
 //   A group's order of work per item: second half of item i, FIRST half of item i+1, then the epilogue of item i — the
 //   PV of item i's second half finishes behind the next softmax instead of in front of an idle group.
+// The kernel is bound by the exponentials (65536 MUFU.EX2 per item = 4.1k cycles per SM) and their issue slots; moving a
+// quarter or half of them to a degree-3 polynomial on the FMA pipes was measured and is not faster (0.150 / 0.152 ms).
 // =============================================================================================
+constexpr int G_BUF = 98304;                 // one item's operands: Q 32 KB | K 32 KB | V 32 KB
 constexpr int R_OFF_RED = 2 * G_BUF;         // [2 tiles][ max lo | max hi | sum ][2 halves][128] fp32 = 6 KB (8 KB reserved)
 constexpr int R_OFF_BAR = R_OFF_RED + 8192;
 constexpr int R_SMEM = R_OFF_BAR + 256 + 1024;
 constexpr int R_THREADS = 640;
 constexpr float R_TAU = 32.0f;               // log2 of the largest P the lazy reference may produce
-
-// TAE_ATTN_EXP2_POLY = E (0..4, default 0): E of every 4 score pairs of the ring kernel take 2^x from the FMA pipes instead
-// of MUFU.EX2 (the forward is MUFU-bound once the chains overlap: 65536 exponentials per item = 4.1k cycles per SM).
-// x = s*sl2 - m2 <= 0 is split by the round-to-nearest magic constant: t = fma(s, sl2, MAGIC - m2) carries n = rint(x)
-// in its low mantissa bits, f = x - n in [-0.5, 0.5] comes from a second fma, 2^f from a degree-3 polynomial (max
-// relative error 7.5e-5 = 2^-13.7, fitted for relative error; P is rounded to bf16 = 2^-9 afterwards), and n is added
-// into the exponent field with one integer shift-add.  Everything but the clamp and the shift-add runs on packed pairs.
-#ifndef TAE_ATTN_EXP2_POLY
-#define TAE_ATTN_EXP2_POLY 0
-#endif
-__device__ __forceinline__ void exp2_poly_pair(float s0, float s1, float sl2, float kmagic, float& p0, float& p1) {
-  constexpr float kMagic = 12582912.0f;  // 1.5 * 2^23
-  const f32x2 s = f2_pack(s0, s1), a = f2_bcast(sl2), k = f2_bcast(kmagic);  // kmagic = kMagic - m2
-  float t0, t1;
-  f2_unpack(f2_fma(s, a, k), t0, t1);
-  t0 = fmaxf(t0, kMagic - 126.0f);  // x < -126 would run the exponent field below zero
-  t1 = fmaxf(t1, kMagic - 126.0f);
-  const f32x2 t = f2_pack(t0, t1);
-  const f32x2 f = f2_fma(s, a, f2_fma(t, f2_bcast(-1.0f), k));  // x - n = s*sl2 + (kmagic - t)
-  f32x2 p = f2_fma(f, f2_bcast(0.0551716685f), f2_bcast(0.2426111251f));
-  p = f2_fma(p, f, f2_bcast(0.6932609677f));
-  p = f2_fma(p, f, f2_bcast(0.9999280572f));
-  float q0, q1;
-  f2_unpack(p, q0, q1);
-  p0 = __uint_as_float(__float_as_uint(q0) + (__float_as_uint(t0) << 23));
-  p1 = __uint_as_float(__float_as_uint(q1) + (__float_as_uint(t1) << 23));
-}
 
 __global__ void __launch_bounds__(R_THREADS, 1)
 attn_fwd_tc_ring(const __grid_constant__ CUtensorMap tm_qkv,  // box 256 rows x 64 cols over qkv [B*N, 3D]
@@ -273,13 +239,8 @@ attn_fwd_tc_ring(const __grid_constant__ CUtensorMap tm_qkv,  // box 256 rows x 
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          float p0, p1;
-          if ((i & 3) < TAE_ATTN_EXP2_POLY) {
-            exp2_poly_pair(__uint_as_float(buf[c][2 * i]), __uint_as_float(buf[c][2 * i + 1]), sl2, 12582912.0f - m2, p0, p1);
-          } else {
-            p0 = ex2_approx(fmaf(__uint_as_float(buf[c][2 * i]), sl2, -m2));
-            p1 = ex2_approx(fmaf(__uint_as_float(buf[c][2 * i + 1]), sl2, -m2));
-          }
+          const float p0 = ex2_approx(fmaf(__uint_as_float(buf[c][2 * i]), sl2, -m2));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(buf[c][2 * i + 1]), sl2, -m2));
           l0 += p0;
           l1 += p1;
           pk[i] = pack_bf16x2(p0, p1);

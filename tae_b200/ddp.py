@@ -38,9 +38,23 @@ class _Bucket:
         self.seen.clear()
 
 
-def plan_buckets(order, offsets, numel_of, bucket_elems):
+def plan_buckets(order, offsets, numel_of, bucket_elems, tail_elems=0):
     """Split an arena (parameters `order` at element `offsets`) into contiguous buckets of ~bucket_elems elements.
-    Returns [(start, end, [params...])] covering the arena in order."""
+    Returns [(start, end, [params...])] covering the arena in order.
+
+    `tail_elems` > 0 cuts a separate LAST bucket of at most that many elements: the gradients that become ready last
+    (PatchEmbed, the pos-embeds) then travel in a short all-reduce of their own — it is the one nothing can overlap —
+    instead of at the end of a full-size bucket that cannot leave before them."""
+    tail_from = len(order)
+    if tail_elems > 0:
+        acc = 0
+        while tail_from > 1:
+            p = order[tail_from - 1]
+            end = offsets[id(order[tail_from])] if tail_from < len(order) else offsets[id(p)] + numel_of(p)
+            acc = end - offsets[id(order[tail_from - 1])] + acc
+            if acc > tail_elems:
+                break
+            tail_from -= 1
     buckets, cur, start = [], [], None
     for i, p in enumerate(order):
         o = offsets[id(p)]
@@ -49,7 +63,7 @@ def plan_buckets(order, offsets, numel_of, bucket_elems):
         cur.append(p)
         end = offsets[id(order[i + 1])] if i + 1 < len(order) else None
         size = (end if end is not None else o + numel_of(p)) - start
-        if size >= bucket_elems or end is None:
+        if size >= bucket_elems or end is None or i + 1 == tail_from:
             buckets.append((start, end, cur))
             cur, start = [], None
     return buckets
@@ -57,11 +71,12 @@ def plan_buckets(order, offsets, numel_of, bucket_elems):
 
 class DistributedDataParallel(nn.Module):
     def __init__(self, module: nn.Module, optimizer=None, bucket_mb: float = 64.0, process_group=None,
-                 device_ids=None, broadcast: bool = True):
+                 device_ids=None, broadcast: bool = True, tail_mb: float = 8.0):
         super().__init__()
         self.module = module
         self.process_group = process_group
         self.bucket_elems = int(bucket_mb * (1 << 20) / 4)
+        self.tail_elems = int(tail_mb * (1 << 20) / 4)
         self.world_size = dist.get_world_size(process_group) if dist.is_initialized() else 1
         self._buckets = None
         self._require_sync = True
@@ -88,7 +103,8 @@ class DistributedDataParallel(nn.Module):
         self._optimizer = optimizer
         self._buckets = []
         for ar in arenas:
-            for start, end, params in plan_buckets(ar.order, ar.offsets, lambda p: p.numel(), self.bucket_elems):
+            for start, end, params in plan_buckets(ar.order, ar.offsets, lambda p: p.numel(), self.bucket_elems,
+                                                   self.tail_elems):
                 flat = ar.g[start:end if end is not None else ar.numel]
                 b = _Bucket(flat, params)
                 self._buckets.append(b)
@@ -158,6 +174,11 @@ class DistributedDataParallel(nn.Module):
     def _launch(self, b):
         if self._comm_stream is not None:
             self._comm_stream.wait_stream(torch.cuda.current_stream())
+            from .tae import wgrad_side_stream
+
+            side = wgrad_side_stream(b.flat.device)  # weight gradients of short-grid models are written on a side stream
+            if side is not None:
+                self._comm_stream.wait_stream(side)
             with torch.cuda.stream(self._comm_stream):
                 b.work = dist.all_reduce(b.flat, op=dist.ReduceOp.AVG, group=self.process_group, async_op=True)
         else:  # CPU / gloo (tests): gloo has no AVG

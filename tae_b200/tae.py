@@ -86,10 +86,52 @@ def _done(p, g):
     return g
 
 
+# ---- weight gradients on a side stream (short token grids) -------------------------------------------------------
+# With few token rows (patch64: M = 4096, patch128: M = 1024 at B = 256) a dgrad GEMM has fewer output tiles than the GPU
+# has SM pairs (40 tiles of 256 x 256 on 74 pairs for the D = 2560 outputs), while the weight-gradient GEMM of the same
+# layer — independent of it, same input dy — has hundreds.  The weight gradients are therefore enqueued on a second
+# stream: they fill the SMs the short dgrad / LayerNorm / attention kernels of the critical path leave idle.  The side
+# stream is forked after dy has been produced and joined at the end of backward (and before a gradient bucket leaves).
+WGRAD_OVERLAP_MAX_ROWS = 8192   # 0 disables
+_wg_streams: dict = {}          # device index -> side stream
+_wg_state = {"join_queued": False, "used": False}
+
+
+def wgrad_side_stream(device=None):
+    """The side stream carrying weight-gradient GEMMs on `device`, or None if none has been used yet."""
+    idx = torch.cuda.current_device() if device is None else torch.device(device).index
+    return _wg_streams.get(idx)
+
+
+def join_wgrad_stream():
+    """Order the current stream after every weight-gradient GEMM enqueued so far (no host synchronisation)."""
+    side = wgrad_side_stream()
+    if side is not None and _wg_state["used"]:
+        torch.cuda.current_stream().wait_stream(side)
+        _wg_state["used"] = False
+    _wg_state["join_queued"] = False
+
+
 def _wgrad(p, dy_b, x_b):
     """dW[out,in] = dy^T x  (fp32, written straight into the gradient arena in direct mode)."""
     t, acc = _sink(p)
     out = None if t is None else t.view(dy_b.shape[1], x_b.shape[1])
+    if out is not None and 0 < dy_b.shape[0] <= WGRAD_OVERLAP_MAX_ROWS:
+        dev = dy_b.device.index
+        side = _wg_streams.get(dev)
+        if side is None:
+            side = _wg_streams[dev] = torch.cuda.Stream(device=dy_b.device)
+            ops.set_dynamic_scheduling(True)  # co-running persistent kernels must draw tiles dynamically to stay balanced
+        if not _wg_state["join_queued"]:
+            torch.autograd.Variable._execution_engine.queue_callback(join_wgrad_stream)
+            _wg_state["join_queued"] = True
+        side.wait_stream(torch.cuda.current_stream())  # dy_b / x_b (and earlier writes to `out`) are ordered before
+        with torch.cuda.stream(side):
+            ops.gemm(dy_b, x_b, a_mn=True, b_mn=True, epilogue=EPI_F32_ACC, out=out, beta=acc)
+        dy_b.record_stream(side)  # the caching allocator must not recycle the operands while the side stream reads them
+        x_b.record_stream(side)
+        _wg_state["used"] = True
+        return _done(p, None)
     g = ops.gemm(dy_b, x_b, a_mn=True, b_mn=True, epilogue=EPI_F32_ACC, out=out, beta=acc)
     return _done(p, g.view(p.shape))
 

@@ -61,7 +61,7 @@ def _worker(rank, world, port, q):
         class Opt:
             arenas = [ar]
 
-        ddp = DistributedDataParallel(lin, optimizer=Opt(), bucket_mb=0.0005)  # ~128-element buckets -> several buckets
+        ddp = DistributedDataParallel(lin, optimizer=Opt(), bucket_mb=0.0005, tail_mb=0.0003)  # ~128-element buckets -> several buckets
         assert len(ddp._buckets) >= 2
         # parameters broadcast from rank 0
         ref = [torch.empty_like(ar.p) for _ in range(world)]
@@ -83,7 +83,7 @@ def _worker(rank, world, port, q):
             _WriteGrads.apply(x, params, rank).backward()
         assert torch.allclose(params[-1].grad, torch.full_like(params[-1].grad, float(rank + 1)))
         # a parameter that reports twice in one backward: harmless while its bucket has not left, an error afterwards
-        b0 = ddp._buckets[0]
+        b0 = next(b for b in ddp._buckets if len(b.params) >= 2)
         first = b0.params[0]
         ddp._callback_queued = True  # outside a backward pass: finalised by hand below
         ddp._on_ready(first)
@@ -119,3 +119,31 @@ def test_bucketed_allreduce_gloo_world2():
     for p in procs:
         p.join(timeout=30)
     assert all(msg == "ok" for _, msg in results), results
+
+
+def test_plan_buckets_covers_arena_and_cuts_a_short_tail():
+    """Bucket planning: contiguous cover of the arena in gradient-ready order; with tail_elems the gradients that become
+    ready last form a short bucket of their own (the one all-reduce nothing can overlap)."""
+    from tae_b200.ddp import plan_buckets
+
+    class P:
+        def __init__(self, n):
+            self.n = n
+
+        def numel(self):
+            return self.n
+
+    ps = [P(n) for n in (1000, 64, 5000, 300, 10, 2000, 7, 90, 33)]
+    off, o = {}, 0
+    for p in ps:
+        off[id(p)] = o
+        o += (p.n + 63) // 64 * 64
+    for tail in (0, 200, 2500, 10 ** 9):
+        b = plan_buckets(ps, off, lambda p: p.numel(), 4000, tail)
+        assert b[0][0] == 0 and b[-1][1] is None and all(b[i][1] == b[i + 1][0] for i in range(len(b) - 1))
+        assert [p for _, _, pl in b for p in pl] == ps
+        if 0 < tail < 10 ** 9:
+            start = b[-1][0]
+            assert o - start <= tail                                  # the tail bucket respects its cap ...
+            assert o - off[id(ps[ps.index(b[-1][2][0]) - 1])] > tail  # ... and is maximal
+    assert [len(pl) for _, _, pl in plan_buckets(ps, off, lambda p: p.numel(), 4000, 200)] == [3, 4, 2]
