@@ -711,7 +711,6 @@ static int launch_small(bool bwd, const bf16* qkv, const bf16* dout, bf16* out_o
   TAE_CHECK_LAUNCH();
   return TAE_OK;
 }
-static bool force_simt();
 // N <= 16 and a head dimension the tensor-core kernels are instantiated for
 static bool small_ok(int N, int hd) { return N <= 16 && (hd == 32 || hd == 64 || hd == 80); }
 static int dispatch_small(bool bwd, const bf16* qkv, const bf16* dout, bf16* o, const float* lse_in, float* lse_out, int B,
@@ -881,16 +880,6 @@ __global__ void attn_bwd_simt(const bf16* __restrict__ qkv, const bf16* __restri
   }
 }
 
-// TAE_ATTN_SIMT=1 forces the fp32 shared-memory kernels for N <= 16 (A/B testing of the tensor-core small-grid kernels)
-static bool force_simt() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("TAE_ATTN_SIMT");
-    v = (e != nullptr && e[0] == '1') ? 1 : 0;
-  }
-  return v == 1;
-}
-
 constexpr int SIMT_MAX_SMEM = 200 * 1024;
 
 static int simt_config(int N, int hd, bool bwd, int* wpc, int* per_warp_floats) {
@@ -971,7 +960,7 @@ extern "C" int tae_attention_fwd(const tae_bf16* qkv_, tae_bf16* out_, float* ls
     TAE_CHECK_LAUNCH();
     return TAE_OK;
   }
-  if (small_ok(N, hd) && !force_simt()) return dispatch_small(false, qkv, nullptr, out, nullptr, lse, B, N, H, hd, scale, stream);
+  if (small_ok(N, hd)) return dispatch_small(false, qkv, nullptr, out, nullptr, lse, B, N, H, hd, scale, stream);
   int wpc, pw;
   TAE_CHECK_SHAPE(simt_config(N, hd, false, &wpc, &pw) == 0, "tae_attention_fwd: N=%d hd=%d does not fit shared memory", N, hd);
   const int smem = wpc * pw * 4;
@@ -997,7 +986,7 @@ extern "C" int tae_attention_bwd(const tae_bf16* qkv_, const tae_bf16* out_, con
   const float scale = 1.0f / sqrtf((float)hd);
   if (hd == HD && N == 256) return attention_bwd_tcgen05(qkv, out, dout, lse, nullptr, dqkv, B, H, stream);
   if (hd == HD && N == 64) return launch_bwd64(qkv, out, dout, lse, nullptr, dqkv, B, H, scale, stream);
-  if (small_ok(N, hd) && !force_simt()) return dispatch_small(true, qkv, dout, dqkv, lse, nullptr, B, N, H, hd, scale, stream);
+  if (small_ok(N, hd)) return dispatch_small(true, qkv, dout, dqkv, lse, nullptr, B, N, H, hd, scale, stream);
   int wpc, pw;
   TAE_CHECK_SHAPE(simt_config(N, hd, true, &wpc, &pw) == 0, "tae_attention_bwd: N=%d hd=%d does not fit shared memory", N, hd);
   const int smem = wpc * pw * 4;

@@ -1027,21 +1027,14 @@ static int launch_2sm_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const CU
 template <int EPI>
 static int launch_2sm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& to2,
                       const Params& p, int clusters, cudaStream_t stream) {
-  // epilogue-heavy: GELU always; residual / GELU' epilogues when the main loop per tile is short (K <= 2048)
-  const bool heavy = (EPI == TAE_EPI_BF16_GELU && TAE_GELU_EW == 16) ||
-                     ((EPI == TAE_EPI_F32_RESID || (EPI == TAE_EPI_BF16_DGELU && !TAE_DGELU_TMA_EPI)) && p.K <= 2048);
-  if (heavy) return launch_2sm_cfg<EPI, 16>(ta, tb, to, to2, p, clusters, stream);
-  return launch_2sm_cfg<EPI, 8>(ta, tb, to, to2, p, clusters, stream);
-}
-
-// TAE_GEMM_1SM=1 forces the single-CTA kernel (A/B testing)
-static bool allow_2sm() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("TAE_GEMM_1SM");
-    v = (e != nullptr && e[0] == '1') ? 0 : 1;
+  // 16 epilogue warps where the generic (transposing) epilogue carries the work: the residual epilogue (and the GELU /
+  // GELU' epilogues if built without their row-layout paths) when the main loop per tile is short (K <= 2048)
+  constexpr bool kMayBeHeavy = (EPI == TAE_EPI_BF16_GELU && TAE_GELU_EW == 16) || EPI == TAE_EPI_F32_RESID ||
+                               (EPI == TAE_EPI_BF16_DGELU && !TAE_DGELU_TMA_EPI);
+  if constexpr (kMayBeHeavy) {
+    if (EPI == TAE_EPI_BF16_GELU || p.K <= 2048) return launch_2sm_cfg<EPI, 16>(ta, tb, to, to2, p, clusters, stream);
   }
-  return v == 1;
+  return launch_2sm_cfg<EPI, 8>(ta, tb, to, to2, p, clusters, stream);
 }
 
 }  // namespace gemm
@@ -1088,7 +1081,7 @@ extern "C" int tae_gemm(const tae_gemm_args* a, void* stream_) {
   const int sms = num_sms();
   if (sms <= 0) return TAE_ERR_CUDA;
   // CTA-pair kernel (256-row tiles on two SMs) whenever there are at least two 128-row tiles of work
-  const bool use2 = allow_2sm() && a->M > BLOCK_M && sms >= 2;
+  const bool use2 = a->M > BLOCK_M && sms >= 2;
   const int tile_m = use2 ? 2 * BLOCK_M : BLOCK_M;
   const int units = use2 ? sms / 2 : sms;  // concurrently resident work items (clusters or CTAs)
   p.m_tiles = (a->M + tile_m - 1) / tile_m;
