@@ -98,7 +98,7 @@ def _ddp_worker(rank, world, port, q, kw, per_rank, bucket_mb):
             assert abs(float(lsum) / world - float(lr_)) < 2e-3 * abs(float(lr_)), (it, float(lsum) / world, float(lr_))
         torch.cuda.synchronize()
         for ar in opt.arenas:
-            for t in (ar.p, ar.pb.view(torch.int16), ar.m, ar.v):
+            for t in (ar.p, ar.pb, ar.m, ar.v):  # fp32 masters, bf16 shadows, both moments
                 gathered = [torch.empty_like(t) for _ in range(world)]
                 dist.all_gather(gathered, t)
                 assert all(torch.equal(gathered[0], g) for g in gathered[1:]), "replicas diverged"
