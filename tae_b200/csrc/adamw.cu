@@ -36,7 +36,6 @@ __global__ void __launch_bounds__(256)
 adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
              bf16* __restrict__ pb, size_t n, AdamArgs a, const AdamArgs* __restrict__ dev_args, float* grad_sq_sum,
              const int* __restrict__ found_inf) {
-  pdl_entry();
   if (found_inf != nullptr && *found_inf != 0) return;
   if (dev_args != nullptr) a = *dev_args;
   const size_t n4 = n / 4;
@@ -88,7 +87,6 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
 }
 
 __global__ void __launch_bounds__(256) cast_kernel(const float* __restrict__ src, bf16* __restrict__ dst, size_t n) {
-  pdl_entry();
   const size_t n8 = n / 8;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
     const float4 a = ld_nc_f4(src + i * 8), b = ld_nc_f4(src + i * 8 + 4);
@@ -186,7 +184,7 @@ static int adamw_launch(float* p, const float* g, float* m, float* v, tae_bf16* 
                     reinterpret_cast<uintptr_t>(v)) & 15) == 0 && (reinterpret_cast<uintptr_t>(p_bf16) & 7) == 0 &&
                       (reinterpret_cast<uintptr_t>(dev_hyper) & 3) == 0,
                   "tae_adamw_step: arenas must be 16-byte aligned");
-  TAE_LAUNCH((adamw_kernel), flat_grid(n / 4 + 1), 256, 0, stream, p, g, m, v, reinterpret_cast<bf16*>(p_bf16), n, a,
+  adamw_kernel<<<flat_grid(n / 4 + 1), 256, 0, stream>>>(p, g, m, v, reinterpret_cast<bf16*>(p_bf16), n, a,
                                                           reinterpret_cast<const AdamArgs*>(dev_hyper), grad_sq_sum,
                                                           reinterpret_cast<const int*>(found_inf));
   TAE_CHECK_LAUNCH();
@@ -220,7 +218,7 @@ extern "C" int tae_cast_f32_to_bf16(const float* src, tae_bf16* dst, size_t n, v
   TAE_CHECK_SHAPE(src && dst, "tae_cast_f32_to_bf16: NULL pointer");
   TAE_CHECK_SHAPE((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0,
                   "tae_cast_f32_to_bf16: pointers must be 16-byte aligned");
-  TAE_LAUNCH((cast_kernel), flat_grid(n / 8 + 1), 256, 0, stream, src, reinterpret_cast<bf16*>(dst), n);
+  cast_kernel<<<flat_grid(n / 8 + 1), 256, 0, stream>>>(src, reinterpret_cast<bf16*>(dst), n);
   TAE_CHECK_LAUNCH();
   return TAE_OK;
 }

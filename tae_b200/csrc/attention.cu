@@ -102,7 +102,6 @@ template <int N>
 __global__ void __launch_bounds__(N * 2, 1)
 attn_fwd_mma(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* __restrict__ lse, int H, int BH,
              float scale_log2) {
-  pdl_entry();
   constexpr int NT = N * 2;  // threads: one warp per 16 queries
   constexpr int NBUF = N <= 64 ? 2 : 1;
   constexpr int BUF = 3 * N * LDS;  // elements of one operand buffer (Q | K | V)
@@ -275,7 +274,6 @@ __global__ void __launch_bounds__(128, HAS_DELTA ? 3 : 2)
 attn_bwd_mma64(const bf16* __restrict__ qkv, const bf16* __restrict__ out, const bf16* __restrict__ dout,
                const float* __restrict__ lse, const float* __restrict__ delta_in, bf16* __restrict__ dqkv, int H, int BH,
                float scale, float scale_log2) {
-  pdl_entry();
   constexpr int N = 64, NT = 128;
   constexpr int NMAT = HAS_DELTA ? 4 : 5;    // Q | K | V | dO (| O)
   constexpr int BUF = NMAT * N * LDS;        // elements of one operand buffer
@@ -527,7 +525,6 @@ template <int HDT>
 __global__ void __launch_bounds__(128)
 attn_fwd_small(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* __restrict__ lse, int BH, int N, int H,
                float scale_log2) {
-  pdl_entry();
   using C = Small<HDT>;
   extern __shared__ uint4 smem_u4[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -593,7 +590,6 @@ template <int HDT>
 __global__ void __launch_bounds__(128)
 attn_bwd_small(const bf16* __restrict__ qkv, const bf16* __restrict__ dout, const float* __restrict__ lse,
                bf16* __restrict__ dqkv, int BH, int N, int H, float scale, float scale_log2) {
-  pdl_entry();
   using C = Small<HDT>;
   extern __shared__ uint4 smem_u4[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -706,11 +702,11 @@ static int launch_small(bool bwd, const bf16* qkv, const bf16* dout, bf16* out_o
   if (!bwd) {
     const int rc = set_smem(attn_fwd_small<HDT>, smem);
     if (rc) return rc;
-    TAE_LAUNCH((attn_fwd_small<HDT>), (BH + 3) / 4, 128, smem, stream, qkv, out_or_dqkv, lse_out, BH, N, H, sl2);
+    attn_fwd_small<HDT><<<(BH + 3) / 4, 128, smem, stream>>>(qkv, out_or_dqkv, lse_out, BH, N, H, sl2);
   } else {
     const int rc = set_smem(attn_bwd_small<HDT>, smem);
     if (rc) return rc;
-    TAE_LAUNCH((attn_bwd_small<HDT>), (BH + 3) / 4, 128, smem, stream, qkv, dout, lse_in, out_or_dqkv, BH, N, H, scale, sl2);
+    attn_bwd_small<HDT><<<(BH + 3) / 4, 128, smem, stream>>>(qkv, dout, lse_in, out_or_dqkv, BH, N, H, scale, sl2);
   }
   TAE_CHECK_LAUNCH();
   return TAE_OK;
@@ -928,13 +924,13 @@ static int launch_bwd64(const bf16* qkv, const bf16* out, const bf16* dout, cons
     int rc = set_smem(attn_bwd_mma64<true>, smem);
     if (rc) return rc;
     const int grid = B * H < sms * 3 ? B * H : sms * 3;
-    TAE_LAUNCH((attn_bwd_mma64<true>), grid, 128, smem, stream, qkv, nullptr, dout, lse, delta, dqkv, H, B * H, scale, sl2);
+    attn_bwd_mma64<true><<<grid, 128, smem, stream>>>(qkv, nullptr, dout, lse, delta, dqkv, H, B * H, scale, sl2);
   } else {
     const int smem = 2 * 5 * N * LDS * 2 + 2 * N * 4;  // 92 672 B: two CTAs per SM
     int rc = set_smem(attn_bwd_mma64<false>, smem);
     if (rc) return rc;
     const int grid = B * H < sms * 2 ? B * H : sms * 2;
-    TAE_LAUNCH((attn_bwd_mma64<false>), grid, 128, smem, stream, qkv, out, dout, lse, nullptr, dqkv, H, B * H, scale, sl2);
+    attn_bwd_mma64<false><<<grid, 128, smem, stream>>>(qkv, out, dout, lse, nullptr, dqkv, H, B * H, scale, sl2);
   }
   TAE_CHECK_LAUNCH();
   return TAE_OK;
@@ -960,7 +956,7 @@ extern "C" int tae_attention_fwd(const tae_bf16* qkv_, tae_bf16* out_, float* ls
     if (rc) return rc;
     const int sms = num_sms() > 0 ? num_sms() : 148;
     const int grid = B * H < sms * 3 ? B * H : sms * 3;  // 3 resident CTAs per SM (140 registers, 54 KB each)
-    TAE_LAUNCH((attn_fwd_mma<64>), grid, 128, smem2, stream, qkv, out, lse, H, B * H, sl2);
+    attn_fwd_mma<64><<<grid, 128, smem2, stream>>>(qkv, out, lse, H, B * H, sl2);
     TAE_CHECK_LAUNCH();
     return TAE_OK;
   }

@@ -107,7 +107,6 @@ attn_fwd_tc_ring(const __grid_constant__ CUtensorMap tm_qkv,  // box 256 rows x 
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem = *tmem_slot;
-  pdl_entry();  // set-up done: everything below reads or writes data ordered by the stream
 
   if (warp == 1) {
     if (elect_one()) {
@@ -407,7 +406,6 @@ attn_bwd_tc_persist(const __grid_constant__ CUtensorMap tm_qkv,   // box 64 rows
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem = *tmem_slot;
-  pdl_entry();  // set-up done: everything below reads or writes data ordered by the stream
   const uint32_t sQ = smem_u32(smem + P_OFF_Q), sK = smem_u32(smem + P_OFF_K), sV = smem_u32(smem + P_OFF_V);
   const uint32_t sdO = smem_u32(smem + P_OFF_DO), sPT = smem_u32(smem + P_OFF_PT), sdST = smem_u32(smem + P_OFF_DST);
 
@@ -771,7 +769,7 @@ int attention_fwd_tcgen05(const bf16* qkv, bf16* out, float* lse, int B, int H, 
   const int sms = num_sms();
   if (sms <= 0) return TAE_ERR_CUDA;
   const int items = B * H;
-  TAE_LAUNCH((attn_fwd_tc_ring), items < sms ? items : sms, R_THREADS, R_SMEM, stream, tkv, to, lse, H, items, scale,
+  attn_fwd_tc_ring<<<items < sms ? items : sms, R_THREADS, R_SMEM, stream>>>(tkv, to, lse, H, items, scale,
                                                                              scale * 1.44269504088896340736f);
   TAE_CHECK_LAUNCH();
   return TAE_OK;
@@ -798,7 +796,7 @@ int attention_bwd_tcgen05(const bf16* qkv, const bf16* out, const bf16* dout, co
   if (sms <= 0) return TAE_ERR_CUDA;
   const int items = B * H;
   const int grid = items < sms ? items : sms;
-  TAE_LAUNCH((attn_bwd_tc_persist), grid, S_THREADS, S_SMEM, stream, tq64, tdo64, tdq, out, dout, lse, delta, H, items, scale, sl2,
+  attn_bwd_tc_persist<<<grid, S_THREADS, S_SMEM, stream>>>(tq64, tdo64, tdq, out, dout, lse, delta, H, items, scale, sl2,
                                                             g_attn_trace);
   TAE_CHECK_LAUNCH();
   return TAE_OK;

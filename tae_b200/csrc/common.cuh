@@ -47,34 +47,6 @@ inline void count_launch(int n = 1) { g_launch_count.fetch_add((uint64_t)n, std:
     ::tae::count_launch();                                                                \
   } while (0)
 
-// Programmatic dependent launch.  The hot-path kernels are launched with cudaLaunchAttributeProgrammaticStreamSerialization:
-// the next kernel of the stream may be scheduled while this one drains, so its launch latency and prologue (barrier
-// init, TMEM allocation, descriptor prefetch) overlap the tail instead of following it — a training step is 1200-3100
-// dependent launches.  Every such kernel executes griddepcontrol.wait (pdl_wait) before its first global-memory access,
-// which blocks until the preceding grid has completed and its writes are visible, so the data dependences of the
-// stream are unchanged.  TAE_PDL=0 builds launch conventionally (A/B).
-#ifndef TAE_PDL
-#define TAE_PDL 1
-#endif
-#ifdef __CUDACC__
-template <typename... P, typename... A>
-inline cudaError_t launch_pdl(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, A&&... args) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = grid;
-  cfg.blockDim = block;
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = TAE_PDL;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(args)...);
-}
-#define TAE_LAUNCH(kernel, grid, block, smem, stream, ...) \
-  (void)::tae::launch_pdl(kernel, dim3(grid), dim3(block), (size_t)(smem), stream, __VA_ARGS__)
-#endif
-
 int num_sms();  // cached per process (current device)
 // Work counters for dynamically scheduled persistent kernels: returns a zeroed {next item, workers done} pair in device
 // memory (a ring of slots, one per launch; the kernel re-arms its slot when its last worker finishes), or NULL when
@@ -88,14 +60,6 @@ int set_dynamic_scheduling(int enable);
 
 typedef __nv_bfloat16 bf16;
 typedef __nv_bfloat162 bf162;
-
-// see launch_pdl above: block until the preceding grid's writes are visible / allow the following grid to be scheduled
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void pdl_entry() {
-  pdl_wait();
-  pdl_launch_dependents();
-}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

@@ -15,7 +15,6 @@ namespace ew {
 // im2col: one thread converts 8 consecutive pixels of one image row (32 B in, 16 B out)
 // ---------------------------------------------------------------------------------------------
 __global__ void im2col_kernel(const float* __restrict__ imgs, bf16* __restrict__ cols, int B, int S, int p) {
-  pdl_entry();
   const int g = S / p;
   const int xg = S / 8;  // 8-pixel groups per image row
   const size_t total = (size_t)B * 3 * S * xg;
@@ -74,7 +73,6 @@ __global__ void patch_permute_kernel(const T* __restrict__ src, T* __restrict__ 
 __global__ void __launch_bounds__(256)
 mse_loss_kernel(const bf16* __restrict__ pred, const float* __restrict__ imgs, float* loss_accum,
                 bf16* __restrict__ dpred, const float* __restrict__ grad_scale, int B, int S, int p) {
-  pdl_entry();
   const int g = S / p;
   const int jg = p / 8;  // 8-pixel groups per patch row
   const size_t total = (size_t)B * g * g * p * jg;
@@ -149,7 +147,6 @@ mse_loss_kernel(const bf16* __restrict__ pred, const float* __restrict__ imgs, f
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 colsum_stage1(const bf16* __restrict__ x, int M, int N, int ldx, float* __restrict__ partial, int rows_per_chunk) {
-  pdl_entry();
   // block: 32 column groups (8 cols each = 256 cols) x 8 row lanes
   const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int col = blockIdx.x * 256 + cg * 8;
@@ -183,7 +180,6 @@ colsum_stage1(const bf16* __restrict__ x, int M, int N, int ldx, float* __restri
   }
 }
 __global__ void colsum_stage2(const float* __restrict__ partial, int chunks, int N, float* out, int accumulate) {
-  pdl_entry();
   const int col = blockIdx.x * blockDim.x + threadIdx.x;
   if (col >= N) return;
   float s = 0.f;
@@ -206,7 +202,6 @@ static void colsum_config(int M, int N, int* chunks, int* rows_per_chunk) {
 
 // out[n] (+)= sum_r x[r, n] for a (small) fp32 [R, N] matrix: block = 32 columns x 16 row-slices, 4 loads in flight
 __global__ void __launch_bounds__(512) colsum_f32_kernel(const float* __restrict__ x, int R, int N, float* out, int accumulate) {
-  pdl_entry();
   __shared__ float red[16][33];
   const int cx = threadIdx.x & 31, sl = threadIdx.x >> 5;
   const int col = blockIdx.x * 32 + cx;
@@ -263,7 +258,6 @@ __global__ void token_mean_bwd_kernel(const float* __restrict__ dy, float* __res
 
 // out[r, :] (+)= sum_b x[b*R + r, :]
 __global__ void batch_sum_kernel(const float* __restrict__ x, int B, int R, int D, float* out, int accumulate) {
-  pdl_entry();
   const int d4 = D / 4;
   const size_t total = (size_t)R * d4;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -318,7 +312,7 @@ extern "C" int tae_im2col_bf16(const float* imgs, tae_bf16* cols, int32_t B, int
   TAE_CHECK_SHAPE(B > 0 && S > 0 && p > 0 && S % p == 0, "tae_im2col_bf16: need S %% p == 0 (S=%d p=%d)", S, p);
   TAE_CHECK_SHAPE(p % 8 == 0, "tae_im2col_bf16: patch size must be a multiple of 8 (p=%d)", p);
   const size_t total = (size_t)B * 3 * S * (S / 8);
-  TAE_LAUNCH((im2col_kernel), stream_grid(total, 256), 256, 0, stream, imgs, reinterpret_cast<bf16*>(cols), B, S, p);
+  im2col_kernel<<<stream_grid(total, 256), 256, 0, stream>>>(imgs, reinterpret_cast<bf16*>(cols), B, S, p);
   TAE_CHECK_LAUNCH();
   return TAE_OK;
 }
@@ -376,7 +370,7 @@ extern "C" int tae_mse_loss(const tae_bf16* pred, const float* imgs, float* loss
   int grid = stream_grid(total, 256);
   const int sms = num_sms() > 0 ? num_sms() : 148;
   if (grid > sms * 4) grid = sms * 4;  // bound the number of loss atomics
-  TAE_LAUNCH((mse_loss_kernel), grid, 256, 0, stream, reinterpret_cast<const bf16*>(pred), imgs, loss_accum,
+  mse_loss_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const bf16*>(pred), imgs, loss_accum,
                                             reinterpret_cast<bf16*>(dpred), grad_scale, B, S, p);
   TAE_CHECK_LAUNCH();
   return TAE_OK;
@@ -399,9 +393,9 @@ extern "C" int tae_colsum_bf16(const tae_bf16* x, int32_t M, int32_t N, int32_t 
   int chunks, rpc;
   colsum_config(M, N, &chunks, &rpc);
   dim3 grid((N + 255) / 256, chunks);
-  TAE_LAUNCH((colsum_stage1), grid, 256, 0, stream, reinterpret_cast<const bf16*>(x), M, N, ldx, workspace, rpc);
+  colsum_stage1<<<grid, 256, 0, stream>>>(reinterpret_cast<const bf16*>(x), M, N, ldx, workspace, rpc);
   TAE_CHECK_LAUNCH();
-  TAE_LAUNCH((colsum_stage2), (N + 255) / 256, 256, 0, stream, workspace, chunks, N, out, accumulate);
+  colsum_stage2<<<(N + 255) / 256, 256, 0, stream>>>(workspace, chunks, N, out, accumulate);
   TAE_CHECK_LAUNCH();
   return TAE_OK;
 }
@@ -411,7 +405,7 @@ extern "C" int tae_colsum_f32(const float* x, int32_t R, int32_t N, float* out, 
   using namespace tae::ew;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   TAE_CHECK_SHAPE(R > 0 && N > 0 && x != nullptr && out != nullptr, "tae_colsum_f32: bad arguments");
-  TAE_LAUNCH((colsum_f32_kernel), (N + 31) / 32, 512, 0, stream, x, R, N, out, accumulate);
+  colsum_f32_kernel<<<(N + 31) / 32, 512, 0, stream>>>(x, R, N, out, accumulate);
   TAE_CHECK_LAUNCH();
   return TAE_OK;
 }
@@ -443,7 +437,7 @@ extern "C" int tae_batch_sum_f32(const float* x, int32_t B, int32_t R, int32_t D
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   TAE_CHECK_SHAPE(B > 0 && R > 0 && D > 0 && D % 4 == 0, "tae_batch_sum_f32: bad shape B=%d R=%d D=%d", B, R, D);
   const size_t total = (size_t)R * (D / 4);
-  TAE_LAUNCH((batch_sum_kernel), (unsigned)((total + 127) / 128), 128, 0, stream, x, B, R, D, out, accumulate);
+  batch_sum_kernel<<<(unsigned)((total + 127) / 128), 128, 0, stream>>>(x, B, R, D, out, accumulate);
   TAE_CHECK_LAUNCH();
   return TAE_OK;
 }

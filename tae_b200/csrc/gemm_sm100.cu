@@ -416,7 +416,6 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_entry();  // barriers, TMEM and descriptors are set up: from here on the kernel touches data of the preceding grid
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -631,7 +630,6 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
   cluster_sync_all();  // barriers of BOTH CTAs are initialised before any remote signal can arrive
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_entry();  // barriers, TMEM and descriptors are set up: from here on the kernel touches data of the preceding grid
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
@@ -1003,7 +1001,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p,
     set_error("cudaFuncSetAttribute(smem=%d) failed: %s", SMEM_BYTES, cudaGetErrorString(attr_err));
     return TAE_ERR_CUDA;
   }
-  TAE_LAUNCH((gemm_bf16_tcgen05<EPI>), grid, NUM_THREADS, SMEM_BYTES, stream, ta, tb, p);
+  gemm_bf16_tcgen05<EPI><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, p);
   TAE_CHECK_LAUNCH();
   return TAE_OK;
 }
@@ -1021,7 +1019,7 @@ static int launch_2sm_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const CU
     set_error("cudaFuncSetAttribute(smem=%d) failed: %s", Cfg2<EW>::kSmemBytes, cudaGetErrorString(attr_err));
     return TAE_ERR_CUDA;
   }
-  TAE_LAUNCH((gemm_bf16_tcgen05_2sm<EPI, EW>), 2 * clusters, Cfg2<EW>::kThreads, Cfg2<EW>::kSmemBytes, stream, ta, tb, to, to2, p);
+  gemm_bf16_tcgen05_2sm<EPI, EW><<<2 * clusters, Cfg2<EW>::kThreads, Cfg2<EW>::kSmemBytes, stream>>>(ta, tb, to, to2, p);
   TAE_CHECK_LAUNCH();
   return TAE_OK;
 }

@@ -165,7 +165,6 @@ __global__ void __launch_bounds__(256)
 ln_fwd_warp_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                    bf16* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows,
                    float eps) {
-  pdl_entry();
   constexpr int D = NV * 128;
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
@@ -210,7 +209,7 @@ static void launch_fwd_warp(const float* x, const float* gamma, const float* bet
   const int sms = num_sms() > 0 ? num_sms() : 148;
   int grid = (rows + 7) / 8;
   if (grid > sms * 8) grid = sms * 8;
-  TAE_LAUNCH((ln_fwd_warp_kernel<NV>), grid, 256, 0, stream, x, gamma, beta, y, mean, rstd, rows, eps);
+  ln_fwd_warp_kernel<NV><<<grid, 256, 0, stream>>>(x, gamma, beta, y, mean, rstd, rows, eps);
 }
 
 // Backward.  partials layout: [gridDim.x][3][D]  (0: dgamma, 1: dbeta, 2: colsum(bf16(dres_out)))
@@ -325,7 +324,6 @@ __global__ void __launch_bounds__(256, 1)
 ln_bwd_warp_kernel(const bf16* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
                    const float* __restrict__ rstd, const float* __restrict__ gamma, const float* dres_in,
                    float* dres_out, bf16* __restrict__ dres_out_b, float* __restrict__ partials, int rows, int* sched) {
-  pdl_entry();
   constexpr int D = NV * 128;
   constexpr int CHUNK = 1;  // rows per dynamically scheduled work item (1 keeps concurrent warps on consecutive rows)
   const int lane = threadIdx.x & 31;
@@ -451,7 +449,6 @@ __global__ void __launch_bounds__(32 * W * R, 1)
 ln_bwd_group_kernel(const bf16* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
                     const float* __restrict__ rstd, const float* __restrict__ gamma, const float* dres_in,
                     float* dres_out, bf16* __restrict__ dres_out_b, float* __restrict__ partials, int rows, int* sched) {
-  pdl_entry();
   constexpr int NV = 4;
   constexpr int D = W * 512;
   __shared__ float s_stat[R][2][W][2];
@@ -612,7 +609,6 @@ static int bwd_warp_grid(int rows) {
 __global__ void __launch_bounds__(1024)
 ln_bwd_finalize_kernel(const float* __restrict__ partials, int num_partials, int D, float* dgamma, float* dbeta,
                        float* dcolsum, int accumulate) {
-  pdl_entry();
   __shared__ float red[32][33];
   const int cx = threadIdx.x & 31, sl = threadIdx.x >> 5;
   const int idx = blockIdx.x * 32 + cx;  // over 3*D
@@ -732,10 +728,10 @@ extern "C" int tae_layernorm_bwd(const tae_bf16* dy, const float* x, const float
     const int wg = bwd_warp_grid(rows);
     int* sched = rows > wg * 8 ? sched_counter_slot() : nullptr;  // more rows than warps: dynamic row chunks
     switch (D / 128) {
-      case 1: TAE_LAUNCH((ln_bwd_warp_kernel<1>), wg, 256, 0, stream, dyy, x, mean, rstd, gamma, dres_in, dres_out, ob, partials, rows, sched); break;
-      case 2: TAE_LAUNCH((ln_bwd_warp_kernel<2>), wg, 256, 0, stream, dyy, x, mean, rstd, gamma, dres_in, dres_out, ob, partials, rows, sched); break;
-      case 6: TAE_LAUNCH((ln_bwd_warp_kernel<6>), wg, 256, 0, stream, dyy, x, mean, rstd, gamma, dres_in, dres_out, ob, partials, rows, sched); break;
-      default: TAE_LAUNCH((ln_bwd_warp_kernel<8>), wg, 256, 0, stream, dyy, x, mean, rstd, gamma, dres_in, dres_out, ob, partials, rows, sched); break;
+      case 1: ln_bwd_warp_kernel<1><<<wg, 256, 0, stream>>>(dyy, x, mean, rstd, gamma, dres_in, dres_out, ob, partials, rows, sched); break;
+      case 2: ln_bwd_warp_kernel<2><<<wg, 256, 0, stream>>>(dyy, x, mean, rstd, gamma, dres_in, dres_out, ob, partials, rows, sched); break;
+      case 6: ln_bwd_warp_kernel<6><<<wg, 256, 0, stream>>>(dyy, x, mean, rstd, gamma, dres_in, dres_out, ob, partials, rows, sched); break;
+      default: ln_bwd_warp_kernel<8><<<wg, 256, 0, stream>>>(dyy, x, mean, rstd, gamma, dres_in, dres_out, ob, partials, rows, sched); break;
     }
     TAE_CHECK_LAUNCH();
     return TAE_OK;
@@ -745,10 +741,10 @@ extern "C" int tae_layernorm_bwd(const tae_bf16* dy, const float* x, const float
     const int gg = bwd_group_grid(rows, R);
     int* sched = rows > gg * R ? sched_counter_slot() : nullptr;  // more rows than groups: dynamic rows (if enabled)
     if (D == 2048)
-      TAE_LAUNCH((ln_bwd_group_kernel<4, GROUP_R_2048>), gg, 32 * 4 * GROUP_R_2048, 0, stream, dyy, x, mean, rstd, gamma, dres_in, dres_out, ob,
+      ln_bwd_group_kernel<4, GROUP_R_2048><<<gg, 32 * 4 * GROUP_R_2048, 0, stream>>>(dyy, x, mean, rstd, gamma, dres_in, dres_out, ob,
                                                                                    partials, rows, sched);
     else
-      TAE_LAUNCH((ln_bwd_group_kernel<5, GROUP_R_2560>), gg, 32 * 5 * GROUP_R_2560, 0, stream, dyy, x, mean, rstd, gamma, dres_in, dres_out, ob,
+      ln_bwd_group_kernel<5, GROUP_R_2560><<<gg, 32 * 5 * GROUP_R_2560, 0, stream>>>(dyy, x, mean, rstd, gamma, dres_in, dres_out, ob,
                                                                                    partials, rows, sched);
     TAE_CHECK_LAUNCH();
     return TAE_OK;
@@ -770,7 +766,7 @@ extern "C" int tae_layernorm_bwd_finalize(const float* partials, int32_t num_par
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   TAE_CHECK_SHAPE(num_partials > 0 && D > 0 && partials != nullptr, "tae_layernorm_bwd_finalize: bad arguments");
   const int total = 3 * D;
-  TAE_LAUNCH((ln_bwd_finalize_kernel), total / 32, 1024, 0, stream, partials, num_partials, D, dgamma, dbeta, dcolsum, accumulate);
+  ln_bwd_finalize_kernel<<<total / 32, 1024, 0, stream>>>(partials, num_partials, D, dgamma, dbeta, dcolsum, accumulate);
   TAE_CHECK_LAUNCH();
   return TAE_OK;
 }

@@ -1,7 +1,7 @@
 #!/bin/bash
 # Evidence run: ncu launch list of one bench step + ncu --set full of every kernel family (second repetition of each tool script).
 mkdir -p gpurun_out
-R=${1:-r1}
+R=${1:-r2}
 STEP="python tools/ncu_step.py"
 $STEP > gpurun_out/ncu_plain_step.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/launches_$R.csv $STEP > gpurun_out/ncu_step.log 2>&1

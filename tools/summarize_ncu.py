@@ -102,7 +102,13 @@ def traffic(*paths):
             d["time_us"] += float(r[it]) * tscale[units[it]]
     res = {k: {"launches_profiled": v["launches"], "dram_bytes_per_launch": v["dram_bytes"] / v["launches"],
                "avg_time_us": v["time_us"] / v["launches"]} for k, v in fam.items()}
-    print(json.dumps({"source": "ncu --set full (tools/gpu_profile.sh); dram__bytes_read.sum + dram__bytes_write.sum per launch, "
+    import os
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from bench import gemm_sources_fingerprint  # bench.py only quotes the GEMM traffic for the sources it was captured from
+
+    print(json.dumps({"gemm_sources_fingerprint": gemm_sources_fingerprint(),
+                      "source": "ncu --set full (tools/gpu_profile.sh); dram__bytes_read.sum + dram__bytes_write.sum per launch, "
                                 "averaged over the profiled launches of each kernel family at the bench shapes",
                       "kernels": res}, indent=1))
 
