@@ -26,16 +26,25 @@ def golden_tensors():
     import torch
 
     cache = {}
+    with open(os.path.join(GOLDEN_DIR, "golden_meta.json")) as f:
+        meta = json.load(f)
 
     def load(name):
         if name not in cache:
-            cache[name] = torch.load(os.path.join(GOLDEN_DIR, f"{name}.pt"), map_location="cpu")
+            t = torch.load(os.path.join(GOLDEN_DIR, f"{name}.pt"), map_location="cpu")
+            if "input" not in t:  # compact fixtures: the input is regenerated from its recorded seed (make_golden.py)
+                rec = meta[name]
+                S = rec["kwargs"]["img_size"]
+                t["input"] = torch.randn(rec["batch"], 3, S, S, generator=torch.Generator().manual_seed(rec["seeds"]["input"]))
+            cache[name] = {k: (v.float() if v.dtype == torch.bfloat16 else v) for k, v in t.items()}
         return cache[name]
 
     return load
 
 
 TINY_CASES = ["tiny_p8_n64_hd64", "tiny_p8_n16_hd32", "tiny_p16_n4_hd80"]
+# + the real patch16 width / grid / head size with one block per side, generated from the unmodified reference as well
+GOLDEN_CASES = TINY_CASES + ["mid_p16_n256_hd64"]
 
 
 def oracle_cfg(kw):

@@ -31,7 +31,12 @@ CASES = {
                               decoder_embed_dim=128, decoder_depth=1, decoder_num_heads=4, mlp_ratio=4.), 3),
     "tiny_p16_n4_hd80": (dict(img_size=32, patch_size=16, in_chans=3, embed_dim=640, vocab_size=256, depth=1, num_heads=8,
                               decoder_embed_dim=640, decoder_depth=1, decoder_num_heads=8, mlp_ratio=4.), 4),
+    # the real patch16 width, grid and head size (D=1024, N=256, hd=64: the tcgen05 attention and CTA-pair GEMM paths) with
+    # one block per side; the input is regenerated from its seed and bf16 tensors are stored as bf16 to keep the file small
+    "mid_p16_n256_hd64": (dict(img_size=256, patch_size=16, in_chans=3, embed_dim=1024, vocab_size=256, depth=1, num_heads=16,
+                               decoder_embed_dim=1024, decoder_depth=1, decoder_num_heads=16, mlp_ratio=4.), 2),
 }
+COMPACT = {"mid_p16_n256_hd64"}
 MODEL_SEED, INPUT_SEED, PROBE_SEED = 0, 1234, 99
 
 
@@ -77,8 +82,9 @@ def run_case(tae, misc, name, kwargs, batch):
             h.remove()
         rec = {"loss": float(loss), "block_out_norms": acts,
                "pred_dtype": str(pred.dtype), "latent_dtype": str(latent.dtype), "loss_dtype": str(loss.dtype)}
-        tensors[f"{mode}.pred"] = pred.detach().float().clone()
-        tensors[f"{mode}.latent"] = latent.detach().float().clone()
+        keep = (lambda t: t.detach().clone()) if (name in COMPACT and mode == "bf16") else (lambda t: t.detach().float().clone())
+        tensors[f"{mode}.pred"] = keep(pred)
+        tensors[f"{mode}.latent"] = keep(latent)
         gn, gp = {}, {}
         for k, (n, p) in enumerate(model.named_parameters()):
             g = p.grad.detach().float()
@@ -104,7 +110,8 @@ def run_case(tae, misc, name, kwargs, batch):
     out["adamw"] = {"lr": 1e-3, "betas": [0.9, 0.95], "weight_decay": 0.05,
                     "update_norm": {n: float((p.detach() - before[n]).norm()) for n, p in model.named_parameters()},
                     "param_norm_after": {n: float(p.detach().norm()) for n, p in model.named_parameters()}}
-    tensors["input"] = x
+    if name not in COMPACT:
+        tensors["input"] = x  # compact cases: torch.randn(batch, 3, S, S, generator=manual_seed(seeds.input)) regenerates it
     return out, tensors
 
 
@@ -115,11 +122,21 @@ def main():
 
     torch.set_num_threads(8)
     meta = {}
+    only = [a for a in sys.argv[1:] if a in CASES]  # `make_golden.py CASE...` adds cases to the existing fixtures
+    if only:
+        with open(os.path.join(HERE, "golden_meta.json")) as f:
+            meta = json.load(f)
     for name, (kwargs, batch) in CASES.items():
+        if only and name not in only:
+            continue
         rec, tensors = run_case(tae, misc, name, kwargs, batch)
         meta[name] = rec
         torch.save(tensors, os.path.join(HERE, f"{name}.pt"))
         print(name, "fp32 loss", rec["fp32"]["loss"], "bf16 loss", rec["bf16"]["loss"])
+    if only:
+        with open(os.path.join(HERE, "golden_meta.json"), "w") as f:
+            json.dump(meta, f)
+        return
 
     # seed-pinned scalars of the real config #1, re-measured here from the reference itself
     torch.manual_seed(0)

@@ -11,7 +11,7 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-from conftest import TINY_CASES, oracle_cfg, report  # noqa: E402
+from conftest import GOLDEN_CASES, oracle_cfg, report  # noqa: E402
 from oracle import tae_oracle as O  # noqa: E402  (checker only)
 
 BF16_TOL = 2e-2
@@ -30,7 +30,7 @@ def build(kw):
     return m
 
 
-@pytest.mark.parametrize("case", TINY_CASES)
+@pytest.mark.parametrize("case", GOLDEN_CASES)
 def test_forward_backward_matches_golden_and_oracle(case, golden_meta, golden_tensors):
     rec = golden_meta[case]
     kw = rec["kwargs"]
@@ -89,7 +89,7 @@ def test_forward_backward_matches_golden_and_oracle(case, golden_meta, golden_te
     assert abs(gnorm - g["global_grad_norm"]) < BF16_TOL * g["global_grad_norm"]
 
 
-@pytest.mark.parametrize("case", TINY_CASES)
+@pytest.mark.parametrize("case", GOLDEN_CASES)
 def test_encoder_decoder_entry_points(case, golden_meta, golden_tensors):
     rec, t = golden_meta[case], golden_tensors(case)
     model = build(rec["kwargs"]).cuda().eval()
@@ -251,7 +251,7 @@ def test_fused_adamw_training_matches_torch_adamw():
 FP32_TOL = 1e-4
 
 
-@pytest.mark.parametrize("case", TINY_CASES)
+@pytest.mark.parametrize("case", GOLDEN_CASES)
 def test_fp32_mode_matches_reference_fp32(case, golden_meta, golden_tensors):
     rec = golden_meta[case]
     kw = rec["kwargs"]

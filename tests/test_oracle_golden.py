@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import TINY_CASES, oracle_cfg
+from conftest import GOLDEN_CASES, oracle_cfg
 from oracle import tae_oracle as O
 
 
@@ -24,7 +24,7 @@ def _model_state(kw):
     return m, {k: v.detach().clone() for k, v in m.state_dict().items()}
 
 
-@pytest.mark.parametrize("case", TINY_CASES)
+@pytest.mark.parametrize("case", GOLDEN_CASES)
 def test_seeded_init_matches_reference_checksums(case, golden_meta):
     rec = golden_meta[case]
     m, sd = _model_state(rec["kwargs"])
@@ -34,7 +34,7 @@ def test_seeded_init_matches_reference_checksums(case, golden_meta):
         assert abs(float(sd[n].double().abs().sum()) - a) <= 1e-9 * max(1.0, a), n
 
 
-@pytest.mark.parametrize("case", TINY_CASES)
+@pytest.mark.parametrize("case", GOLDEN_CASES)
 def test_oracle_fp32_matches_reference(case, golden_meta, golden_tensors):
     rec, t = golden_meta[case], golden_tensors(case)
     _, sd = _model_state(rec["kwargs"])
@@ -60,7 +60,7 @@ def test_oracle_fp32_matches_reference(case, golden_meta, golden_tensors):
     assert abs(float(O.grad_norm(grads.values())) - g["global_grad_norm"]) < 1e-4 * g["global_grad_norm"]
 
 
-@pytest.mark.parametrize("case", TINY_CASES)
+@pytest.mark.parametrize("case", GOLDEN_CASES)
 def test_oracle_bf16_matches_reference_autocast(case, golden_meta, golden_tensors):
     rec, t = golden_meta[case], golden_tensors(case)
     _, sd = _model_state(rec["kwargs"])
@@ -76,7 +76,7 @@ def test_oracle_bf16_matches_reference_autocast(case, golden_meta, golden_tensor
         assert abs(float(grads[n].float().norm()) - gn) < 2e-2 * gn + 1e-9, n
 
 
-@pytest.mark.parametrize("case", TINY_CASES)
+@pytest.mark.parametrize("case", GOLDEN_CASES)
 def test_oracle_adamw_matches_reference_step(case, golden_meta, golden_tensors):
     rec, t = golden_meta[case], golden_tensors(case)
     _, sd = _model_state(rec["kwargs"])
