@@ -151,7 +151,8 @@ int tae_layernorm_bwd_finalize(const float* partials, int32_t num_partials, int3
 int tae_attention_fwd(const tae_bf16* qkv, tae_bf16* out, float* lse, int32_t B, int32_t N,
                       int32_t H, int32_t hd, void* stream);
 /* dqkv bf16 [B*N, 3*H*hd] from dout bf16 [B*N, H*hd].  tae_attention_bwd_delta takes delta = rowsum(dout * out) per
- * (image, head, token) as fp32 [B, H, N] (e.g. from a TAE_EPI_BF16_ROWDOT GEMM) instead of `out`. */
+ * (image, head, token) as fp32 [B, H, N] (e.g. from a TAE_EPI_BF16_ROWDOT GEMM) instead of `out`; supported for the
+ * N = 256 and N = 64 kernels with hd = 64 (the output tile is then neither read nor staged). */
 int tae_attention_bwd_delta(const tae_bf16* qkv, const tae_bf16* dout, const float* lse, const float* delta,
                             tae_bf16* dqkv, int32_t B, int32_t N, int32_t H, int32_t hd, void* stream);
 int tae_attention_bwd(const tae_bf16* qkv, const tae_bf16* out, const tae_bf16* dout,

@@ -16,3 +16,6 @@ python tools/ncu_misc.py > gpurun_out/ncu_plain_misc.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:'ln_|colsum|mse|im2col|adamw' -s 9 -c 9 -f -o gpurun_out/misc_$R python tools/ncu_misc.py > gpurun_out/ncu_misc.log 2>&1
 echo "misc rc $?"
 for f in ncu_step ncu_gemm ncu_attn ncu_misc; do tail -n 3 gpurun_out/$f.log; done
+python tools/ncu_short.py > gpurun_out/ncu_plain_short.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:'attn_fwd_mma|attn_bwd_mma64|ln_bwd_group' -s 4 -c 4 -f -o gpurun_out/short_$R python tools/ncu_short.py > gpurun_out/ncu_short.log 2>&1
+echo "short rc $?"; tail -n 3 gpurun_out/ncu_short.log
