@@ -80,6 +80,7 @@ struct Params {
   int M, N, K;
   int a_mn, b_mn;
   int m_tiles, n_tiles, kb_total, kb_per_split, splits;
+  int tile_n;          // CTA-pair kernel: output tile width (a multiple of 32, <= BLOCK_N; BLOCK_N unless chosen against wave quantisation)
   void* out;
   int ldo;
   void* out2;
@@ -655,12 +656,13 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         if (w >= total_work) break;
         const WorkItem it = decode_work(p, w);
         const int m0 = it.mt * (2 * BLOCK_M) + (int)rank * BLOCK_M;
-        const int n0 = it.nt * BLOCK_N + (int)rank * (BLOCK_N / 2);
+        const int n0 = it.nt * p.tile_n + (int)rank * (p.tile_n / 2);
         for (int kb = it.kb0; kb < it.kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           uint8_t* sa = smem + stage * STAGE2_BYTES;
           uint8_t* sb = sa + A_STAGE_BYTES;
-          if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * STAGE2_BYTES);  // bytes of both CTAs
+          // bytes of both CTAs: 128 rows of A and tile_n / 2 rows of B each (a ragged box still delivers all its bytes)
+          if (rank == 0) mbar_expect_tx(&full_bar[stage], 2u * (uint32_t)(A_STAGE_BYTES + (p.tile_n / 2) * BLOCK_K * 2));
           const int k0 = kb * BLOCK_K;
           if (!p.a_mn) {
             tma_load_2d_2sm(sa, &tmap_a, &full_bar[stage], k0, m0);
@@ -695,7 +697,7 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread of the leader CTA) =====================
     if (rank == 0 && elect_one()) {
-      const uint32_t idesc = make_idesc_bf16(2 * BLOCK_M, BLOCK_N, p.a_mn, p.b_mn);
+      const uint32_t idesc = make_idesc_bf16(2 * BLOCK_M, p.tile_n, p.a_mn, p.b_mn);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -745,11 +747,12 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       if (w >= total_work) break;
       const WorkItem it = decode_work(p, w);
       const int row_base = it.mt * (2 * BLOCK_M) + (int)rank * BLOCK_M + q * 32;
+      const int n_lim = min(p.N, (it.nt + 1) * p.tile_n);  // first column this tile does not own (tile_n % 32 == 0)
       if constexpr (kInTma) {
         // the first input box of the tile (gelu'(h), the row-dot operand, or the fp32 residual: 2 KB each) is requested
         // before the wait for the accumulator
-        const int colw = it.nt * BLOCK_N + cg * COLS_PER_WARP;
-        if (colw < p.N && row_base < p.M && elect_one()) {
+        const int colw = it.nt * p.tile_n + cg * COLS_PER_WARP;
+        if (colw < n_lim && row_base < p.M && elect_one()) {
           tma_store_wait_read();  // this warp's earlier TMA stores have finished reading both boxes
           mbar_expect_tx(&aux_bar[ew * 2], 2048u);
           tma_load_2d_sa(stg, &tmap_o2, &aux_bar[ew * 2], colw, row_base);
@@ -763,8 +766,8 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         // TMA store, and the per-32-row column sums of the rounded products (the fc1 bias gradient) are read back from
         // the staged box: lane -> (column pair, odd/even rows), one shuffle to fold the two row halves.
         constexpr int NSTEP = COLS_PER_WARP / EPI_COLS;
-        const int colw = it.nt * BLOCK_N + cg * COLS_PER_WARP;
-        const bool active = colw < p.N && row_base < p.M;  // warp-uniform
+        const int colw = it.nt * p.tile_n + cg * COLS_PER_WARP;
+        const bool active = colw < n_lim && row_base < p.M;  // warp-uniform
         bool released = false;
         // Row-dot variant: out = bf16(acc + bias) written over the aux tile, and dot = sum over the 64 columns of a head
         // of out * aux stays in this thread (it owns the row); written after the head's second step.
@@ -774,8 +777,8 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
 #pragma unroll 1
         for (int c = 0; c < NSTEP; ++c) {
           const int col0 = colw + c * EPI_COLS;
-          if (!active || col0 >= p.N) break;
-          const bool last = (c == NSTEP - 1) || (col0 + EPI_COLS >= p.N);
+          if (!active || col0 >= n_lim) break;
+          const bool last = (c == NSTEP - 1) || (col0 + EPI_COLS >= n_lim);
           const int b = c & 1;
           const uint32_t box = stg + (uint32_t)b * 2048u;
           const uint32_t taddr =
@@ -891,9 +894,9 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         bool released = false;
 #pragma unroll 1
         for (int c = 0; c < NSTEP; ++c) {
-          const int col0 = it.nt * BLOCK_N + cg * COLS_PER_WARP + c * EPI_COLS;
-          if (col0 >= p.N) break;  // warp-uniform
-          const bool last = (c == NSTEP - 1) || (col0 + EPI_COLS >= p.N);
+          const int col0 = it.nt * p.tile_n + cg * COLS_PER_WARP + c * EPI_COLS;
+          if (col0 >= n_lim) break;  // warp-uniform
+          const bool last = (c == NSTEP - 1) || (col0 + EPI_COLS >= n_lim);
           const uint32_t taddr =
               tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + cg * COLS_PER_WARP + c * EPI_COLS);
           // the step's 32 bias values are warp-uniform: lane j fetches and rounds column col0 + j, the warp shares them
@@ -950,8 +953,8 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       float rdot[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
       for (int c = 0; c < COLS_PER_WARP / EPI_COLS; ++c) {
-        const int col0 = it.nt * BLOCK_N + cg * COLS_PER_WARP + c * EPI_COLS;
-        if (col0 >= p.N) break;  // warp-uniform
+        const int col0 = it.nt * p.tile_n + cg * COLS_PER_WARP + c * EPI_COLS;
+        if (col0 >= n_lim) break;  // warp-uniform
         const uint32_t taddr =
             tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + cg * COLS_PER_WARP + c * EPI_COLS);
         const float4 bias4 = epi_load_bias<EPI>(p, col0, lane);
@@ -1085,7 +1088,28 @@ extern "C" int tae_gemm(const tae_gemm_args* a, void* stream_) {
   const int tile_m = use2 ? 2 * BLOCK_M : BLOCK_M;
   const int units = use2 ? sms / 2 : sms;  // concurrently resident work items (clusters or CTAs)
   p.m_tiles = (a->M + tile_m - 1) / tile_m;
-  p.n_tiles = (a->N + BLOCK_N - 1) / BLOCK_N;
+  // Tile width.  With few token rows (patch64 / patch128: 16 / 4 row tiles) a 256-wide tiling leaves the last wave of the
+  // 74 clusters mostly empty (N = 2560: 160 tiles = 2.16 waves at M = 4096, 40 tiles = 0.54 at M = 1024).  For K-major B
+  // (every forward GEMM; MN-major B is tied to 64-column TMA boxes) the width is chosen from {256, 224, 192, 160, 128} to
+  // maximise wave efficiency x MMA efficiency, the latter from the measured shared-memory operand limit of the pair MMA
+  // (72 B/clk/SM: 4 KB of A + 16 tile_n B of B per instruction against tile_n / 2 cycles of array time).
+  p.tile_n = BLOCK_N;
+#ifndef TAE_FIXED_TILE_N  // A/B builds: -DTAE_FIXED_TILE_N keeps 256-wide tiles everywhere
+  if (use2 && !p.b_mn && a->epilogue != TAE_EPI_F32_ACC && a->epilogue != TAE_EPI_BF16_ROWDOT) {  // (a row-dot head = 64 columns)
+    double best = 0.0;
+    for (int tn = BLOCK_N; tn >= 128; tn -= 32) {
+      const long tiles = (long)p.m_tiles * ((a->N + tn - 1) / tn);
+      const double wave = (double)tiles / (double)(((tiles + units - 1) / units) * units);
+      const double smem_cycles = (4096.0 + 16.0 * tn) / 72.0, array_cycles = tn / 2.0;
+      const double score = wave * (array_cycles / (smem_cycles > array_cycles ? smem_cycles : array_cycles));
+      if (score > best + (tn == BLOCK_N ? 0.0 : 0.03)) {  // a narrower tile has to pay for itself
+        best = score;
+        p.tile_n = tn;
+      }
+    }
+  }
+#endif
+  p.n_tiles = (a->N + (use2 ? p.tile_n : BLOCK_N) - 1) / (use2 ? p.tile_n : BLOCK_N);
   p.kb_total = (a->K + BLOCK_K - 1) / BLOCK_K;
   int splits = a->splits;
   if (a->epilogue != TAE_EPI_F32_ACC) {
@@ -1140,7 +1164,7 @@ extern "C" int tae_gemm(const tae_gemm_args* a, void* stream_) {
     rc = make_tmap(&ta, a->A, (uint64_t)a->M, (uint64_t)a->K, (uint64_t)a->lda, BLOCK_K);
   if (rc) return rc;
   if (!p.b_mn)
-    rc = make_tmap(&tb, a->B, (uint64_t)a->K, (uint64_t)a->N, (uint64_t)a->ldb, use2 ? BLOCK_N / 2 : BLOCK_N);
+    rc = make_tmap(&tb, a->B, (uint64_t)a->K, (uint64_t)a->N, (uint64_t)a->ldb, use2 ? p.tile_n / 2 : BLOCK_N);
   else
     rc = make_tmap(&tb, a->B, (uint64_t)a->N, (uint64_t)a->K, (uint64_t)a->ldb, BLOCK_K);
   if (rc) return rc;

@@ -92,6 +92,42 @@ def test_gemm_epilogue_bias_gelu(M, N, K):
     assert bool((big2[M:] == 7).all()) and bool((big2[:, N:] == 7).all())
 
 
+@pytest.mark.parametrize("M,N,K", [(1024, 2560, 2560), (1024, 7680, 512), (1024, 10240, 256), (4096, 2560, 640), (4096, 4096, 256),
+                                   (1024, 2568, 320), (520, 1160, 128), (2048, 16384, 64)])
+def test_gemm_narrow_tiles_for_short_grids(M, N, K):
+    """K-major-B GEMMs with few row tiles pick a tile width below 256 against wave quantisation (160 / 192 / 224 / 128 for
+    these shapes; the last three also have ragged N or M): every forward epilogue must be unaffected by the width."""
+    ops = _ops()
+    from tae_b200._lib import EPI_BF16, EPI_BF16_DGELU, EPI_BF16_GELU, EPI_F32_RESID
+
+    A, B = randn(M, K, seed=80), randn(N, K, seed=81, scale=0.1)
+    bias = randn(N, dtype=torch.float32, seed=82)
+    acc = A.float() @ B.float().t() + bias.to(torch.bfloat16).float()
+    big = torch.full((M + 2, N + 40), 7.0, dtype=torch.bfloat16, device="cuda")
+    out = ops.gemm(A, B, epilogue=EPI_BF16, bias=bias, out=big[:M, :N])
+    assert rel_err(out.float(), acc) < 5e-3 and max_err_scaled(out.float(), acc) < 1e-2
+    assert bool((big[M:] == 7).all()) and bool((big[:, N:] == 7).all())
+    gp, a = ops.gemm(A, B, epilogue=EPI_BF16_GELU, bias=bias)
+    hf = acc.to(torch.bfloat16).float()
+    assert rel_err(a.float(), O.gelu(hf)) < 4e-3
+    gpref = 0.5 * (1 + torch.erf(hf / math.sqrt(2))) + hf * torch.exp(-0.5 * hf * hf) / math.sqrt(2 * math.pi)
+    assert rel_err(gp.float(), gpref) < 4e-3
+    resid = randn(M, N, dtype=torch.float32, seed=83)
+    y = acc.to(torch.bfloat16).float()
+    outr = ops.gemm(A, B, epilogue=EPI_F32_RESID, bias=bias, resid=resid)
+    assert rel_err(outr - resid, y) < 5e-3
+    if M % 8 == 0:
+        pos = randn(8, N, dtype=torch.float32, seed=84)
+        outp = ops.gemm(A, B, epilogue=EPI_F32_RESID, bias=bias, resid=pos, resid_rows=8)
+        assert rel_err(outp - pos.repeat(M // 8, 1), y) < 5e-3
+    gpm = randn(M, N, seed=85, scale=0.5)
+    part = torch.empty((M + 31) // 32, N, device="cuda")
+    dh = ops.gemm(A, B, epilogue=EPI_BF16_DGELU, aux=gpm, colsum_partials=part)
+    ref = (A.float() @ B.float().t()).to(torch.bfloat16).float() * gpm.float()
+    assert rel_err(dh.float(), ref) < 5e-3
+    assert rel_err(ops.colsum_f32(part), dh.float().sum(0)) < 1e-4
+
+
 def test_gemm_epilogue_residual_and_posembed():
     ops = _ops()
     from tae_b200._lib import EPI_F32_RESID
