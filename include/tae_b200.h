@@ -70,7 +70,8 @@ enum tae_gemm_epilogue {
   TAE_EPI_BF16 = 0,
   /* h = bf16(acc + bias[n]);  out2 = bf16(gelu_erf(h))  (tae.py:101-102);  out = bf16(gelu_erf'(h)) — the only
    * thing backward needs from the pre-activation, so it is saved instead of h and the fc2 dgrad epilogue
-   * (TAE_EPI_BF16_DGELU) is a plain multiply */
+   * (TAE_EPI_BF16_DGELU) is a plain multiply.  out == NULL: inference (forward_encoder / forward under no_grad,
+   * encode.py:85) — gelu'(h) is not written */
   TAE_EPI_BF16_GELU = 1,
   /* out(f32)[m,n] = resid[(m % resid_rows), n] + float(bf16(acc + bias[n]))
    * residual add tae.py:129-130; pos-embed add tae.py:229,245 (resid_rows = tokens per image) */

@@ -249,7 +249,7 @@ __device__ __forceinline__ void epi_write_rows(const Params& p, uint32_t stg, in
       uint32_t g01, gp01, g23, gp23;
       gelu_and_grad_pair(f2_pack(a0, a1), f2_pack(bias4.x, bias4.y), g01, gp01);
       gelu_and_grad_pair(f2_pack(a2, a3), f2_pack(bias4.z, bias4.w), g23, gp23);
-      *reinterpret_cast<uint2*>(optr) = make_uint2(gp01, gp23);
+      if (p.out != nullptr) *reinterpret_cast<uint2*>(optr) = make_uint2(gp01, gp23);  // NULL: inference, gelu' not kept
       *reinterpret_cast<uint2*>(obase2 + it * rstride) = make_uint2(g01, g23);
 #else
       float g[4], gp[4];
@@ -258,7 +258,7 @@ __device__ __forceinline__ void epi_write_rows(const Params& p, uint32_t stg, in
       gelu_and_grad_fast(h01.y, g[1], gp[1]);
       gelu_and_grad_fast(h23.x, g[2], gp[2]);
       gelu_and_grad_fast(h23.y, g[3], gp[3]);
-      *reinterpret_cast<uint2*>(optr) = make_uint2(pack_bf16x2(gp[0], gp[1]), pack_bf16x2(gp[2], gp[3]));
+      if (p.out != nullptr) *reinterpret_cast<uint2*>(optr) = make_uint2(pack_bf16x2(gp[0], gp[1]), pack_bf16x2(gp[2], gp[3]));
       *reinterpret_cast<uint2*>(obase2 + it * rstride) = make_uint2(pack_bf16x2(g[0], g[1]), pack_bf16x2(g[2], g[3]));
 #endif
     } else if (EPI == TAE_EPI_BF16_DGELU) {
@@ -929,13 +929,14 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                                  f2_pack(__uint_as_float(bw[j] << 16), __uint_as_float(bw[j] & 0xffff0000u)), gw[j], pw[j]);
             }
             st_shared_v4(stg + stg64_off(lane, k), gw[0], gw[1], gw[2], gw[3]);          // gelu(h)  -> out2
-            st_shared_v4(stg + 2048u + stg64_off(lane, k), pw[0], pw[1], pw[2], pw[3]);  // gelu'(h) -> out
+            if (p.out != nullptr)  // NULL: inference (forward_encoder under no_grad): gelu'(h) is not kept
+              st_shared_v4(stg + 2048u + stg64_off(lane, k), pw[0], pw[1], pw[2], pw[3]);  // gelu'(h) -> out
           }
           fence_proxy_async_smem();
           __syncwarp();
           if (row_base < p.M && elect_one()) {
             tma_store_2d_sa(&tmap_o2, stg, col0, row_base);
-            tma_store_2d_sa(&tmap_o, stg + 2048u, col0, row_base);
+            if (p.out != nullptr) tma_store_2d_sa(&tmap_o, stg + 2048u, col0, row_base);
             tma_store_commit();
           }
         }
@@ -1055,7 +1056,9 @@ extern "C" int tae_gemm(const tae_gemm_args* a, void* stream_) {
   TAE_CHECK_SHAPE((reinterpret_cast<uintptr_t>(a->A) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->B) & 15) == 0 &&
                       (reinterpret_cast<uintptr_t>(a->out) & 15) == 0,
                   "tae_gemm: A, B and out must be 16-byte aligned");
-  TAE_CHECK_SHAPE(a->out != nullptr && a->A != nullptr && a->B != nullptr, "tae_gemm: NULL operand");
+  TAE_CHECK_SHAPE((a->out != nullptr || (a->epilogue == TAE_EPI_BF16_GELU && a->out2 != nullptr)) && a->A != nullptr &&
+                      a->B != nullptr,
+                  "tae_gemm: NULL operand (out may be NULL only for TAE_EPI_BF16_GELU: inference, gelu' not kept)");
   TAE_CHECK_SHAPE(a->epilogue >= TAE_EPI_BF16 && a->epilogue <= TAE_EPI_BF16_ROWDOT, "tae_gemm: bad epilogue %d", a->epilogue);
   const bool out_f32 = (a->epilogue == TAE_EPI_F32_RESID || a->epilogue == TAE_EPI_F32_ACC);
   TAE_CHECK_SHAPE(a->ldo % (out_f32 ? 4 : 8) == 0 && a->ldo >= a->N, "tae_gemm: bad ldo %d", a->ldo);
@@ -1174,8 +1177,10 @@ extern "C" int tae_gemm(const tae_gemm_args* a, void* stream_) {
   if (use2 && ((TAE_GELU_TMA_EPI && a->epilogue == TAE_EPI_BF16_GELU) ||
                (TAE_DGELU_TMA_EPI && a->epilogue == TAE_EPI_BF16_DGELU) || a->epilogue == TAE_EPI_BF16_ROWDOT)) {
     const CUtensorMapSwizzle swz = TAE_GELU_TMA_SWZ64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE;
-    rc = make_tmap_box(&to, a->out, (uint64_t)a->N, (uint64_t)a->M, (uint64_t)a->ldo, 32, 32, swz);
-    if (rc) return rc;
+    if (a->out != nullptr) {
+      rc = make_tmap_box(&to, a->out, (uint64_t)a->N, (uint64_t)a->M, (uint64_t)a->ldo, 32, 32, swz);
+      if (rc) return rc;
+    }
     if (a->epilogue == TAE_EPI_BF16_GELU) {
       rc = make_tmap_box(&to2, a->out2, (uint64_t)a->N, (uint64_t)a->M, (uint64_t)a->ldo, 32, 32, swz);
       if (rc) return rc;

@@ -42,7 +42,8 @@ def _req(t: torch.Tensor, dtype, name: str) -> None:
 def gemm(A: torch.Tensor, B: torch.Tensor, *, a_mn: bool = False, b_mn: bool = False, epilogue: int = EPI_BF16,
          out: torch.Tensor | None = None, out2: torch.Tensor | None = None, bias: torch.Tensor | None = None,
          resid: torch.Tensor | None = None, resid_rows: int = 0, aux: torch.Tensor | None = None, beta: int = 0,
-         splits: int = 0, colsum_partials: torch.Tensor | None = None, rowdot_tokens: int = 0):
+         splits: int = 0, colsum_partials: torch.Tensor | None = None, rowdot_tokens: int = 0,
+         gelu_grad: bool = True):
     """D[M,N] = sum_k A(m,k) B(n,k) on the tcgen05 tensor cores; see include/tae_b200.h for the conventions.
 
     A: [M,K] (or [K,M] if a_mn); B: [N,K] (or [K,N] if b_mn); 2-D bf16, inner stride 1.
@@ -61,6 +62,22 @@ def gemm(A: torch.Tensor, B: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
     if K != Kb:
         raise _lib.TaeError(f"gemm: reduction dims differ (A gives K={K}, B gives K={Kb})")
     out_dtype = f32 if epilogue in (EPI_F32_RESID, EPI_F32_ACC) else bf16
+    if epilogue == EPI_BF16_GELU and not gelu_grad:
+        # inference: only gelu(h) is produced; returns (None, gelu(h))
+        if out2 is None:
+            out2 = torch.empty((M, N), dtype=bf16, device=A.device)
+        _req(out2, bf16, "gemm out2")
+        assert out2.dim() == 2 and out2.shape == (M, N) and out2.stride(1) == 1
+        a = GemmArgs()
+        a.A, a.B, a.M, a.N, a.K = A.data_ptr(), B.data_ptr(), M, N, K
+        a.lda, a.ldb, a.a_mn_major, a.b_mn_major = A.stride(0), B.stride(0), int(a_mn), int(b_mn)
+        a.epilogue, a.out, a.ldo, a.out2 = epilogue, 0, out2.stride(0), out2.data_ptr()
+        if bias is not None:
+            _req(bias, f32, "gemm bias")
+            assert bias.numel() == N
+            a.bias = bias.data_ptr()
+        check(_L().tae_gemm(C.byref(a), _stream()), "tae_gemm")
+        return None, out2
     if out is None:
         out = torch.empty((M, N), dtype=out_dtype, device=A.device)
     else:

@@ -236,7 +236,8 @@ class _BlockFn(torch.autograd.Function):
         att, lse = ops.attention_fwd(qkv, B, N, H, hd)
         xm = ops.gemm(att, shadow_bf16(pw), epilogue=EPI_F32_RESID, bias=det(pb), resid=x2)
         ln2, mean2, rstd2 = ops.layernorm_fwd(xm, det(n2w), det(n2b), blk.norm2.eps)
-        gp, a = ops.gemm(ln2, shadow_bf16(f1w), epilogue=EPI_BF16_GELU, bias=det(f1b))  # gelu'(h), gelu(h)
+        # gelu'(h), gelu(h); without a backward to come (no_grad: encode.py / evaluate.py) gelu' is not produced
+        gp, a = ops.gemm(ln2, shadow_bf16(f1w), epilogue=EPI_BF16_GELU, bias=det(f1b), gelu_grad=any(ctx.needs_input_grad))
         xo = ops.gemm(a, shadow_bf16(f2w), epilogue=EPI_F32_RESID, bias=det(f2b), resid=xm)
         ctx.blk, ctx.dims = blk, (B, N, D, H, hd)
         ctx.save_for_backward(x2, mean1, rstd1, ln1, qkv, att, lse, xm, mean2, rstd2, ln2, gp, a)

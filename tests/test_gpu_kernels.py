@@ -83,6 +83,9 @@ def test_gemm_epilogue_bias_gelu(M, N, K):
     gpref = 0.5 * (1 + torch.erf(hf / math.sqrt(2))) + hf * torch.exp(-0.5 * hf * hf) / math.sqrt(2 * math.pi)
     assert max_err_scaled(a.float(), aref) < 1e-2 and rel_err(a.float(), aref) < 4e-3
     assert max_err_scaled(gp.float(), gpref) < 1e-2 and rel_err(gp.float(), gpref) < 4e-3
+    # inference form (out == NULL): the same gelu(h), no gelu' written
+    none, a_inf = ops.gemm(A, B, epilogue=EPI_BF16_GELU, bias=bias, gelu_grad=False)
+    assert none is None and torch.equal(a_inf, a)
     # the two outputs are views into larger buffers in the model (leading dimension > N): nothing outside [M, N] is touched
     big = torch.full((M + 8, N + 64), 7.0, dtype=torch.bfloat16, device="cuda")
     big2 = torch.full((M + 8, N + 64), 7.0, dtype=torch.bfloat16, device="cuda")

@@ -105,6 +105,12 @@ def test_encoder_decoder_entry_points(case, golden_meta, golden_tensors):
         assert abs(float(loss) - rec["bf16"]["loss"]) < BF16_TOL * rec["bf16"]["loss"]
         loss2, pred2 = model(x)
         assert torch.equal(pred2, pred) and abs(float(loss2) - float(loss)) < 1e-6
+    # the no_grad forward skips what only a backward would need (gelu'(h)); the values are those of the training forward
+    model.train()
+    _, pred_t, z_t = model(x, return_latent=True)
+    assert torch.equal(pred_t, pred) and torch.equal(z_t, z)
+    model.eval()
+    with torch.no_grad():
         # reconstruction display path (train.py:190): unpatchify(pred) and its inverse
         img = model.unpatchify(pred)
         assert img.shape == x.shape
