@@ -54,7 +54,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
     ap.add_argument("--mode", default=None, choices=["train", "encode"])
     ap.add_argument("--no-graph", action="store_true",
-                    help="single GPU: run the step eagerly instead of replaying it as one CUDA graph (engine.GraphedTrainStep)")
+                    help="run eagerly instead of replaying CUDA graphs (engine.GraphedTrainStep on one GPU, GraphedEncoder)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-encode", action="store_true", help="skip the encode.py-path measurement (config 5)")
@@ -549,7 +549,8 @@ def run_b200(args):
     B = args.batch
 
     if args.mode == "encode":  # config 5 as the headline of this invocation
-        enc = encode_throughput(torch, dist, engine, args.model, B, dev, world, iters=args.steps, warmup=args.warmup)
+        enc = encode_throughput(torch, dist, engine, args.model, B, dev, world, iters=args.steps, warmup=args.warmup,
+                                use_graph=not args.no_graph)
         if rank == 0:
             print(json.dumps({
                 "metric": metric_name(args.model, "encode"), "value": enc["value"], "unit": "images/s", "n_gpus": world,
@@ -581,7 +582,7 @@ def run_b200(args):
                                                                       "gpu_launches", "final_loss", "ddp_check", "graph") if k in r}
     enc = None
     if not args.no_encode:
-        enc = encode_throughput(torch, dist, engine, CONFIGS[5][0], B, dev, world)
+        enc = encode_throughput(torch, dist, engine, CONFIGS[5][0], B, dev, world, use_graph=not args.no_graph)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -623,7 +624,7 @@ def run_b200(args):
     print(json.dumps(line), flush=True)
 
 
-def encode_throughput(torch, dist, engine, model_name, B, dev, world, iters=10, warmup=3):
+def encode_throughput(torch, dist, engine, model_name, B, dev, world, iters=10, warmup=3, use_graph=True):
     """BASELINE.json configs[4]: the encode.py path (forward_encoder under no_grad, encode.py:80-88), batch-sharded over
     the ranks with no communication.  Returns images/s resident and end-to-end (H2D of every batch + latent D2H)."""
     from tae_b200 import ops
@@ -635,8 +636,9 @@ def encode_throughput(torch, dist, engine, model_name, B, dev, world, iters=10, 
     model.eval()
     host = [torch.randn(B, 3, 256, 256).pin_memory() for _ in range(2)]
     res = [h.to(dev) for h in host]
-    for i in range(max(3, warmup)):
-        z = engine.encode_batch(model, res[i % 2])
+    enc = engine.GraphedEncoder(model, res[0]) if use_graph else (lambda x: engine.encode_batch(model, x))
+    for i in range(max(4, warmup)):
+        z = enc(res[i % 2])
     lat_host = torch.empty(z.shape, dtype=z.dtype).pin_memory()
 
     def timed(fn):
@@ -655,13 +657,17 @@ def encode_throughput(torch, dist, engine, model_name, B, dev, world, iters=10, 
         return float(t)
 
     n0 = ops.launch_count()
-    ms = timed(lambda i: engine.encode_batch(model, res[i % 2]))
+    ms = timed(lambda i: enc(res[i % 2]))
     launches = ops.launch_count() - n0
+    if use_graph:  # replayed launches are not counted by the library: count one eager batch
+        n0 = ops.launch_count()
+        engine.encode_batch(model, res[0])
+        launches = (ops.launch_count() - n0) * iters
     feeder = engine.HostBatchFeeder(host, dev)
 
     def e2e_step(i):
         x = feeder.next()
-        z = engine.encode_batch(model, x)
+        z = enc(x)
         feeder.release()
         lat_host.copy_(z, non_blocking=True)  # encode.py:87 `latents.cpu()`
 
@@ -671,7 +677,7 @@ def encode_throughput(torch, dist, engine, model_name, B, dev, world, iters=10, 
     return {"metric": metric_name(model_name, "encode"), "model": model_name, "batch_per_gpu": B,
             "value": world * B * iters / (ms / 1e3), "e2e": world * B * iters / (ms_e2e / 1e3), "unit": "images/s",
             "ms_per_step": ms / iters, "h2d_bytes_per_step": host[0].numel() * 4, "d2h_bytes_per_step": lat_host.numel() * 2,
-            "gpu_launches": int(launches)}
+            "gpu_launches": int(launches), "graph": bool(use_graph)}
 
 
 def kernel_rooflines(torch, ops, step_fn, peaks):

@@ -476,21 +476,27 @@ struct Small {
   __device__ static uint32_t bt_addr(uint32_t base, int n0, int lane) {  // B from [k][n] (.trans): k 0..15, n0..n0+15
     return base + (uint32_t)(((lane & 7) + ((lane >> 3) & 1) * 8) * LD + n0 + (lane >> 4) * 8) * 2u;
   }
-  // [N x HDT] rows of global (row stride ld_g) -> padded smem tile, rows >= N zeroed
-  __device__ static void load_tile(bf16* s, const bf16* g, size_t ld_g, int N, int lane) {
+  // P heads x [N x HDT] rows of global (row stride ld_g, heads HDT columns apart) -> padded smem tile: tile row r holds
+  // token r % N of head r / N; rows >= P * N zeroed
+  __device__ static void load_tile(bf16* s, const bf16* g, size_t ld_g, int N, int PN, int lane) {
     constexpr int CPR = HDT / 8;
     for (int c = lane; c < 16 * CPR; c += 32) {
       const int row = c / CPR, ch = c - row * CPR;
       uint4 v = make_uint4(0u, 0u, 0u, 0u);
-      if (row < N) v = ld_nc_v4(g + (size_t)row * ld_g + ch * 8);
+      if (row < PN) {
+        const int hh = row / N, tok = row - hh * N;
+        v = ld_nc_v4(g + (size_t)tok * ld_g + hh * HDT + ch * 8);
+      }
       *reinterpret_cast<uint4*>(s + row * LD + ch * 8) = v;
     }
   }
 };
 
-// S (exp2 domain, masked) of one 16x16 tile: s[nt][0..3] = rows (g, g+8), keys nt*8 + 2t + {0,1}
+// S (exp2 domain, masked) of one 16x16 tile: s[nt][0..3] = rows (g, g+8), keys nt*8 + 2t + {0,1}.  The tile packs
+// PN / N heads of N tokens each: a key counts for a query only inside the same head (block-diagonal mask).
 template <int HDT>
-__device__ __forceinline__ void small_scores(float (&s)[2][4], uint32_t bQ, uint32_t bK, int N, float scale_log2, int lane) {
+__device__ __forceinline__ void small_scores(float (&s)[2][4], uint32_t bQ, uint32_t bK, int N, int PN, float scale_log2,
+                                             int lane) {
   using C = Small<HDT>;
 #pragma unroll
   for (int i = 0; i < 2; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
@@ -502,14 +508,16 @@ __device__ __forceinline__ void small_scores(float (&s)[2][4], uint32_t bQ, uint
     mma16816(s[0], qa, kb[0], kb[1]);
     mma16816(s[1], qa, kb[2], kb[3]);
   }
-  const int t = lane & 3;
+  const int t = lane & 3, g = lane >> 2;
+  const int blk0 = g / N, blk1 = (g + 8) / N;  // head (block) of this lane's two query rows
 #pragma unroll
   for (int nt = 0; nt < 2; ++nt) {
-    const int j0 = nt * 8 + 2 * t;
-    s[nt][0] = j0 < N ? s[nt][0] * scale_log2 : -INFINITY;
-    s[nt][2] = j0 < N ? s[nt][2] * scale_log2 : -INFINITY;
-    s[nt][1] = j0 + 1 < N ? s[nt][1] * scale_log2 : -INFINITY;
-    s[nt][3] = j0 + 1 < N ? s[nt][3] * scale_log2 : -INFINITY;
+    const int j0 = nt * 8 + 2 * t, j1 = j0 + 1;
+    const int kb0 = j0 < PN ? j0 / N : -1, kb1 = j1 < PN ? j1 / N : -1;  // -1: padding key
+    s[nt][0] = kb0 == blk0 ? s[nt][0] * scale_log2 : -INFINITY;
+    s[nt][2] = kb0 == blk1 ? s[nt][2] * scale_log2 : -INFINITY;
+    s[nt][1] = kb1 == blk0 ? s[nt][1] * scale_log2 : -INFINITY;
+    s[nt][3] = kb1 == blk1 ? s[nt][3] * scale_log2 : -INFINITY;
   }
 }
 __device__ __forceinline__ float quad_max(float v) {
@@ -523,27 +531,29 @@ __device__ __forceinline__ float quad_sum(float v) {
 
 template <int HDT>
 __global__ void __launch_bounds__(128)
-attn_fwd_small(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* __restrict__ lse, int BH, int N, int H,
-               float scale_log2) {
+attn_fwd_small(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* __restrict__ lse, int items, int N, int H,
+               int P, float scale_log2) {
   using C = Small<HDT>;
   extern __shared__ uint4 smem_u4[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int wg = blockIdx.x * 4 + warp;
-  if (wg >= BH) return;  // no CTA-wide barriers below
-  const int b = wg / H, h = wg - b * H;
+  if (wg >= items) return;  // no CTA-wide barriers below
+  // one warp = P consecutive heads of one image (P = 16 / N when that divides the heads: 4 heads of the 4-token grid),
+  // packed as a block-diagonal 16x16 problem
+  const int gpi = H / P, b = wg / gpi, h = (wg - b * gpi) * P, PN = P * N;
   const int D = H * HDT;
   const size_t ldq = (size_t)3 * D;
   bf16* sQ = reinterpret_cast<bf16*>(smem_u4) + (size_t)warp * 3 * C::TILE;
   bf16* sK = sQ + C::TILE;
   bf16* sV = sK + C::TILE;
   const bf16* gq = qkv + (size_t)b * N * ldq + (size_t)h * HDT;
-  C::load_tile(sQ, gq, ldq, N, lane);
-  C::load_tile(sK, gq + D, ldq, N, lane);
-  C::load_tile(sV, gq + 2 * D, ldq, N, lane);
+  C::load_tile(sQ, gq, ldq, N, PN, lane);
+  C::load_tile(sK, gq + D, ldq, N, PN, lane);
+  C::load_tile(sV, gq + 2 * D, ldq, N, PN, lane);
   __syncwarp();
   const uint32_t bQ = smem_u32(sQ), bK = smem_u32(sK), bV = smem_u32(sV);
   float s[2][4];
-  small_scores<HDT>(s, bQ, bK, N, scale_log2, lane);
+  small_scores<HDT>(s, bQ, bK, N, PN, scale_log2, lane);
   const float m0 = quad_max(fmaxf(fmaxf(s[0][0], s[0][1]), fmaxf(s[1][0], s[1][1])));
   const float m1 = quad_max(fmaxf(fmaxf(s[0][2], s[0][3]), fmaxf(s[1][2], s[1][3])));
   float p[2][4];
@@ -561,12 +571,16 @@ attn_fwd_small(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* __re
                           pack_bf16x2(p[1][2], p[1][3])};
   const int g = lane >> 2, t = lane & 3;
   const float inv0 = 1.f / l0, inv1 = 1.f / l1;
+  // tile rows g and g + 8 -> (head offset, token)
+  const int hh0 = g / N, tok0 = g - hh0 * N, hh1 = (g + 8) / N, tok1 = g + 8 - hh1 * N;
   if (t == 0) {
-    float* lrow = lse + ((size_t)b * H + h) * N;
-    if (g < N) lrow[g] = (m0 + log2f(l0)) * 0.69314718055994530942f;
-    if (g + 8 < N) lrow[g + 8] = (m1 + log2f(l1)) * 0.69314718055994530942f;
+    float* lrow = lse + ((size_t)b * H + h) * N;  // [B, H, N]: head h + hh at offset hh * N
+    if (g < PN) lrow[hh0 * N + tok0] = (m0 + log2f(l0)) * 0.69314718055994530942f;
+    if (g + 8 < PN) lrow[hh1 * N + tok1] = (m1 + log2f(l1)) * 0.69314718055994530942f;
   }
   bf16* go = out + (size_t)b * N * D + (size_t)h * HDT;
+  bf16* go0 = go + (size_t)tok0 * D + hh0 * HDT;
+  bf16* go1 = go + (size_t)tok1 * D + hh1 * HDT;
 #pragma unroll
   for (int dp = 0; dp < C::NT8 / 2; ++dp) {
     uint32_t vb[4];
@@ -575,13 +589,13 @@ attn_fwd_small(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* __re
     mma16816(o0, pa, vb[0], vb[1]);
     mma16816(o1, pa, vb[2], vb[3]);
     const int col = dp * 16 + 2 * t;
-    if (g < N) {
-      *reinterpret_cast<uint32_t*>(go + (size_t)g * D + col) = pack_bf16x2(o0[0] * inv0, o0[1] * inv0);
-      *reinterpret_cast<uint32_t*>(go + (size_t)g * D + col + 8) = pack_bf16x2(o1[0] * inv0, o1[1] * inv0);
+    if (g < PN) {
+      *reinterpret_cast<uint32_t*>(go0 + col) = pack_bf16x2(o0[0] * inv0, o0[1] * inv0);
+      *reinterpret_cast<uint32_t*>(go0 + col + 8) = pack_bf16x2(o1[0] * inv0, o1[1] * inv0);
     }
-    if (g + 8 < N) {
-      *reinterpret_cast<uint32_t*>(go + (size_t)(g + 8) * D + col) = pack_bf16x2(o0[2] * inv1, o0[3] * inv1);
-      *reinterpret_cast<uint32_t*>(go + (size_t)(g + 8) * D + col + 8) = pack_bf16x2(o1[2] * inv1, o1[3] * inv1);
+    if (g + 8 < PN) {
+      *reinterpret_cast<uint32_t*>(go1 + col) = pack_bf16x2(o0[2] * inv1, o0[3] * inv1);
+      *reinterpret_cast<uint32_t*>(go1 + col + 8) = pack_bf16x2(o1[2] * inv1, o1[3] * inv1);
     }
   }
 }
@@ -589,13 +603,13 @@ attn_fwd_small(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* __re
 template <int HDT>
 __global__ void __launch_bounds__(128)
 attn_bwd_small(const bf16* __restrict__ qkv, const bf16* __restrict__ dout, const float* __restrict__ lse,
-               bf16* __restrict__ dqkv, int BH, int N, int H, float scale, float scale_log2) {
+               bf16* __restrict__ dqkv, int items, int N, int H, int P, float scale, float scale_log2) {
   using C = Small<HDT>;
   extern __shared__ uint4 smem_u4[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int wg = blockIdx.x * 4 + warp;
-  if (wg >= BH) return;
-  const int b = wg / H, h = wg - b * H;
+  if (wg >= items) return;
+  const int gpi = H / P, b = wg / gpi, h = (wg - b * gpi) * P, PN = P * N;  // P heads per warp, see attn_fwd_small
   const int D = H * HDT;
   const size_t ldq = (size_t)3 * D;
   bf16* sQ = reinterpret_cast<bf16*>(smem_u4) + (size_t)warp * 4 * C::TILE;
@@ -603,19 +617,20 @@ attn_bwd_small(const bf16* __restrict__ qkv, const bf16* __restrict__ dout, cons
   bf16* sV = sK + C::TILE;
   bf16* sdO = sV + C::TILE;
   const bf16* gq = qkv + (size_t)b * N * ldq + (size_t)h * HDT;
-  C::load_tile(sQ, gq, ldq, N, lane);
-  C::load_tile(sK, gq + D, ldq, N, lane);
-  C::load_tile(sV, gq + 2 * D, ldq, N, lane);
-  C::load_tile(sdO, dout + (size_t)b * N * D + (size_t)h * HDT, (size_t)D, N, lane);
+  C::load_tile(sQ, gq, ldq, N, PN, lane);
+  C::load_tile(sK, gq + D, ldq, N, PN, lane);
+  C::load_tile(sV, gq + 2 * D, ldq, N, PN, lane);
+  C::load_tile(sdO, dout + (size_t)b * N * D + (size_t)h * HDT, (size_t)D, N, PN, lane);
   __syncwarp();
   const uint32_t bQ = smem_u32(sQ), bK = smem_u32(sK), bV = smem_u32(sV), bdO = smem_u32(sdO);
   const int g = lane >> 2, t = lane & 3;
   // P = exp2(S * c - lse2[row])   (masked keys give exp2(-inf) = 0; padded rows are discarded at the stores)
   float s[2][4];
-  small_scores<HDT>(s, bQ, bK, N, scale_log2, lane);
+  small_scores<HDT>(s, bQ, bK, N, PN, scale_log2, lane);
+  const int hh0 = g / N, tok0 = g - hh0 * N, hh1 = (g + 8) / N, tok1 = g + 8 - hh1 * N;  // tile rows g, g + 8
   const float* lrow = lse + ((size_t)b * H + h) * N;
-  const float ls0 = g < N ? lrow[g] * 1.44269504088896340736f : 0.f;
-  const float ls1 = g + 8 < N ? lrow[g + 8] * 1.44269504088896340736f : 0.f;
+  const float ls0 = g < PN ? lrow[hh0 * N + tok0] * 1.44269504088896340736f : 0.f;
+  const float ls1 = g + 8 < PN ? lrow[hh1 * N + tok1] * 1.44269504088896340736f : 0.f;
   float p[2][4], dp[2][4];
 #pragma unroll
   for (int nt = 0; nt < 2; ++nt) {
@@ -669,8 +684,8 @@ attn_bwd_small(const bf16* __restrict__ qkv, const bf16* __restrict__ dout, cons
     mma16816(v0, pt_, ob[0], ob[1]);   // dV = P^T dO
     mma16816(v1, pt_, ob[2], ob[3]);
     const int col = dpi * 16 + 2 * t;
-    if (g < N) {
-      bf16* r = gd + (size_t)g * ldq + col;
+    if (g < PN) {
+      bf16* r = gd + (size_t)tok0 * ldq + hh0 * HDT + col;
       *reinterpret_cast<uint32_t*>(r) = pack_bf16x2(q0[0], q0[1]);
       *reinterpret_cast<uint32_t*>(r + 8) = pack_bf16x2(q1[0], q1[1]);
       *reinterpret_cast<uint32_t*>(r + D) = pack_bf16x2(k0[0], k0[1]);
@@ -678,8 +693,8 @@ attn_bwd_small(const bf16* __restrict__ qkv, const bf16* __restrict__ dout, cons
       *reinterpret_cast<uint32_t*>(r + 2 * D) = pack_bf16x2(v0[0], v0[1]);
       *reinterpret_cast<uint32_t*>(r + 2 * D + 8) = pack_bf16x2(v1[0], v1[1]);
     }
-    if (g + 8 < N) {
-      bf16* r = gd + (size_t)(g + 8) * ldq + col;
+    if (g + 8 < PN) {
+      bf16* r = gd + (size_t)tok1 * ldq + hh1 * HDT + col;
       *reinterpret_cast<uint32_t*>(r) = pack_bf16x2(q0[2], q0[3]);
       *reinterpret_cast<uint32_t*>(r + 8) = pack_bf16x2(q1[2], q1[3]);
       *reinterpret_cast<uint32_t*>(r + D) = pack_bf16x2(k0[2], k0[3]);
@@ -696,17 +711,21 @@ static int set_smem(K kernel, int bytes);
 template <int HDT>
 static int launch_small(bool bwd, const bf16* qkv, const bf16* dout, bf16* out_or_dqkv, const float* lse_in, float* lse_out,
                         int B, int N, int H, float scale, cudaStream_t stream) {
-  const int BH = B * H;
+  // heads per warp: the 16-row tile holds 16 / N heads of one image when that count divides the heads (4-token grid of
+  // patch128: 4 heads per warp — a quarter of the warps, loads and stores of the one-head-per-warp layout)
+  int P = 1;
+  if (N < 16 && 16 % N == 0 && H % (16 / N) == 0) P = 16 / N;
+  const int items = B * (H / P);
   const int smem = 4 * (bwd ? 4 : 3) * Small<HDT>::TILE * 2;  // 4 warps per CTA
   const float sl2 = scale * 1.44269504088896340736f;
   if (!bwd) {
     const int rc = set_smem(attn_fwd_small<HDT>, smem);
     if (rc) return rc;
-    attn_fwd_small<HDT><<<(BH + 3) / 4, 128, smem, stream>>>(qkv, out_or_dqkv, lse_out, BH, N, H, sl2);
+    attn_fwd_small<HDT><<<(items + 3) / 4, 128, smem, stream>>>(qkv, out_or_dqkv, lse_out, items, N, H, P, sl2);
   } else {
     const int rc = set_smem(attn_bwd_small<HDT>, smem);
     if (rc) return rc;
-    attn_bwd_small<HDT><<<(BH + 3) / 4, 128, smem, stream>>>(qkv, dout, lse_in, out_or_dqkv, BH, N, H, scale, sl2);
+    attn_bwd_small<HDT><<<(items + 3) / 4, 128, smem, stream>>>(qkv, dout, lse_in, out_or_dqkv, items, N, H, P, scale, sl2);
   }
   TAE_CHECK_LAUNCH();
   return TAE_OK;

@@ -4,6 +4,7 @@
   evaluate_batch    train.py:203-223 / evaluate.py:84-102   forward under no_grad, loss only
   encode_batch      encode.py:80-88    forward_encoder under no_grad
   GraphedTrainStep  the same iteration captured once as a CUDA graph and replayed
+  GraphedEncoder    encode_batch as a replayed CUDA graph
   HostBatchFeeder   train.py:134 / encode.py:82   pinned-host -> device copies, double-buffered on a copy stream
                     (the synchronous 201 MB H2D per step is the adjacent host overhead)
   shard_for_rank    batch sharding for multi-GPU encode / evaluate (no communication; rank r takes slice r)
@@ -120,6 +121,40 @@ class GraphedTrainStep:
         self.optimizer.prepare_step()
         self.graph.replay()
         return self.static_loss.clone()
+
+
+class GraphedEncoder:
+    """encode_batch() captured once as a CUDA graph and replayed (encode.py:80-88 is ~150 launches per batch of a few
+    hundred microseconds each; there is no communication, so this also holds per rank under batch sharding).
+
+        enc = GraphedEncoder(model, example_batch)
+        for samples, targets in loader: writer.put(enc(samples.to(device, non_blocking=True)), targets)
+
+    The returned latent is the graph's static output buffer: consume it (LatentWriter.put enqueues its copy on a side
+    stream ordered after the replay) or clone it before the next call."""
+
+    def __init__(self, model, example, warmup_steps: int = 2):
+        self.model = model
+        self.static_in = torch.empty_like(example)
+        self.static_out = None
+        self.graph = None
+        self.calls = 0
+        self.warmup_steps = warmup_steps
+
+    @torch.no_grad()
+    def __call__(self, samples):
+        self.calls += 1
+        if self.calls <= self.warmup_steps or samples.shape != self.static_in.shape:
+            return self.model.forward_encoder(samples)  # warm-up, or a ragged last batch: eager
+        if self.graph is None:
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.static_out = self.model.forward_encoder(self.static_in)
+            self.graph = g
+        self.static_in.copy_(samples, non_blocking=True)
+        self.graph.replay()
+        return self.static_out
 
 
 @torch.no_grad()

@@ -315,7 +315,10 @@ def _attn_ref(qkv, B, N, H, hd, dout=None):
 
 
 @pytest.mark.parametrize("B,N,H,hd", [(3, 256, 4, 64), (5, 64, 8, 64), (6, 16, 8, 80), (7, 4, 8, 80), (2, 16, 4, 32),
-                                      (2, 64, 2, 32)])
+                                      (2, 64, 2, 32),
+                                      # short grids with several heads packed per warp (4 / 2 / 8 heads), and the shapes
+                                      # where the packing does not apply (6 heads of 4 tokens, 12 tokens)
+                                      (5, 4, 32, 80), (3, 8, 4, 64), (2, 2, 8, 32), (3, 4, 6, 80), (2, 12, 4, 64)])
 def test_attention_fwd_bwd(B, N, H, hd):
     ops = _ops()
     D = H * hd

@@ -339,3 +339,18 @@ def test_graphed_train_step_replays_eager_losses():
     for (n, p), (_, q) in zip(m0.named_parameters(), m1.named_parameters()):
         if not n.endswith("attn.qkv.bias"):
             assert rel(q, p) < 1e-4, n
+
+
+def test_graphed_encoder_replays_eager_latents():
+    from tae_b200 import engine
+
+    model = build().eval()
+    xs = [torch.randn(4, 3, 64, 64, generator=torch.Generator().manual_seed(20 + s)).cuda() for s in range(5)]
+    enc = engine.GraphedEncoder(model, xs[0], warmup_steps=1)
+    for x in xs:
+        z = enc(x).clone()
+        assert torch.equal(z, engine.encode_batch(model, x))
+    assert enc.graph is not None
+    # a ragged last batch falls back to the eager path
+    xr = torch.randn(3, 3, 64, 64, generator=torch.Generator().manual_seed(30)).cuda()
+    assert torch.equal(enc(xr), engine.encode_batch(model, xr))
