@@ -54,7 +54,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
     ap.add_argument("--mode", default=None, choices=["train", "encode"])
     ap.add_argument("--no-graph", action="store_true",
-                    help="run eagerly instead of replaying CUDA graphs (engine.GraphedTrainStep on one GPU, GraphedEncoder)")
+                    help="run eagerly instead of replaying CUDA graphs (engine.GraphedTrainStep, GraphedEncoder)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-encode", action="store_true", help="skip the encode.py-path measurement (config 5)")
@@ -411,10 +411,10 @@ def bench_train(D: Dist, model_name, B, steps, warmup, *, want_roofline, want_cl
     host = [torch.randn(B, 3, S, S, generator=gen).pin_memory() for _ in range(n_host)]
     resident = [h.to(dev) for h in host]
     graphed = None
-    if use_graph and world == 1:
+    if use_graph:
         # the whole step (forward, loss, backward, AdamW, zero_grad) captured once and replayed: ~1200-3100 launches per
         # step leave the host as one cudaGraphLaunch and the inter-kernel gaps shrink (patch128: 49.3 -> 47.1 ms)
-        graphed = engine.GraphedTrainStep(model, optimizer, resident[0], warmup_steps=min(2, warmup))
+        graphed = engine.GraphedTrainStep(net, optimizer, resident[0], warmup_steps=max(1, min(2, warmup)))
 
     def step_on(x, i):
         if graphed is not None:
@@ -484,7 +484,7 @@ def bench_train(D: Dist, model_name, B, steps, warmup, *, want_roofline, want_cl
         torch.cuda.empty_cache()
     roof = detail = None
     if want_roofline:
-        if use_graph and world == 1:
+        if use_graph:
             # the graph's pool is gone and the allocator cache is empty: two untimed eager steps bring the activations'
             # blocks back, so that no cudaMalloc lands inside the per-launch events of the instrumented steps
             for i in range(2):
@@ -507,7 +507,7 @@ def bench_train(D: Dist, model_name, B, steps, warmup, *, want_roofline, want_cl
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / steps},
         "model_tflops_per_gpu": fpi * ips / world / 1e12,
         "frac_of_bf16_peak_sustained": fpi * ips / world / 1e12 / peaks["bf16_tflops_sustained"],
-        "gpu_launches": int(launches), "clocks": clocks, "graph": bool(use_graph and world == 1),
+        "gpu_launches": int(launches), "clocks": clocks, "graph": bool(use_graph),
     }
     if ddp_check is not None:
         res["ddp_check"] = ddp_check["max_abs_delta"]

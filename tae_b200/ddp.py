@@ -176,7 +176,7 @@ class DistributedDataParallel(nn.Module):
             self._comm_stream.wait_stream(torch.cuda.current_stream())
             from .tae import wgrad_side_stream
 
-            side = wgrad_side_stream(b.flat.device)  # weight gradients of short-grid models are written on a side stream
+            side = wgrad_side_stream(b.flat.device, busy_only=True)  # weight gradients of short-grid models: side stream
             if side is not None:
                 self._comm_stream.wait_stream(side)
             with torch.cuda.stream(self._comm_stream):

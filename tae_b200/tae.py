@@ -97,9 +97,13 @@ _wg_streams: dict = {}          # device index -> side stream
 _wg_state = {"join_queued": False, "used": False}
 
 
-def wgrad_side_stream(device=None):
-    """The side stream carrying weight-gradient GEMMs on `device`, or None if none has been used yet."""
+def wgrad_side_stream(device=None, busy_only: bool = False):
+    """The side stream carrying weight-gradient GEMMs on `device`, or None if none has been used yet (with `busy_only`:
+    None unless it holds work enqueued since the last join — a stream without pending work must not be waited on while a
+    CUDA graph is being captured, it is not part of the capture)."""
     idx = torch.cuda.current_device() if device is None else torch.device(device).index
+    if busy_only and not _wg_state["used"]:
+        return None
     return _wg_streams.get(idx)
 
 

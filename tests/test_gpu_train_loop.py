@@ -116,6 +116,24 @@ def _ddp_worker(rank, world, port, q, kw, per_rank, bucket_mb):
         worst = max((rel(p.grad, dict(ref.named_parameters())[n].grad), n) for n, p in model.named_parameters()
                     if float(p.grad.norm()) > 1e-6)
         assert worst[0] < 5e-3, worst  # the two runs' weights already differ by fp32 reduction noise through 3 Adam steps
+        # the data-parallel step as ONE replayed CUDA graph: the bucketed NCCL all-reduces (and, for this short grid, the
+        # side-stream weight gradients) are captured with the kernels; losses track the 1-rank run, replicas stay identical
+        opt.zero_grad()
+        ref_opt.zero_grad()
+        step = engine.GraphedTrainStep(ddp, opt, xs[0][shard].contiguous(), max_lr=1e-3, min_lr=1e-3, switch_it=10 ** 9,
+                                       warmup_steps=1)
+        for it in range(5):
+            l = step(xs[it % 3][shard].contiguous(), it)
+            lr_ = engine.train_step(ref, ref_opt, scaler, xs[it % 3], it, max_lr=1e-3, min_lr=1e-3, switch_it=10 ** 9)
+            lsum = l.detach().clone()
+            dist.all_reduce(lsum)
+            assert abs(float(lsum) / world - float(lr_)) < 5e-3 * abs(float(lr_)), (it, float(lsum) / world, float(lr_))
+        assert step.captured
+        torch.cuda.synchronize()
+        for ar in opt.arenas:
+            gathered = [torch.empty_like(ar.p) for _ in range(world)]
+            dist.all_gather(gathered, ar.p)
+            assert all(torch.equal(gathered[0], g) for g in gathered[1:]), "replicas diverged under graph replay"
         dist.barrier()
         dist.destroy_process_group()
         q.put((rank, "ok"))

@@ -12,7 +12,7 @@ if "roofline" in d:
         val = v.get("tflops", v.get("GB/s", 0))
         frac = v.get("frac_of_hbm_peak", v.get("frac_of_bf16_peak"))
         print(f"  {k:16s} {val:9.1f} {'GB/s' if 'GB/s' in v else 'TF/s'}  {v['ms_per_step']:7.2f} ms/step" + (f"  frac {frac:.2f}" if frac else ""))
-print(d["clocks"])
+print(d.get("clocks"))
 if "encode" in d:
     print("encode", {k: (round(v, 1) if isinstance(v, float) else v) for k, v in d["encode"].items()})
 if "cpu_baseline" in d:
