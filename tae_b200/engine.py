@@ -87,6 +87,10 @@ class GraphedTrainStep:
         self.calls = 0
         self.launches_per_step = 0
         self._scaler = misc.NativeScalerWithGradNormCount(compute_norm=False)
+        # warm-up and capture run on ONE dedicated stream: autograd replays a node's backward on the stream of its forward
+        # and synchronises leaf streams at the end of backward, so a warm-up on another stream than the capturing one
+        # would make the capture depend on uncaptured work
+        self.stream = torch.cuda.Stream(device=example.device)
         optimizer.make_capturable()
 
     @property
@@ -101,7 +105,7 @@ class GraphedTrainStep:
         torch.cuda.empty_cache()  # the eager warm-up's cached activations and the graph's pool must not both stay resident
         n0 = ops.launch_count()
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
+        with torch.cuda.graph(g, stream=self.stream):
             loss, _ = model(self.static_in)
             self._scaler(loss, opt, parameters=None, update_grad=True)
             opt.zero_grad()
@@ -113,10 +117,17 @@ class GraphedTrainStep:
         misc.adjust_learning_rate(self.optimizer, self.sched[0], self.sched[1], it, self.sched[2])
         self.calls += 1
         if self.calls <= self.warmup_steps:
-            loss, _ = self.model(samples)
-            self._scaler(loss, self.optimizer, parameters=None, update_grad=True)
-            self.optimizer.zero_grad()
-            return loss.detach()
+            cur = torch.cuda.current_stream()
+            self.stream.wait_stream(cur)
+            with torch.cuda.stream(self.stream):
+                loss, _ = self.model(samples)
+                self._scaler(loss, self.optimizer, parameters=None, update_grad=True)
+                self.optimizer.zero_grad()
+                loss = loss.detach()
+            cur.wait_stream(self.stream)
+            samples.record_stream(self.stream)
+            loss.record_stream(cur)
+            return loss
         if self.graph is None:
             self._capture()
         self.static_in.copy_(samples, non_blocking=True)

@@ -41,19 +41,15 @@ class _Arena:
         self.v = torch.zeros(off, dtype=f32, device=dev)
         self.pb = torch.zeros(off, dtype=torch.bfloat16, device=dev)
         # host-side bookkeeping that lets step() skip the per-parameter walk in the common case: how many parameters
-        # had their gradient written by the hand-written backward since zero_grad(), and whether autograd's own
-        # AccumulateGrad ran for any of them (a torch-native op used the parameter)
+        # had their gradient written by the hand-written backward since zero_grad().  A parameter that ALSO receives a
+        # gradient through autograd's AccumulateGrad needs no flag: `p.grad` is the arena slice by then (or is folded in
+        # by `_sink`), so the accumulation lands in the arena.  (No post-accumulate-grad hook: a hook keeps the
+        # AccumulateGrad node — and the stream it was created on — alive, which breaks CUDA-graph capture.)
         self.n_direct = 0
-        self.foreign = False
 
     def view(self, arena, p):
         o = self.offsets[id(p)]
         return arena[o:o + p.numel()].view(p.shape)
-
-
-def _foreign_grad_hook(p):
-    """Runs after autograd's AccumulateGrad touched p.grad: the gradient did not come through tae_b200's backward."""
-    p._tae_arena.foreign = True
 
 
 class FusedAdamW(torch.optim.Optimizer):
@@ -101,7 +97,6 @@ class FusedAdamW(torch.optim.Optimizer):
                     p._tae_arena = ar
                     p._tae_dirty = 1 if old_grad is not None else 0
                     ar.n_direct += p._tae_dirty
-                    p.register_post_accumulate_grad_hook(_foreign_grad_hook)
                     p._tae_bf16 = ar.view(ar.pb, p)
                     p._tae_bf16_version = p._version
                     p._tae_bf16_ptr = p.data_ptr()
@@ -128,7 +123,6 @@ class FusedAdamW(torch.optim.Optimizer):
                 p._tae_dirty = 0
                 p.grad = None
             ar.n_direct = 0
-            ar.foreign = False
 
     # ------------------------------------------------------------------------------------------
     # CUDA-graph support: scalars in device memory
@@ -173,7 +167,7 @@ class FusedAdamW(torch.optim.Optimizer):
         for gi, (group, ar) in enumerate(zip(self.param_groups, self._arenas)):
             if ar is None:
                 continue
-            if ar.foreign or ar.n_direct != len(ar.params):
+            if ar.n_direct != len(ar.params):
                 # slow path (never taken by a plain TAE step): fold in gradients that autograd accumulated itself, and
                 # give parameters without any gradient a ZERO gradient.  torch.optim.AdamW skips such parameters
                 # entirely (no weight decay, no moment decay); one launch over a flat arena cannot, so here they decay

@@ -138,8 +138,10 @@ def _ddp_worker(rank, world, port, q, kw, per_rank, bucket_mb):
         dist.destroy_process_group()
         q.put((rank, "ok"))
     except Exception:  # pragma: no cover
+        import sys
         import traceback
 
+        traceback.print_exc(file=sys.stderr)  # pytest's assertion repr truncates the queued message
         q.put((rank, "FAIL: " + traceback.format_exc()))
 
 
