@@ -105,11 +105,20 @@ class GraphedTrainStep:
         torch.cuda.empty_cache()  # the eager warm-up's cached activations and the graph's pool must not both stay resident
         n0 = ops.launch_count()
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g, stream=self.stream):
-            loss, _ = model(self.static_in)
-            self._scaler(loss, opt, parameters=None, update_grad=True)
-            opt.zero_grad()
-            self.static_loss = loss.detach()
+        try:
+            with torch.cuda.graph(g, stream=self.stream):
+                loss, _ = model(self.static_in)
+                self._scaler(loss, opt, parameters=None, update_grad=True)
+                opt.zero_grad()
+                self.static_loss = loss.detach()
+        except RuntimeError as e:
+            if "uncaptured work" in str(e) or "capture" in str(e).lower():
+                raise RuntimeError(
+                    "CUDA-graph capture of the training step failed.  A common cause: an un-detached loss / output of an "
+                    "EARLIER eager step of this model is still referenced — its autograd graph keeps the parameters' "
+                    "AccumulateGrad nodes bound to the stream of that step, and autograd then synchronises the capture "
+                    "with it.  Keep only `.detach()`-ed results of eager steps (engine.train_step returns them).") from e
+            raise
         self.launches_per_step = ops.launch_count() - n0
         self.graph = g
 

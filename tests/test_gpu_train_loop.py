@@ -120,6 +120,9 @@ def _ddp_worker(rank, world, port, q, kw, per_rank, bucket_mb):
         # side-stream weight gradients) are captured with the kernels; losses track the 1-rank run, replicas stay identical
         opt.zero_grad()
         ref_opt.zero_grad()
+        # un-detached losses of the eager steps above would keep their autograd graphs — and through them the parameters'
+        # AccumulateGrad nodes, bound to the stream of those steps — alive; capture must not depend on that stream
+        del loss, l, la, lb, lr_, loss_ref
         step = engine.GraphedTrainStep(ddp, opt, xs[0][shard].contiguous(), max_lr=1e-3, min_lr=1e-3, switch_it=10 ** 9,
                                        warmup_steps=1)
         for it in range(5):
