@@ -410,11 +410,12 @@ def bench_train(D: Dist, model_name, B, steps, warmup, *, want_roofline, want_cl
     n_host = 2
     host = [torch.randn(B, 3, S, S, generator=gen).pin_memory() for _ in range(n_host)]
     resident = [h.to(dev) for h in host]
+    use_graph = use_graph and world == 1  # data-parallel steps run eagerly (engine.GraphedTrainStep is single-process)
     graphed = None
     if use_graph:
         # the whole step (forward, loss, backward, AdamW, zero_grad) captured once and replayed: ~1200-3100 launches per
         # step leave the host as one cudaGraphLaunch and the inter-kernel gaps shrink (patch128: 49.3 -> 47.1 ms)
-        graphed = engine.GraphedTrainStep(net, optimizer, resident[0], warmup_steps=max(1, min(2, warmup)))
+        graphed = engine.GraphedTrainStep(model, optimizer, resident[0], warmup_steps=max(1, min(2, warmup)))
 
     def step_on(x, i):
         if graphed is not None:

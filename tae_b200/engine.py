@@ -66,18 +66,17 @@ class GraphedTrainStep:
     What makes the step capturable: every kernel of the path is launched by the C ABI on the current stream with no
     allocation, synchronisation or host read-back; activations come from the graph's private memory pool; the optimizer's
     scalars (lr from adjust_learning_rate, bias corrections) live in device memory (`FusedAdamW.make_capturable`).  The
-    first `warmup_steps` calls run eagerly (they are real training steps), the next one captures.  `model` may be the
-    tae_b200.ddp wrapper: the bucketed all-reduces are captured on their communication stream (forked from and joined to
-    the capturing stream by the same wait_stream calls that order them in eager mode), so the replayed graph contains
-    the NCCL kernels; warm up at least once eagerly first (NCCL connects lazily).
+    first `warmup_steps` calls run eagerly (they are real training steps), the next one captures.  Single process: under
+    tae_b200.ddp use the eager step.  (Capturing the bucketed NCCL all-reduces with the step works — measured +1 % at
+    2 GPUs — but a replay interleaved with eager collectives hung one of the round-2 test runs, so it is not offered.)
 
         step = GraphedTrainStep(model, optimizer, example_batch, max_lr=1e-4, min_lr=1e-5, switch_it=450_000)
         for it, samples in enumerate(loader): loss = step(samples, it)      # device tensor, no host sync
     """
 
     def __init__(self, model, optimizer, example, *, max_lr=1e-4, min_lr=1e-5, switch_it=450_000, warmup_steps=3):
-        if misc.get_world_size() > 1 and warmup_steps < 1:
-            raise RuntimeError("GraphedTrainStep under data parallelism needs warmup_steps >= 1 (NCCL connects lazily)")
+        if misc.get_world_size() > 1:
+            raise RuntimeError("GraphedTrainStep is single-process; use train_step under tae_b200.ddp")
         self.model, self.optimizer = model, optimizer
         self.sched = (max_lr, min_lr, switch_it)
         self.warmup_steps = warmup_steps

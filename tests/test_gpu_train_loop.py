@@ -116,27 +116,6 @@ def _ddp_worker(rank, world, port, q, kw, per_rank, bucket_mb):
         worst = max((rel(p.grad, dict(ref.named_parameters())[n].grad), n) for n, p in model.named_parameters()
                     if float(p.grad.norm()) > 1e-6)
         assert worst[0] < 5e-3, worst  # the two runs' weights already differ by fp32 reduction noise through 3 Adam steps
-        # the data-parallel step as ONE replayed CUDA graph: the bucketed NCCL all-reduces (and, for this short grid, the
-        # side-stream weight gradients) are captured with the kernels; losses track the 1-rank run, replicas stay identical
-        opt.zero_grad()
-        ref_opt.zero_grad()
-        # un-detached losses of the eager steps above would keep their autograd graphs — and through them the parameters'
-        # AccumulateGrad nodes, bound to the stream of those steps — alive; capture must not depend on that stream
-        del loss, l, la, lb, lr_, loss_ref
-        step = engine.GraphedTrainStep(ddp, opt, xs[0][shard].contiguous(), max_lr=1e-3, min_lr=1e-3, switch_it=10 ** 9,
-                                       warmup_steps=1)
-        for it in range(5):
-            l = step(xs[it % 3][shard].contiguous(), it)
-            lr_ = engine.train_step(ref, ref_opt, scaler, xs[it % 3], it, max_lr=1e-3, min_lr=1e-3, switch_it=10 ** 9)
-            lsum = l.detach().clone()
-            dist.all_reduce(lsum)
-            assert abs(float(lsum) / world - float(lr_)) < 5e-3 * abs(float(lr_)), (it, float(lsum) / world, float(lr_))
-        assert step.captured
-        torch.cuda.synchronize()
-        for ar in opt.arenas:
-            gathered = [torch.empty_like(ar.p) for _ in range(world)]
-            dist.all_gather(gathered, ar.p)
-            assert all(torch.equal(gathered[0], g) for g in gathered[1:]), "replicas diverged under graph replay"
         dist.barrier()
         dist.destroy_process_group()
         q.put((rank, "ok"))
@@ -148,7 +127,7 @@ def _ddp_worker(rank, world, port, q, kw, per_rank, bucket_mb):
         q.put((rank, "FAIL: " + traceback.format_exc()))
 
 
-@pytest.mark.timeout(600)
+@pytest.mark.timeout(300)
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs (run under gpurun --gpus 2)")
 @pytest.mark.parametrize("kw,per_rank,bucket_mb", [
     (KW, 4, 0.25),
@@ -164,10 +143,15 @@ def test_ddp_nccl_matches_single_rank_and_replicas_stay_identical(kw, per_rank, 
     procs = [ctx.Process(target=_ddp_worker, args=(r, world, port, q, kw, per_rank, bucket_mb)) for r in range(world)]
     for p in procs:
         p.start()
-    results = [q.get(timeout=500) for _ in range(world)]
-    for p in procs:
-        p.join(timeout=60)
-    assert all(msg == "ok" for _, msg in results), results
+    results = []
+    try:
+        results = [q.get(timeout=200) for _ in range(world)]
+    finally:
+        for p in procs:
+            p.join(timeout=20)
+            if p.is_alive():  # a rank stuck in a collective its peer never entered must not outlive the test
+                p.kill()
+    assert len(results) == world and all(msg == "ok" for _, msg in results), results
 
 
 # ----------------------------------------------------------------------------------------------------
