@@ -27,9 +27,9 @@ for v in "$@"; do
   unset TAE_B200_LIB
 done
 for i in 1 2; do
-  timeout 300 python bench.py --steps 8 --warmup 3 --no-cpu-baseline > gpurun_out/ab_default_$i.log 2>&1; summ gpurun_out/ab_default_$i.log
+  timeout 300 python bench.py --steps 8 --warmup 3 --no-cpu-baseline --no-gpu-reference --no-secondary --no-encode > gpurun_out/ab_default_$i.log 2>&1; summ gpurun_out/ab_default_$i.log
   for v in $ok; do
-    TAE_B200_LIB=tae_b200/libtae_b200.$v.so timeout 300 python bench.py --steps 8 --warmup 3 --no-cpu-baseline > gpurun_out/ab_${v}_$i.log 2>&1
+    TAE_B200_LIB=tae_b200/libtae_b200.$v.so timeout 300 python bench.py --steps 8 --warmup 3 --no-cpu-baseline --no-gpu-reference --no-secondary --no-encode > gpurun_out/ab_${v}_$i.log 2>&1
     summ gpurun_out/ab_${v}_$i.log
   done
 done

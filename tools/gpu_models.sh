@@ -1,7 +1,10 @@
 #!/bin/bash
-# 1-GPU training-step throughput of the other model sizes (BASELINE.json configs 3-5), with the per-kernel-family detail.
+# 1-GPU lines of the other BASELINE configs with the per-kernel-family detail: 3 (patch32 training), 4 (patch128 training),
+# patch64 training, 5 (patch64 encode).
 mkdir -p gpurun_out
-for m in tae_patch32_vocab1024_px256 tae_patch64_vocab4096_px256 tae_patch128_vocab16384_px256; do
-  timeout 600 python bench.py --model $m --steps 3 --warmup 3 --no-cpu-baseline --no-encode > gpurun_out/bench_$m.log 2>&1; echo "$m exit $?"
-  python tools/print_bench.py gpurun_out/bench_$m.log
+F="--steps 6 --warmup 3 --no-cpu-baseline --no-gpu-reference --no-secondary --no-encode"
+for c in 3 4; do
+  timeout 600 python bench.py --config $c $F > gpurun_out/bench_c$c.log 2>&1; echo "config $c exit $?"; python tools/print_bench.py gpurun_out/bench_c$c.log
 done
+timeout 600 python bench.py --model tae_patch64_vocab4096_px256 $F > gpurun_out/bench_p64.log 2>&1; echo "patch64 train exit $?"; python tools/print_bench.py gpurun_out/bench_p64.log
+timeout 600 python bench.py --config 5 --steps 20 --warmup 5 > gpurun_out/bench_c5.log 2>&1; echo "config 5 exit $?"; python tools/print_bench.py gpurun_out/bench_c5.log
