@@ -41,6 +41,7 @@ sys.path.insert(0, ROOT)
 CONFIGS = {2: ("tae_patch16_vocab256_px256", "train"), 3: ("tae_patch32_vocab1024_px256", "train"),
            4: ("tae_patch128_vocab16384_px256", "train"), 5: ("tae_patch64_vocab4096_px256", "encode")}
 REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+DDP_NO_OVERLAP = False  # set by --ddp-no-overlap (A/B)
 
 
 def parse():
@@ -63,6 +64,8 @@ def parse():
     ap.add_argument("--ref-mode", default="bf16_eager", choices=["bf16_eager", "bf16_compile", "fp16_scaler"])
     ap.add_argument("--ref-modes", default="bf16_eager,fp16_scaler,bf16_compile")
     ap.add_argument("--cpu-batch", type=int, default=2)
+    ap.add_argument("--ddp-no-overlap", action="store_true",
+                    help="A/B: all-reduce the gradient buckets at the end of backward instead of overlapping them with it")
     ap.add_argument("--wgrad-overlap-rows", type=int, default=None,
                     help="A/B: override tae_b200.tae.WGRAD_OVERLAP_MAX_ROWS (0 = weight gradients on the main stream)")
     a = ap.parse_args()
@@ -404,7 +407,7 @@ def bench_train(D: Dist, model_name, B, steps, warmup, *, want_roofline, want_cl
     N, Dm, L, V, S = model_dims(model)
     optimizer = engine.build_optimizer(model, max_lr=1e-4, weight_decay=0.05)
     scaler = misc.NativeScalerWithGradNormCount(compute_norm=False)
-    net = DistributedDataParallel(model, optimizer=optimizer) if world > 1 else model
+    net = DistributedDataParallel(model, optimizer=optimizer, overlap=not DDP_NO_OVERLAP) if world > 1 else model
 
     gen = torch.Generator(device="cpu").manual_seed(1234 + rank)
     n_host = 2
@@ -542,6 +545,9 @@ def run_b200(args):
         # short collective timeout: a rank mismatch must abort in minutes, not hang the box
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=240))
     _lib.require_device()
+    if args.ddp_no_overlap:
+        global DDP_NO_OVERLAP
+        DDP_NO_OVERLAP = True
     if args.wgrad_overlap_rows is not None:
         from tae_b200 import tae as _tae
 

@@ -71,9 +71,12 @@ def plan_buckets(order, offsets, numel_of, bucket_elems, tail_elems=0):
 
 class DistributedDataParallel(nn.Module):
     def __init__(self, module: nn.Module, optimizer=None, bucket_mb: float = 64.0, process_group=None,
-                 device_ids=None, broadcast: bool = True, tail_mb: float = 8.0):
+                 device_ids=None, broadcast: bool = True, tail_mb: float = 8.0, overlap: bool = True):
         super().__init__()
         self.module = module
+        # overlap=False: the buckets are all-reduced back to back at the END of backward instead of while it runs — the
+        # whole exchange is then exposed, but no NCCL kernel holds SMs (and HBM bandwidth) under the backward GEMMs
+        self.overlap = overlap
         self.process_group = process_group
         self.bucket_elems = int(bucket_mb * (1 << 20) / 4)
         self.tail_elems = int(tail_mb * (1 << 20) / 4)
@@ -168,7 +171,7 @@ class DistributedDataParallel(nn.Module):
             return
         b.seen.add(id(p))
         b.pending -= 1
-        if b.pending == 0:
+        if b.pending == 0 and self.overlap:
             self._launch(b)
 
     def _launch(self, b):
@@ -186,7 +189,7 @@ class DistributedDataParallel(nn.Module):
         self._launched.append(b)
 
     def _finalize_backward(self):
-        # buckets whose parameters did not all report (unused parameters) are reduced now
+        # buckets whose parameters did not all report (unused parameters) are reduced now — and, without overlap, all
         for b in self._buckets:
             if b.work is None and b.pending != len(b.params):
                 self._launch(b)

@@ -78,6 +78,14 @@ def _worker(rank, world, port, q):
             for i, p in enumerate(reversed(params)):
                 want = mean_scale * (i + 1)
                 assert torch.allclose(p.grad, torch.full_like(p.grad, want)), (rank, i, p.grad.flatten()[:3], want)
+        # overlap=False: every bucket leaves at the end of backward; same averages
+        ddp.overlap = False
+        with torch.enable_grad():
+            _WriteGrads.apply(x, params, rank).backward()
+        for i, p in enumerate(reversed(params)):
+            assert torch.allclose(p.grad, torch.full_like(p.grad, mean_scale * (i + 1))), (rank, i)
+        assert all(b.work is None and b.pending == len(b.params) for b in ddp._buckets)
+        ddp.overlap = True
         # no_sync: gradients stay local
         with ddp.no_sync():
             _WriteGrads.apply(x, params, rank).backward()
