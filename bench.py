@@ -248,6 +248,56 @@ def cpu_reference_step_time(model_name: str, batch: int, steps: int, warmup: int
     return batch / sec, cores, sec, kind
 
 
+def cpu_config1(repeats: int = 3):
+    """BASELINE.json configs[0] / BASELINE.md §4: the reference's CPU-runnable case — tae_patch16_vocab16_px256, batch 2,
+    fp32, seeded — timed on the host cores with the unmodified reference (oracle/_ref; the oracle port if it is absent):
+    forward + loss under no_grad, forward_encoder, forward + backward; best and median of `repeats` after one warm-up.
+    Also re-checks the seed-pinned loss of SURVEY.md §8c (2.184759855, 1e-4 relative)."""
+    import torch
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    ref = load_reference_modules()
+    torch.manual_seed(0)
+    x = torch.randn(2, 3, 256, 256, generator=torch.Generator().manual_seed(1234))
+    if ref is not None:
+        model = ref[0].tae_patch16_vocab16_px256()
+        fwd_loss = lambda: model(x)[0]
+        enc = lambda: model.forward_encoder(x)
+        kind = "reference"
+    else:
+        from oracle import tae_oracle as O
+
+        cfg = O.zoo_config("tae_patch16_vocab16_px256")
+        sd = {k: v.requires_grad_(True) for k, v in O.init_state_dict(cfg, seed=0).items()}
+        fwd_loss = lambda: O.forward(sd, x, cfg, "fp32")[0]
+        enc = lambda: O.forward(sd, x, cfg, "fp32")[2]
+        kind = "port"
+
+    def timed(fn, grad):
+        ts, val = [], None
+        for i in range(repeats + 1):
+            t0 = time.perf_counter()
+            if grad:
+                val = fn()
+                val.backward()
+            else:
+                with torch.no_grad():
+                    val = fn()
+            if i:
+                ts.append(time.perf_counter() - t0)
+        ts.sort()
+        return {"best_s": ts[0], "median_s": ts[len(ts) // 2], "images_per_s": 2 / ts[0]}, val
+
+    out = {"model": "tae_patch16_vocab16_px256", "batch": 2, "dtype": "f32", "cores": cores, "kind": kind}
+    out["fwd_loss"], loss = timed(fwd_loss, False)
+    out["forward_encoder"], _ = timed(enc, False)
+    out["fwd_bwd"], _ = timed(fwd_loss, True)
+    out["loss"] = float(loss)
+    out["pinned_loss_ok"] = abs(float(loss) - 2.184759855) < 1e-4 * 2.184759855
+    return out
+
+
 def run_reference(args):
     """CPU arm of the driver's ratio: the reference's own implementation on the host cores, bounded sample."""
     rank = int(os.environ.get("RANK", "0"))
@@ -628,6 +678,10 @@ def run_b200(args):
                                     "sample": f"10 timed steps x {args.cpu_batch} images of the same training step, fp32, "
                                               f"{'unmodified reference tae.py' if kind == 'reference' else 'oracle port'}, "
                                               f"{cores} threads ({csec:.1f} s/step)"}
+            try:  # BASELINE configs[0]: the reference's own CPU-runnable case; never at the expense of the line itself
+                line["cpu_baseline"]["config1"] = cpu_config1()
+            except Exception as e:
+                line["cpu_baseline"]["config1"] = {"unavailable": f"{type(e).__name__}: {str(e)[:200]}"}
     print(json.dumps(line), flush=True)
 
 

@@ -74,3 +74,13 @@ def test_reference_arm_json_contract():
     assert line["cpu_baseline"]["value"] == line["value"] == line["e2e"]["value"]
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0 and line["gpu_launches"] == 0
     assert line["config"]["workload"].startswith("tae_patch16_vocab16_px256")
+
+
+@pytest.mark.timeout(600)
+def test_cpu_config1_reproduces_the_pinned_loss():
+    """BASELINE.json configs[0]: the reference's CPU-runnable case, as bench.py reports it beside the GPU numbers."""
+    r = bench.cpu_config1(repeats=1)
+    assert r["model"] == "tae_patch16_vocab16_px256" and r["batch"] == 2 and r["kind"] in ("reference", "port")
+    assert r["pinned_loss_ok"] and abs(r["loss"] - 2.184759855) < 1e-4 * 2.184759855
+    for k in ("fwd_loss", "forward_encoder", "fwd_bwd"):
+        assert r[k]["best_s"] > 0 and r[k]["images_per_s"] > 0
